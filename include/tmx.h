@@ -1,0 +1,80 @@
+/*
+ * tmx.h -- C ABI of libtmx.so, the B200 (sm_100a) witness generator and Goldilocks prover for
+ * TendermintX's skip / step circuits.
+ *
+ * The reference has no FFI of its own: the boundary it sits behind is plonky2x's Rust surface
+ * (`Circuit::define`, `builder.build()`, `circuit.prove()`, `circuit.verify()`, the `build` /
+ * `prove input.json` CLI).  Each entry point below names the reference interface it replaces
+ * (paths relative to /root/reference).  INTEGRATION.md shows the Rust `extern "C"` block a
+ * maintainer would add.
+ *
+ * Conventions
+ *   - every function returns a tmx_status (0 = TMX_OK); tmx_last_error() gives a thread-local message.
+ *   - handles are opaque, created and freed by the library; caller-owned input buffers are only read
+ *     during the call; output buffers are caller-allocated with explicit capacity.
+ *   - "d_" parameters are DEVICE pointers in the context's GPU; `stream` is a cudaStream_t passed as
+ *     void* (NULL = the context's own stream).  Field elements are canonical Goldilocks u64
+ *     (little-endian), matrices are COLUMN-MAJOR: element (row, col) at col * n_rows + row.
+ *   - one tmx_ctx per GPU, used by one host thread at a time; distinct contexts are independent.
+ *   - nothing here falls back to a CPU implementation: without a CUDA device tmx_ctx_create fails.
+ */
+#ifndef TMX_H
+#define TMX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    TMX_OK = 0,
+    TMX_E_INPUT = 1, /* malformed argument / input bytes / fixture (reference: panic on expect/assert) */
+    TMX_E_UNSAT = 2, /* witness does not satisfy the circuit (reference: generator panic)          */
+    TMX_E_CUDA = 3,  /* CUDA runtime / kernel failure, or no device                                   */
+    TMX_E_IO = 4,    /* file missing / unreadable (reference: fs::read_to_string(..).unwrap())       */
+    TMX_E_VERIFY = 5 /* proof rejected (reference: circuit.verify panics)                            */
+} tmx_status;
+
+typedef struct tmx_ctx tmx_ctx;
+
+const char *tmx_last_error(void);
+const char *tmx_version(void);
+
+/* One context per GPU: owns a stream, twiddle tables, Poseidon constants and scratch memory. */
+int tmx_ctx_create(int device, tmx_ctx **out);
+void tmx_ctx_destroy(tmx_ctx *ctx);
+int tmx_ctx_sync(tmx_ctx *ctx);
+/* kernels launched by this context since creation (bench.py's gpu_launches counter) */
+uint64_t tmx_ctx_launch_count(const tmx_ctx *ctx);
+
+/* ------------------------------------------------------------------------------------------------
+ * Kernel-level entry points (parity tests, ncu, roofline).  They replace, on the GPU, loops that run
+ * inside plonky2 / starkyx when the reference calls `circuit.prove()` [circuits/skip.rs:214,244;
+ * circuits/step.rs:196,223]; SURVEY.md section 8 row a23 lists them.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* K1a: in-place batched NTT / inverse NTT, natural order in and out (plonky2_field fft / ifft). */
+int tmx_ntt(tmx_ctx *ctx, uint64_t *d_data, size_t n_cols, unsigned log_n, int inverse, void *stream);
+
+/* K1b: PolynomialBatch low-degree extension: values[n_cols][n] -> iNTT -> zero-pad by 2^rate_bits ->
+ * coset NTT (shift 7) -> out[n_cols][n << rate_bits] in BIT-REVERSED row order (the Merkle leaf order).
+ * d_coeffs (optional, may be NULL) receives the coset-scaled coefficients c_i * 7^i, [n_cols][n]. */
+int tmx_lde(tmx_ctx *ctx, const uint64_t *d_values, uint64_t *d_out, uint64_t *d_coeffs, size_t n_cols,
+            unsigned log_n, unsigned rate_bits, void *stream);
+
+/* K2: Poseidon Merkle tree over the rows of a column-major matrix; leaf j = hash_or_noop(row j).
+ * d_digests receives 4 u64 per node, levels concatenated: level 0 (n_rows leaf digests), level 1, ...,
+ * cap level (1 << cap_height digests).  tmx_merkle_digest_count gives the total node count. */
+size_t tmx_merkle_digest_count(unsigned log_rows, unsigned cap_height);
+int tmx_poseidon_merkle(tmx_ctx *ctx, const uint64_t *d_cols, size_t n_cols, unsigned log_rows,
+                        unsigned cap_height, uint64_t *d_digests, void *stream);
+
+/* Poseidon permutation of n independent 12-element states (known-answer tests). */
+int tmx_poseidon_permute(tmx_ctx *ctx, uint64_t *d_states, size_t n, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

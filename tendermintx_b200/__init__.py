@@ -1,0 +1,98 @@
+"""tendermintx_b200 -- B200-native witness generator and Goldilocks prover for TendermintX's skip / step
+circuits.  Python is a thin ctypes shim over the C ABI (include/tmx.h); torch is used only for device
+memory, streams and torch.distributed plumbing.
+
+Field elements are canonical Goldilocks u64; torch has no uint64 arithmetic so device buffers are
+``torch.int64`` tensors holding the same bits (``numpy_u64.view(numpy.int64)``).
+"""
+import ctypes
+
+from . import _lib
+from ._lib import TmxError
+
+__all__ = ["Context", "TmxError", "lib"]
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = _lib.load()
+    return _LIB
+
+
+def _check(rc):
+    if rc != 0:
+        raise TmxError(rc, lib().tmx_last_error().decode())
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+class Context:
+    """One per GPU (mirrors `tmx_ctx`).  Kernel-level entry points take torch CUDA int64 tensors."""
+
+    def __init__(self, device=0):
+        self._h = ctypes.c_void_p()
+        self.device = device
+        _check(lib().tmx_ctx_create(device, ctypes.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().tmx_ctx_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def _stream(self):
+        import torch
+
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def launch_count(self):
+        return int(lib().tmx_ctx_launch_count(self._h))
+
+    def sync(self):
+        _check(lib().tmx_ctx_sync(self._h))
+
+    # ---- K1 ----
+    def ntt(self, data, log_n, inverse=False):
+        """In-place NTT of a [n_cols, 2^log_n] int64 CUDA tensor (each row of the tensor is one column
+        of the column-major matrix), natural order in and out."""
+        n_cols = data.numel() >> log_n
+        _check(lib().tmx_ntt(self._h, _ptr(data), n_cols, log_n, int(inverse), self._stream()))
+        return data
+
+    def lde(self, values, log_n, rate_bits, out=None, coeffs=None):
+        import torch
+
+        n_cols = values.numel() >> log_n
+        if out is None:
+            out = torch.empty((n_cols, 1 << (log_n + rate_bits)), dtype=torch.int64, device=values.device)
+        _check(lib().tmx_lde(self._h, _ptr(values), _ptr(out), _ptr(coeffs), n_cols, log_n, rate_bits, self._stream()))
+        return out
+
+    # ---- K2 ----
+    def poseidon_merkle(self, cols, log_rows, cap_height, digests=None):
+        import torch
+
+        n_cols = cols.numel() >> log_rows
+        cnt = lib().tmx_merkle_digest_count(log_rows, cap_height)
+        if digests is None:
+            digests = torch.empty((cnt, 4), dtype=torch.int64, device=cols.device)
+        _check(lib().tmx_poseidon_merkle(self._h, _ptr(cols), n_cols, log_rows, cap_height, _ptr(digests), self._stream()))
+        return digests
+
+    def poseidon_permute(self, states):
+        _check(lib().tmx_poseidon_permute(self._h, _ptr(states), states.numel() // 12, self._stream()))
+        return states

@@ -1,0 +1,62 @@
+"""ctypes loader for libtmx.so (the C ABI declared in include/tmx.h).
+
+There is no CPU fallback: if the shared library has not been built (``python -c "import
+__graft_entry__ as g; g.build()"`` or ``make -C tendermintx_b200/csrc``) importing this module
+raises, and without a CUDA device ``tmx_ctx_create`` fails.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtmx.so")
+
+TMX_OK, TMX_E_INPUT, TMX_E_UNSAT, TMX_E_CUDA, TMX_E_IO, TMX_E_VERIFY = range(6)
+_STATUS_NAMES = {
+    TMX_E_INPUT: "TMX_E_INPUT",
+    TMX_E_UNSAT: "TMX_E_UNSAT",
+    TMX_E_CUDA: "TMX_E_CUDA",
+    TMX_E_IO: "TMX_E_IO",
+    TMX_E_VERIFY: "TMX_E_VERIFY",
+}
+
+
+class TmxError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{_STATUS_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+def load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build the CUDA extension first (make -C tendermintx_b200/csrc). "
+            "tendermintx_b200 has no CPU fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    c = ctypes
+    vp, u64p, sz, u32, i32 = c.c_void_p, c.c_void_p, c.c_size_t, c.c_uint, c.c_int
+    sig = {
+        "tmx_last_error": (c.c_char_p, []),
+        "tmx_version": (c.c_char_p, []),
+        "tmx_ctx_create": (i32, [i32, c.POINTER(vp)]),
+        "tmx_ctx_destroy": (None, [vp]),
+        "tmx_ctx_sync": (i32, [vp]),
+        "tmx_ctx_launch_count": (c.c_uint64, [vp]),
+        "tmx_ntt": (i32, [vp, u64p, sz, u32, i32, vp]),
+        "tmx_lde": (i32, [vp, u64p, u64p, u64p, sz, u32, u32, vp]),
+        "tmx_merkle_digest_count": (sz, [u32, u32]),
+        "tmx_poseidon_merkle": (i32, [vp, u64p, sz, u32, u32, u64p, vp]),
+        "tmx_poseidon_permute": (i32, [vp, u64p, sz, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+EXPORTED_SYMBOLS = [
+    "tmx_last_error", "tmx_version", "tmx_ctx_create", "tmx_ctx_destroy", "tmx_ctx_sync",
+    "tmx_ctx_launch_count", "tmx_ntt", "tmx_lde", "tmx_merkle_digest_count", "tmx_poseidon_merkle",
+    "tmx_poseidon_permute",
+]

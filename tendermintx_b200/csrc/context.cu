@@ -1,0 +1,215 @@
+// tmx_ctx lifetime, error reporting, twiddle / power tables, Poseidon round-constant generation.
+#include "ctx.cuh"
+#include "poseidon.cuh"
+#include <cstring>
+
+namespace tmx {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+// ---- Poseidon round constants: ChaCha8 keystream keyed by rand-0.8's seed_from_u64(0) (PCG32 expansion),
+// u64 = lo | hi << 32, mapped into [0, p) with rand's widening-multiply rejection sampler (zone = p - 1).
+gl h_poseidon_rc[POSEIDON_ROUNDS * POSEIDON_WIDTH];
+static bool g_rc_ready = false;
+
+static inline uint32_t rol(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+static void chacha8(const uint32_t key[8], uint64_t counter, uint32_t out[16]) {
+    uint32_t in[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u};
+    for (int i = 0; i < 8; i++) in[4 + i] = key[i];
+    in[12] = (uint32_t)counter;
+    in[13] = (uint32_t)(counter >> 32);
+    in[14] = in[15] = 0;
+    uint32_t x[16];
+    memcpy(x, in, sizeof x);
+    auto qr = [&](int a, int b, int c, int d) {
+        x[a] += x[b]; x[d] = rol(x[d] ^ x[a], 16);
+        x[c] += x[d]; x[b] = rol(x[b] ^ x[c], 12);
+        x[a] += x[b]; x[d] = rol(x[d] ^ x[a], 8);
+        x[c] += x[d]; x[b] = rol(x[b] ^ x[c], 7);
+    };
+    for (int dr = 0; dr < 4; dr++) {
+        qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15);
+        qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14);
+    }
+    for (int i = 0; i < 16; i++) out[i] = x[i] + in[i];
+}
+
+void poseidon_generate_constants() {
+    if (g_rc_ready) return;
+    uint64_t st = 0;
+    uint32_t key[8];
+    for (int i = 0; i < 8; i++) {
+        st = st * 6364136223846793005ULL + 11634580027462260723ULL;
+        uint32_t xs = (uint32_t)(((st >> 18) ^ st) >> 27);
+        uint32_t rot = (uint32_t)(st >> 59);
+        key[i] = (xs >> rot) | (xs << ((32 - rot) & 31));
+    }
+    uint32_t block[16];
+    uint64_t ctr = 0;
+    int pos = 16, n = 0;
+    auto next32 = [&]() {
+        if (pos == 16) {
+            chacha8(key, ctr++, block);
+            pos = 0;
+        }
+        return block[pos++];
+    };
+    while (n < POSEIDON_ROUNDS * POSEIDON_WIDTH) {
+        uint64_t lo = next32();
+        uint64_t hi = next32();
+        unsigned __int128 m = (unsigned __int128)(lo | (hi << 32)) * GL_P;
+        if ((uint64_t)m <= GL_P - 1) h_poseidon_rc[n++] = (gl)(m >> 64);
+    }
+    g_rc_ready = true;
+}
+
+// ---- device tables ----
+static int upload(tmx_ctx* ctx, const std::vector<gl>& h, gl** out) {
+    void* d = nullptr;
+    TMX_CUDA(cudaMalloc(&d, h.size() * sizeof(gl)));
+    TMX_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(gl), cudaMemcpyHostToDevice));
+    ctx->owned.push_back(d);
+    *out = (gl*)d;
+    return TMX_OK;
+}
+
+// base^e for e < 2^log_size, optionally every entry of the hi table scaled by `hi_scale`
+static int build_pow_table(tmx_ctx* ctx, gl base, unsigned log_size, gl hi_scale, PowTable* t) {
+    t->log_size = log_size;
+    t->klo = (log_size + 1) / 2;
+    const size_t nlo = (size_t)1 << t->klo, nhi = (size_t)1 << (log_size - t->klo);
+    std::vector<gl> lo(nlo), hi(nhi);
+    gl cur = 1;
+    for (size_t i = 0; i < nlo; i++) {
+        lo[i] = cur;
+        cur = gl_mul(cur, base);
+    }
+    gl step = cur;  // base^(2^klo)
+    cur = hi_scale;
+    for (size_t i = 0; i < nhi; i++) {
+        hi[i] = cur;
+        cur = gl_mul(cur, step);
+    }
+    int rc = upload(ctx, lo, &t->lo);
+    if (rc) return rc;
+    return upload(ctx, hi, &t->hi);
+}
+
+int ctx_ntt_tables(tmx_ctx* ctx, unsigned log_n, bool inverse, const NttTables** out) {
+    auto& cache = inverse ? ctx->inv : ctx->fwd;
+    auto it = cache.find(log_n);
+    if (it != cache.end()) {
+        *out = &it->second;
+        return TMX_OK;
+    }
+    NttTables t;
+    gl w = gl_root_of_unity(log_n);
+    if (inverse) w = gl_inv(w);
+    if (log_n >= 1 && log_n <= 10) {
+        const size_t half = (size_t)1 << (log_n - 1);
+        std::vector<gl> s(half);
+        gl cur = 1;
+        for (size_t i = 0; i < half; i++) {
+            s[i] = cur;
+            cur = gl_mul(cur, w);
+        }
+        int rc = upload(ctx, s, &t.small);
+        if (rc) return rc;
+    }
+    int rc = build_pow_table(ctx, w, log_n, 1, &t.big);
+    if (rc) return rc;
+    auto ins = cache.emplace(log_n, t);
+    *out = &ins.first->second;
+    return TMX_OK;
+}
+
+int ctx_coset_scale(tmx_ctx* ctx, unsigned log_n, const PowTable** out) {
+    auto it = ctx->coset_scale.find(log_n);
+    if (it != ctx->coset_scale.end()) {
+        *out = &it->second;
+        return TMX_OK;
+    }
+    PowTable t;
+    int rc = build_pow_table(ctx, GL_GEN, log_n, gl_inv((gl)((uint64_t)1 << log_n)), &t);
+    if (rc) return rc;
+    auto ins = ctx->coset_scale.emplace(log_n, t);
+    *out = &ins.first->second;
+    return TMX_OK;
+}
+
+int ctx_scratch(tmx_ctx* ctx, int slot, size_t bytes, void** out) {
+    if (ctx->scratch_bytes[slot] < bytes) {
+        if (ctx->scratch[slot]) {
+            TMX_CUDA(cudaStreamSynchronize(ctx->stream));
+            TMX_CUDA(cudaFree(ctx->scratch[slot]));
+            ctx->scratch[slot] = nullptr;
+            ctx->scratch_bytes[slot] = 0;
+        }
+        size_t want = bytes + bytes / 8;
+        TMX_CUDA(cudaMalloc(&ctx->scratch[slot], want));
+        ctx->scratch_bytes[slot] = want;
+    }
+    *out = ctx->scratch[slot];
+    return TMX_OK;
+}
+
+}  // namespace tmx
+
+using namespace tmx;
+
+extern "C" const char* tmx_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char* tmx_version(void) { return "tmx-b200 0.1 (sm_100a)"; }
+
+extern "C" int tmx_ctx_create(int device, tmx_ctx** out) {
+    if (!out) return fail(TMX_E_INPUT, "tmx_ctx_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(TMX_E_CUDA, std::string("tmx_ctx_create: no CUDA device (") + cudaGetErrorString(e) +
+                                    "); this library has no CPU fallback");
+    if (device < 0 || device >= count) return fail(TMX_E_INPUT, "tmx_ctx_create: device index out of range");
+    TMX_CUDA(cudaSetDevice(device));
+    tmx_ctx* ctx = new tmx_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    TMX_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        delete ctx;
+        return fail(TMX_E_CUDA, "tmx_ctx_create: device is not sm_100 class (kernels are built for sm_100a only)");
+    }
+    TMX_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    poseidon_generate_constants();
+    int rc = merkle_tu_init();
+    if (rc) {
+        delete ctx;
+        return rc;
+    }
+    *out = ctx;
+    return TMX_OK;
+}
+
+extern "C" void tmx_ctx_destroy(tmx_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (void* p : ctx->owned) cudaFree(p);
+    for (int i = 0; i < 4; i++)
+        if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int tmx_ctx_sync(tmx_ctx* ctx) {
+    if (!ctx) return fail(TMX_E_INPUT, "tmx_ctx_sync: ctx is NULL");
+    TMX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return TMX_OK;
+}
+
+extern "C" uint64_t tmx_ctx_launch_count(const tmx_ctx* ctx) { return ctx ? ctx->launches : 0; }

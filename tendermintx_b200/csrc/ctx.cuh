@@ -1,0 +1,60 @@
+// Internal definition of tmx_ctx (one per GPU) and launch helpers shared by the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include <map>
+#include "gl.cuh"
+#include "../../include/tmx.h"
+
+namespace tmx {
+
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+
+#define TMX_CUDA(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            return ::tmx::fail(TMX_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+// Two-level power table: base^e = lo[e & ((1<<klo)-1)] * hi[e >> klo]
+struct PowTable {
+    gl* lo = nullptr;
+    gl* hi = nullptr;
+    unsigned klo = 0;
+    unsigned log_size = 0;  // table covers exponents < 2^log_size
+};
+
+struct NttTables {
+    gl* small = nullptr;  // w_L^e, e < L/2 (L = 2^k)
+    PowTable big;         // w_{2^k}^e, e < 2^k
+};
+
+}  // namespace tmx
+
+struct tmx_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    int sm_count = 148;
+    std::map<unsigned, tmx::NttTables> fwd, inv;      // keyed by log size
+    std::map<unsigned, tmx::PowTable> coset_scale;    // keyed by log n: 7^i / n
+    // grow-only scratch buffers
+    void* scratch[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t scratch_bytes[4] = {0, 0, 0, 0};
+    std::vector<void*> owned;  // device allocations freed at destroy
+};
+
+namespace tmx {
+
+int ctx_scratch(tmx_ctx* ctx, int slot, size_t bytes, void** out);
+int ctx_ntt_tables(tmx_ctx* ctx, unsigned log_n, bool inverse, const NttTables** out);
+int ctx_coset_scale(tmx_ctx* ctx, unsigned log_n, const PowTable** out);
+inline cudaStream_t pick_stream(tmx_ctx* ctx, void* stream) { return stream ? (cudaStream_t)stream : ctx->stream; }
+
+// per translation unit Poseidon constant upload hooks
+int merkle_tu_init();
+
+}  // namespace tmx

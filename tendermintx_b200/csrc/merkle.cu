@@ -1,0 +1,97 @@
+// K2: Poseidon-12 leaf hashing and Merkle tree (with cap) over the rows of a column-major matrix.
+//
+// Replaces plonky2 0.2.0 hash/merkle_tree.rs MerkleTree::new + hash/poseidon.rs as used by
+// PolynomialBatch::from_values, reached from the reference through `circuit.prove()`
+// [REF circuits/skip.rs:214, circuits/step.rs:196].
+//
+// One thread per leaf: the LDE matrix is column-major, so the 32 threads of a warp read 32 consecutive rows of
+// one column per load (256 coalesced bytes) and no transpose pass is ever materialised (plonky2 transposes
+// on the CPU).  The sponge state lives in registers; round constants sit in __constant__ memory (every
+// thread of a warp reads the same constant in the same cycle).  This kernel is bound by 32-bit integer
+// multiply issue (about 1.1 k Goldilocks multiplications per permutation), not by HBM.
+#include "ctx.cuh"
+#include "poseidon.cuh"
+
+namespace tmx {
+
+__global__ void __launch_bounds__(128) leaf_hash_kernel(const gl* __restrict__ cols, size_t n_cols, size_t n_rows,
+                                                         gl* __restrict__ digests) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_rows) return;
+    gl out[4];
+    poseidon_hash_row(cols + j, n_rows, n_cols, out);
+    reinterpret_cast<ulonglong2*>(digests + 4 * j)[0] = make_ulonglong2(out[0], out[1]);
+    reinterpret_cast<ulonglong2*>(digests + 4 * j)[1] = make_ulonglong2(out[2], out[3]);
+}
+
+__global__ void __launch_bounds__(128) merkle_level_kernel(const gl* __restrict__ children, gl* __restrict__ parents,
+                                                            size_t n_parents) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_parents) return;
+    const ulonglong2* c = reinterpret_cast<const ulonglong2*>(children + 8 * i);
+    ulonglong2 a = c[0], b = c[1], d = c[2], e = c[3];
+    gl l[4] = {a.x, a.y, b.x, b.y}, r[4] = {d.x, d.y, e.x, e.y}, out[4];
+    poseidon_two_to_one(l, r, out);
+    reinterpret_cast<ulonglong2*>(parents + 4 * i)[0] = make_ulonglong2(out[0], out[1]);
+    reinterpret_cast<ulonglong2*>(parents + 4 * i)[1] = make_ulonglong2(out[2], out[3]);
+}
+
+__global__ void poseidon_permute_kernel(gl* states, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    gl s[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) s[k] = states[12 * i + k];
+    poseidon_permute(s);
+#pragma unroll
+    for (int k = 0; k < 12; k++) states[12 * i + k] = s[k];
+}
+
+int merkle_tu_init() {
+    TMX_CUDA(poseidon_upload_constants_tu());
+    return TMX_OK;
+}
+
+}  // namespace tmx
+
+using namespace tmx;
+
+extern "C" size_t tmx_merkle_digest_count(unsigned log_rows, unsigned cap_height) {
+    if (cap_height > log_rows) cap_height = log_rows;
+    size_t total = 0;
+    for (unsigned l = 0; l + cap_height <= log_rows; l++) total += (size_t)1 << (log_rows - l);
+    return total;
+}
+
+extern "C" int tmx_poseidon_merkle(tmx_ctx* ctx, const uint64_t* d_cols, size_t n_cols, unsigned log_rows,
+                                   unsigned cap_height, uint64_t* d_digests, void* stream) {
+    if (!ctx || !d_cols || !d_digests || n_cols == 0 || log_rows > 30)
+        return fail(TMX_E_INPUT, "tmx_poseidon_merkle: bad arguments");
+    if (cap_height > log_rows) cap_height = log_rows;
+    cudaStream_t st = pick_stream(ctx, stream);
+    const size_t n = (size_t)1 << log_rows;
+    leaf_hash_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_cols, n_cols, n, d_digests);
+    ctx->launches++;
+    TMX_CUDA(cudaGetLastError());
+    gl* lvl = d_digests;
+    size_t m = n;
+    for (unsigned l = 0; l + cap_height < log_rows; l++) {
+        gl* nxt = lvl + 4 * m;
+        m >>= 1;
+        merkle_level_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(lvl, nxt, m);
+        ctx->launches++;
+        TMX_CUDA(cudaGetLastError());
+        lvl = nxt;
+    }
+    return TMX_OK;
+}
+
+extern "C" int tmx_poseidon_permute(tmx_ctx* ctx, uint64_t* d_states, size_t n, void* stream) {
+    if (!ctx || !d_states) return fail(TMX_E_INPUT, "tmx_poseidon_permute: bad arguments");
+    if (n == 0) return TMX_OK;
+    cudaStream_t st = pick_stream(ctx, stream);
+    poseidon_permute_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_states, n);
+    ctx->launches++;
+    TMX_CUDA(cudaGetLastError());
+    return TMX_OK;
+}
