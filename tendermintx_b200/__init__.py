@@ -57,7 +57,10 @@ class Context:
     def _stream(self):
         import torch
 
-        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        # torch's default stream is the legacy NULL stream; the C ABI reserves NULL for "the context's own
+        # stream", so pass cudaStreamLegacy (0x1) to stay ordered with torch work.
+        h = torch.cuda.current_stream(self.device).cuda_stream
+        return ctypes.c_void_p(h if h else 1)
 
     def launch_count(self):
         return int(lib().tmx_ctx_launch_count(self._h))

@@ -1,7 +1,10 @@
 """Kernel micro-benchmarks (run on the B200 box): LDE and Poseidon Merkle at trace-like shapes.
 Prints one line per shape: algorithmic GB/s for K1 (8*n*B*(1+2^r) bytes), permutations/s for K2."""
 import json
+import os
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import time
 
 import numpy as np
