@@ -113,3 +113,74 @@ def commit_columns(cols, cap_height):
     out = np.ctypeslib.as_array(t.digests, shape=(total * 4,)).copy().reshape(total, 4)
     lib().merkle_free(ctypes.byref(t))
     return out
+
+
+# ---------------------------------------------------------------- witness side (oracle_w.h)
+CHECK_NAMES = ["OK", "SKIP_DISTANCE", "TRUSTED_HEADER_PROOF", "TRUSTED_VALHASH", "TRUSTED_THRESHOLD", "SIGNATURE",
+               "VALHASH", "VALHASH_PROOF", "THRESHOLD", "SIGN_BYTES", "CHAIN_ID", "HEIGHT", "LAST_BLOCK_ID",
+               "NEXT_VALHASH", "VOTING_OVERFLOW", "VARINT_SIGN", "ROUND_SIGN", "INPUT"]
+
+
+def _buf(b):
+    return (ctypes.c_uint8 * len(b)).from_buffer_copy(bytes(b)) if len(b) else (ctypes.c_uint8 * 1)()
+
+
+def sha256(msg):
+    out = (ctypes.c_uint8 * 32)()
+    lib().sha256(_buf(msg), ctypes.c_size_t(len(msg)), out)
+    return bytes(out)
+
+
+def sha512(msg):
+    out = (ctypes.c_uint8 * 64)()
+    lib().sha512(_buf(msg), ctypes.c_size_t(len(msg)), out)
+    return bytes(out)
+
+
+def ed25519_verify(pk, sig, msg):
+    return bool(lib().ed25519_verify(_buf(pk), _buf(sig), _buf(msg), ctypes.c_size_t(len(msg))))
+
+
+def sc_reduce512(x):
+    out = (ctypes.c_uint8 * 32)()
+    lib().sc_reduce512(out, _buf(x))
+    return bytes(out)
+
+
+def marshal_int64_varint(v):
+    out = (ctypes.c_uint8 * 9)()
+    lib().tm_marshal_int64_varint(ctypes.c_uint64(v), out)
+    return bytes(out)
+
+
+def marshal_validator(pk, power):
+    out = (ctypes.c_uint8 * 46)()
+    lib().tm_marshal_validator.restype = ctypes.c_size_t
+    n = lib().tm_marshal_validator(_buf(pk), ctypes.c_uint64(power), out)
+    return bytes(out), n
+
+
+def root_from_hashed_leaves(leaves, nb_enabled):
+    out = (ctypes.c_uint8 * 32)()
+    lib().tm_root_from_hashed_leaves(_buf(b"".join(leaves)), ctypes.c_size_t(len(leaves)), ctypes.c_size_t(nb_enabled), out)
+    return bytes(out)
+
+
+def voting_threshold(power, in_group, nb_enabled, num, den):
+    n = len(power)
+    p = (ctypes.c_uint64 * n)(*power)
+    g = (ctypes.c_uint8 * n)(*[1 if x else 0 for x in in_group])
+    res = ctypes.c_int(0)
+    rc = lib().tm_voting_threshold(p, g, ctypes.c_size_t(n), ctypes.c_size_t(nb_enabled), ctypes.c_uint64(num),
+                                   ctypes.c_uint64(den), ctypes.byref(res))
+    return rc, bool(res.value)
+
+
+def verify_circuit(public_input, blob, chain_id, skip_max=100800):
+    """verify_skip / verify_step predicate.  Returns (check_name, output32 or None)."""
+    out = (ctypes.c_uint8 * 32)()
+    cid = chain_id.encode() if isinstance(chain_id, str) else chain_id
+    rc = lib().tm_verify_circuit(_buf(public_input), ctypes.c_size_t(len(public_input)), _buf(blob),
+                                 ctypes.c_size_t(len(blob)), _buf(cid), ctypes.c_size_t(len(cid)),
+                                 ctypes.c_uint64(skip_max), out)
+    return CHECK_NAMES[rc], (bytes(out) if rc == 0 else None)
