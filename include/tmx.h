@@ -23,6 +23,7 @@
 
 #include <stddef.h>
 #include <stdint.h>
+#include "tmx_types.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -73,6 +74,29 @@ int tmx_poseidon_merkle(tmx_ctx *ctx, const uint64_t *d_cols, size_t n_cols, uns
 
 /* Poseidon permutation of n independent 12-element states (known-answer tests). */
 int tmx_poseidon_permute(tmx_ctx *ctx, uint64_t *d_states, size_t n, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Witness tables (layout: include/tmx_trace.h).  They replace the trace generation that runs inside
+ * `curta_sha256_variable`, the Tendermint Merkle gadgets and `curta_eddsa_verify_sigs_conditional` when the
+ * reference proves [circuits/builder/verify.rs:147,165,202,205,248-259,285,376; validator.rs:228,248;
+ * shared.rs:194,197].  d_blob is a DEVICE copy of the off-chain input blob (tmx_types.h).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* dims = {rows, cols} of the SHA-256, SHA-512 and Ed25519 tables for a circuit shape */
+int tmx_trace_dims(uint32_t kind, uint32_t n_max, size_t dims[6]);
+/* bytes of the small result buffer the witness kernels fill: computed validators hashes [2][32], the root
+ * reached by each header proof [5][32] (order: see witness_jobs.cuh), then one byte per validator slot
+ * (1 = [s]B == R + [h]A holds for the slot's effective key / signature / message). */
+size_t tmx_witness_aux_bytes(uint32_t n_max);
+/* K6: SHA-256 table (validator leaves, validator-set trees, header inclusion proofs) */
+int tmx_sha256_trace(tmx_ctx *ctx, const uint8_t *d_blob, uint32_t kind, uint32_t n_max, uint64_t *d_t256,
+                     uint8_t *d_aux, void *stream);
+/* K7 + K8 fused, one validator per CTA: SHA-512(R || A || M) table and the Ed25519 double-and-add table */
+int tmx_ed25519_trace(tmx_ctx *ctx, const uint8_t *d_blob, uint32_t kind, uint32_t n_max, uint64_t *d_t512,
+                      uint64_t *d_ted, uint8_t *d_aux, void *stream);
+/* all three tables */
+int tmx_witness_generate(tmx_ctx *ctx, const uint8_t *d_blob, uint32_t kind, uint32_t n_max, uint64_t *d_t256,
+                         uint64_t *d_t512, uint64_t *d_ted, uint8_t *d_aux, void *stream);
 
 #ifdef __cplusplus
 }

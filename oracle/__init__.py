@@ -184,3 +184,27 @@ def verify_circuit(public_input, blob, chain_id, skip_max=100800):
                                  ctypes.c_size_t(len(blob)), _buf(cid), ctypes.c_size_t(len(cid)),
                                  ctypes.c_uint64(skip_max), out)
     return CHECK_NAMES[rc], (bytes(out) if rc == 0 else None)
+
+
+class _Trace(ctypes.Structure):
+    _fields_ = [("n_rows", ctypes.c_size_t), ("n_cols", ctypes.c_size_t), ("data", ctypes.POINTER(ctypes.c_uint64))]
+
+
+def trace_dims(kind, n_max):
+    d = (ctypes.c_size_t * 6)()
+    lib().tm_trace_dims(ctypes.c_uint32(kind), ctypes.c_uint32(n_max), d)
+    return [(d[0], d[1]), (d[2], d[3]), (d[4], d[5])]
+
+
+def build_traces(blob):
+    """Returns [sha256, sha512, ed25519] tables as uint64 arrays of shape [n_cols, n_rows] (column-major)."""
+    tr = (_Trace * 3)()
+    rc = lib().tm_build_traces(_buf(blob), ctypes.c_size_t(len(blob)), tr)
+    if rc != 0:
+        raise ValueError(f"tm_build_traces: {CHECK_NAMES[rc]}")
+    out = []
+    for t in tr:
+        a = np.ctypeslib.as_array(t.data, shape=(t.n_cols * t.n_rows,)).copy().reshape(t.n_cols, t.n_rows)
+        out.append(a)
+    lib().tm_free_traces(tr)
+    return out

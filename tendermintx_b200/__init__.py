@@ -99,3 +99,23 @@ class Context:
     def poseidon_permute(self, states):
         _check(lib().tmx_poseidon_permute(self._h, _ptr(states), states.numel() // 12, self._stream()))
         return states
+
+    # ---- K6 / K7 / K8 ----
+    @staticmethod
+    def trace_dims(kind, n_max):
+        d = (ctypes.c_size_t * 6)()
+        _check(lib().tmx_trace_dims(kind, n_max, d))
+        return [(d[0], d[1]), (d[2], d[3]), (d[4], d[5])]
+
+    def witness_generate(self, blob, kind, n_max):
+        """blob: bytes (host).  Returns (sha256, sha512, ed25519 tables as [cols, rows] int64 CUDA tensors, aux
+        uint8 CUDA tensor)."""
+        import torch
+
+        dev = f"cuda:{self.device}"
+        d_blob = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
+        tabs = [torch.empty((c, r), dtype=torch.int64, device=dev) for r, c in self.trace_dims(kind, n_max)]
+        aux = torch.zeros(lib().tmx_witness_aux_bytes(n_max), dtype=torch.uint8, device=dev)
+        _check(lib().tmx_witness_generate(self._h, _ptr(d_blob), kind, n_max, _ptr(tabs[0]), _ptr(tabs[1]),
+                                          _ptr(tabs[2]), _ptr(aux), self._stream()))
+        return tabs, aux

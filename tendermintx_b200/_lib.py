@@ -47,6 +47,11 @@ def load():
         "tmx_merkle_digest_count": (sz, [u32, u32]),
         "tmx_poseidon_merkle": (i32, [vp, u64p, sz, u32, u32, u64p, vp]),
         "tmx_poseidon_permute": (i32, [vp, u64p, sz, vp]),
+        "tmx_trace_dims": (i32, [u32, u32, c.POINTER(sz)]),
+        "tmx_witness_aux_bytes": (sz, [u32]),
+        "tmx_sha256_trace": (i32, [vp, vp, u32, u32, u64p, vp, vp]),
+        "tmx_ed25519_trace": (i32, [vp, vp, u32, u32, u64p, u64p, vp, vp]),
+        "tmx_witness_generate": (i32, [vp, vp, u32, u32, u64p, u64p, u64p, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -58,5 +63,6 @@ def load():
 EXPORTED_SYMBOLS = [
     "tmx_last_error", "tmx_version", "tmx_ctx_create", "tmx_ctx_destroy", "tmx_ctx_sync",
     "tmx_ctx_launch_count", "tmx_ntt", "tmx_lde", "tmx_merkle_digest_count", "tmx_poseidon_merkle",
-    "tmx_poseidon_permute",
+    "tmx_poseidon_permute", "tmx_trace_dims", "tmx_witness_aux_bytes", "tmx_sha256_trace", "tmx_ed25519_trace",
+    "tmx_witness_generate",
 ]

@@ -187,6 +187,7 @@ extern "C" int tmx_ctx_create(int device, tmx_ctx** out) {
     TMX_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     poseidon_generate_constants();
     int rc = merkle_tu_init();
+    if (!rc) rc = witness_tu_init();
     if (rc) {
         delete ctx;
         return rc;

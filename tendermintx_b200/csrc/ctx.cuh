@@ -56,5 +56,6 @@ inline cudaStream_t pick_stream(tmx_ctx* ctx, void* stream) { return stream ? (c
 
 // per translation unit Poseidon constant upload hooks
 int merkle_tu_init();
+int witness_tu_init();
 
 }  // namespace tmx

@@ -1,0 +1,392 @@
+// Per-thread building blocks of the witness kernels (K6 SHA-256, K7 SHA-512, K8 Ed25519): compression with
+// per-round history, and the functions that turn one round / one ladder step into the cells of its trace row
+// (layout: include/tmx_trace.h).  Host+device so tests can run the same per-thread logic on a CPU
+// (tools/hostsim.cpp); the kernels in witness.cu are thin wrappers that map rows to threads.
+//
+// Replaces the trace generation inside plonky2x's `curta_sha256_variable` and
+// `curta_eddsa_verify_sigs_conditional` [REF circuits/builder/verify.rs:202,248-259; validator.rs:228;
+// shared.rs:194] and the Merkle gadgets get_root_from_merkle_proof / get_root_from_hashed_leaves
+// [REF verify.rs:147,165,285,376; validator.rs:248].
+#pragma once
+#include "fe25519.cuh"
+#include "../../include/tmx_types.h"
+
+namespace tmx {
+
+#define TMX_K256_INIT                                                                                               \
+    {0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98,    \
+     0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786,    \
+     0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8,    \
+     0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967, 0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13,    \
+     0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85, 0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819,    \
+     0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a,    \
+     0x5b9cca4f, 0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7,    \
+     0xc67178f2}
+#define TMX_K512_INIT                                                                                               \
+    {0x428a2f98d728ae22ULL, 0x7137449123ef65cdULL, 0xb5c0fbcfec4d3b2fULL, 0xe9b5dba58189dbbcULL, 0x3956c25bf348b538ULL, \
+     0x59f111f1b605d019ULL, 0x923f82a4af194f9bULL, 0xab1c5ed5da6d8118ULL, 0xd807aa98a3030242ULL, 0x12835b0145706fbeULL, \
+     0x243185be4ee4b28cULL, 0x550c7dc3d5ffb4e2ULL, 0x72be5d74f27b896fULL, 0x80deb1fe3b1696b1ULL, 0x9bdc06a725c71235ULL, \
+     0xc19bf174cf692694ULL, 0xe49b69c19ef14ad2ULL, 0xefbe4786384f25e3ULL, 0x0fc19dc68b8cd5b5ULL, 0x240ca1cc77ac9c65ULL, \
+     0x2de92c6f592b0275ULL, 0x4a7484aa6ea6e483ULL, 0x5cb0a9dcbd41fbd4ULL, 0x76f988da831153b5ULL, 0x983e5152ee66dfabULL, \
+     0xa831c66d2db43210ULL, 0xb00327c898fb213fULL, 0xbf597fc7beef0ee4ULL, 0xc6e00bf33da88fc2ULL, 0xd5a79147930aa725ULL, \
+     0x06ca6351e003826fULL, 0x142929670a0e6e70ULL, 0x27b70a8546d22ffcULL, 0x2e1b21385c26c926ULL, 0x4d2c6dfc5ac42aedULL, \
+     0x53380d139d95b3dfULL, 0x650a73548baf63deULL, 0x766a0abb3c77b2a8ULL, 0x81c2c92e47edaee6ULL, 0x92722c851482353bULL, \
+     0xa2bfe8a14cf10364ULL, 0xa81a664bbc423001ULL, 0xc24b8b70d0f89791ULL, 0xc76c51a30654be30ULL, 0xd192e819d6ef5218ULL, \
+     0xd69906245565a910ULL, 0xf40e35855771202aULL, 0x106aa07032bbd1b8ULL, 0x19a4c116b8d2d0c8ULL, 0x1e376c085141ab53ULL, \
+     0x2748774cdf8eeb99ULL, 0x34b0bcb5e19b48a8ULL, 0x391c0cb3c5c95a63ULL, 0x4ed8aa4ae3418acbULL, 0x5b9cca4f7763e373ULL, \
+     0x682e6ff3d6b2b8a3ULL, 0x748f82ee5defb2fcULL, 0x78a5636f43172f60ULL, 0x84c87814a1f0ab72ULL, 0x8cc702081a6439ecULL, \
+     0x90befffa23631e28ULL, 0xa4506cebde82bde9ULL, 0xbef9a3f7b2c67915ULL, 0xc67178f2e372532bULL, 0xca273eceea26619cULL, \
+     0xd186b8c721c0c207ULL, 0xeada7dd6cde0eb1eULL, 0xf57d4f7fee6ed178ULL, 0x06f067aa72176fbaULL, 0x0a637dc5a2c898a6ULL, \
+     0x113f9804bef90daeULL, 0x1b710b35131c471bULL, 0x28db77f523047d84ULL, 0x32caab7b40c72493ULL, 0x3c9ebe0a15c9bebcULL, \
+     0x431d67c49c100d4cULL, 0x4cc5d4becb3e42b6ULL, 0x597f299cfc657e2aULL, 0x5fcb6fab3ad6faecULL, 0x6c44198c4a475817ULL}
+
+static const uint32_t h_K256[64] = TMX_K256_INIT;
+static const uint64_t h_K512[80] = TMX_K512_INIT;
+#if defined(__CUDACC__)
+static __constant__ uint32_t d_K256[64] = TMX_K256_INIT;
+static __constant__ uint64_t d_K512[80] = TMX_K512_INIT;
+#endif
+TMX_HD uint32_t k256(int i) {
+#if defined(__CUDA_ARCH__)
+    return d_K256[i];
+#else
+    return h_K256[i];
+#endif
+}
+TMX_HD uint64_t k512(int i) {
+#if defined(__CUDA_ARCH__)
+    return d_K512[i];
+#else
+    return h_K512[i];
+#endif
+}
+TMX_HD uint32_t iv256(int i) {
+    const uint32_t iv[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+    return iv[i];
+}
+TMX_HD uint64_t iv512(int i) {
+    const uint64_t iv[8] = {0x6a09e667f3bcc908ULL, 0xbb67ae8584caa73bULL, 0x3c6ef372fe94f82bULL, 0xa54ff53a5f1d36f1ULL,
+                            0x510e527fade682d1ULL, 0x9b05688c2b3e6c1fULL, 0x1f83d9abfb41bd6bULL, 0x5be0cd19137e2179ULL};
+    return iv[i];
+}
+
+TMX_HD uint32_t rotr32(uint32_t x, int r) { return (x >> r) | (x << (32 - r)); }
+TMX_HD uint64_t rotr64(uint64_t x, int r) { return (x >> r) | (x << (64 - r)); }
+
+// ------------------------------------------------------------------------------------------- SHA-256
+// History of one compression: ah[t + 3] = a before round t (t = -3..64), same for eh; W[0..63]; cv[8].
+struct Sha256Hist {
+    uint32_t ah[68], eh[68], W[64], cv[8];
+};
+
+// blk: 64 message bytes.  Fills hist, writes the new chaining value to out (may alias cv).
+TMX_HD void sha256_compress_hist(const uint32_t cv[8], const uint8_t* blk, Sha256Hist* hs, uint32_t out[8]) {
+    uint32_t* W = hs->W;
+    for (int i = 0; i < 16; i++)
+        W[i] = ((uint32_t)blk[4 * i] << 24) | ((uint32_t)blk[4 * i + 1] << 16) | ((uint32_t)blk[4 * i + 2] << 8) | blk[4 * i + 3];
+    for (int i = 16; i < 64; i++) {
+        uint32_t x = W[i - 15], y = W[i - 2];
+        W[i] = W[i - 16] + (rotr32(x, 7) ^ rotr32(x, 18) ^ (x >> 3)) + W[i - 7] + (rotr32(y, 17) ^ rotr32(y, 19) ^ (y >> 10));
+    }
+    for (int i = 0; i < 8; i++) hs->cv[i] = cv[i];
+    uint32_t a = cv[0], b = cv[1], c = cv[2], d = cv[3], e = cv[4], f = cv[5], g = cv[6], h = cv[7];
+    hs->ah[0] = d; hs->ah[1] = c; hs->ah[2] = b; hs->ah[3] = a;
+    hs->eh[0] = h; hs->eh[1] = g; hs->eh[2] = f; hs->eh[3] = e;
+    for (int t = 0; t < 64; t++) {
+        uint32_t t1 = h + (rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25)) + ((e & f) ^ (~e & g)) + k256(t) + W[t];
+        uint32_t t2 = (rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
+        h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+        hs->ah[t + 4] = a;
+        hs->eh[t + 4] = e;
+    }
+    uint32_t fin[8] = {a, b, c, d, e, f, g, h};
+    for (int i = 0; i < 8; i++) out[i] = hs->cv[i] + fin[i];
+}
+
+// All S256_COLS cells of round t (row `row`) from the history.
+TMX_HD void sha256_row_cells(gl* trace, size_t n_rows, size_t row, int t, const Sha256Hist* hs) {
+    gl* p = trace + row;
+    const uint32_t a = hs->ah[t + 3], b = hs->ah[t + 2], c = hs->ah[t + 1], d = hs->ah[t];
+    const uint32_t e = hs->eh[t + 3], f = hs->eh[t + 2], g = hs->eh[t + 1], h = hs->eh[t];
+    const uint32_t an = hs->ah[t + 4], en = hs->eh[t + 4];
+#pragma unroll 4
+    for (int i = 0; i < 32; i++) {
+        p[(size_t)(S256_A + i) * n_rows] = (a >> i) & 1;
+        p[(size_t)(S256_B + i) * n_rows] = (b >> i) & 1;
+        p[(size_t)(S256_C + i) * n_rows] = (c >> i) & 1;
+        p[(size_t)(S256_E + i) * n_rows] = (e >> i) & 1;
+        p[(size_t)(S256_F + i) * n_rows] = (f >> i) & 1;
+        p[(size_t)(S256_G + i) * n_rows] = (g >> i) & 1;
+        p[(size_t)(S256_AN + i) * n_rows] = (an >> i) & 1;
+        p[(size_t)(S256_EN + i) * n_rows] = (en >> i) & 1;
+    }
+    p[(size_t)S256_D * n_rows] = d;
+    p[(size_t)S256_H * n_rows] = h;
+    const uint64_t t1 = (uint64_t)h + (rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25)) + ((e & f) ^ (~e & g)) + k256(t) + hs->W[t];
+    const uint64_t t2 = (uint64_t)(rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
+    const uint64_t ca = (t1 + t2) >> 32, ce = ((uint64_t)d + t1) >> 32;
+    for (int i = 0; i < 3; i++) {
+        p[(size_t)(S256_CA + i) * n_rows] = (ca >> i) & 1;
+        p[(size_t)(S256_CE + i) * n_rows] = (ce >> i) & 1;
+    }
+    for (int j = 0; j < 16; j++) {
+        const int idx = t - 15 + j;
+        p[(size_t)(S256_W + j) * n_rows] = idx >= 0 ? hs->W[idx] : 0;
+    }
+    const uint32_t w14 = t >= 1 ? hs->W[t - 1] : 0, w1 = t >= 14 ? hs->W[t - 14] : 0;
+#pragma unroll 4
+    for (int i = 0; i < 32; i++) {
+        p[(size_t)(S256_WB14 + i) * n_rows] = (w14 >> i) & 1;
+        p[(size_t)(S256_WB1 + i) * n_rows] = (w1 >> i) & 1;
+    }
+    for (int j = 0; j < 8; j++) p[(size_t)(S256_CV + j) * n_rows] = hs->cv[j];
+    uint64_t cw = 0;
+    if (t >= 15 && t <= 62) {
+        const uint32_t x = hs->W[t - 1], y = hs->W[t - 14];
+        cw = ((uint64_t)(rotr32(x, 17) ^ rotr32(x, 19) ^ (x >> 10)) + hs->W[t - 6] + (rotr32(y, 7) ^ rotr32(y, 18) ^ (y >> 3)) +
+              hs->W[t - 15]) >> 32;
+    }
+    p[(size_t)S256_CW * n_rows] = cw & 1;
+    p[(size_t)(S256_CW + 1) * n_rows] = (cw >> 1) & 1;
+    const uint32_t fin[8] = {an, a, b, c, en, e, f, g};
+    for (int j = 0; j < 8; j++) {
+        uint64_t s = t == 63 ? (uint64_t)hs->cv[j] + fin[j] : 0;
+        p[(size_t)(S256_DG + j) * n_rows] = (uint32_t)s;
+        p[(size_t)(S256_DC + j) * n_rows] = s >> 32;
+    }
+}
+
+// FIPS 180-4 padding of msg[0..len) into nb = ceil((len + 9) / 64) blocks written to buf (nb * 64 bytes)
+TMX_HD int sha256_pad_blocks(const uint8_t* msg, int len, uint8_t* buf) {
+    const int nb = (len + 9 + 63) / 64;
+    for (int i = 0; i < nb * 64; i++) buf[i] = i < len ? msg[i] : 0;
+    buf[len] = 0x80;
+    const uint64_t bits = (uint64_t)len * 8;
+    for (int i = 0; i < 8; i++) buf[nb * 64 - 1 - i] = (uint8_t)(bits >> (8 * i));
+    return nb;
+}
+TMX_HD void sha256_state_to_bytes(const uint32_t st[8], uint8_t out[32]) {
+    for (int i = 0; i < 8; i++) {
+        out[4 * i] = (uint8_t)(st[i] >> 24); out[4 * i + 1] = (uint8_t)(st[i] >> 16);
+        out[4 * i + 2] = (uint8_t)(st[i] >> 8); out[4 * i + 3] = (uint8_t)st[i];
+    }
+}
+
+// REF circuits/builder/shared.rs:67-156 -- nine bytes, continuation bit on every septet below the last non-zero one
+TMX_HD void marshal_int64_varint(uint64_t v, uint8_t out[9]) {
+    int last = 0;
+    for (int i = 0; i < 9; i++)
+        if ((v >> (7 * i)) & 0x7F) last = i;
+    for (int i = 0; i < 9; i++) out[i] = (uint8_t)(((v >> (7 * i)) & 0x7F) | (i < last ? 0x80 : 0));
+}
+// REF circuits/builder/validator.rs:185-229 -- leaf message 0x00 || 0a 22 0a 20 <pk> 10 <varint9>, 47 bytes
+TMX_HD void validator_leaf_message(const uint8_t pk[32], uint64_t power, uint8_t out[47]) {
+    out[0] = 0; out[1] = 10; out[2] = 34; out[3] = 10; out[4] = 32;
+    for (int i = 0; i < 32; i++) out[5 + i] = pk[i];
+    out[37] = 16;
+    marshal_int64_varint(power, out + 38);
+}
+
+// ------------------------------------------------------------------------------------------- SHA-512
+struct Sha512Hist {
+    uint64_t ah[84], eh[84], W[80], cv[8];
+};
+
+TMX_HD void sha512_compress_hist(const uint64_t cv[8], const uint8_t* blk, Sha512Hist* hs, uint64_t out[8]) {
+    uint64_t* W = hs->W;
+    for (int i = 0; i < 16; i++) {
+        uint64_t x = 0;
+        for (int j = 0; j < 8; j++) x = (x << 8) | blk[8 * i + j];
+        W[i] = x;
+    }
+    for (int i = 16; i < 80; i++) {
+        uint64_t x = W[i - 15], y = W[i - 2];
+        W[i] = W[i - 16] + (rotr64(x, 1) ^ rotr64(x, 8) ^ (x >> 7)) + W[i - 7] + (rotr64(y, 19) ^ rotr64(y, 61) ^ (y >> 6));
+    }
+    for (int i = 0; i < 8; i++) hs->cv[i] = cv[i];
+    uint64_t a = cv[0], b = cv[1], c = cv[2], d = cv[3], e = cv[4], f = cv[5], g = cv[6], h = cv[7];
+    hs->ah[0] = d; hs->ah[1] = c; hs->ah[2] = b; hs->ah[3] = a;
+    hs->eh[0] = h; hs->eh[1] = g; hs->eh[2] = f; hs->eh[3] = e;
+    for (int t = 0; t < 80; t++) {
+        uint64_t t1 = h + (rotr64(e, 14) ^ rotr64(e, 18) ^ rotr64(e, 41)) + ((e & f) ^ (~e & g)) + k512(t) + W[t];
+        uint64_t t2 = (rotr64(a, 28) ^ rotr64(a, 34) ^ rotr64(a, 39)) + ((a & b) ^ (a & c) ^ (b & c));
+        h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+        hs->ah[t + 4] = a;
+        hs->eh[t + 4] = e;
+    }
+    uint64_t fin[8] = {a, b, c, d, e, f, g, h};
+    for (int i = 0; i < 8; i++) out[i] = hs->cv[i] + fin[i];
+}
+
+TMX_HD void sha512_row_cells(gl* trace, size_t n_rows, size_t row, int t, const Sha512Hist* hs) {
+    gl* p = trace + row;
+    const uint64_t a = hs->ah[t + 3], b = hs->ah[t + 2], c = hs->ah[t + 1], d = hs->ah[t];
+    const uint64_t e = hs->eh[t + 3], f = hs->eh[t + 2], g = hs->eh[t + 1], h = hs->eh[t];
+    const uint64_t an = hs->ah[t + 4], en = hs->eh[t + 4];
+#pragma unroll 4
+    for (int i = 0; i < 64; i++) {
+        p[(size_t)(S512_A + i) * n_rows] = (a >> i) & 1;
+        p[(size_t)(S512_B + i) * n_rows] = (b >> i) & 1;
+        p[(size_t)(S512_C + i) * n_rows] = (c >> i) & 1;
+        p[(size_t)(S512_E + i) * n_rows] = (e >> i) & 1;
+        p[(size_t)(S512_F + i) * n_rows] = (f >> i) & 1;
+        p[(size_t)(S512_G + i) * n_rows] = (g >> i) & 1;
+        p[(size_t)(S512_AN + i) * n_rows] = (an >> i) & 1;
+        p[(size_t)(S512_EN + i) * n_rows] = (en >> i) & 1;
+    }
+#define TMX_LO(x) ((uint64_t)(uint32_t)(x))
+#define TMX_HI(x) ((uint64_t)((x) >> 32))
+    p[(size_t)S512_D * n_rows] = TMX_LO(d);
+    p[(size_t)(S512_D + 1) * n_rows] = TMX_HI(d);
+    p[(size_t)S512_H * n_rows] = TMX_LO(h);
+    p[(size_t)(S512_H + 1) * n_rows] = TMX_HI(h);
+    const uint64_t S1 = rotr64(e, 14) ^ rotr64(e, 18) ^ rotr64(e, 41), ch = (e & f) ^ (~e & g);
+    const uint64_t S0 = rotr64(a, 28) ^ rotr64(a, 34) ^ rotr64(a, 39), mj = (a & b) ^ (a & c) ^ (b & c);
+    const uint64_t K = k512(t), w = hs->W[t];
+    const uint64_t t1lo = TMX_LO(h) + TMX_LO(S1) + TMX_LO(ch) + TMX_LO(K) + TMX_LO(w);
+    const uint64_t t1hi = TMX_HI(h) + TMX_HI(S1) + TMX_HI(ch) + TMX_HI(K) + TMX_HI(w);
+    const uint64_t calo = (t1lo + TMX_LO(S0) + TMX_LO(mj)) >> 32;
+    const uint64_t cahi = (t1hi + TMX_HI(S0) + TMX_HI(mj) + calo) >> 32;
+    const uint64_t celo = (TMX_LO(d) + t1lo) >> 32;
+    const uint64_t cehi = (TMX_HI(d) + t1hi + celo) >> 32;
+    for (int i = 0; i < 3; i++) {
+        p[(size_t)(S512_CA + i) * n_rows] = (calo >> i) & 1;
+        p[(size_t)(S512_CA + 3 + i) * n_rows] = (cahi >> i) & 1;
+        p[(size_t)(S512_CE + i) * n_rows] = (celo >> i) & 1;
+        p[(size_t)(S512_CE + 3 + i) * n_rows] = (cehi >> i) & 1;
+    }
+    for (int j = 0; j < 16; j++) {
+        const int idx = t - 15 + j;
+        const uint64_t v = idx >= 0 ? hs->W[idx] : 0;
+        p[(size_t)(S512_W + 2 * j) * n_rows] = TMX_LO(v);
+        p[(size_t)(S512_W + 2 * j + 1) * n_rows] = TMX_HI(v);
+    }
+    const uint64_t w14 = t >= 1 ? hs->W[t - 1] : 0, w1 = t >= 14 ? hs->W[t - 14] : 0;
+#pragma unroll 4
+    for (int i = 0; i < 64; i++) {
+        p[(size_t)(S512_WB14 + i) * n_rows] = (w14 >> i) & 1;
+        p[(size_t)(S512_WB1 + i) * n_rows] = (w1 >> i) & 1;
+    }
+    for (int j = 0; j < 8; j++) {
+        p[(size_t)(S512_CV + 2 * j) * n_rows] = TMX_LO(hs->cv[j]);
+        p[(size_t)(S512_CV + 2 * j + 1) * n_rows] = TMX_HI(hs->cv[j]);
+    }
+    uint64_t cwlo = 0, cwhi = 0;
+    if (t >= 15 && t <= 78) {
+        const uint64_t x = hs->W[t - 1], y = hs->W[t - 14];
+        const uint64_t s1 = rotr64(x, 19) ^ rotr64(x, 61) ^ (x >> 6), s0 = rotr64(y, 1) ^ rotr64(y, 8) ^ (y >> 7);
+        cwlo = (TMX_LO(s1) + TMX_LO(hs->W[t - 6]) + TMX_LO(s0) + TMX_LO(hs->W[t - 15])) >> 32;
+        cwhi = (TMX_HI(s1) + TMX_HI(hs->W[t - 6]) + TMX_HI(s0) + TMX_HI(hs->W[t - 15]) + cwlo) >> 32;
+    }
+    p[(size_t)S512_CW * n_rows] = cwlo & 1;
+    p[(size_t)(S512_CW + 1) * n_rows] = (cwlo >> 1) & 1;
+    p[(size_t)(S512_CW + 2) * n_rows] = cwhi & 1;
+    p[(size_t)(S512_CW + 3) * n_rows] = (cwhi >> 1) & 1;
+    const uint64_t fin[8] = {an, a, b, c, en, e, f, g};
+    for (int j = 0; j < 8; j++) {
+        uint64_t dlo = 0, dhi = 0, clo = 0, chi = 0;
+        if (t == 79) {
+            const uint64_t lo = TMX_LO(hs->cv[j]) + TMX_LO(fin[j]);
+            clo = lo >> 32;
+            const uint64_t hi = TMX_HI(hs->cv[j]) + TMX_HI(fin[j]) + clo;
+            chi = hi >> 32;
+            dlo = TMX_LO(lo);
+            dhi = TMX_LO(hi);
+        }
+        p[(size_t)(S512_DG + 2 * j) * n_rows] = dlo;
+        p[(size_t)(S512_DG + 2 * j + 1) * n_rows] = dhi;
+        p[(size_t)(S512_DC + 2 * j) * n_rows] = clo;
+        p[(size_t)(S512_DC + 2 * j + 1) * n_rows] = chi;
+    }
+#undef TMX_LO
+#undef TMX_HI
+}
+
+TMX_HD int sha512_pad_blocks(const uint8_t* msg, int len, uint8_t* buf) {
+    const int nb = (len + 17 + 127) / 128;
+    for (int i = 0; i < nb * 128; i++) buf[i] = i < len ? msg[i] : 0;
+    buf[len] = 0x80;
+    const uint64_t bits = (uint64_t)len * 8;
+    for (int i = 0; i < 8; i++) buf[nb * 128 - 1 - i] = (uint8_t)(bits >> (8 * i));
+    return nb;
+}
+
+// ------------------------------------------------------------------------------------------- Ed25519
+TMX_HD void fe256_to_limbs(const fe256& x, int32_t l[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) l[i] = (int32_t)((x.w[i >> 2] >> (16 * (i & 3))) & 0xFFFF);
+}
+TMX_HD int32_t p_limb(int i) { return i == 0 ? 0xFFED : (i == 15 ? 0x7FFF : 0xFFFF); }
+
+// All ED_COLS cells of one ladder row from the packed canonical (res, temp) and the scalar bit.  The operand
+// builders are the limb-wise linear combinations of DESIGN.md "Ed25519 table" (same slots as the CPU oracle).
+TMX_HD void ed_row_cells(gl* trace, size_t n_rows, size_t row, int bit, const ge_packed& res, const ge_packed& tmp) {
+    gl* p = trace + row;
+    p[(size_t)ED_BIT * n_rows] = (gl)bit;
+    int32_t X1[16], Y1[16], Z1[16], T1[16], X2[16], Y2[16], Z2[16], T2[16];
+    fe256_to_limbs(res.X, X1); fe256_to_limbs(res.Y, Y1); fe256_to_limbs(res.Z, Z1); fe256_to_limbs(res.T, T1);
+    fe256_to_limbs(tmp.X, X2); fe256_to_limbs(tmp.Y, Y2); fe256_to_limbs(tmp.Z, Z2); fe256_to_limbs(tmp.T, T2);
+    for (int i = 0; i < 16; i++) {
+        p[(size_t)(ED_RES + i) * n_rows] = (gl)X1[i];
+        p[(size_t)(ED_RES + 16 + i) * n_rows] = (gl)Y1[i];
+        p[(size_t)(ED_RES + 32 + i) * n_rows] = (gl)Z1[i];
+        p[(size_t)(ED_RES + 48 + i) * n_rows] = (gl)T1[i];
+        p[(size_t)(ED_TMP + i) * n_rows] = (gl)X2[i];
+        p[(size_t)(ED_TMP + 16 + i) * n_rows] = (gl)Y2[i];
+        p[(size_t)(ED_TMP + 32 + i) * n_rows] = (gl)Z2[i];
+        p[(size_t)(ED_TMP + 48 + i) * n_rows] = (gl)T2[i];
+    }
+    const int32_t twod[16] = {0xF159, 0x26B2, 0x9B94, 0xEBD6, 0xB156, 0x8283, 0x149A, 0x00E0,
+                              0xD130, 0xEEF3, 0x80F2, 0x198E, 0xFCE7, 0x56DF, 0xD9DC, 0x2406};
+    int32_t u[16], v[16], A[16], B[16], U[16], C[16], Dh[16], E[16], F[16], G[16], H[16], dump[16];
+    auto cells = [&](int m) { return p + (size_t)(ED_MUL + m * ED_MUL_STRIDE) * n_rows; };
+    for (int i = 0; i < 16; i++) { u[i] = Y1[i] - X1[i] + p_limb(i); v[i] = Y2[i] - X2[i] + p_limb(i); }
+    mul_gadget_cells(u, v, cells(0), n_rows, A);
+    for (int i = 0; i < 16; i++) { u[i] = Y1[i] + X1[i]; v[i] = Y2[i] + X2[i]; }
+    mul_gadget_cells(u, v, cells(1), n_rows, B);
+    mul_gadget_cells(T1, T2, cells(2), n_rows, U);
+    mul_gadget_cells(U, twod, cells(3), n_rows, C);
+    mul_gadget_cells(Z1, Z2, cells(4), n_rows, Dh);
+    for (int i = 0; i < 16; i++) {
+        E[i] = B[i] - A[i] + p_limb(i);
+        F[i] = 2 * Dh[i] - C[i] + p_limb(i);
+        G[i] = 2 * Dh[i] + C[i];
+        H[i] = B[i] + A[i];
+    }
+    mul_gadget_cells(E, F, cells(5), n_rows, dump);
+    mul_gadget_cells(G, H, cells(6), n_rows, dump);
+    mul_gadget_cells(E, H, cells(7), n_rows, dump);
+    mul_gadget_cells(F, G, cells(8), n_rows, dump);
+    int32_t* A2 = A; int32_t* B2 = B; int32_t* Cz = C; int32_t* S = U;
+    mul_gadget_cells(X2, X2, cells(9), n_rows, A2);
+    mul_gadget_cells(Y2, Y2, cells(10), n_rows, B2);
+    mul_gadget_cells(Z2, Z2, cells(11), n_rows, Cz);
+    for (int i = 0; i < 16; i++) u[i] = X2[i] + Y2[i];
+    mul_gadget_cells(u, u, cells(12), n_rows, S);
+    for (int i = 0; i < 16; i++) {
+        E[i] = S[i] - A2[i] - B2[i] + 2 * p_limb(i);
+        G[i] = B2[i] - A2[i] + p_limb(i);
+        F[i] = B2[i] - A2[i] - 2 * Cz[i] + 3 * p_limb(i);
+        H[i] = 2 * p_limb(i) - A2[i] - B2[i];
+    }
+    mul_gadget_cells(E, F, cells(13), n_rows, dump);
+    mul_gadget_cells(G, H, cells(14), n_rows, dump);
+    mul_gadget_cells(E, H, cells(15), n_rows, dump);
+    mul_gadget_cells(F, G, cells(16), n_rows, dump);
+}
+
+// One sequential ladder: stores canonical (res_i, temp_i) for the 256 rows and returns res_256.
+TMX_HD ge51 ed_ladder(const uint64_t scalar[4], const ge51& point, ge_packed* res_out, ge_packed* tmp_out) {
+    ge51 res = ge_identity51(), tmp = point;
+#pragma unroll 1
+    for (int i = 0; i < 256; i++) {
+        res_out[i] = ge_pack(res);
+        tmp_out[i] = ge_pack(tmp);
+        // continue from the canonical representatives so that the stored rows define the next ones exactly
+        if ((scalar[i >> 6] >> (i & 63)) & 1) res = ge_add51(res, tmp);
+        tmp = ge_dbl51(tmp);
+    }
+    return res;
+}
+
+}  // namespace tmx
