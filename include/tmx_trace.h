@@ -26,10 +26,11 @@
 #define S256_CV 338   /* 8 chaining-value words of this chunk */
 #define S256_CA 346   /* 3 carry bits: T1 + T2 = an + 2^32 * ca */
 #define S256_CE 349   /* 3 carry bits: d + T1 = en + 2^32 * ce */
-#define S256_CW 352   /* 2 carry bits of the schedule sum that defines the next row's w[15] (rows 15..62) */
+#define S256_CW 352   /* 2 carry bits of the schedule sum s1(w[14]) + w[9] + s0(w[1]) + w[0] = ws + 2^32 * cw (all rows) */
 #define S256_DG 354   /* 8 digest words, last round of the chunk only */
 #define S256_DC 362   /* 8 digest carry bits, last round only */
-#define S256_COLS 370
+#define S256_WS 370   /* low 32 bits of the schedule sum; equals the next row's w[15] on rows 15..62 */
+#define S256_COLS 371
 #define S256_ROUNDS 64
 
 /* ---------------- SHA-512: one row per round, 80 rows per 128-byte chunk, 2 chunks per validator -------- */

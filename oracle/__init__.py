@@ -208,3 +208,27 @@ def build_traces(blob):
         out.append(a)
     lib().tm_free_traces(tr)
     return out
+
+
+def prove(public_input, blob, chain_id, skip_max=100800):
+    """CPU oracle prover.  Returns (status, proof as uint64 array or None, output32 or None)."""
+    cid = chain_id.encode() if isinstance(chain_id, str) else chain_id
+    p = ctypes.POINTER(ctypes.c_uint64)()
+    n = ctypes.c_size_t(0)
+    out = (ctypes.c_uint8 * 32)()
+    rc = lib().tm_prove(_buf(public_input), ctypes.c_size_t(len(public_input)), _buf(blob), ctypes.c_size_t(len(blob)),
+                        _buf(cid), ctypes.c_size_t(len(cid)), ctypes.c_uint64(skip_max), ctypes.byref(p), ctypes.byref(n), out)
+    if rc != 0:
+        return CHECK_NAMES[rc], None, None
+    proof = np.ctypeslib.as_array(p, shape=(n.value,)).copy()
+    lib().tm_proof_free(p)
+    return "OK", proof, bytes(out)
+
+
+def verify_proof(proof, public_input, chain_id, kind, n_max, output32, skip_max=100800):
+    """Returns 0 when the proof verifies; a non-zero diagnostic code otherwise."""
+    cid = chain_id.encode() if isinstance(chain_id, str) else chain_id
+    proof = np.ascontiguousarray(proof, dtype=np.uint64)
+    return lib().tm_verify_proof(proof.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(proof.size), _buf(public_input),
+                                 ctypes.c_size_t(len(public_input)), _buf(cid), ctypes.c_size_t(len(cid)),
+                                 ctypes.c_uint64(skip_max), ctypes.c_uint32(kind), ctypes.c_uint32(n_max), _buf(output32))

@@ -85,15 +85,14 @@ static void sha256_rows(trace_t *t, size_t row0, const uint32_t cv[8], const uin
             CELL(t, S256_WB1 + b, row) = (w1 >> b) & 1;
         }
         for (int j = 0; j < 8; j++) CELL(t, S256_CV + j, row) = cv[j];
-        uint64_t cw = 0;
-        if (i >= 15 && i <= 62) {
-            uint32_t a = W[i - 1], c = W[i - 14];
-            uint64_t s = (uint64_t)(ror32(a, 17) ^ ror32(a, 19) ^ (a >> 10)) + W[i - 6] +
-                         (ror32(c, 7) ^ ror32(c, 18) ^ (c >> 3)) + W[i - 15];
-            cw = s >> 32;
+        {
+            uint32_t a = i >= 1 ? W[i - 1] : 0, c = i >= 14 ? W[i - 14] : 0;
+            uint64_t s = (uint64_t)(ror32(a, 17) ^ ror32(a, 19) ^ (a >> 10)) + (i >= 6 ? W[i - 6] : 0) +
+                         (ror32(c, 7) ^ ror32(c, 18) ^ (c >> 3)) + (i >= 15 ? W[i - 15] : 0);
+            CELL(t, S256_CW, row) = (s >> 32) & 1;
+            CELL(t, S256_CW + 1, row) = (s >> 33) & 1;
+            CELL(t, S256_WS, row) = (uint32_t)s;
         }
-        CELL(t, S256_CW, row) = cw & 1;
-        CELL(t, S256_CW + 1, row) = (cw >> 1) & 1;
         for (int j = 0; j < 8; j++) {
             uint64_t dg = 0, dc = 0;
             if (i == 63) {

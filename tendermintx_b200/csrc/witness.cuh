@@ -140,14 +140,14 @@ TMX_HD void sha256_row_cells(gl* trace, size_t n_rows, size_t row, int t, const 
         p[(size_t)(S256_WB1 + i) * n_rows] = (w1 >> i) & 1;
     }
     for (int j = 0; j < 8; j++) p[(size_t)(S256_CV + j) * n_rows] = hs->cv[j];
-    uint64_t cw = 0;
-    if (t >= 15 && t <= 62) {
-        const uint32_t x = hs->W[t - 1], y = hs->W[t - 14];
-        cw = ((uint64_t)(rotr32(x, 17) ^ rotr32(x, 19) ^ (x >> 10)) + hs->W[t - 6] + (rotr32(y, 7) ^ rotr32(y, 18) ^ (y >> 3)) +
-              hs->W[t - 15]) >> 32;
+    {
+        const uint32_t x = t >= 1 ? hs->W[t - 1] : 0, y = t >= 14 ? hs->W[t - 14] : 0;
+        const uint64_t s = (uint64_t)(rotr32(x, 17) ^ rotr32(x, 19) ^ (x >> 10)) + (t >= 6 ? hs->W[t - 6] : 0) +
+                           (rotr32(y, 7) ^ rotr32(y, 18) ^ (y >> 3)) + (t >= 15 ? hs->W[t - 15] : 0);
+        p[(size_t)S256_CW * n_rows] = (s >> 32) & 1;
+        p[(size_t)(S256_CW + 1) * n_rows] = (s >> 33) & 1;
+        p[(size_t)S256_WS * n_rows] = (uint32_t)s;
     }
-    p[(size_t)S256_CW * n_rows] = cw & 1;
-    p[(size_t)(S256_CW + 1) * n_rows] = (cw >> 1) & 1;
     const uint32_t fin[8] = {an, a, b, c, en, e, f, g};
     for (int j = 0; j < 8; j++) {
         uint64_t s = t == 63 ? (uint64_t)hs->cv[j] + fin[j] : 0;

@@ -105,6 +105,8 @@ TMX_HD bool sha256_leaf_prepare(const WitnessArgs& a, uint32_t s, uint32_t i, Sh
     sha256_compress_hist(cv, buf, hs, st);
     sha256_state_to_bytes(st, node);
     *en = i < nb ? 1 : 0;
+    if (a.log_np == 0)  // single-slot set: the leaf is the root
+        for (int k = 0; k < 32; k++) a.aux[AUX_SET_ROOT + 32 * s + k] = node[k];
     return true;
 }
 TMX_HD size_t sha256_leaf_row0(const WitnessArgs& a, uint32_t s, uint32_t i) {

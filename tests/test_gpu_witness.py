@@ -39,7 +39,7 @@ def test_witness_tables_match_oracle_on_fixtures(ctx, oracle, name):
     assert aux[224:224 + n_max].all(), "every slot's signature equation must hold"
     # the computed validators hash (last set) equals the one inside the header proof leaf
     kind = struct.unpack_from("<I", blob, 4)[0]
-    head_valhash = blob[40 + 184 + 144 + 2: 40 + 184 + 144 + 34]
+    head_valhash = blob[64 + 184 + 144 + 2: 64 + 184 + 144 + 34]
     assert bytes(aux[32 * kind: 32 * kind + 32]) == head_valhash
     # every header proof reaches a header: the target proofs reach the output header
     assert bytes(aux[64 + 32: 64 + 64]).hex() == c["expected_output"] or bytes(aux[64: 64 + 32]).hex() == c["expected_output"]
