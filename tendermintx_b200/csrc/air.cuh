@@ -1,0 +1,267 @@
+// Constraint systems (AIR) of the SHA-256, SHA-512 and Ed25519 tables, generic over the field: the quotient
+// kernel (K5) instantiates them on base-field LDE values, the verifier on extension-field openings at zeta.
+//
+// The arithmetisation is this repo's own -- upstream the equivalent lives in starkyx's SHA-256 / SHA-512 /
+// Ed25519 AIRs, reached by the reference through `curta_sha256_variable` and
+// `curta_eddsa_verify_sigs_conditional` [REF circuits/builder/verify.rs:202,248-259].  Rules: every constraint
+// has degree <= 3 in (trace, periodic) columns; a constraint that reads the next row carries a periodic
+// selector that is zero on the last row of the table; emission order is fixed (it defines the alpha powers).
+#pragma once
+#include "gl.cuh"
+#include "../../include/tmx_trace.h"
+
+namespace tmx {
+
+// ---- field wrappers with operators ----
+struct FB {
+    gl v;
+    TMX_HD FB() : v(0) {}
+    TMX_HD explicit FB(gl x) : v(x) {}
+    TMX_HD static FB c(uint64_t x) { return FB((gl)x); }
+};
+TMX_HD FB operator+(FB a, FB b) { return FB(gl_add(a.v, b.v)); }
+TMX_HD FB operator-(FB a, FB b) { return FB(gl_sub(a.v, b.v)); }
+TMX_HD FB operator*(FB a, FB b) { return FB(gl_mul(a.v, b.v)); }
+
+struct FE {
+    gl2 v;
+    TMX_HD FE() { v = gl2_from(0); }
+    TMX_HD explicit FE(gl2 x) : v(x) {}
+    TMX_HD static FE c(uint64_t x) { return FE(gl2_from((gl)x)); }
+};
+TMX_HD FE operator+(FE a, FE b) { return FE(gl2_add(a.v, b.v)); }
+TMX_HD FE operator-(FE a, FE b) { return FE(gl2_sub(a.v, b.v)); }
+TMX_HD FE operator*(FE a, FE b) { return FE(gl2_mul(a.v, b.v)); }
+
+// Horner accumulator over the two constraint challenges: acc <- acc * alpha + c
+template <class F>
+struct ConstraintAcc {
+    F acc[2], alpha[2];
+    TMX_HD void operator()(F c) {
+        acc[0] = acc[0] * alpha[0] + c;
+        acc[1] = acc[1] * alpha[1] + c;
+    }
+};
+
+template <class F>
+TMX_HD F is_bool(F x) { return x * (x - F::c(1)); }
+template <class F>
+TMX_HD F xor3(F a, F b, F c) {
+    F ab = a * b;
+    F pairs = ab + b * c + c * a;
+    return (a + b + c) - (pairs + pairs) + F::c(4) * (ab * c);
+}
+// sum_i 2^i row[col0 + i]
+template <class F, class Row>
+TMX_HD F pack_bits(const Row& r, int col0, int nbits) {
+    F acc = F::c(0);
+    for (int i = nbits - 1; i >= 0; i--) acc = acc + acc + r[col0 + i];
+    return acc;
+}
+
+constexpr int AIR_SHA256 = 0, AIR_SHA512 = 1, AIR_ED25519 = 2;
+TMX_HD int air_cols(int t) { return t == AIR_SHA256 ? S256_COLS : (t == AIR_SHA512 ? S512_COLS : ED_COLS); }
+TMX_HD int air_n_periodic(int t) { return t == AIR_SHA256 ? 4 : (t == AIR_SHA512 ? 0 : 1); }
+TMX_HD int air_period(int t) { return t == AIR_SHA256 ? 64 : (t == AIR_SHA512 ? 1 : 256); }
+
+// ------------------------------------------------------------------------------------------ SHA-256
+// per = {K_t, is_last_round, not_last_round, schedule_active (rounds 15..62)}
+template <class F, class Row, class Emit>
+TMX_HD void air_sha256(const Row& l, const Row& n, const F* per, Emit& emit) {
+    const F K = per[0], LAST = per[1], NOTLAST = per[2], SCHED = per[3];
+    const F two32 = F::c(1ULL << 32);
+    for (int i = S256_A; i < S256_D; i++) emit(is_bool<F>(l[i]));
+    for (int i = S256_AN; i < S256_W; i++) emit(is_bool<F>(l[i]));
+    for (int i = S256_WB14; i < S256_CV; i++) emit(is_bool<F>(l[i]));
+    for (int i = S256_CA; i < S256_DG; i++) emit(is_bool<F>(l[i]));
+    for (int i = 0; i < 8; i++) emit(is_bool<F>(l[S256_DC + i]));
+    // round function: Sigma1(e), Ch(e,f,g), Sigma0(a), Maj(a,b,c) as degree-3 expressions of the bit columns
+    F S1 = F::c(0), CH = F::c(0), S0 = F::c(0), MJ = F::c(0);
+    for (int i = 31; i >= 0; i--) {
+        const F ei = l[S256_E + i], fi = l[S256_F + i], gi = l[S256_G + i];
+        const F ai = l[S256_A + i], bi = l[S256_B + i], ci = l[S256_C + i];
+        const F s1 = xor3<F>(l[S256_E + ((i + 6) & 31)], l[S256_E + ((i + 11) & 31)], l[S256_E + ((i + 25) & 31)]);
+        const F ch = ei * fi + (F::c(1) - ei) * gi;
+        const F s0 = xor3<F>(l[S256_A + ((i + 2) & 31)], l[S256_A + ((i + 13) & 31)], l[S256_A + ((i + 22) & 31)]);
+        const F ab = ai * bi;
+        const F mj = (ab + ai * ci + bi * ci) - F::c(2) * (ab * ci);
+        S1 = S1 + S1 + s1;
+        CH = CH + CH + ch;
+        S0 = S0 + S0 + s0;
+        MJ = MJ + MJ + mj;
+    }
+    const F T1 = l[S256_H] + S1 + (CH + K) + l[S256_W + 15];
+    const F T2 = S0 + MJ;
+    const F an = pack_bits<F>(l, S256_AN, 32), en = pack_bits<F>(l, S256_EN, 32);
+    const F ca = pack_bits<F>(l, S256_CA, 3), ce = pack_bits<F>(l, S256_CE, 3), cw = pack_bits<F>(l, S256_CW, 2);
+    emit((an + two32 * ca) - (T1 + T2));
+    emit((en + two32 * ce) - (l[S256_D] + T1));
+    for (int i = 0; i < 32; i++) {
+        emit(NOTLAST * (n[S256_A + i] - l[S256_AN + i]));
+        emit(NOTLAST * (n[S256_B + i] - l[S256_A + i]));
+        emit(NOTLAST * (n[S256_C + i] - l[S256_B + i]));
+        emit(NOTLAST * (n[S256_E + i] - l[S256_EN + i]));
+        emit(NOTLAST * (n[S256_F + i] - l[S256_E + i]));
+        emit(NOTLAST * (n[S256_G + i] - l[S256_F + i]));
+    }
+    const F pc = pack_bits<F>(l, S256_C, 32), pg = pack_bits<F>(l, S256_G, 32);
+    emit(NOTLAST * (n[S256_D] - pc));
+    emit(NOTLAST * (n[S256_H] - pg));
+    for (int j = 0; j < 15; j++) emit(NOTLAST * (n[S256_W + j] - l[S256_W + j + 1]));
+    for (int j = 0; j < 8; j++) emit(NOTLAST * (n[S256_CV + j] - l[S256_CV + j]));
+    // message schedule
+    emit(pack_bits<F>(l, S256_WB14, 32) - l[S256_W + 14]);
+    emit(pack_bits<F>(l, S256_WB1, 32) - l[S256_W + 1]);
+    F s1 = F::c(0), s0 = F::c(0);
+    for (int i = 31; i >= 0; i--) {
+        const F hi1 = i + 10 < 32 ? l[S256_WB14 + i + 10] : F::c(0);
+        const F hi0 = i + 3 < 32 ? l[S256_WB1 + i + 3] : F::c(0);
+        s1 = s1 + s1 + xor3<F>(l[S256_WB14 + ((i + 17) & 31)], l[S256_WB14 + ((i + 19) & 31)], hi1);
+        s0 = s0 + s0 + xor3<F>(l[S256_WB1 + ((i + 7) & 31)], l[S256_WB1 + ((i + 18) & 31)], hi0);
+    }
+    emit((l[S256_WS] + two32 * cw) - ((s1 + l[S256_W + 9]) + (s0 + l[S256_W])));
+    emit(SCHED * (n[S256_W + 15] - l[S256_WS]));
+    // digest words on the last round, zero elsewhere
+    const F fin[8] = {an, pack_bits<F>(l, S256_A, 32), pack_bits<F>(l, S256_B, 32), pc,
+                      en, pack_bits<F>(l, S256_E, 32), pack_bits<F>(l, S256_F, 32), pg};
+    for (int j = 0; j < 8; j++) {
+        emit(LAST * ((l[S256_DG + j] + two32 * l[S256_DC + j]) - (l[S256_CV + j] + fin[j])));
+        emit(NOTLAST * l[S256_DG + j]);
+        emit(NOTLAST * l[S256_DC + j]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ SHA-512
+template <class F, class Row, class Emit>
+TMX_HD void air_sha512(const Row& l, const Row& n, const F* per, Emit& emit) {
+    (void)n;
+    (void)per;
+    for (int i = S512_A; i < S512_D; i++) emit(is_bool<F>(l[i]));
+    for (int i = S512_AN; i < S512_W; i++) emit(is_bool<F>(l[i]));
+    for (int i = S512_WB14; i < S512_CV; i++) emit(is_bool<F>(l[i]));
+    for (int i = S512_CA; i < S512_DG; i++) emit(is_bool<F>(l[i]));
+    for (int i = 0; i < 16; i++) emit(is_bool<F>(l[S512_DC + i]));
+    emit(pack_bits<F>(l, S512_WB14, 32) - l[S512_W + 28]);
+    emit(pack_bits<F>(l, S512_WB14 + 32, 32) - l[S512_W + 29]);
+    emit(pack_bits<F>(l, S512_WB1, 32) - l[S512_W + 2]);
+    emit(pack_bits<F>(l, S512_WB1 + 32, 32) - l[S512_W + 3]);
+}
+
+// ------------------------------------------------------------------------------------------ Ed25519
+TMX_HD uint64_t p25519_limb(int i) { return i == 0 ? 0xFFEDULL : (i == 15 ? 0x7FFFULL : 0xFFFFULL); }
+
+// U * V = c + q * p with carries: 32 limb equations of one multiplication gadget whose cells start at column g0
+template <class F, class Row, class Emit>
+TMX_HD void ed_mul_gadget(const F U[16], const F V[16], const Row& l, int g0, Emit& emit) {
+    const F off = F::c(ED_W_OFFSET), two16 = F::c(1 << 16);
+    F q[17];
+    for (int i = 0; i < 17; i++) q[i] = l[g0 + ED_MUL_Q + i];
+    F wprev = F::c(0);
+    for (int k = 0; k < 32; k++) {
+        F s = F::c(0);
+        for (int i = 0; i < 16; i++) {
+            const int j = k - i;
+            if (j >= 0 && j < 16) s = s + U[i] * V[j];
+        }
+        if (k < 16) s = s - l[g0 + k];
+        for (int i = 0; i < 17; i++) {
+            const int j = k - i;
+            if (j >= 0 && j < 16) s = s - q[i] * F::c(p25519_limb(j));
+        }
+        if (k >= 1) s = s + wprev;
+        if (k < 31) {
+            wprev = l[g0 + ED_MUL_W + k] - off;
+            s = s - two16 * wprev;
+        }
+        emit(s);
+    }
+}
+
+// per = {not_block_end} (period 256)
+template <class F, class Row, class Emit>
+TMX_HD void air_ed25519(const Row& l, const Row& n, const F* per, Emit& emit) {
+    const F NOTEND = per[0];
+    const F bit = l[ED_BIT];
+    emit(is_bool<F>(bit));
+    const uint64_t TWOD[16] = {0xF159, 0x26B2, 0x9B94, 0xEBD6, 0xB156, 0x8283, 0x149A, 0x00E0,
+                               0xD130, 0xEEF3, 0x80F2, 0x198E, 0xFCE7, 0x56DF, 0xD9DC, 0x2406};
+    const int X1 = ED_RES, Y1 = ED_RES + 16, Z1 = ED_RES + 32, T1 = ED_RES + 48;
+    const int X2 = ED_TMP, Y2 = ED_TMP + 16, Z2 = ED_TMP + 32, T2 = ED_TMP + 48;
+    auto G = [](int m) { return ED_MUL + m * ED_MUL_STRIDE; };
+    F u[16], v[16], E[16], Fq[16], Gq[16], H[16];
+    for (int i = 0; i < 16; i++) {
+        const F pl = F::c(p25519_limb(i));
+        u[i] = (l[Y1 + i] - l[X1 + i]) + pl;
+        v[i] = (l[Y2 + i] - l[X2 + i]) + pl;
+    }
+    ed_mul_gadget<F>(u, v, l, G(0), emit);
+    for (int i = 0; i < 16; i++) { u[i] = l[Y1 + i] + l[X1 + i]; v[i] = l[Y2 + i] + l[X2 + i]; }
+    ed_mul_gadget<F>(u, v, l, G(1), emit);
+    for (int i = 0; i < 16; i++) { u[i] = l[T1 + i]; v[i] = l[T2 + i]; }
+    ed_mul_gadget<F>(u, v, l, G(2), emit);
+    for (int i = 0; i < 16; i++) { u[i] = l[G(2) + i]; v[i] = F::c(TWOD[i]); }
+    ed_mul_gadget<F>(u, v, l, G(3), emit);
+    for (int i = 0; i < 16; i++) { u[i] = l[Z1 + i]; v[i] = l[Z2 + i]; }
+    ed_mul_gadget<F>(u, v, l, G(4), emit);
+    for (int i = 0; i < 16; i++) {
+        const F pl = F::c(p25519_limb(i));
+        const F A = l[G(0) + i], B = l[G(1) + i], C = l[G(3) + i], Dh = l[G(4) + i];
+        const F d2 = Dh + Dh;
+        E[i] = (B - A) + pl;
+        Fq[i] = (d2 - C) + pl;
+        Gq[i] = d2 + C;
+        H[i] = B + A;
+    }
+    ed_mul_gadget<F>(E, Fq, l, G(5), emit);
+    ed_mul_gadget<F>(Gq, H, l, G(6), emit);
+    ed_mul_gadget<F>(E, H, l, G(7), emit);
+    ed_mul_gadget<F>(Fq, Gq, l, G(8), emit);
+    for (int i = 0; i < 16; i++) u[i] = l[X2 + i];
+    ed_mul_gadget<F>(u, u, l, G(9), emit);
+    for (int i = 0; i < 16; i++) u[i] = l[Y2 + i];
+    ed_mul_gadget<F>(u, u, l, G(10), emit);
+    for (int i = 0; i < 16; i++) u[i] = l[Z2 + i];
+    ed_mul_gadget<F>(u, u, l, G(11), emit);
+    for (int i = 0; i < 16; i++) u[i] = l[X2 + i] + l[Y2 + i];
+    ed_mul_gadget<F>(u, u, l, G(12), emit);
+    for (int i = 0; i < 16; i++) {
+        const F pl = F::c(p25519_limb(i)), p2 = pl + pl;
+        const F A2 = l[G(9) + i], B2 = l[G(10) + i], Cz = l[G(11) + i], S = l[G(12) + i];
+        const F ba = B2 - A2;
+        E[i] = ((S - A2) - B2) + p2;
+        Gq[i] = ba + pl;
+        Fq[i] = (ba - (Cz + Cz)) + (p2 + pl);
+        H[i] = (p2 - A2) - B2;
+    }
+    ed_mul_gadget<F>(E, Fq, l, G(13), emit);
+    ed_mul_gadget<F>(Gq, H, l, G(14), emit);
+    ed_mul_gadget<F>(E, H, l, G(15), emit);
+    ed_mul_gadget<F>(Fq, Gq, l, G(16), emit);
+    const int sum_slot[4] = {5, 6, 8, 7}, dbl_slot[4] = {13, 14, 16, 15};  // X, Y, Z, T
+    for (int co = 0; co < 4; co++)
+        for (int i = 0; i < 16; i++) {
+            const F r = l[ED_RES + 16 * co + i], s = l[G(sum_slot[co]) + i];
+            emit(NOTEND * (n[ED_RES + 16 * co + i] - (r + bit * (s - r))));
+            emit(NOTEND * (n[ED_TMP + 16 * co + i] - l[G(dbl_slot[co]) + i]));
+        }
+}
+
+template <class F, class Row, class Emit>
+TMX_HD void air_eval(int table, const Row& l, const Row& n, const F* per, Emit& emit) {
+    if (table == AIR_SHA256) air_sha256<F>(l, n, per, emit);
+    else if (table == AIR_SHA512) air_sha512<F>(l, n, per, emit);
+    else air_ed25519<F>(l, n, per, emit);
+}
+
+// periodic pattern of column pc at row r of its period
+TMX_HD uint64_t air_periodic_pattern(int table, int pc, int r, const uint32_t* k256_table) {
+    if (table == AIR_SHA256) {
+        if (pc == 0) return k256_table[r];
+        if (pc == 1) return r == 63;
+        if (pc == 2) return r != 63;
+        return r >= 15 && r <= 62;
+    }
+    return r != 255;
+}
+
+}  // namespace tmx
