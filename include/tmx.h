@@ -98,6 +98,47 @@ int tmx_ed25519_trace(tmx_ctx *ctx, const uint8_t *d_blob, uint32_t kind, uint32
 int tmx_witness_generate(tmx_ctx *ctx, const uint8_t *d_blob, uint32_t kind, uint32_t n_max, uint64_t *d_t256,
                          uint64_t *d_t512, uint64_t *d_ted, uint8_t *d_aux, void *stream);
 
+/* K9: proof-of-work grind: the SMALLEST w such that Poseidon(state with state[pos] = w)[7] has `bits` leading
+ * zero bits (plonky2 fri_proof_of_work uses rayon find_any, i.e. any witness).  `state` is a host pointer. */
+int tmx_pow_grind(tmx_ctx *ctx, const uint64_t state[12], int pos, unsigned bits, uint64_t *witness, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Circuit-level surface.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct tmx_circuit tmx_circuit;
+typedef struct tmx_proof tmx_proof;
+
+/* `SkipCircuit::<N, C>::define` + `builder.build()` [circuits/skip.rs:113-143,165-173; circuits/step.rs:100-127]:
+ * kind = TMX_KIND_SKIP / TMX_KIND_STEP; VALIDATOR_SET_SIZE_MAX, chain id and SKIP_MAX are runtime parameters here
+ * (const generics / TendermintConfig in the reference, circuits/config.rs:3-32). */
+int tmx_circuit_build(tmx_ctx *ctx, uint32_t kind, uint32_t n_max, const char *chain_id, size_t chain_id_len,
+                      uint64_t skip_max, tmx_circuit **out);
+void tmx_circuit_free(tmx_circuit *circuit);
+int tmx_circuit_digest(const tmx_circuit *circuit, uint64_t out[4]);
+/* the `build` artefact (./build/main.circuit in succinct.json:8,15) */
+int tmx_circuit_save(const tmx_circuit *circuit, const char *path);
+int tmx_circuit_load(tmx_ctx *ctx, const char *path, tmx_circuit **out);
+
+/* `circuit.prove(&input)` [circuits/skip.rs:213-214,238-244]: input = 48 (skip) / 40 (step) bytes in the
+ * abi.encodePacked layout of circuits/skip.rs:120-122; blob = the off-chain inputs the async hint would fetch
+ * [circuits/skip.rs:64-101] (tmx_types.h).  Returns TMX_E_UNSAT (tmx_last_check() = failing check id) where the
+ * reference's witness generation would panic.  out32 = the proven target / next header hash. */
+int tmx_prove(tmx_circuit *circuit, const uint8_t *input, size_t input_len, const uint8_t *blob, size_t blob_len,
+              tmx_proof **proof, uint8_t out32[32]);
+int tmx_last_check(void);
+size_t tmx_proof_size(const tmx_proof *proof);
+/* serialised proof: little-endian u64 stream, layout documented in DESIGN.md "Proof format" */
+int tmx_proof_bytes(const tmx_proof *proof, uint8_t *buf, size_t cap);
+void tmx_proof_free(tmx_proof *proof);
+
+/* `circuit.verify(&proof, &input, &output)` [circuits/skip.rs:247]: CPU verifier, 0 = accepted. */
+int tmx_verify(const tmx_circuit *circuit, const uint8_t *proof, size_t proof_len, const uint8_t *input,
+               size_t input_len, const uint8_t out32[32]);
+/* the same check from the bare circuit parameters; needs no GPU and no tmx_ctx */
+int tmx_verify_params(uint32_t kind, uint32_t n_max, const char *chain_id, size_t chain_id_len, uint64_t skip_max,
+                      const uint8_t *proof, size_t proof_len, const uint8_t *input, size_t input_len,
+                      const uint8_t out32[32]);
+
 #ifdef __cplusplus
 }
 #endif

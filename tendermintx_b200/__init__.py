@@ -119,3 +119,84 @@ class Context:
         _check(lib().tmx_witness_generate(self._h, _ptr(d_blob), kind, n_max, _ptr(tabs[0]), _ptr(tabs[1]),
                                           _ptr(tabs[2]), _ptr(aux), self._stream()))
         return tabs, aux
+
+
+KIND_STEP, KIND_SKIP = 0, 1
+SKIP_MAX = 100800  # REF circuits/config.rs:12
+CHECK_NAMES = ["OK", "SKIP_DISTANCE", "TRUSTED_HEADER_PROOF", "TRUSTED_VALHASH", "TRUSTED_THRESHOLD", "SIGNATURE",
+               "VALHASH", "VALHASH_PROOF", "THRESHOLD", "SIGN_BYTES", "CHAIN_ID", "HEIGHT", "LAST_BLOCK_ID",
+               "NEXT_VALHASH", "VOTING_OVERFLOW", "VARINT_SIGN", "ROUND_SIGN", "INPUT"]
+
+
+class TendermintConfig:
+    """REF circuits/config.rs:3-32."""
+
+    def __init__(self, chain_id, skip_max=SKIP_MAX):
+        self.chain_id = chain_id.encode() if isinstance(chain_id, str) else bytes(chain_id)
+        self.skip_max = skip_max
+
+
+CelestiaConfig = TendermintConfig("celestia")
+Mocha4Config = TendermintConfig("mocha-4")
+
+
+def verify_proof(kind, n_max, config, proof, public_input, output):
+    """CPU verification from bare circuit parameters (no GPU, no context).  Raises TmxError if rejected."""
+    proof, public_input, output = bytes(proof), bytes(public_input), bytes(output)
+    _check(lib().tmx_verify_params(kind, n_max, config.chain_id, len(config.chain_id), config.skip_max, proof, len(proof),
+                                   public_input, len(public_input), output))
+
+
+class Circuit:
+    """`SkipCircuit::<N, C>` / `StepCircuit::<N, C>` [REF circuits/skip.rs:103-143, circuits/step.rs:90-127]:
+    build() -> prove(input, offchain blob) -> verify(proof, input, output)."""
+
+    def __init__(self, ctx, kind, n_max, config):
+        self.ctx, self.kind, self.n_max, self.config = ctx, kind, n_max, config
+        self._h = ctypes.c_void_p()
+        _check(lib().tmx_circuit_build(ctx.handle, kind, n_max, config.chain_id, len(config.chain_id), config.skip_max,
+                                       ctypes.byref(self._h)))
+
+    @classmethod
+    def build(cls, ctx, kind, n_max, config):
+        return cls(ctx, kind, n_max, config)
+
+    def close(self):
+        if self._h:
+            lib().tmx_circuit_free(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def digest(self):
+        out = (ctypes.c_uint64 * 4)()
+        _check(lib().tmx_circuit_digest(self._h, out))
+        return list(out)
+
+    def save(self, path):
+        _check(lib().tmx_circuit_save(self._h, path.encode()))
+
+    def prove(self, public_input, blob):
+        """Returns (proof bytes, output header bytes).  Raises TmxError(TMX_E_UNSAT) with `.check` set to the name
+        of the failing gadget check where the reference's witness generation would panic."""
+        p = ctypes.c_void_p()
+        out = (ctypes.c_uint8 * 32)()
+        public_input, blob = bytes(public_input), bytes(blob)
+        rc = lib().tmx_prove(self._h, public_input, len(public_input), blob, len(blob), ctypes.byref(p), out)
+        if rc != 0:
+            err = TmxError(rc, lib().tmx_last_error().decode())
+            err.check = CHECK_NAMES[lib().tmx_last_check()]
+            raise err
+        n = lib().tmx_proof_size(p)
+        buf = (ctypes.c_uint8 * n)()
+        _check(lib().tmx_proof_bytes(p, buf, n))
+        lib().tmx_proof_free(p)
+        return bytes(buf), bytes(out)
+
+    def verify(self, proof, public_input, output):
+        proof, public_input, output = bytes(proof), bytes(public_input), bytes(output)
+        _check(lib().tmx_verify(self._h, proof, len(proof), public_input, len(public_input), output))

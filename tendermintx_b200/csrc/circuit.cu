@@ -1,0 +1,390 @@
+// Circuit-level surface: build / prove / verify for the skip and step circuits.
+//
+// Mirrors, behind the C ABI, plonky2x's `Circuit::define` + `builder.build()` [REF circuits/skip.rs:113-143,173;
+// circuits/step.rs:100-127], `circuit.prove()` [REF skip.rs:214,244] and `circuit.verify()` [REF skip.rs:247].
+// The statement proved is `verify_skip` / `verify_step` [REF circuits/builder/verify.rs:469-563]: the hashing and
+// signature work is witnessed by the GPU tables and proved by the STARK; the remaining gadget checks (skip
+// distance, sign-bytes fields, voting thresholds, chain-id bytes, hash linkages) are evaluated here on the host
+// from the input blob and the digests the witness kernels produced, and abort the proof with TMX_E_UNSAT exactly
+// where the reference's witness generation would panic.
+#include "stark.cuh"
+#include "witness_jobs.cuh"
+#include <cstring>
+#include <cstdio>
+
+using namespace tmx;
+
+struct tmx_circuit {
+    tmx_ctx* ctx = nullptr;
+    uint32_t kind = 0, n_max = 0;
+    std::string chain_id;
+    uint64_t skip_max = 0;
+    size_t dims[6] = {0, 0, 0, 0, 0, 0};
+    gl digest[4] = {0, 0, 0, 0};
+    // device state reused across proofs
+    gl* d_trace[3] = {nullptr, nullptr, nullptr};
+    uint8_t* d_blob = nullptr;
+    uint8_t* d_aux = nullptr;
+    TableProver prover;
+};
+
+struct tmx_proof {
+    std::vector<gl> words;
+};
+
+namespace tmx {
+
+static thread_local int g_last_check = 0;
+
+static void hash_no_pad_host(const gl* in, size_t n, gl out[4]) {
+    gl s[12] = {0};
+    for (size_t off = 0; off < n; off += 8) {
+        const size_t k = std::min<size_t>(8, n - off);
+        for (size_t i = 0; i < k; i++) s[i] = in[off + i];
+        poseidon_permute(s);
+    }
+    for (int i = 0; i < 4; i++) out[i] = s[i];
+}
+
+static void circuit_digest(const tmx_circuit* c, gl out[4]) {
+    gl in[96];
+    size_t k = 0;
+    in[k++] = STARK_PROOF_MAGIC; in[k++] = c->kind; in[k++] = c->n_max; in[k++] = c->skip_max;
+    in[k++] = STARK_RATE_BITS; in[k++] = STARK_CAP_HEIGHT; in[k++] = 2; in[k++] = STARK_POW_BITS; in[k++] = STARK_NUM_QUERIES;
+    in[k++] = STARK_ARITY_BITS; in[k++] = STARK_FINAL_POLY_BITS;
+    for (int i = 0; i < 6; i++) in[k++] = c->dims[i];
+    in[k++] = c->chain_id.size();
+    for (size_t i = 0; i < c->chain_id.size() && i < 64; i++) in[k++] = (uint8_t)c->chain_id[i];
+    hash_no_pad_host(in, k, out);
+}
+
+static void transcript_init(const tmx_circuit* c, const uint8_t* input, size_t input_len, const uint8_t out32[32], Challenger& ch) {
+    ch.observe(c->digest, 4);
+    gl pub[128], ph[4];
+    size_t k = 0;
+    for (size_t i = 0; i < input_len; i++) pub[k++] = input[i];
+    for (size_t i = 0; i < 32; i++) pub[k++] = out32[i];
+    hash_no_pad_host(pub, k, ph);
+    ch.observe(ph, 4);
+}
+
+static uint64_t be64(const uint8_t* p) {
+    uint64_t v = 0;
+    for (int i = 0; i < 8; i++) v = (v << 8) | p[i];
+    return v;
+}
+
+// check ids (same numbering as the reference-assertion map in INTEGRATION.md)
+enum {
+    CHECK_OK = 0, CHECK_SKIP_DISTANCE, CHECK_TRUSTED_HEADER_PROOF, CHECK_TRUSTED_VALHASH, CHECK_TRUSTED_THRESHOLD,
+    CHECK_SIGNATURE, CHECK_VALHASH, CHECK_VALHASH_PROOF, CHECK_THRESHOLD, CHECK_SIGN_BYTES, CHECK_CHAIN_ID, CHECK_HEIGHT,
+    CHECK_LAST_BLOCK_ID, CHECK_NEXT_VALHASH, CHECK_VOTING_OVERFLOW, CHECK_VARINT_SIGN, CHECK_ROUND_SIGN, CHECK_INPUT
+};
+
+// REF circuits/builder/voting.rs:31-109 and verify.rs:439-467
+static int voting_threshold(const std::vector<uint64_t>& power, const std::vector<uint8_t>& group, size_t nb_enabled, uint64_t num,
+                            uint64_t den, bool* gt) {
+    uint64_t total = 0, acc = 0;
+    for (size_t i = 0; i < power.size(); i++) {
+        const uint64_t v = i < nb_enabled ? power[i] : 0;
+        if (total + v < total) return CHECK_VOTING_OVERFLOW;
+        total += v;
+    }
+    for (size_t i = 0; i < power.size(); i++) {
+        const uint64_t v = group[i] ? power[i] : 0;
+        if (acc + v < acc) return CHECK_VOTING_OVERFLOW;
+        acc += v;
+    }
+    const uint64_t sa = acc * den, st = total * num;
+    if (sa / den != acc || st / num != total) return CHECK_VOTING_OVERFLOW;
+    *gt = sa > st;
+    return CHECK_OK;
+}
+
+// REF circuits/builder/validator.rs:73-183
+static bool sign_bytes_ok(const tmx_validator& v, bool enabled, const uint8_t header[32], uint64_t height, uint64_t round) {
+    const uint8_t* m = v.message;
+    uint8_t le[8];
+    const bool hash_in_message = memcmp(m + (round == 0 ? 16 : 25), header, 32) == 0;
+    const bool precommit = m[1] == 8 && m[2] == 2;
+    for (int i = 0; i < 8; i++) le[i] = (uint8_t)(height >> (8 * i));
+    const bool height_ok = memcmp(m + 4, le, 8) == 0;
+    for (int i = 0; i < 8; i++) le[i] = (uint8_t)(round >> (8 * i));
+    const bool round_ok = round == 0 || memcmp(m + 13, le, 8) == 0;
+    const bool valid = v.is_signed && enabled && hash_in_message && precommit && height_ok && round_ok;
+    return (v.is_signed != 0) == valid;
+}
+
+// The gadget checks of verify_header [REF verify.rs:224-334] given the digests computed on the GPU.
+static int check_header(const tmx_circuit* c, const tmx_offchain_head* h, const tmx_validator* vals, const uint8_t* aux,
+                        uint32_t set, const uint8_t* root_valhash, const uint8_t* root_chain, const uint8_t* root_height,
+                        uint64_t height) {
+    const size_t n = c->n_max;
+    if (h->round >> 63) return CHECK_ROUND_SIGN;
+    for (size_t i = 0; i < n; i++)
+        if (vals[i].is_signed && vals[i].message_byte_length > TMX_VALIDATOR_MESSAGE_BYTES_LENGTH_MAX) return CHECK_SIGNATURE;
+    for (size_t i = 0; i < n; i++)
+        if (!aux[AUX_SIG_OK + i]) return CHECK_SIGNATURE;
+    std::vector<uint64_t> power(n);
+    std::vector<uint8_t> sgn(n);
+    for (size_t i = 0; i < n; i++) {
+        power[i] = vals[i].voting_power;
+        sgn[i] = vals[i].is_signed != 0;
+        if (power[i] >> 63) return CHECK_VARINT_SIGN;
+    }
+    if (memcmp(aux + AUX_SET_ROOT + 32 * set, h->validators_hash_proof.leaf + 2, 32)) return CHECK_VALHASH;
+    if (memcmp(root_valhash, h->header, 32)) return CHECK_VALHASH_PROOF;
+    bool gt = false;
+    int rc = voting_threshold(power, sgn, h->nb_validators, 2, 3, &gt);
+    if (rc) return rc;
+    if (!gt) return CHECK_THRESHOLD;
+    for (size_t i = 0; i < n; i++)
+        if (!sign_bytes_ok(vals[i], i < h->nb_validators, h->header, height, h->round)) return CHECK_SIGN_BYTES;
+    // chain id [REF verify.rs:180-222]
+    if ((size_t)h->chain_id_proof.enc_chain_id_byte_length + 1 > 55) return CHECK_CHAIN_ID;
+    if (memcmp(root_chain, h->header, 32)) return CHECK_CHAIN_ID;
+    if (c->chain_id.size() + 2 > TMX_PROTOBUF_CHAIN_ID_SIZE_BYTES ||
+        memcmp(h->chain_id_proof.chain_id + 2, c->chain_id.data(), c->chain_id.size()))
+        return CHECK_CHAIN_ID;
+    // height [REF shared.rs:169-207]
+    if (h->height_proof.height >> 63) return CHECK_VARINT_SIGN;
+    if ((size_t)h->height_proof.enc_height_byte_length + 1 > 55) return CHECK_HEIGHT;
+    if (memcmp(root_height, h->header, 32)) return CHECK_HEIGHT;
+    if (h->height_proof.height != height) return CHECK_HEIGHT;
+    return CHECK_OK;
+}
+
+static int check_statement(const tmx_circuit* c, const uint8_t* input, const uint8_t* blob, const uint8_t* aux) {
+    const tmx_offchain_head* h = blob_head(blob);
+    const tmx_validator* vals = blob_validators(blob);
+    const size_t n = c->n_max;
+    const uint8_t* proots = aux + AUX_PROOF_ROOT;
+    if (c->kind == TMX_KIND_SKIP) {
+        const uint64_t trusted = be64(input), target = be64(input + 40);
+        const uint8_t* trusted_header = input + 8;
+        if (!(target > trusted + 1 && target <= trusted + c->skip_max)) return CHECK_SKIP_DISTANCE;  // REF verify.rs:508-526
+        // verify_trusted_validators [REF verify.rs:361-437]
+        const tmx_hash_field* tf = blob_hash_fields(blob, c->n_max);
+        if (memcmp(proots, trusted_header, 32)) return CHECK_TRUSTED_HEADER_PROOF;
+        std::vector<uint64_t> power(n);
+        for (size_t i = 0; i < n; i++) {
+            power[i] = tf[i].voting_power;
+            if (power[i] >> 63) return CHECK_VARINT_SIGN;
+        }
+        if (memcmp(aux + AUX_SET_ROOT, h->aux_hash_proof.leaf + 2, 32)) return CHECK_TRUSTED_VALHASH;
+        std::vector<uint8_t> flag(n, 0);
+        for (size_t i = 0; i < n; i++)
+            if (vals[i].is_signed)
+                for (size_t j = 0; j < n; j++)
+                    if (!memcmp(vals[i].pubkey, tf[j].pubkey, 32)) flag[j] = 1;
+        bool gt = false;
+        int rc = voting_threshold(power, flag, h->nb_trusted, 1, 3, &gt);
+        if (rc) return rc;
+        if (!gt) return CHECK_TRUSTED_THRESHOLD;
+        return check_header(c, h, vals, aux, 1, proots + 32, proots + 64, proots + 96, target);
+    }
+    const uint64_t prev = be64(input);
+    const uint8_t* prev_header = input + 8;
+    int rc = check_header(c, h, vals, aux, 0, proots, proots + 32, proots + 64, prev + 1);
+    if (rc) return rc;
+    // REF verify.rs:137-178
+    if (memcmp(proots + 96, h->header, 32)) return CHECK_LAST_BLOCK_ID;
+    if (memcmp(h->last_block_id_proof.leaf + 2, prev_header, 32)) return CHECK_LAST_BLOCK_ID;
+    if (memcmp(proots + 128, prev_header, 32)) return CHECK_NEXT_VALHASH;
+    if (memcmp(h->aux_hash_proof.leaf + 2, h->validators_hash_proof.leaf + 2, 32)) return CHECK_NEXT_VALHASH;
+    return CHECK_OK;
+}
+
+}  // namespace tmx
+
+extern "C" int tmx_last_check(void) { return g_last_check; }
+extern "C" int tmx_verify(const tmx_circuit* c, const uint8_t* proof, size_t proof_len, const uint8_t* input, size_t input_len,
+                          const uint8_t out32[32]);
+
+extern "C" int tmx_circuit_build(tmx_ctx* ctx, uint32_t kind, uint32_t n_max, const char* chain_id, size_t chain_id_len,
+                                 uint64_t skip_max, tmx_circuit** out) {
+    if (!ctx || !out || !chain_id || kind > 1 || n_max == 0 || n_max > 4096 || chain_id_len == 0 || chain_id_len > 50)
+        return fail(TMX_E_INPUT, "tmx_circuit_build: bad arguments");
+    tmx_circuit* c = new tmx_circuit();
+    c->ctx = ctx;
+    c->kind = kind;
+    c->n_max = n_max;
+    c->chain_id.assign(chain_id, chain_id_len);
+    c->skip_max = skip_max;
+    tmx_trace_dims(kind, n_max, c->dims);
+    poseidon_generate_constants();
+    circuit_digest(c, c->digest);
+    cudaSetDevice(ctx->device);
+    for (int t = 0; t < 3; t++) {
+        cudaError_t e = cudaMalloc((void**)&c->d_trace[t], c->dims[2 * t] * c->dims[2 * t + 1] * sizeof(gl));
+        if (e != cudaSuccess) {
+            tmx_circuit_free(c);
+            return fail(TMX_E_CUDA, std::string("tmx_circuit_build: cudaMalloc: ") + cudaGetErrorString(e));
+        }
+    }
+    if (cudaMalloc((void**)&c->d_blob, TMX_BLOB_SIZE(kind, n_max)) != cudaSuccess ||
+        cudaMalloc((void**)&c->d_aux, aux_bytes(n_max)) != cudaSuccess) {
+        tmx_circuit_free(c);
+        return fail(TMX_E_CUDA, "tmx_circuit_build: cudaMalloc failed");
+    }
+    *out = c;
+    return TMX_OK;
+}
+
+extern "C" void tmx_circuit_free(tmx_circuit* c) {
+    if (!c) return;
+    cudaSetDevice(c->ctx->device);
+    for (int t = 0; t < 3; t++)
+        if (c->d_trace[t]) cudaFree(c->d_trace[t]);
+    if (c->d_blob) cudaFree(c->d_blob);
+    if (c->d_aux) cudaFree(c->d_aux);
+    c->prover.release();
+    delete c;
+}
+
+extern "C" int tmx_circuit_digest(const tmx_circuit* c, uint64_t out[4]) {
+    if (!c || !out) return fail(TMX_E_INPUT, "tmx_circuit_digest: NULL argument");
+    for (int i = 0; i < 4; i++) out[i] = c->digest[i];
+    return TMX_OK;
+}
+
+// build artefact: the parameters that define the circuit plus its digest (the preprocessed data is recomputed
+// from them on load; see DESIGN.md "Preprocessed data")
+extern "C" int tmx_circuit_save(const tmx_circuit* c, const char* path) {
+    if (!c || !path) return fail(TMX_E_INPUT, "tmx_circuit_save: NULL argument");
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(TMX_E_IO, std::string("tmx_circuit_save: cannot open ") + path);
+    uint64_t hdr[4] = {STARK_PROOF_MAGIC ^ 0x43ULL, c->kind, c->n_max, c->skip_max};
+    uint64_t len = c->chain_id.size();
+    bool ok = fwrite(hdr, sizeof hdr, 1, f) == 1 && fwrite(&len, 8, 1, f) == 1 && fwrite(c->chain_id.data(), 1, len, f) == len &&
+              fwrite(c->digest, sizeof c->digest, 1, f) == 1;
+    fclose(f);
+    return ok ? TMX_OK : fail(TMX_E_IO, "tmx_circuit_save: short write");
+}
+
+extern "C" int tmx_circuit_load(tmx_ctx* ctx, const char* path, tmx_circuit** out) {
+    if (!ctx || !path || !out) return fail(TMX_E_INPUT, "tmx_circuit_load: NULL argument");
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(TMX_E_IO, std::string("tmx_circuit_load: cannot open ") + path);
+    uint64_t hdr[4], len = 0;
+    char cid[64];
+    gl dg[4];
+    bool ok = fread(hdr, sizeof hdr, 1, f) == 1 && fread(&len, 8, 1, f) == 1 && len <= 50 && fread(cid, 1, len, f) == len &&
+              fread(dg, sizeof dg, 1, f) == 1;
+    fclose(f);
+    if (!ok || hdr[0] != (STARK_PROOF_MAGIC ^ 0x43ULL)) return fail(TMX_E_INPUT, "tmx_circuit_load: not a circuit file");
+    int rc = tmx_circuit_build(ctx, (uint32_t)hdr[1], (uint32_t)hdr[2], cid, len, hdr[3], out);
+    if (rc) return rc;
+    if (memcmp(dg, (*out)->digest, sizeof dg)) {
+        tmx_circuit_free(*out);
+        *out = nullptr;
+        return fail(TMX_E_INPUT, "tmx_circuit_load: digest mismatch (built by a different version?)");
+    }
+    return TMX_OK;
+}
+
+extern "C" int tmx_prove(tmx_circuit* c, const uint8_t* input, size_t input_len, const uint8_t* blob, size_t blob_len,
+                         tmx_proof** proof_out, uint8_t out32[32]) {
+    if (!c || !input || !blob || !proof_out || !out32) return fail(TMX_E_INPUT, "tmx_prove: NULL argument");
+    g_last_check = 0;
+    *proof_out = nullptr;
+    const tmx_offchain_head* h = blob_head(blob);
+    if (blob_len < sizeof(tmx_offchain_head) || h->magic != TMX_BLOB_MAGIC || h->kind != c->kind || h->n_max != c->n_max ||
+        blob_len != TMX_BLOB_SIZE(c->kind, c->n_max) || input_len != (c->kind == TMX_KIND_SKIP ? 48u : 40u)) {
+        g_last_check = CHECK_INPUT;
+        return fail(TMX_E_INPUT, "tmx_prove: input / blob does not match the circuit shape");
+    }
+    tmx_ctx* ctx = c->ctx;
+    TMX_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    // witness generation on the GPU
+    TMX_CUDA(cudaMemcpyAsync(c->d_blob, blob, blob_len, cudaMemcpyHostToDevice, st));
+    TMX_CUDA(cudaMemsetAsync(c->d_aux, 0, aux_bytes(c->n_max), st));
+    int rc = tmx_witness_generate(ctx, c->d_blob, c->kind, c->n_max, c->d_trace[0], c->d_trace[1], c->d_trace[2], c->d_aux, st);
+    if (rc) return rc;
+    std::vector<uint8_t> aux(aux_bytes(c->n_max));
+    TMX_CUDA(cudaMemcpyAsync(aux.data(), c->d_aux, aux.size(), cudaMemcpyDeviceToHost, st));
+    TMX_CUDA(cudaStreamSynchronize(st));
+    const int chk = check_statement(c, input, blob, aux.data());
+    if (chk) {
+        g_last_check = chk;
+        return fail(TMX_E_UNSAT, "tmx_prove: witness does not satisfy the circuit (check id " + std::to_string(chk) + ")");
+    }
+    memcpy(out32, h->header, 32);
+    // proof: header, then one STARK per table on a shared transcript
+    tmx_proof* p = new tmx_proof();
+    std::vector<gl>& w = p->words;
+    w.push_back(STARK_PROOF_MAGIC);
+    w.push_back(c->kind);
+    w.push_back(c->n_max);
+    w.push_back(STARK_N_TABLES);
+    for (int i = 0; i < 4; i++) {
+        gl x = 0;
+        for (int j = 0; j < 8; j++) x |= (gl)out32[8 * i + j] << (8 * j);
+        w.push_back(x);
+    }
+    Challenger ch;
+    transcript_init(c, input, input_len, out32, ch);
+    for (int t = 0; t < STARK_N_TABLES; t++) {
+        rc = c->prover.prove(ctx, t, c->d_trace[t], ilog2(c->dims[2 * t]), ch, w, st);
+        if (rc) {
+            delete p;
+            return rc;
+        }
+    }
+    *proof_out = p;
+    return TMX_OK;
+}
+
+extern "C" size_t tmx_proof_size(const tmx_proof* p) { return p ? p->words.size() * sizeof(gl) : 0; }
+
+extern "C" int tmx_proof_bytes(const tmx_proof* p, uint8_t* buf, size_t cap) {
+    if (!p || !buf) return fail(TMX_E_INPUT, "tmx_proof_bytes: NULL argument");
+    if (cap < p->words.size() * sizeof(gl)) return fail(TMX_E_INPUT, "tmx_proof_bytes: buffer too small");
+    memcpy(buf, p->words.data(), p->words.size() * sizeof(gl));  // u64 little-endian stream
+    return TMX_OK;
+}
+
+extern "C" void tmx_proof_free(tmx_proof* p) { delete p; }
+
+// Verification needs no GPU: the same check from the bare circuit parameters (what a light client would hold).
+extern "C" int tmx_verify_params(uint32_t kind, uint32_t n_max, const char* chain_id, size_t chain_id_len, uint64_t skip_max,
+                                 const uint8_t* proof, size_t proof_len, const uint8_t* input, size_t input_len,
+                                 const uint8_t out32[32]) {
+    if (!chain_id || kind > 1 || n_max == 0 || n_max > 4096 || chain_id_len == 0 || chain_id_len > 50)
+        return fail(TMX_E_INPUT, "tmx_verify_params: bad arguments");
+    tmx_circuit c;
+    c.kind = kind;
+    c.n_max = n_max;
+    c.chain_id.assign(chain_id, chain_id_len);
+    c.skip_max = skip_max;
+    tmx_trace_dims(kind, n_max, c.dims);
+    poseidon_generate_constants();
+    circuit_digest(&c, c.digest);
+    return tmx_verify(&c, proof, proof_len, input, input_len, out32);
+}
+
+extern "C" int tmx_verify(const tmx_circuit* c, const uint8_t* proof, size_t proof_len, const uint8_t* input, size_t input_len,
+                          const uint8_t out32[32]) {
+    if (!c || !proof || !input || !out32) return fail(TMX_E_INPUT, "tmx_verify: NULL argument");
+    if (proof_len % 8 || input_len != (c->kind == TMX_KIND_SKIP ? 48u : 40u)) return fail(TMX_E_VERIFY, "tmx_verify: malformed proof / input length");
+    std::vector<gl> w(proof_len / 8);
+    memcpy(w.data(), proof, proof_len);
+    if (w.size() < 8 || w[0] != STARK_PROOF_MAGIC || w[1] != c->kind || w[2] != c->n_max || w[3] != STARK_N_TABLES)
+        return fail(TMX_E_VERIFY, "tmx_verify: proof header does not match the circuit");
+    for (int i = 0; i < 4; i++) {
+        gl x = 0;
+        for (int j = 0; j < 8; j++) x |= (gl)out32[8 * i + j] << (8 * j);
+        if (w[4 + i] != x) return fail(TMX_E_VERIFY, "tmx_verify: output does not match the proof");
+    }
+    poseidon_generate_constants();
+    Challenger ch;
+    transcript_init(c, input, input_len, out32, ch);
+    size_t pos = 8;
+    for (int t = 0; t < STARK_N_TABLES; t++) {
+        const int rc = verify_table(t, c->dims[2 * t], w.data(), w.size(), &pos, ch);
+        if (rc) return fail(TMX_E_VERIFY, "tmx_verify: table " + std::to_string(t) + " rejected (code " + std::to_string(rc) + ")");
+    }
+    if (pos != w.size()) return fail(TMX_E_VERIFY, "tmx_verify: trailing data");
+    return TMX_OK;
+}

@@ -54,6 +54,16 @@ int ctx_ntt_tables(tmx_ctx* ctx, unsigned log_n, bool inverse, const NttTables**
 int ctx_coset_scale(tmx_ctx* ctx, unsigned log_n, const PowTable** out);
 inline cudaStream_t pick_stream(tmx_ctx* ctx, void* stream) { return stream ? (cudaStream_t)stream : ctx->stream; }
 
+// internal cross-file entry points
+int lde_forward_cosets(tmx_ctx* ctx, const gl* coeffs, gl* d_out, size_t n_cols, unsigned log_n, unsigned rate_bits,
+                       cudaStream_t st);
+// Merkle tree over n_rows = 2^log_rows leaves; leaf j = hash_or_noop of leaf_len elements at
+// base[j * row_stride + i * elem_stride]
+int merkle_generic(tmx_ctx* ctx, const gl* base, size_t leaf_len, size_t row_stride, size_t elem_stride, unsigned log_rows,
+                   unsigned cap_height, gl* d_digests, cudaStream_t st);
+// smallest w < 2^40 such that Poseidon(state with state[pos] = w)[7] has `bits` leading zero bits
+int pow_grind(tmx_ctx* ctx, const gl state[12], int pos, unsigned bits, uint64_t* witness, cudaStream_t st);
+
 // per translation unit Poseidon constant upload hooks
 int merkle_tu_init();
 int witness_tu_init();

@@ -14,12 +14,12 @@
 
 namespace tmx {
 
-__global__ void __launch_bounds__(128) leaf_hash_kernel(const gl* __restrict__ cols, size_t n_cols, size_t n_rows,
-                                                         gl* __restrict__ digests) {
+__global__ void __launch_bounds__(128) leaf_hash_kernel(const gl* __restrict__ base, size_t leaf_len, size_t row_stride,
+                                                         size_t elem_stride, size_t n_rows, gl* __restrict__ digests) {
     const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_rows) return;
     gl out[4];
-    poseidon_hash_row(cols + j, n_rows, n_cols, out);
+    poseidon_hash_row(base + j * row_stride, elem_stride, leaf_len, out);
     reinterpret_cast<ulonglong2*>(digests + 4 * j)[0] = make_ulonglong2(out[0], out[1]);
     reinterpret_cast<ulonglong2*>(digests + 4 * j)[1] = make_ulonglong2(out[2], out[3]);
 }
@@ -63,14 +63,12 @@ extern "C" size_t tmx_merkle_digest_count(unsigned log_rows, unsigned cap_height
     return total;
 }
 
-extern "C" int tmx_poseidon_merkle(tmx_ctx* ctx, const uint64_t* d_cols, size_t n_cols, unsigned log_rows,
-                                   unsigned cap_height, uint64_t* d_digests, void* stream) {
-    if (!ctx || !d_cols || !d_digests || n_cols == 0 || log_rows > 30)
-        return fail(TMX_E_INPUT, "tmx_poseidon_merkle: bad arguments");
+namespace tmx {
+int merkle_generic(tmx_ctx* ctx, const gl* base, size_t leaf_len, size_t row_stride, size_t elem_stride, unsigned log_rows,
+                   unsigned cap_height, gl* d_digests, cudaStream_t st) {
     if (cap_height > log_rows) cap_height = log_rows;
-    cudaStream_t st = pick_stream(ctx, stream);
     const size_t n = (size_t)1 << log_rows;
-    leaf_hash_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_cols, n_cols, n, d_digests);
+    leaf_hash_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(base, leaf_len, row_stride, elem_stride, n, d_digests);
     ctx->launches++;
     TMX_CUDA(cudaGetLastError());
     gl* lvl = d_digests;
@@ -84,6 +82,63 @@ extern "C" int tmx_poseidon_merkle(tmx_ctx* ctx, const uint64_t* d_cols, size_t 
         lvl = nxt;
     }
     return TMX_OK;
+}
+
+// K9: proof-of-work grind.  Every thread tries one candidate; the smallest hit wins (deterministic, unlike
+// plonky2's rayon find_any).
+__global__ void __launch_bounds__(128) pow_grind_kernel(const gl* __restrict__ state, int pos, unsigned bits, uint64_t first,
+                                                         unsigned long long* best) {
+    const uint64_t cand = first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    gl s[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = state[i];
+#pragma unroll
+    for (int i = 0; i < 12; i++)
+        if (i == pos) s[i] = cand;
+    poseidon_permute(s);
+    if ((s[7] >> (64 - bits)) == 0) atomicMin(best, (unsigned long long)cand);
+}
+
+int pow_grind(tmx_ctx* ctx, const gl state[12], int pos, unsigned bits, uint64_t* witness, cudaStream_t st) {
+    if (bits == 0) {
+        *witness = 0;
+        return TMX_OK;
+    }
+    void* p = nullptr;
+    int rc = ctx_scratch(ctx, 3, 13 * sizeof(gl), &p);
+    if (rc) return rc;
+    gl* d_state = (gl*)p;
+    unsigned long long* d_best = (unsigned long long*)(d_state + 12);
+    unsigned long long best = ~0ULL;
+    TMX_CUDA(cudaMemcpyAsync(d_state, state, 12 * sizeof(gl), cudaMemcpyHostToDevice, st));
+    TMX_CUDA(cudaMemcpyAsync(d_best, &best, sizeof best, cudaMemcpyHostToDevice, st));
+    const uint64_t batch = (uint64_t)1 << (bits + 3 > 30 ? 30 : bits + 3);
+    for (uint64_t first = 0; first < ((uint64_t)1 << 40); first += batch) {
+        pow_grind_kernel<<<(unsigned)(batch / 128), 128, 0, st>>>(d_state, pos, bits, first, d_best);
+        ctx->launches++;
+        TMX_CUDA(cudaGetLastError());
+        TMX_CUDA(cudaMemcpyAsync(&best, d_best, sizeof best, cudaMemcpyDeviceToHost, st));
+        TMX_CUDA(cudaStreamSynchronize(st));
+        if (best != ~0ULL) {
+            *witness = best;
+            return TMX_OK;
+        }
+    }
+    return fail(TMX_E_CUDA, "pow_grind: no witness below 2^40");
+}
+}  // namespace tmx
+
+extern "C" int tmx_poseidon_merkle(tmx_ctx* ctx, const uint64_t* d_cols, size_t n_cols, unsigned log_rows,
+                                   unsigned cap_height, uint64_t* d_digests, void* stream) {
+    if (!ctx || !d_cols || !d_digests || n_cols == 0 || log_rows > 30)
+        return fail(TMX_E_INPUT, "tmx_poseidon_merkle: bad arguments");
+    return merkle_generic(ctx, d_cols, n_cols, 1, (size_t)1 << log_rows, log_rows, cap_height, d_digests,
+                          pick_stream(ctx, stream));
+}
+
+extern "C" int tmx_pow_grind(tmx_ctx* ctx, const uint64_t state[12], int pos, unsigned bits, uint64_t* witness, void* stream) {
+    if (!ctx || !state || !witness || pos < 0 || pos >= 8 || bits > 40) return fail(TMX_E_INPUT, "tmx_pow_grind: bad arguments");
+    return pow_grind(ctx, state, pos, bits, witness, pick_stream(ctx, stream));
 }
 
 extern "C" int tmx_poseidon_permute(tmx_ctx* ctx, uint64_t* d_states, size_t n, void* stream) {

@@ -369,6 +369,40 @@ extern "C" int tmx_ntt(tmx_ctx* ctx, uint64_t* d_data, size_t n_cols, unsigned l
     return rc;
 }
 
+namespace tmx {
+// coset-scaled coefficients c_i * 7^i ([n_cols][n], natural order) -> evaluations on the 2^rate_bits cosets,
+// out[n_cols][n << rate_bits] bit-reversed.  Region rho of a column holds coset s = bitrev_r(rho), whose input is
+// pre-scaled by w_{n*2^r}^(s*i); the DIF passes leave it bit-reversed in place.
+int lde_forward_cosets(tmx_ctx* ctx, const gl* coeffs, gl* d_out, size_t n_cols, unsigned log_n, unsigned rate_bits,
+                       cudaStream_t st) {
+    const size_t n = (size_t)1 << log_n;
+    const size_t m = n << rate_bits;
+    const NttTables* Tm = nullptr;
+    int rc = ctx_ntt_tables(ctx, log_n + rate_bits, false, &Tm);
+    if (rc) return rc;
+    for (unsigned rho = 0; rho < (1u << rate_bits); rho++) {
+        const unsigned s = bitrev32(rho, rate_bits);
+        XformDesc f;
+        memset(&f, 0, sizeof f);
+        f.in = coeffs;
+        f.in_col_stride = n;
+        f.out = d_out + (size_t)rho * n;
+        f.out_col_stride = m;
+        f.n_cols = n_cols;
+        f.log_n = log_n;
+        f.inverse = false;
+        f.natural_out = false;
+        if (s != 0) {
+            f.ps = Tm->big;
+            f.ps_mult = s;
+        }
+        rc = run_xform(ctx, f, st);
+        if (rc) return rc;
+    }
+    return TMX_OK;
+}
+}  // namespace tmx
+
 extern "C" int tmx_lde(tmx_ctx* ctx, const uint64_t* d_values, uint64_t* d_out, uint64_t* d_coeffs, size_t n_cols,
                        unsigned log_n, unsigned rate_bits, void* stream) {
     if (!ctx || !d_values || !d_out || log_n < 1 || log_n + rate_bits > 30 || rate_bits > 4)
@@ -404,29 +438,5 @@ extern "C" int tmx_lde(tmx_ctx* ctx, const uint64_t* d_values, uint64_t* d_out, 
     d.os = *cs;
     rc = run_xform(ctx, d, st);
     if (rc) return rc;
-    // 2. one forward transform per coset; region rho holds coset s = bitrev_r(rho), pre-scaled by
-    //    w_{n*2^r}^(s*i); result left bit-reversed in place
-    const NttTables* Tm = nullptr;
-    rc = ctx_ntt_tables(ctx, log_n + rate_bits, false, &Tm);
-    if (rc) return rc;
-    for (unsigned rho = 0; rho < (1u << rate_bits); rho++) {
-        const unsigned s = bitrev32(rho, rate_bits);
-        XformDesc f;
-        memset(&f, 0, sizeof f);
-        f.in = coeffs;
-        f.in_col_stride = n;
-        f.out = d_out + (size_t)rho * n;
-        f.out_col_stride = m;
-        f.n_cols = n_cols;
-        f.log_n = log_n;
-        f.inverse = false;
-        f.natural_out = false;
-        if (s != 0) {
-            f.ps = Tm->big;
-            f.ps_mult = s;
-        }
-        rc = run_xform(ctx, f, st);
-        if (rc) return rc;
-    }
-    return TMX_OK;
+    return lde_forward_cosets(ctx, coeffs, d_out, n_cols, log_n, rate_bits, st);
 }

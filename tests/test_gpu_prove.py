@@ -1,0 +1,87 @@
+"""GPU parity at the proof level: tmx_prove (CUDA) must emit exactly the bytes of the CPU oracle prover, and the
+proof must verify under both verifiers.  Also the UNSAT behaviour (reference: witness generation panics)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _cases():
+    with open(os.path.join(HERE, "golden", "fixture_vectors.json")) as f:
+        return {c["name"]: c for c in json.load(f)["cases"]}
+
+
+def _first_diff(a, b):
+    n = min(a.size, b.size)
+    d = np.nonzero(a[:n] != b[:n])[0]
+    return int(d[0]) if d.size else n
+
+
+@pytest.mark.parametrize("name", ["step_10000_n2", "skip_3000_3100_n4", "skip_10000_10500_n4", "step_10500_n4_with_dummy"])
+def test_proof_bytes_equal_oracle(ctx, oracle, name):
+    import tendermintx_b200 as tmx
+
+    c = _cases()[name]
+    pub, blob = bytes.fromhex(c["input"]), bytes.fromhex(c["blob"])
+    kind = tmx.KIND_SKIP if c["kind"] == "skip" else tmx.KIND_STEP
+    circuit = tmx.Circuit.build(ctx, kind, c["n_max"], tmx.Mocha4Config)
+    proof, out = circuit.prove(pub, blob)
+    assert out.hex() == c["expected_output"]
+    status, want, want_out = oracle.prove(pub, blob, "mocha-4")
+    assert status == "OK" and want_out == out
+    got = np.frombuffer(proof, dtype=np.uint64)
+    assert got.size == want.size, (got.size, want.size, _first_diff(got, want))
+    assert np.array_equal(got, want), f"first differing word {_first_diff(got, want)} of {want.size}"
+    circuit.verify(proof, pub, out)
+    assert oracle.verify_proof(got, pub, "mocha-4", kind, c["n_max"], out) == 0
+    # a second proof from the same circuit object reuses its device buffers and is identical
+    proof2, _ = circuit.prove(pub, blob)
+    assert proof2 == proof
+    circuit.close()
+
+
+def test_unsat_reports_the_failing_check(ctx):
+    import tendermintx_b200 as tmx
+
+    c = _cases()["skip_10000_10500_n4"]
+    pub, blob = bytes.fromhex(c["input"]), bytearray.fromhex(c["blob"])
+    circuit = tmx.Circuit.build(ctx, tmx.KIND_SKIP, 4, tmx.Mocha4Config)
+    cases = []
+    b = bytearray(blob); b[920 + 32 + 3] ^= 0x40; cases.append((pub, bytes(b), "SIGNATURE"))
+    b = bytearray(blob); b[920 + 224] ^= 1; cases.append((pub, bytes(b), "VALHASH"))
+    for i in range(4):
+        b = bytearray(blob) if i == 0 else b
+        b[920 + 240 * i + 236] = 0
+    cases.append((pub, bytes(b), "TRUSTED_THRESHOLD"))
+    cases.append((pub[:40] + (10001).to_bytes(8, "big"), bytes(blob), "SKIP_DISTANCE"))
+    bp = bytearray(pub); bp[10] ^= 1; cases.append((bytes(bp), bytes(blob), "TRUSTED_HEADER_PROOF"))
+    for p, bl, want in cases:
+        with pytest.raises(tmx.TmxError) as e:
+            circuit.prove(p, bl)
+        assert e.value.code == 2 and e.value.check == want, (want, e.value.check)
+    wrong = tmx.Circuit.build(ctx, tmx.KIND_SKIP, 4, tmx.CelestiaConfig)
+    with pytest.raises(tmx.TmxError) as e:
+        wrong.prove(pub, bytes(blob))
+    assert e.value.check == "CHAIN_ID"
+    wrong.close()
+    circuit.close()
+
+
+def test_synthetic_celestia_skip_n16(ctx, oracle):
+    import tendermintx_b200 as tmx
+    from oracle import tm_inputs as ti
+
+    src, t, g = ti.synthetic_source(seed=0, n_validators=16)
+    th = ti.header_hash(src.signed_header(t)["header"])
+    blob, pub = ti.skip_inputs(src, 16, t, th, g), ti.skip_public_input(t, th, g)
+    circuit = tmx.Circuit.build(ctx, tmx.KIND_SKIP, 16, tmx.CelestiaConfig)
+    proof, out = circuit.prove(pub, blob)
+    assert out == ti.header_hash(src.signed_header(g)["header"])
+    status, want, _ = oracle.prove(pub, blob, "celestia")
+    assert np.array_equal(np.frombuffer(proof, dtype=np.uint64), want)
+    circuit.verify(proof, pub, out)
+    circuit.close()
