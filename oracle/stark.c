@@ -647,3 +647,40 @@ int tm_verify_proof(const uint64_t *proof, size_t proof_len, const uint8_t *inpu
     if (r.err || r.pos != r.n) return 103;
     return 0;
 }
+
+/* debug / test hook: LDE of a trace and the quotient values on the LDE coset in natural order, [2][m] */
+void tm_debug_quotient(int table, const uint64_t *trace, size_t n, size_t C, const uint64_t alpha[2], uint64_t *lde_out,
+                       uint64_t *qv_out) {
+    const size_t m = n << RATE_BITS;
+    const unsigned km = tmx_log2(m);
+    gl_t *coeffs = (gl_t *)malloc(C * n * sizeof(gl_t));
+    ntt_lde_batch(trace, C, n, RATE_BITS, lde_out, coeffs);
+    free(coeffs);
+    const int nper = TABLE_NPER[table], P = TABLE_PERIOD[table];
+    gl_t *pertab = (gl_t *)calloc((size_t)(nper ? nper : 1) * 2 * P, sizeof(gl_t));
+    gl_t shift = gl_pow(GL_GENERATOR, n / P);
+    for (int pc = 0; pc < nper; pc++) {
+        gl_t *t = pertab + (size_t)pc * 2 * P;
+        for (int r = 0; r < P; r++) t[r] = periodic_pattern(table, pc, r);
+        ntt_inverse(t, P);
+        memset(t + P, 0, P * sizeof(gl_t));
+        ntt_coset_forward(t, 2 * P, shift);
+    }
+    const gl_t gn = gl_pow(GL_GENERATOR, n);
+    const gl_t zh_inv[2] = {gl_inv(gl_sub(gn, 1)), gl_inv(gl_sub(gl_neg(gn), 1))};
+    gl_t *loc = (gl_t *)malloc(C * sizeof(gl_t)), *nxt = (gl_t *)malloc(C * sizeof(gl_t));
+    for (size_t j = 0; j < m; j++) {
+        size_t p = tmx_bitrev(j, km), p2 = tmx_bitrev((j + 2) & (m - 1), km);
+        for (size_t c = 0; c < C; c++) {
+            loc[c] = lde_out[c * m + p];
+            nxt[c] = lde_out[c * m + p2];
+        }
+        gl_t per[8];
+        for (int pc = 0; pc < nper; pc++) per[pc] = pertab[(size_t)pc * 2 * P + (j & (2 * P - 1))];
+        acc_b_t a;
+        for (int i = 0; i < 2; i++) { a.acc[i] = 0; a.alpha[i] = alpha[i]; }
+        air_eval_b(table, loc, nxt, per, &a);
+        for (int i = 0; i < 2; i++) qv_out[(size_t)i * m + j] = gl_mul(a.acc[i], zh_inv[j & 1]);
+    }
+    free(loc); free(nxt); free(pertab);
+}

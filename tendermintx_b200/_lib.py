@@ -52,6 +52,7 @@ def load():
         "tmx_sha256_trace": (i32, [vp, vp, u32, u32, u64p, vp, vp]),
         "tmx_ed25519_trace": (i32, [vp, vp, u32, u32, u64p, u64p, vp, vp]),
         "tmx_witness_generate": (i32, [vp, vp, u32, u32, u64p, u64p, u64p, vp, vp]),
+        "tmx_quotient": (i32, [vp, i32, u64p, u32, vp, u64p, vp]),
         "tmx_pow_grind": (i32, [vp, vp, i32, u32, c.POINTER(c.c_uint64), vp]),
         "tmx_circuit_build": (i32, [vp, u32, u32, c.c_char_p, sz, c.c_uint64, c.POINTER(vp)]),
         "tmx_circuit_free": (None, [vp]),
@@ -77,7 +78,7 @@ EXPORTED_SYMBOLS = [
     "tmx_last_error", "tmx_version", "tmx_ctx_create", "tmx_ctx_destroy", "tmx_ctx_sync",
     "tmx_ctx_launch_count", "tmx_ntt", "tmx_lde", "tmx_merkle_digest_count", "tmx_poseidon_merkle",
     "tmx_poseidon_permute", "tmx_trace_dims", "tmx_witness_aux_bytes", "tmx_sha256_trace", "tmx_ed25519_trace",
-    "tmx_witness_generate", "tmx_pow_grind", "tmx_circuit_build", "tmx_circuit_free", "tmx_circuit_digest",
+    "tmx_witness_generate", "tmx_quotient", "tmx_pow_grind", "tmx_circuit_build", "tmx_circuit_free", "tmx_circuit_digest",
     "tmx_circuit_save", "tmx_circuit_load", "tmx_prove", "tmx_last_check", "tmx_proof_size", "tmx_proof_bytes",
     "tmx_proof_free", "tmx_verify", "tmx_verify_params",
 ]

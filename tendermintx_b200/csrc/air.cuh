@@ -9,37 +9,37 @@
 #pragma once
 #include "gl.cuh"
 #include "../../include/tmx_trace.h"
+#include <vector>
 
 namespace tmx {
 
 // ---- field wrappers with operators ----
+// (plain aggregates on purpose: no constructors, so local arrays of them carry no hidden initialisation)
 struct FB {
     gl v;
-    TMX_HD FB() : v(0) {}
-    TMX_HD explicit FB(gl x) : v(x) {}
-    TMX_HD static FB c(uint64_t x) { return FB((gl)x); }
+    TMX_HD static FB mk(gl x) { FB r; r.v = x; return r; }
+    TMX_HD static FB c(uint64_t x) { return mk((gl)x); }
 };
-TMX_HD FB operator+(FB a, FB b) { return FB(gl_add(a.v, b.v)); }
-TMX_HD FB operator-(FB a, FB b) { return FB(gl_sub(a.v, b.v)); }
-TMX_HD FB operator*(FB a, FB b) { return FB(gl_mul(a.v, b.v)); }
+TMX_HD FB operator+(FB a, FB b) { return FB::mk(gl_add(a.v, b.v)); }
+TMX_HD FB operator-(FB a, FB b) { return FB::mk(gl_sub(a.v, b.v)); }
+TMX_HD FB operator*(FB a, FB b) { return FB::mk(gl_mul(a.v, b.v)); }
 
 struct FE {
     gl2 v;
-    TMX_HD FE() { v = gl2_from(0); }
-    TMX_HD explicit FE(gl2 x) : v(x) {}
-    TMX_HD static FE c(uint64_t x) { return FE(gl2_from((gl)x)); }
+    TMX_HD static FE mk(gl2 x) { FE r; r.v = x; return r; }
+    TMX_HD static FE c(uint64_t x) { return mk(gl2_from((gl)x)); }
 };
-TMX_HD FE operator+(FE a, FE b) { return FE(gl2_add(a.v, b.v)); }
-TMX_HD FE operator-(FE a, FE b) { return FE(gl2_sub(a.v, b.v)); }
-TMX_HD FE operator*(FE a, FE b) { return FE(gl2_mul(a.v, b.v)); }
+TMX_HD FE operator+(FE a, FE b) { return FE::mk(gl2_add(a.v, b.v)); }
+TMX_HD FE operator-(FE a, FE b) { return FE::mk(gl2_sub(a.v, b.v)); }
+TMX_HD FE operator*(FE a, FE b) { return FE::mk(gl2_mul(a.v, b.v)); }
 
 // Horner accumulator over the two constraint challenges: acc <- acc * alpha + c
 template <class F>
 struct ConstraintAcc {
-    F acc[2], alpha[2];
+    F acc0, acc1, alpha0, alpha1;
     TMX_HD void operator()(F c) {
-        acc[0] = acc[0] * alpha[0] + c;
-        acc[1] = acc[1] * alpha[1] + c;
+        acc0 = acc0 * alpha0 + c;
+        acc1 = acc1 * alpha1 + c;
     }
 };
 
@@ -66,8 +66,8 @@ TMX_HD int air_period(int t) { return t == AIR_SHA256 ? 64 : (t == AIR_SHA512 ? 
 
 // ------------------------------------------------------------------------------------------ SHA-256
 // per = {K_t, is_last_round, not_last_round, schedule_active (rounds 15..62)}
-template <class F, class Row, class Emit>
-TMX_HD void air_sha256(const Row& l, const Row& n, const F* per, Emit& emit) {
+template <class F, class Row, class Per, class Emit>
+TMX_HD void air_sha256(const Row& l, const Row& n, const Per& per, Emit& emit) {
     const F K = per[0], LAST = per[1], NOTLAST = per[2], SCHED = per[3];
     const F two32 = F::c(1ULL << 32);
     for (int i = S256_A; i < S256_D; i++) emit(is_bool<F>(l[i]));
@@ -132,8 +132,8 @@ TMX_HD void air_sha256(const Row& l, const Row& n, const F* per, Emit& emit) {
 }
 
 // ------------------------------------------------------------------------------------------ SHA-512
-template <class F, class Row, class Emit>
-TMX_HD void air_sha512(const Row& l, const Row& n, const F* per, Emit& emit) {
+template <class F, class Row, class Per, class Emit>
+TMX_HD void air_sha512(const Row& l, const Row& n, const Per& per, Emit& emit) {
     (void)n;
     (void)per;
     for (int i = S512_A; i < S512_D; i++) emit(is_bool<F>(l[i]));
@@ -178,8 +178,8 @@ TMX_HD void ed_mul_gadget(const F U[16], const F V[16], const Row& l, int g0, Em
 }
 
 // per = {not_block_end} (period 256)
-template <class F, class Row, class Emit>
-TMX_HD void air_ed25519(const Row& l, const Row& n, const F* per, Emit& emit) {
+template <class F, class Row, class Per, class Emit>
+TMX_HD void air_ed25519(const Row& l, const Row& n, const Per& per, Emit& emit) {
     const F NOTEND = per[0];
     const F bit = l[ED_BIT];
     emit(is_bool<F>(bit));
@@ -246,8 +246,8 @@ TMX_HD void air_ed25519(const Row& l, const Row& n, const F* per, Emit& emit) {
         }
 }
 
-template <class F, class Row, class Emit>
-TMX_HD void air_eval(int table, const Row& l, const Row& n, const F* per, Emit& emit) {
+template <class F, class Row, class Per, class Emit>
+TMX_HD void air_eval(int table, const Row& l, const Row& n, const Per& per, Emit& emit) {
     if (table == AIR_SHA256) air_sha256<F>(l, n, per, emit);
     else if (table == AIR_SHA512) air_sha512<F>(l, n, per, emit);
     else air_ed25519<F>(l, n, per, emit);
@@ -262,6 +262,34 @@ TMX_HD uint64_t air_periodic_pattern(int table, int pc, int r, const uint32_t* k
         return r >= 15 && r <= 62;
     }
     return r != 255;
+}
+
+// Host: values of the periodic columns on the LDE coset, [nper][2P], indexed by (natural LDE index mod 2P).
+// Column pc is the interpolant s of its one-period pattern composed with x -> x^(n/P); on the coset
+// x_j = 7 w_m^j this only depends on j mod 2P: s(7^(n/P) w_2P^j).
+inline std::vector<gl> air_periodic_lde_table(int table, unsigned log_n, const uint32_t* k256_table) {
+    const int nper = air_n_periodic(table), P = air_period(table);
+    const size_t n = (size_t)1 << log_n;
+    std::vector<gl> tab((size_t)nper * 2 * P);
+    const unsigned lgP = ilog2(P);
+    const gl wPi = gl_inv(gl_root_of_unity(lgP)), Pinv = gl_inv((gl)P);
+    const gl w2P = gl_root_of_unity(lgP + 1), sh = gl_pow(GL_GEN, n / P);
+    for (int pc = 0; pc < nper; pc++) {
+        std::vector<gl> coef(P);
+        for (int k = 0; k < P; k++) {
+            gl acc = 0;
+            for (int r = 0; r < P; r++)
+                acc = gl_add(acc, gl_mul((gl)air_periodic_pattern(table, pc, r, k256_table), gl_pow(wPi, ((uint64_t)r * k) % P)));
+            coef[k] = gl_mul(acc, Pinv);
+        }
+        for (int j = 0; j < 2 * P; j++) {
+            const gl x = gl_mul(sh, gl_pow(w2P, j));
+            gl acc = 0;
+            for (int k = P - 1; k >= 0; k--) acc = gl_add(gl_mul(acc, x), coef[k]);
+            tab[(size_t)pc * 2 * P + j] = acc;
+        }
+    }
+    return tab;
 }
 
 }  // namespace tmx

@@ -18,8 +18,29 @@ namespace tmx {
 struct LdeRow {
     const gl* base;  // lde + position
     size_t stride;   // m
-    TMX_D FB operator[](int c) const { return FB(base[(size_t)c * stride]); }
+    TMX_D FB operator[](int c) const { return FB::mk(base[(size_t)c * stride]); }
 };
+// periodic column values at one LDE position, read straight from the device table
+struct LdePeriodic {
+    const gl* base;  // pertab + (j mod 2P)
+    size_t stride;   // 2P
+    TMX_D FB operator[](int pc) const { return FB::mk(base[(size_t)pc * stride]); }
+};
+
+// Position (bit-reversed order) of the row that follows position p on the trace domain: natural index j + 2^r.
+// The low log_n bits of p hold the bit-reversed row counter, so "+1" is a reverse-carry increment (flip ones from
+// the top bit down, set the first zero); the top r bits (the coset id) are unchanged.
+TMX_D size_t next_row_position(size_t p, unsigned log_n) {
+    const size_t low_mask = ((size_t)1 << log_n) - 1;
+    size_t q = p & low_mask;
+    size_t bit = (size_t)1 << (log_n - 1);
+    while (bit && (q & bit)) {
+        q ^= bit;
+        bit >>= 1;
+    }
+    q |= bit;
+    return (p & ~low_mask) | q;
+}
 
 struct QuotientArgs {
     const gl* lde;
@@ -38,18 +59,16 @@ __global__ void __launch_bounds__(128) quotient_kernel(QuotientArgs a) {
     const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= a.m) return;
     const uint32_t j = bitrev32((uint32_t)p, a.log_m);
-    const uint32_t jn = (j + (1u << a.rate_bits)) & (uint32_t)(a.m - 1);
-    const size_t pn = bitrev32(jn, a.log_m);
+    const size_t pn = next_row_position(p, a.log_m - a.rate_bits);
     LdeRow l{a.lde + p, a.m}, n{a.lde + pn, a.m};
-    FB per[4];
-    for (int pc = 0; pc < a.nper; pc++) per[pc] = FB(a.pertab[(size_t)pc * 2 * a.P + (j & (2 * a.P - 1))]);
+    LdePeriodic per{a.pertab + (j & (2 * a.P - 1)), (size_t)2 * a.P};
     ConstraintAcc<FB> acc;
-    acc.acc[0] = FB(0); acc.acc[1] = FB(0);
-    acc.alpha[0] = FB(a.alpha[0]); acc.alpha[1] = FB(a.alpha[1]);
+    acc.acc0 = FB::c(0); acc.acc1 = FB::c(0);
+    acc.alpha0 = FB::mk(a.alpha[0]); acc.alpha1 = FB::mk(a.alpha[1]);
     air_eval<FB>(TABLE, l, n, per, acc);
     const gl zi = a.zh_inv[j & ((1u << a.rate_bits) - 1)];
-    a.out[j] = gl_mul(acc.acc[0].v, zi);
-    a.out[a.m + j] = gl_mul(acc.acc[1].v, zi);
+    a.out[j] = gl_mul(acc.acc0.v, zi);
+    a.out[a.m + j] = gl_mul(acc.acc1.v, zi);
 }
 
 // after the inverse NTT of size m = 2n the buffer holds q_i * 7^i; chunk k of challenge c is coefficients
@@ -184,6 +203,26 @@ __global__ void gather_paths_kernel(const gl* __restrict__ digests, unsigned log
     }
 }
 
+static int launch_quotient(tmx_ctx* ctx, int table, const QuotientArgs& qa, cudaStream_t st) {
+    const unsigned qblocks = (unsigned)((qa.m + 127) / 128);
+    if (table == AIR_SHA256) quotient_kernel<AIR_SHA256><<<qblocks, 128, 0, st>>>(qa);
+    else if (table == AIR_SHA512) quotient_kernel<AIR_SHA512><<<qblocks, 128, 0, st>>>(qa);
+    else quotient_kernel<AIR_ED25519><<<qblocks, 128, 0, st>>>(qa);
+    ctx->launches++;
+    TMX_CUDA(cudaGetLastError());
+    return TMX_OK;
+}
+
+static void fill_zh_inv(QuotientArgs& qa, size_t n) {
+    const gl gn = gl_pow(GL_GEN, n);
+    const gl wr = gl_root_of_unity(qa.rate_bits);  // x_j^n = 7^n * wr^j
+    gl cur = gn;
+    for (unsigned j = 0; j < (1u << qa.rate_bits); j++) {
+        qa.zh_inv[j] = gl_inv(gl_sub(cur, 1));
+        cur = gl_mul(cur, wr);
+    }
+}
+
 // ------------------------------------------------------------------------------------------ host driver
 static gl2 host_poly_eval_ext(const std::vector<gl2>& c, gl2 x) {
     gl2 acc = gl2_from(0);
@@ -238,26 +277,15 @@ int TableProver::prove(tmx_ctx* ctx, int table, const gl* d_trace, unsigned log_
     qa.nper = air_n_periodic(table); qa.P = air_period(table);
     qa.alpha[0] = ch.get();
     qa.alpha[1] = ch.get();
-    {
-        const gl gn = gl_pow(GL_GEN, n);
-        const gl wr = gl_root_of_unity(STARK_RATE_BITS);  // x_j^n = 7^n * wr^j
-        gl cur = gn;
-        for (unsigned j = 0; j < (1u << STARK_RATE_BITS); j++) {
-            qa.zh_inv[j] = gl_inv(gl_sub(cur, 1));
-            cur = gl_mul(cur, wr);
-        }
-    }
+    fill_zh_inv(qa, n);
     if (qa.nper) {
         rc = periodic_tables(ctx, table, log_n, &qa.pertab);
         if (rc) return rc;
     }
     qa.out = d_qv;
     const unsigned qblocks = (unsigned)((m + 127) / 128);
-    if (table == AIR_SHA256) quotient_kernel<AIR_SHA256><<<qblocks, 128, 0, st>>>(qa);
-    else if (table == AIR_SHA512) quotient_kernel<AIR_SHA512><<<qblocks, 128, 0, st>>>(qa);
-    else quotient_kernel<AIR_ED25519><<<qblocks, 128, 0, st>>>(qa);
-    ctx->launches++;
-    TMX_CUDA(cudaGetLastError());
+    rc = launch_quotient(ctx, table, qa, st);
+    if (rc) return rc;
     // values on the coset (natural order) -> coefficients of Q(7 X); the 1/m factor comes with the inverse NTT
     rc = tmx_ntt(ctx, d_qv, 2, km, 1, st);
     if (rc) return rc;
@@ -473,28 +501,7 @@ int TableProver::periodic_tables(tmx_ctx* ctx, int table, unsigned log_n, const 
         *out = it->second;
         return TMX_OK;
     }
-    // pattern over one period -> interpolant s (P coefficients) -> s on the coset 7^(n/P) * <w_2P>, natural order
-    const int nper = air_n_periodic(table), P = air_period(table);
-    const size_t n = (size_t)1 << log_n;
-    std::vector<gl> tab((size_t)nper * 2 * P);
-    const unsigned lgP = ilog2(P);
-    const gl wP = gl_root_of_unity(lgP), wPi = gl_inv(wP), Pinv = gl_inv((gl)P);
-    const gl w2P = gl_root_of_unity(lgP + 1), sh = gl_pow(GL_GEN, n / P);
-    for (int pc = 0; pc < nper; pc++) {
-        std::vector<gl> coef(P);
-        for (int k = 0; k < P; k++) {
-            gl acc = 0;
-            for (int r = 0; r < P; r++)
-                acc = gl_add(acc, gl_mul((gl)air_periodic_pattern(table, pc, r, h_K256), gl_pow(wPi, ((uint64_t)r * k) % P)));
-            coef[k] = gl_mul(acc, Pinv);
-        }
-        for (int j = 0; j < 2 * P; j++) {
-            const gl x = gl_mul(sh, gl_pow(w2P, j));
-            gl acc = 0;
-            for (int k = P - 1; k >= 0; k--) acc = gl_add(gl_mul(acc, x), coef[k]);
-            tab[(size_t)pc * 2 * P + j] = acc;
-        }
-    }
+    std::vector<gl> tab = air_periodic_lde_table(table, log_n, h_K256);
     void* d = nullptr;
     TMX_CUDA(cudaMalloc(&d, tab.size() * sizeof(gl)));
     TMX_CUDA(cudaMemcpy(d, tab.data(), tab.size() * sizeof(gl), cudaMemcpyHostToDevice));
@@ -514,3 +521,26 @@ void TableProver::release() {
 }
 
 }  // namespace tmx
+
+using namespace tmx;
+
+// K5 as a kernel-level entry point (parity tests, ncu): constraint quotient of one table on its LDE coset.
+extern "C" int tmx_quotient(tmx_ctx* ctx, int table, const uint64_t* d_lde, unsigned log_n, const uint64_t alpha[2],
+                            uint64_t* d_out, void* stream) {
+    if (!ctx || !d_lde || !alpha || !d_out || table < 0 || table > 2 || log_n < 8 || log_n > 28)
+        return fail(TMX_E_INPUT, "tmx_quotient: bad arguments");
+    static thread_local TableProver tp;  // only its periodic-table cache is used
+    QuotientArgs qa;
+    memset(&qa, 0, sizeof qa);
+    const size_t n = (size_t)1 << log_n;
+    qa.lde = d_lde; qa.m = n << STARK_RATE_BITS; qa.log_m = log_n + STARK_RATE_BITS; qa.rate_bits = STARK_RATE_BITS;
+    qa.nper = air_n_periodic(table); qa.P = air_period(table);
+    qa.alpha[0] = alpha[0]; qa.alpha[1] = alpha[1];
+    fill_zh_inv(qa, n);
+    if (qa.nper) {
+        int rc = tp.periodic_tables(ctx, table, log_n, &qa.pertab);
+        if (rc) return rc;
+    }
+    qa.out = d_out;
+    return launch_quotient(ctx, table, qa, pick_stream(ctx, stream));
+}

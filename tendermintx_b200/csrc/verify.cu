@@ -103,8 +103,8 @@ int verify_table(int table, size_t n, const gl* proof, size_t proof_len, size_t*
     const gl2 zeta_next = gl2_scale(zeta, gl_root_of_unity(k));
     std::vector<FE> loc(C), nxt(C);
     gl2 quot[4];
-    for (size_t c = 0; c < C; c++) loc[c] = FE(r.ext());
-    for (size_t c = 0; c < C; c++) nxt[c] = FE(r.ext());
+    for (size_t c = 0; c < C; c++) loc[c] = FE::mk(r.ext());
+    for (size_t c = 0; c < C; c++) nxt[c] = FE::mk(r.ext());
     for (int q = 0; q < 4; q++) quot[q] = r.ext();
     if (r.err) return 1;
     for (size_t c = 0; c < C; c++) ch.observe_ext(loc[c].v);
@@ -113,7 +113,7 @@ int verify_table(int table, size_t n, const gl* proof, size_t proof_len, size_t*
     // constraint identity at zeta: (chunk0 + zeta^n chunk1) * (zeta^n - 1) == sum_i alpha^(M-1-i) C_i(zeta)
     {
         const int nper = air_n_periodic(table), P = air_period(table);
-        FE per[4];
+        FE per[4] = {FE::c(0), FE::c(0), FE::c(0), FE::c(0)};
         const gl2 y = gl2_pow(zeta, n / P);
         const gl wPi = gl_inv(gl_root_of_unity(ilog2(P))), Pinv = gl_inv((gl)P);
         for (int pc = 0; pc < nper; pc++) {
@@ -124,17 +124,17 @@ int verify_table(int table, size_t n, const gl* proof, size_t proof_len, size_t*
                     acc = gl_add(acc, gl_mul((gl)air_periodic_pattern(table, pc, rr, h_K256), gl_pow(wPi, ((uint64_t)rr * kk) % P)));
                 coef[kk] = gl2_from(gl_mul(acc, Pinv));
             }
-            per[pc] = FE(ext_horner(coef.data(), P, y));
+            per[pc] = FE::mk(ext_horner(coef.data(), P, y));
         }
         ConstraintAcc<FE> acc;
-        acc.acc[0] = FE(); acc.acc[1] = FE();
-        acc.alpha[0] = FE(gl2_from(alpha[0])); acc.alpha[1] = FE(gl2_from(alpha[1]));
-        ExtRow l{loc.data()}, nn{nxt.data()};
-        air_eval<FE>(table, l, nn, per, acc);
+        acc.acc0 = FE::c(0); acc.acc1 = FE::c(0);
+        acc.alpha0 = FE::mk(gl2_from(alpha[0])); acc.alpha1 = FE::mk(gl2_from(alpha[1]));
+        ExtRow l{loc.data()}, nn{nxt.data()}, pp{per};
+        air_eval<FE>(table, l, nn, pp, acc);
         const gl2 zn = gl2_pow(zeta, n), zh = gl2_sub(zn, gl2_from(1));
         for (int i = 0; i < 2; i++) {
             const gl2 q = gl2_add(quot[2 * i], gl2_mul(zn, quot[2 * i + 1]));
-            if (!gl2_eq(gl2_mul(q, zh), acc.acc[i].v)) return 2;
+            if (!gl2_eq(gl2_mul(q, zh), (i == 0 ? acc.acc0 : acc.acc1).v)) return 2;
         }
     }
     const gl2 fa = ch.get_ext();

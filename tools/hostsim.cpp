@@ -5,6 +5,7 @@
 #include <cstring>
 #include <vector>
 #include "../tendermintx_b200/csrc/witness_jobs.cuh"
+#include "../tendermintx_b200/csrc/air.cuh"
 
 using namespace tmx;
 
@@ -87,4 +88,31 @@ extern "C" int hostsim_build_traces(const uint8_t* blob, uint64_t* t256, size_t 
         for (size_t row = (size_t)a.n_max * 512; row < ned; row++) ed_row_cells(a.ted, a.ned, row, 0, res[row & 255], tmp[row & 255]);
     }
     return 0;
+}
+
+// quotient kernel logic (stark.cu quotient_kernel) on the host: lde [C][m] bit-reversed -> out [2][m] natural
+struct HostRow {
+    const gl* base;
+    size_t stride;
+    FB operator[](int c) const { return FB::mk(base[(size_t)c * stride]); }
+};
+extern "C" void hostsim_quotient(int table, const uint64_t* lde, size_t n, const uint64_t alpha[2], uint64_t* out) {
+    const unsigned log_n = log2u((uint32_t)n), log_m = log_n + 1;
+    const size_t m = n << 1;
+    std::vector<gl> tab = air_periodic_lde_table(table, log_n, h_K256);
+    const int P = air_period(table);
+    const gl gn = gl_pow(GL_GEN, n);
+    const gl zh_inv[2] = {gl_inv(gl_sub(gn, 1)), gl_inv(gl_sub(gl_neg(gn), 1))};
+    for (size_t p = 0; p < m; p++) {
+        const uint32_t j = bitrev32((uint32_t)p, log_m);
+        const uint32_t jn = (j + 2) & (uint32_t)(m - 1);
+        const size_t pn = bitrev32(jn, log_m);
+        HostRow l{lde + p, m}, nx{lde + pn, m}, per{tab.data() + (j & (2 * P - 1)), (size_t)2 * P};
+        ConstraintAcc<FB> acc;
+        acc.acc0 = FB::c(0); acc.acc1 = FB::c(0);
+        acc.alpha0 = FB::mk(alpha[0]); acc.alpha1 = FB::mk(alpha[1]);
+        air_eval<FB>(table, l, nx, per, acc);
+        out[j] = gl_mul(acc.acc0.v, zh_inv[j & 1]);
+        out[m + j] = gl_mul(acc.acc1.v, zh_inv[j & 1]);
+    }
 }
