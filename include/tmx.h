@@ -132,6 +132,19 @@ int tmx_circuit_load(tmx_ctx *ctx, const char *path, tmx_circuit **out);
 int tmx_prove(tmx_circuit *circuit, const uint8_t *input, size_t input_len, const uint8_t *blob, size_t blob_len,
               tmx_proof **proof, uint8_t out32[32]);
 int tmx_last_check(void);
+
+/* Input assembly = the fixture mode of InputDataFetcher [circuits/input/mod.rs:188-282,316-523;
+ * circuits/input/conversion.rs:59-178]: reads <dir>/<height>/commit.json and validators_<page>.json (the RPC JSON
+ * shapes, 100 validators per page) and fills the blob.  Sanity checks that `expect`/`assert!` in the reference
+ * (header hash mismatch, set larger than n_max, missing file) return TMX_E_INPUT / TMX_E_IO. */
+int tmx_header_hash_from_fixture(const char *fixture_dir, uint64_t block, uint8_t out[32]);
+int tmx_skip_inputs_from_fixture(const char *fixture_dir, uint32_t n_max, uint64_t trusted_block,
+                                 const uint8_t trusted_hash[32], uint64_t target_block, uint8_t *blob, size_t cap);
+int tmx_step_inputs_from_fixture(const char *fixture_dir, uint32_t n_max, uint64_t prev_block, const uint8_t prev_hash[32],
+                                 uint8_t *blob, size_t cap);
+/* tmx_prove with the off-chain inputs fetched from a fixture directory (the complete `prove input.json` path) */
+int tmx_prove_fixture(tmx_circuit *circuit, const uint8_t *input, size_t input_len, const char *fixture_dir,
+                      tmx_proof **proof, uint8_t out32[32]);
 size_t tmx_proof_size(const tmx_proof *proof);
 /* serialised proof: little-endian u64 stream, layout documented in DESIGN.md "Proof format" */
 int tmx_proof_bytes(const tmx_proof *proof, uint8_t *buf, size_t cap);

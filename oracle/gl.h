@@ -32,15 +32,19 @@ typedef unsigned __int128 u128;
 #define GL_ROOT_2_32 1753635133440165772ULL
 #define GL_W 7ULL /* extension non-residue */
 
-static inline gl_t gl_canon(gl_t a) { return a >= GL_P ? a - GL_P : a; }
+static inline gl_t gl_canon(gl_t a) { return a - (GL_P & (0 - (uint64_t)(a >= GL_P))); }
 
+/* branch-free: data-dependent branches mispredict half the time on random field elements */
 static inline gl_t gl_add(gl_t a, gl_t b) {
-    u128 s = (u128)a + b;
-    if (s >= GL_P) s -= GL_P;
-    return (gl_t)s;
+    uint64_t s = a + b;
+    uint64_t over = (uint64_t)(s < a) | (uint64_t)(s >= GL_P); /* wrapped past 2^64, or landed in [p, 2^64) */
+    return s - (GL_P & (0 - over));                           /* s - p (mod 2^64) is right in both cases */
 }
 
-static inline gl_t gl_sub(gl_t a, gl_t b) { return a >= b ? a - b : a + (GL_P - b); }
+static inline gl_t gl_sub(gl_t a, gl_t b) {
+    uint64_t d = a - b;
+    return d + (GL_P & (0 - (uint64_t)(a < b)));
+}
 
 static inline gl_t gl_neg(gl_t a) { return a ? GL_P - a : 0; }
 
@@ -49,10 +53,10 @@ static inline gl_t gl_reduce128(u128 x) {
     uint64_t lo = (uint64_t)x, hi = (uint64_t)(x >> 64);
     uint64_t hh = hi >> 32, hl = hi & GL_EPS;
     uint64_t t0 = lo - hh;
-    if (lo < hh) t0 -= GL_EPS; /* borrow: add p back, i.e. subtract 2^32-1 mod 2^64 */
+    t0 -= GL_EPS & (0 - (uint64_t)(lo < hh)); /* borrow: add p back, i.e. subtract 2^32-1 mod 2^64 */
     uint64_t t1 = hl * GL_EPS;
     uint64_t t2 = t0 + t1;
-    if (t2 < t1) t2 += GL_EPS; /* carry: 2^64 = 2^32-1 */
+    t2 += GL_EPS & (0 - (uint64_t)(t2 < t1)); /* carry: 2^64 = 2^32-1 */
     return gl_canon(t2);
 }
 

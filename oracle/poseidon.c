@@ -74,23 +74,34 @@ const gl_t *poseidon_round_constants(void) {
     return RC;
 }
 
-static const uint64_t MDS_C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
-static const uint64_t MDS_D[12] = {8, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 
 static inline gl_t sbox7(gl_t x) {
     gl_t x2 = gl_sqr(x), x4 = gl_sqr(x2), x3 = gl_mul(x, x2);
     return gl_mul(x3, x4);
 }
 
+/* out[r] = sum_i s[(i + r) % 12] * C[i] + D[r] * s[r].  The constants are below 2^6, so the two 32-bit halves of
+ * every lane are summed separately in 64 bits (no 128-bit products) and recombined once per output. */
 static void mds_layer(gl_t s[12]) {
-    gl_t out[12];
-    for (int r = 0; r < 12; r++) {
-        u128 acc = 0;
-        for (int i = 0; i < 12; i++) acc += (u128)s[(i + r) % 12] * MDS_C[i];
-        acc += (u128)s[r] * MDS_D[r];
-        out[r] = gl_reduce128(acc);
+    static const uint32_t C32[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+    uint32_t lo[24], hi[24];
+    for (int i = 0; i < 12; i++) {
+        lo[i] = lo[i + 12] = (uint32_t)s[i];
+        hi[i] = hi[i + 12] = (uint32_t)(s[i] >> 32);
     }
-    memcpy(s, out, sizeof out);
+    uint64_t al[12], ah[12];
+    for (int r = 0; r < 12; r++) {
+        uint64_t a = 0, b = 0;
+        for (int i = 0; i < 12; i++) {
+            a += (uint64_t)lo[i + r] * C32[i];
+            b += (uint64_t)hi[i + r] * C32[i];
+        }
+        al[r] = a;
+        ah[r] = b;
+    }
+    al[0] += (uint64_t)lo[0] * 8;
+    ah[0] += (uint64_t)hi[0] * 8;
+    for (int r = 0; r < 12; r++) s[r] = gl_reduce128((u128)al[r] + ((u128)ah[r] << 32));
 }
 
 void poseidon_permute(gl_t s[12]) {

@@ -19,6 +19,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <stdio.h>
+#include <omp.h>
 
 #define RATE_BITS 1
 #define CAP_HEIGHT 4
@@ -250,18 +251,29 @@ static void merkle_open(wbuf_t *w, const merkle_tree_t *t, size_t idx) {
     wb_push_many(w, sib, 4 * k);
 }
 
+static double t_last;
+static void tick(const char *what) {
+    if (!getenv("TMX_ORACLE_TIMING")) return;
+    double t = omp_get_wtime();
+    fprintf(stderr, "  [oracle] %-28s %.2f s\n", what, t - t_last);
+    t_last = t;
+}
+
 static void prove_table(int table, const trace_t *tr, challenger_t *ch, wbuf_t *w) {
+    t_last = omp_get_wtime();
     const size_t n = tr->n_rows, C = tr->n_cols, m = n << RATE_BITS;
     const unsigned k = tmx_log2(n), km = k + RATE_BITS;
     /* 1. trace commitment */
     gl_t *lde = (gl_t *)malloc(C * m * sizeof(gl_t));
     gl_t *coeffs = (gl_t *)malloc(C * n * sizeof(gl_t));
     ntt_lde_batch(tr->data, C, n, RATE_BITS, lde, coeffs);
+    tick("lde");
     merkle_tree_t tree_t;
     commit_columns(&tree_t, lde, C, m, CAP_HEIGHT);
     const size_t cap_n = (size_t)1 << tree_t.cap_height;
     wb_push_many(w, tree_t.cap, 4 * cap_n);
     observe_cap(ch, tree_t.cap, cap_n);
+    tick("trace merkle");
     /* 2. constraint challenges */
     gl_t alpha[NUM_CHALLENGES];
     for (int i = 0; i < NUM_CHALLENGES; i++) alpha[i] = challenger_get(ch);
@@ -305,6 +317,7 @@ static void prove_table(int table, const trace_t *tr, challenger_t *ch, wbuf_t *
         free(loc);
         free(nxt);
     }
+    tick("quotient eval");
     /* quotient chunks: coefficients of degree < 2n split in two */
     gl_t *qcoef = (gl_t *)malloc((size_t)N_QUOT * n * sizeof(gl_t));
     for (int i = 0; i < NUM_CHALLENGES; i++) {
@@ -323,6 +336,7 @@ static void prove_table(int table, const trace_t *tr, challenger_t *ch, wbuf_t *
     commit_columns(&tree_q, qlde, N_QUOT, m, CAP_HEIGHT);
     wb_push_many(w, tree_q.cap, 4 * cap_n);
     observe_cap(ch, tree_q.cap, cap_n);
+    tick("quotient commit");
     /* 4. openings */
     const gl2_t zeta = challenger_get_ext(ch);
     const gl2_t zeta_next = gl2_scale(zeta, gl_root_of_unity(k));
@@ -340,6 +354,7 @@ static void prove_table(int table, const trace_t *tr, challenger_t *ch, wbuf_t *
     for (size_t c = 0; c < C; c++) observe_ext(ch, op_local[c]);
     for (int q = 0; q < N_QUOT; q++) observe_ext(ch, op_quot[q]);
     for (size_t c = 0; c < C; c++) observe_ext(ch, op_next[c]);
+    tick("openings");
     /* 5. FRI batch polynomial, coefficient space (plonky2 fri/oracle.rs prove_openings) */
     const gl2_t fa = challenger_get_ext(ch);
     gl2_t *final_poly = (gl2_t *)calloc(m, sizeof(gl2_t));
@@ -371,6 +386,7 @@ static void prove_table(int table, const trace_t *tr, challenger_t *ch, wbuf_t *
         }
         free(comp);
     }
+    tick("fri batch poly");
     /* 6. FRI commit phase (fri_committed_trees) */
     const size_t n_layers = fri_num_layers(k);
     merkle_tree_t *layer_trees = (merkle_tree_t *)calloc(n_layers ? n_layers : 1, sizeof(merkle_tree_t));
@@ -412,11 +428,13 @@ static void prove_table(int table, const trace_t *tr, challenger_t *ch, wbuf_t *
         wb_push_ext(w, cf[i]);
         observe_ext(ch, cf[i]);
     }
+    tick("fri commit phase");
     /* 7. proof of work: minimum witness */
     gl_t pow_witness = challenger_pow_grind(ch, POW_BITS);
     challenger_observe(ch, pow_witness);
     (void)challenger_get(ch);
     wb_push(w, pow_witness);
+    tick("pow");
     /* 8. queries */
     for (int qi = 0; qi < NUM_QUERIES; qi++) {
         size_t x = (size_t)(challenger_get(ch) % m);

@@ -147,6 +147,34 @@ def verify_proof(kind, n_max, config, proof, public_input, output):
                                    public_input, len(public_input), output))
 
 
+def blob_size(kind, n_max):
+    return 920 + 240 * n_max + (48 * n_max if kind == KIND_SKIP else 0)
+
+
+class InputDataFetcher:
+    """Fixture mode of the reference's InputDataFetcher [REF circuits/input/mod.rs:37-43,96-116]: `fixture_path`
+    holds <height>/commit.json and <height>/validators_<page>.json.  Methods return the packed off-chain blob."""
+
+    def __init__(self, fixture_path):
+        self.fixture_path = str(fixture_path).encode()
+
+    def header_hash(self, block):
+        out = (ctypes.c_uint8 * 32)()
+        _check(lib().tmx_header_hash_from_fixture(self.fixture_path, block, out))
+        return bytes(out)
+
+    def get_skip_inputs(self, n_max, trusted_block, trusted_hash, target_block):
+        buf = (ctypes.c_uint8 * blob_size(KIND_SKIP, n_max))()
+        _check(lib().tmx_skip_inputs_from_fixture(self.fixture_path, n_max, trusted_block, bytes(trusted_hash), target_block,
+                                                  buf, len(buf)))
+        return bytes(buf)
+
+    def get_step_inputs(self, n_max, prev_block, prev_hash):
+        buf = (ctypes.c_uint8 * blob_size(KIND_STEP, n_max))()
+        _check(lib().tmx_step_inputs_from_fixture(self.fixture_path, n_max, prev_block, bytes(prev_hash), buf, len(buf)))
+        return bytes(buf)
+
+
 class Circuit:
     """`SkipCircuit::<N, C>` / `StepCircuit::<N, C>` [REF circuits/skip.rs:103-143, circuits/step.rs:90-127]:
     build() -> prove(input, offchain blob) -> verify(proof, input, output)."""
@@ -187,6 +215,22 @@ class Circuit:
         out = (ctypes.c_uint8 * 32)()
         public_input, blob = bytes(public_input), bytes(blob)
         rc = lib().tmx_prove(self._h, public_input, len(public_input), blob, len(blob), ctypes.byref(p), out)
+        if rc != 0:
+            err = TmxError(rc, lib().tmx_last_error().decode())
+            err.check = CHECK_NAMES[lib().tmx_last_check()]
+            raise err
+        n = lib().tmx_proof_size(p)
+        buf = (ctypes.c_uint8 * n)()
+        _check(lib().tmx_proof_bytes(p, buf, n))
+        lib().tmx_proof_free(p)
+        return bytes(buf), bytes(out)
+
+    def prove_fixture(self, public_input, fixture_path):
+        """`prove input.json` with off-chain inputs read from a fixture directory (the async-hint path)."""
+        p = ctypes.c_void_p()
+        out = (ctypes.c_uint8 * 32)()
+        public_input = bytes(public_input)
+        rc = lib().tmx_prove_fixture(self._h, public_input, len(public_input), str(fixture_path).encode(), ctypes.byref(p), out)
         if rc != 0:
             err = TmxError(rc, lib().tmx_last_error().decode())
             err.check = CHECK_NAMES[lib().tmx_last_check()]

@@ -336,6 +336,22 @@ extern "C" int tmx_prove(tmx_circuit* c, const uint8_t* input, size_t input_len,
     return TMX_OK;
 }
 
+// `prove input.json` with the off-chain inputs taken from a fixture directory, i.e. the whole async-hint path
+// [REF circuits/skip.rs:64-101]: parse heights from the public input, assemble the blob, prove.
+extern "C" int tmx_skip_inputs_from_fixture(const char*, uint32_t, uint64_t, const uint8_t*, uint64_t, uint8_t*, size_t);
+extern "C" int tmx_step_inputs_from_fixture(const char*, uint32_t, uint64_t, const uint8_t*, uint8_t*, size_t);
+extern "C" int tmx_prove_fixture(tmx_circuit* c, const uint8_t* input, size_t input_len, const char* fixture_dir,
+                                 tmx_proof** proof_out, uint8_t out32[32]) {
+    if (!c || !input || !fixture_dir || !proof_out || !out32) return fail(TMX_E_INPUT, "tmx_prove_fixture: NULL argument");
+    if (input_len != (c->kind == TMX_KIND_SKIP ? 48u : 40u)) return fail(TMX_E_INPUT, "tmx_prove_fixture: wrong public input length");
+    std::vector<uint8_t> blob(TMX_BLOB_SIZE(c->kind, c->n_max));
+    int rc = c->kind == TMX_KIND_SKIP
+                 ? tmx_skip_inputs_from_fixture(fixture_dir, c->n_max, be64(input), input + 8, be64(input + 40), blob.data(), blob.size())
+                 : tmx_step_inputs_from_fixture(fixture_dir, c->n_max, be64(input), input + 8, blob.data(), blob.size());
+    if (rc) return rc;
+    return tmx_prove(c, input, input_len, blob.data(), blob.size(), proof_out, out32);
+}
+
 extern "C" size_t tmx_proof_size(const tmx_proof* p) { return p ? p->words.size() * sizeof(gl) : 0; }
 
 extern "C" int tmx_proof_bytes(const tmx_proof* p, uint8_t* buf, size_t cap) {
