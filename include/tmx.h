@@ -47,6 +47,8 @@ const char *tmx_version(void);
 int tmx_ctx_create(int device, tmx_ctx **out);
 void tmx_ctx_destroy(tmx_ctx *ctx);
 int tmx_ctx_sync(tmx_ctx *ctx);
+/* the context's own cudaStream_t (for CUDA-event timing of calls that take no stream argument) */
+void *tmx_ctx_stream(const tmx_ctx *ctx);
 /* kernels launched by this context since creation (bench.py's gpu_launches counter) */
 uint64_t tmx_ctx_launch_count(const tmx_ctx *ctx);
 
@@ -132,6 +134,8 @@ int tmx_circuit_load(tmx_ctx *ctx, const char *path, tmx_circuit **out);
 int tmx_prove(tmx_circuit *circuit, const uint8_t *input, size_t input_len, const uint8_t *blob, size_t blob_len,
               tmx_proof **proof, uint8_t out32[32]);
 int tmx_last_check(void);
+/* keep one proof's off-chain inputs resident in HBM; tmx_prove(..., blob = NULL, 0, ...) then proves from them */
+int tmx_circuit_set_inputs(tmx_circuit *circuit, const uint8_t *blob, size_t blob_len);
 
 /* Input assembly = the fixture mode of InputDataFetcher [circuits/input/mod.rs:188-282,316-523;
  * circuits/input/conversion.rs:59-178]: reads <dir>/<height>/commit.json and validators_<page>.json (the RPC JSON

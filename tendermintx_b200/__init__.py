@@ -62,6 +62,12 @@ class Context:
         h = torch.cuda.current_stream(self.device).cuda_stream
         return ctypes.c_void_p(h if h else 1)
 
+    def torch_stream(self):
+        """The context's own stream as a torch ExternalStream (events recorded on it bracket tmx_prove)."""
+        import torch
+
+        return torch.cuda.ExternalStream(lib().tmx_ctx_stream(self._h), device=f"cuda:{self.device}")
+
     def launch_count(self):
         return int(lib().tmx_ctx_launch_count(self._h))
 
@@ -208,13 +214,20 @@ class Circuit:
     def save(self, path):
         _check(lib().tmx_circuit_save(self._h, path.encode()))
 
+    def set_inputs(self, blob):
+        """Upload the off-chain inputs once; prove(public_input, None) then runs from the HBM-resident copy."""
+        blob = bytes(blob)
+        _check(lib().tmx_circuit_set_inputs(self._h, blob, len(blob)))
+
     def prove(self, public_input, blob):
         """Returns (proof bytes, output header bytes).  Raises TmxError(TMX_E_UNSAT) with `.check` set to the name
         of the failing gadget check where the reference's witness generation would panic."""
         p = ctypes.c_void_p()
         out = (ctypes.c_uint8 * 32)()
-        public_input, blob = bytes(public_input), bytes(blob)
-        rc = lib().tmx_prove(self._h, public_input, len(public_input), blob, len(blob), ctypes.byref(p), out)
+        public_input = bytes(public_input)
+        blob = bytes(blob) if blob is not None else None
+        rc = lib().tmx_prove(self._h, public_input, len(public_input), blob, len(blob) if blob is not None else 0,
+                             ctypes.byref(p), out)
         if rc != 0:
             err = TmxError(rc, lib().tmx_last_error().decode())
             err.check = CHECK_NAMES[lib().tmx_last_check()]

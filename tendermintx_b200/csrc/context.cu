@@ -213,4 +213,6 @@ extern "C" int tmx_ctx_sync(tmx_ctx* ctx) {
     return TMX_OK;
 }
 
+extern "C" void* tmx_ctx_stream(const tmx_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
 extern "C" uint64_t tmx_ctx_launch_count(const tmx_ctx* ctx) { return ctx ? ctx->launches : 0; }

@@ -85,3 +85,27 @@ def test_synthetic_celestia_skip_n16(ctx, oracle):
     assert np.array_equal(np.frombuffer(proof, dtype=np.uint64), want)
     circuit.verify(proof, pub, out)
     circuit.close()
+
+
+def test_full_size_skip_n128_celestia(ctx):
+    """BASELINE config 2 at full size: prove from the fixture directory (C++ input assembly -> kernels -> proof),
+    output = the fixture's block hash, CPU verifier accepts, proof is reproducible, a tampered proof is rejected."""
+    import tendermintx_b200 as tmx
+
+    root = os.path.join(HERE, "golden", "celestia")
+    with open(os.path.join(root, "index.json")) as f:
+        idx = json.load(f)["skip_n128_seed0"]
+    th = bytes.fromhex(idx["trusted_hash"])
+    pub = idx["trusted"].to_bytes(8, "big") + th + idx["target"].to_bytes(8, "big")
+    circuit = tmx.Circuit.build(ctx, tmx.KIND_SKIP, 128, tmx.CelestiaConfig)
+    proof, out = circuit.prove_fixture(pub, os.path.join(root, "skip_n128_seed0"))
+    assert out.hex() == idx["target_hash"]
+    circuit.verify(proof, pub, out)
+    tmx.verify_proof(tmx.KIND_SKIP, 128, tmx.CelestiaConfig, proof, pub, out)
+    proof2, _ = circuit.prove_fixture(pub, os.path.join(root, "skip_n128_seed0"))
+    assert proof2 == proof
+    bad = bytearray(proof)
+    bad[len(bad) // 2] ^= 1
+    with pytest.raises(tmx.TmxError):
+        circuit.verify(bytes(bad), pub, out)
+    circuit.close()
