@@ -142,13 +142,11 @@ def run_ours(args):
         else:
             data = None
         if world > 1:
-            n = torch.tensor([0 if data is None else data.size], device="cuda")
-            dist.broadcast(n, 0)
-            buf = torch.zeros(int(n.item()), dtype=torch.uint8, device="cuda")
-            if rank == 0:
-                buf.copy_(torch.from_numpy(data))
-            dist.broadcast(buf, 0)
-            buf.cpu().numpy().tofile(path)
+            from tendermintx_b200 import sharding
+
+            blob_bytes = sharding.broadcast_bytes(data.tobytes() if rank == 0 else b"", 0, device="cuda")
+            with open(path, "wb") as fh:
+                fh.write(blob_bytes)
         h = ctypes.c_void_p()
         rc = tmx.lib().tmx_circuit_load(ctx.handle, path.encode(), ctypes.byref(h))
         assert rc == 0, tmx.lib().tmx_last_error()
