@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 WORKER = textwrap.dedent("""
     import os, sys, hashlib
-    sys.path.insert(0, %r)
+    sys.path.insert(0, __ROOT__)
     import torch.distributed as dist
     from tendermintx_b200 import sharding
     dist.init_process_group("gloo")
@@ -20,9 +20,9 @@ WORKER = textwrap.dedent("""
     assert mine == list(range(rank, 8, world))
     t = sharding.max_over_ranks([10.0 + rank, 5.0 - rank])
     assert t == [10.0 + world - 1, 5.0]
-    sys.stdout.write(f"rank {rank} ok {len(got)} {mine}\n"); sys.stdout.flush()
+    sys.stdout.write("rank %d ok %d %s\\n" % (rank, len(got), mine)); sys.stdout.flush()
     dist.destroy_process_group()
-""") % ROOT
+""").replace("__ROOT__", repr(ROOT))
 
 
 def test_two_ranks_gloo(tmp_path):
