@@ -11,6 +11,8 @@
 #include "witness_jobs.cuh"
 #include <cstring>
 #include <cstdio>
+#include <cstdlib>
+#include <ctime>
 
 using namespace tmx;
 
@@ -25,6 +27,9 @@ struct tmx_circuit {
     gl* d_trace[3] = {nullptr, nullptr, nullptr};
     uint8_t* d_blob = nullptr;
     uint8_t* d_aux = nullptr;
+    void* d_points = nullptr;           // Ed25519 ladder states (phase 1 -> phase 2)
+    cudaStream_t side = nullptr;        // second stream: the latency-bound ladders overlap with table 0's proving
+    cudaEvent_t ev_inputs = nullptr, ev_ladder = nullptr;
     std::vector<uint8_t> h_blob;  // host copy of the resident inputs (tmx_circuit_set_inputs)
     bool resident = false;
     TableProver prover;
@@ -225,7 +230,11 @@ extern "C" int tmx_circuit_build(tmx_ctx* ctx, uint32_t kind, uint32_t n_max, co
         }
     }
     if (cudaMalloc((void**)&c->d_blob, TMX_BLOB_SIZE(kind, n_max)) != cudaSuccess ||
-        cudaMalloc((void**)&c->d_aux, aux_bytes(n_max)) != cudaSuccess) {
+        cudaMalloc((void**)&c->d_aux, aux_bytes(n_max)) != cudaSuccess ||
+        cudaMalloc(&c->d_points, witness_points_bytes(n_max)) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_inputs, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_ladder, cudaEventDisableTiming) != cudaSuccess) {
         tmx_circuit_free(c);
         return fail(TMX_E_CUDA, "tmx_circuit_build: cudaMalloc failed");
     }
@@ -235,11 +244,15 @@ extern "C" int tmx_circuit_build(tmx_ctx* ctx, uint32_t kind, uint32_t n_max, co
 
 extern "C" void tmx_circuit_free(tmx_circuit* c) {
     if (!c) return;
-    cudaSetDevice(c->ctx->device);
+    if (c->ctx) cudaSetDevice(c->ctx->device);
     for (int t = 0; t < 3; t++)
         if (c->d_trace[t]) cudaFree(c->d_trace[t]);
     if (c->d_blob) cudaFree(c->d_blob);
     if (c->d_aux) cudaFree(c->d_aux);
+    if (c->d_points) cudaFree(c->d_points);
+    if (c->side) cudaStreamDestroy(c->side);
+    if (c->ev_inputs) cudaEventDestroy(c->ev_inputs);
+    if (c->ev_ladder) cudaEventDestroy(c->ev_ladder);
     c->prover.release();
     delete c;
 }
@@ -318,22 +331,27 @@ extern "C" int tmx_prove(tmx_circuit* c, const uint8_t* input, size_t input_len,
     tmx_ctx* ctx = c->ctx;
     TMX_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
+    const bool timing = getenv("TMX_TIMING") != nullptr;
+    timespec ts0;
+    clock_gettime(CLOCK_MONOTONIC, &ts0);
     // witness generation on the GPU
     if (!use_resident) {
         TMX_CUDA(cudaMemcpyAsync(c->d_blob, blob, blob_len, cudaMemcpyHostToDevice, st));
         c->resident = false;
     }
     TMX_CUDA(cudaMemsetAsync(c->d_aux, 0, aux_bytes(c->n_max), st));
-    int rc = tmx_witness_generate(ctx, c->d_blob, c->kind, c->n_max, c->d_trace[0], c->d_trace[1], c->d_trace[2], c->d_aux, st);
+    WitnessArgs wa;
+    int rc = witness_make_args(ctx, c->d_blob, c->kind, c->n_max, c->d_trace[0], c->d_trace[1], c->d_trace[2], c->d_aux, &wa);
     if (rc) return rc;
-    std::vector<uint8_t> aux(aux_bytes(c->n_max));
-    TMX_CUDA(cudaMemcpyAsync(aux.data(), c->d_aux, aux.size(), cudaMemcpyDeviceToHost, st));
-    TMX_CUDA(cudaStreamSynchronize(st));
-    const int chk = check_statement(c, input, blob, aux.data());
-    if (chk) {
-        g_last_check = chk;
-        return fail(TMX_E_UNSAT, "tmx_prove: witness does not satisfy the circuit (check id " + std::to_string(chk) + ")");
-    }
+    // side stream: Ed25519 phase 1 (sequential ladders, ~7 ms of latency, few threads) runs while the main stream
+    // fills and proves the SHA-256 table
+    TMX_CUDA(cudaEventRecord(c->ev_inputs, st));
+    TMX_CUDA(cudaStreamWaitEvent(c->side, c->ev_inputs, 0));
+    rc = run_ed25519_ladder(ctx, wa, c->d_points, c->side);
+    if (rc) return rc;
+    TMX_CUDA(cudaEventRecord(c->ev_ladder, c->side));
+    rc = witness_run_sha256(ctx, wa, st);
+    if (rc) return rc;
     memcpy(out32, h->header, 32);
     // proof: header, then one STARK per table on a shared transcript
     tmx_proof* p = new tmx_proof();
@@ -349,7 +367,33 @@ extern "C" int tmx_prove(tmx_circuit* c, const uint8_t* input, size_t input_len,
     }
     Challenger ch;
     transcript_init(c, input, input_len, out32, ch);
-    for (int t = 0; t < STARK_N_TABLES; t++) {
+    rc = c->prover.prove(ctx, 0, c->d_trace[0], ilog2(c->dims[0]), ch, w, st);
+    if (rc) {
+        delete p;
+        return rc;
+    }
+    // join: phase 2 of the Ed25519 / SHA-512 tables, then the gadget checks that need the kernels' digests
+    TMX_CUDA(cudaStreamWaitEvent(st, c->ev_ladder, 0));
+    rc = run_ed25519_expand(ctx, wa, c->d_points, st);
+    if (rc) {
+        delete p;
+        return rc;
+    }
+    std::vector<uint8_t> aux(aux_bytes(c->n_max));
+    TMX_CUDA(cudaMemcpyAsync(aux.data(), c->d_aux, aux.size(), cudaMemcpyDeviceToHost, st));
+    TMX_CUDA(cudaStreamSynchronize(st));
+    if (timing) {
+        timespec ts1;
+        clock_gettime(CLOCK_MONOTONIC, &ts1);
+        fprintf(stderr, "  [tmx] witness + table 0     %8.3f ms\n", (ts1.tv_sec - ts0.tv_sec) * 1e3 + (ts1.tv_nsec - ts0.tv_nsec) / 1e6);
+    }
+    const int chk = check_statement(c, input, blob, aux.data());
+    if (chk) {
+        delete p;
+        g_last_check = chk;
+        return fail(TMX_E_UNSAT, "tmx_prove: witness does not satisfy the circuit (check id " + std::to_string(chk) + ")");
+    }
+    for (int t = 1; t < STARK_N_TABLES; t++) {
         rc = c->prover.prove(ctx, t, c->d_trace[t], ilog2(c->dims[2 * t]), ch, w, st);
         if (rc) {
             delete p;

@@ -24,25 +24,26 @@ constexpr gl GL_EPS = 0xFFFFFFFFULL;  // 2^64 mod p
 constexpr gl GL_GEN = 7ULL;           // multiplicative generator, also the LDE coset shift
 constexpr gl GL_ROOT_2_32 = 1753635133440165772ULL;
 
-TMX_HD gl gl_canon(gl a) { return a >= GL_P ? a - GL_P : a; }
+// Branch-free on purpose: on the host (transcript, verifier) data-dependent branches on random field elements
+// mispredict half the time; on the device the compiler turns these into selects either way.
+TMX_HD gl gl_canon(gl a) { return a - (GL_P & (0 - (gl)(a >= GL_P))); }
 
 TMX_HD gl gl_add(gl a, gl b) {
-    gl s = a + b;
-    if (s < a) s += GL_EPS;  // wrapped: 2^64 = 2^32 - 1; a,b < p so this lands below p
-    else if (s >= GL_P) s -= GL_P;
-    return s;
+    const gl s = a + b;
+    const gl over = (gl)(s < a) | (gl)(s >= GL_P);  // wrapped past 2^64, or landed in [p, 2^64)
+    return s - (GL_P & (0 - over));                 // s - p (mod 2^64) is right in both cases (a, b < p)
 }
-TMX_HD gl gl_sub(gl a, gl b) { return a >= b ? a - b : a + (GL_P - b); }
+TMX_HD gl gl_sub(gl a, gl b) { return (a - b) + (GL_P & (0 - (gl)(a < b))); }
 TMX_HD gl gl_neg(gl a) { return a ? GL_P - a : 0; }
 
 // x = lo + 2^64*hi with 2^64 = 2^32-1, 2^96 = -1  (mod p)
 TMX_HD gl gl_reduce128(gl lo, gl hi) {
-    gl hh = hi >> 32, hl = hi & GL_EPS;
+    const gl hh = hi >> 32, hl = hi & GL_EPS;
     gl t0 = lo - hh;
-    if (lo < hh) t0 -= GL_EPS;
-    gl t1 = hl * GL_EPS;
+    t0 -= GL_EPS & (0 - (gl)(lo < hh));
+    const gl t1 = hl * GL_EPS;
     gl t2 = t0 + t1;
-    if (t2 < t1) t2 += GL_EPS;
+    t2 += GL_EPS & (0 - (gl)(t2 < t1));
     return gl_canon(t2);
 }
 

@@ -10,6 +10,9 @@
 // a 16-point inverse NTT per coset instead of folding coefficients and re-running a coset FFT.
 #include "stark.cuh"
 #include <cstring>
+#include <cstdio>
+#include <cstdlib>
+#include <ctime>
 #include <algorithm>
 
 namespace tmx {
@@ -248,6 +251,28 @@ static int d2h(std::vector<gl>& dst, const gl* src, size_t n, cudaStream_t st) {
 
 static void observe_ext(Challenger& ch, gl2 x) { ch.observe_ext(x); }
 
+// TMX_TIMING=1: host wall-clock per phase (with a stream sync at each boundary) on stderr
+struct PhaseTimer {
+    bool on;
+    cudaStream_t st;
+    double t0;
+    static double now() {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e3 + ts.tv_nsec / 1e6;
+    }
+    PhaseTimer(cudaStream_t s) : on(getenv("TMX_TIMING") != nullptr), st(s), t0(0) {
+        if (on) { cudaStreamSynchronize(st); t0 = now(); }
+    }
+    void tick(const char* what) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        const double t = now();
+        fprintf(stderr, "  [tmx] %-22s %8.3f ms\n", what, t - t0);
+        t0 = t;
+    }
+};
+
 int TableProver::prove(tmx_ctx* ctx, int table, const gl* d_trace, unsigned log_n, Challenger& ch, std::vector<gl>& proof,
                        cudaStream_t st) {
     const size_t n = (size_t)1 << log_n, m = n << STARK_RATE_BITS;
@@ -260,16 +285,20 @@ int TableProver::prove(tmx_ctx* ctx, int table, const gl* d_trace, unsigned log_
     const size_t dig_t = tmx_merkle_digest_count(km, cap_h);
     rc = reserve(ctx, C, n, m, dig_t);
     if (rc) return rc;
+    PhaseTimer pt(st);
     // ---- 1. trace commitment ----
     rc = tmx_lde(ctx, d_trace, d_lde, d_coeffs, C, log_n, STARK_RATE_BITS, st);
     if (rc) return rc;
+    pt.tick("lde");
     rc = merkle_generic(ctx, d_lde, C, 1, m, km, cap_h, d_dig_t, st);
     if (rc) return rc;
+    pt.tick("trace merkle");
     std::vector<gl> cap;
     rc = d2h(cap, d_dig_t + 4 * (dig_t - cap_n), 4 * cap_n, st);
     if (rc) return rc;
     proof.insert(proof.end(), cap.begin(), cap.end());
     ch.observe(cap.data(), cap.size());
+    pt.tick("cap d2h + observe");
     // ---- 2. constraint challenges, 3. quotient ----
     QuotientArgs qa;
     memset(&qa, 0, sizeof qa);
@@ -286,6 +315,7 @@ int TableProver::prove(tmx_ctx* ctx, int table, const gl* d_trace, unsigned log_
     const unsigned qblocks = (unsigned)((m + 127) / 128);
     rc = launch_quotient(ctx, table, qa, st);
     if (rc) return rc;
+    pt.tick("quotient kernel");
     // values on the coset (natural order) -> coefficients of Q(7 X); the 1/m factor comes with the inverse NTT
     rc = tmx_ntt(ctx, d_qv, 2, km, 1, st);
     if (rc) return rc;
@@ -299,6 +329,7 @@ int TableProver::prove(tmx_ctx* ctx, int table, const gl* d_trace, unsigned log_
     if (rc) return rc;
     proof.insert(proof.end(), cap.begin(), cap.end());
     ch.observe(cap.data(), cap.size());
+    pt.tick("quotient commit");
     // ---- 4. openings at zeta and g * zeta (coefficients are stored coset-scaled: evaluate at zeta / 7) ----
     const gl2 zeta = ch.get_ext();
     const gl2 zeta_next = gl2_scale(zeta, gl_root_of_unity(log_n));
@@ -309,6 +340,7 @@ int TableProver::prove(tmx_ctx* ctx, int table, const gl* d_trace, unsigned log_
     eval_columns_kernel<<<4, 256, 0, st>>>(d_qcoef, n, d_ypa, nullptr, d_open + 2 * C, nullptr);
     ctx->launches += 4;
     TMX_CUDA(cudaGetLastError());
+    pt.tick("openings kernels");
     std::vector<gl> op;
     rc = d2h(op, reinterpret_cast<const gl*>(d_open), 2 * (2 * C + 4), st);
     if (rc) return rc;
@@ -317,6 +349,7 @@ int TableProver::prove(tmx_ctx* ctx, int table, const gl* d_trace, unsigned log_
     for (size_t c = 0; c < C; c++) observe_ext(ch, ext_at(c));
     for (size_t q = 0; q < 4; q++) observe_ext(ch, ext_at(2 * C + q));
     for (size_t c = 0; c < C; c++) observe_ext(ch, ext_at(C + c));
+    pt.tick("openings d2h+observe");
     // ---- 5. FRI batch polynomial, pointwise ----
     const gl2 fa = ch.get_ext();
     std::vector<gl2> apow(C + 4);
@@ -339,6 +372,7 @@ int TableProver::prove(tmx_ctx* ctx, int table, const gl* d_trace, unsigned log_
     fri_batch_kernel<<<qblocks, 128, 0, st>>>(fb);
     ctx->launches++;
     TMX_CUDA(cudaGetLastError());
+    pt.tick("fri batch");
     // ---- 6. FRI commit phase: Merkle over cosets of 16, fold with beta ----
     const unsigned n_layers = fri_num_layers(log_n);
     size_t cur = m;
@@ -368,6 +402,7 @@ int TableProver::prove(tmx_ctx* ctx, int table, const gl* d_trace, unsigned log_
         cur = cosets;
         shift = gl_pow(shift, 16);
     }
+    pt.tick("fri layers");
     // final polynomial: the remaining `cur` evaluations (bit-reversed) on shift * <w_cur> -> coefficients
     std::vector<gl> fin;
     rc = d2h(fin, reinterpret_cast<const gl*>(d_fri[n_layers]), 2 * cur, st);
@@ -394,6 +429,7 @@ int TableProver::prove(tmx_ctx* ctx, int table, const gl* d_trace, unsigned log_
             observe_ext(ch, coef[k]);
         }
     }
+    pt.tick("final poly");
     // ---- 7. proof of work (K9) ----
     {
         gl state[12];
@@ -406,6 +442,7 @@ int TableProver::prove(tmx_ctx* ctx, int table, const gl* d_trace, unsigned log_
         (void)ch.get();
         proof.push_back((gl)wit);
     }
+    pt.tick("pow");
     // ---- 8. queries (K4) ----
     std::vector<uint32_t> idx(STARK_NUM_QUERIES);
     for (int q = 0; q < STARK_NUM_QUERIES; q++) idx[q] = (uint32_t)(ch.get() % m);
@@ -442,6 +479,7 @@ int TableProver::prove(tmx_ctx* ctx, int table, const gl* d_trace, unsigned log_
     rc = d2h(qd, d_query, qlen * NQ, st);
     if (rc) return rc;
     proof.insert(proof.end(), qd.begin(), qd.end());
+    pt.tick("queries");
     (void)host_poly_eval_ext;
     return TMX_OK;
 }

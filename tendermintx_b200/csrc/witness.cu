@@ -9,11 +9,12 @@
 //     a 832-byte shared-memory history; then every thread owns one round = one trace row and writes its 370
 //     cells, so each column receives 64 (or 128) consecutive rows = 512-byte coalesced runs.  The validator-set
 //     tree is one launch per level (the only true dependency), header proofs one CTA per proof.
-//   * SHA-512 + Ed25519: one validator per CTA (512 threads).  h = SHA-512(R || A || M) never leaves the SM: it is
-//     reduced mod l in place and feeds the [h]A ladder.  The two 256-step ladders ([s]B and [h]A) run on two
-//     warps with 51-bit-limb field arithmetic in registers, parking canonical (res, temp) per step in 128 KB of
-//     shared memory; then each of the 512 threads expands one ladder row into its 1217 cells (17 multiplication
-//     gadgets: product limbs, quotient, carries).
+//   * SHA-512 + Ed25519: one validator per CTA, in two phases.  Phase 1 (64 threads, small footprint so it can share
+//     the SMs with another stream's kernels): h = SHA-512(R || A || M) is reduced mod l on the SM and feeds the [h]A
+//     ladder; the two 256-step ladders ([s]B and [h]A) run on two warps with 5 x 51-bit-limb field arithmetic in
+//     registers and park the canonical (res, temp) of every step in a 128 KB-per-validator scratch.  Phase 2 (512
+//     threads): each thread expands one ladder row into its 1217 cells (17 multiplication gadgets: product limbs,
+//     quotient, carries) and the 160 SHA-512 round rows are written.
 //   Integer / bit work, HBM-write bound at best: no tensor cores.
 #include "ctx.cuh"
 #include "witness_jobs.cuh"
@@ -72,35 +73,67 @@ __global__ void __launch_bounds__(128) sha512_padding_kernel(WitnessArgs a, size
     if (threadIdx.x < 80 && row < a.n512) sha512_row_cells(a.t512, a.n512, row, threadIdx.x, &hs);
 }
 
-struct EdShared {
+struct LadderShared {
     Sha512Hist h5[2];
     EdTriple triple;
     EdSlot slot;
     uint8_t digest[64];
     ge51 Ps, Ph;
+    bool ok_r;
 };
 
-__global__ void __launch_bounds__(512) ed25519_validator_kernel(WitnessArgs a) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    ge_packed* res = reinterpret_cast<ge_packed*>(smem_raw);
-    ge_packed* tmp = res + 512;
-    EdShared* sh = reinterpret_cast<EdShared*>(tmp + 512);
+// Phase 1 (latency-bound, small footprint: 64 threads, so other kernels share the SMs while it runs): per validator
+// SHA-512(R || A || M) -> h mod l, decompress A and R on two warps, run the [s]B and [h]A ladders on two warps and park
+// the canonical (res, temp) of every step in global scratch (128 B per point); verdict of the signature equation.
+__global__ void __launch_bounds__(64) ed25519_ladder_kernel(WitnessArgs a, ge_packed* __restrict__ points) {
+    __shared__ LadderShared sh;
     const uint32_t i = blockIdx.x, tid = threadIdx.x;
+    ge_packed* res = points + (size_t)i * 1024;
+    ge_packed* tmp = res + 512;
     if (tid == 0) {
-        effective_triple(blob_validators(a.blob) + i, &sh->triple);
-        sha512_validator_prepare(sh->triple, sh->h5, sh->digest);
+        effective_triple(blob_validators(a.blob) + i, &sh.triple);
+        sha512_validator_prepare(sh.triple, sh.h5, sh.digest);
+        fe256 sb = fe256_from_bytes(sh.triple.sig + 32);
+        for (int k = 0; k < 4; k++) sh.slot.s[k] = sb.w[k];
+        sc_reduce512(sh.digest, sh.slot.h);
+        sh.slot.ok = sc_lt_l(sh.slot.s);
     }
     __syncthreads();
-    if (tid < 160) sha512_row_cells(a.t512, a.n512, (size_t)i * S512_ROWS_PER_VALIDATOR + tid, tid % 80, &sh->h5[tid / 80]);
-    if (tid == 0) ed_slot_prepare(sh->triple, sh->digest, &sh->slot);
+    if (tid == 0 && !ge_decompress51(sh.triple.pk, &sh.slot.A)) {
+        sh.slot.ok = false;
+        sh.slot.A = ge_identity51();
+    }
+    if (tid == 32) {
+        sh.ok_r = ge_decompress51(sh.triple.sig, &sh.slot.R);
+        if (!sh.ok_r) sh.slot.R = ge_identity51();
+    }
     __syncthreads();
-    if (tid == 0) sh->Ps = ed_ladder(sh->slot.s, ge_base51(), res, tmp);
-    if (tid == 32) sh->Ph = ed_ladder(sh->slot.h, sh->slot.A, res + 256, tmp + 256);
+    if (tid == 0) sh.Ps = ed_ladder(sh.slot.s, ge_base51(), res, tmp);
+    if (tid == 32) sh.Ph = ed_ladder(sh.slot.h, sh.slot.A, res + 256, tmp + 256);
     __syncthreads();
-    if (tid == 0) a.aux[AUX_SIG_OK + i] = ed_slot_verdict(sh->slot, sh->Ps, sh->Ph) ? 1 : 0;
-    const uint64_t* sc = tid < 256 ? sh->slot.s : sh->slot.h;
-    const int bit = (int)((sc[(tid & 255) >> 6] >> (tid & 63)) & 1);
-    ed_row_cells(a.ted, a.ned, (size_t)i * ED_ROWS_PER_VALIDATOR + tid, bit, res[tid], tmp[tid]);
+    if (tid == 0) a.aux[AUX_SIG_OK + i] = (sh.ok_r && ed_slot_verdict(sh.slot, sh.Ps, sh.Ph)) ? 1 : 0;
+}
+
+// Phase 2 (throughput): one thread per trace row -- 160 SHA-512 rounds and 512 ladder steps per validator.
+__global__ void __launch_bounds__(512) ed25519_expand_kernel(WitnessArgs a, const ge_packed* __restrict__ points) {
+    __shared__ Sha512Hist h5[2];
+    __shared__ uint64_t sc[2][4];
+    const uint32_t i = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) {
+        EdTriple t;
+        uint8_t digest[64];
+        effective_triple(blob_validators(a.blob) + i, &t);
+        sha512_validator_prepare(t, h5, digest);
+        fe256 sb = fe256_from_bytes(t.sig + 32);
+        for (int k = 0; k < 4; k++) sc[0][k] = sb.w[k];
+        sc_reduce512(digest, sc[1]);
+    }
+    __syncthreads();
+    if (tid < 160) sha512_row_cells(a.t512, a.n512, (size_t)i * S512_ROWS_PER_VALIDATOR + tid, tid % 80, &h5[tid / 80]);
+    const uint64_t* s = sc[tid >> 8];
+    const int bit = (int)((s[(tid & 255) >> 6] >> (tid & 63)) & 1);
+    const ge_packed* res = points + (size_t)i * 1024;
+    ed_row_cells(a.ted, a.ned, (size_t)i * ED_ROWS_PER_VALIDATOR + tid, bit, res[tid], res[512 + tid]);
 }
 
 // padding blocks of the Ed25519 table: [0]B ladders (valid rows, bit = 0)
@@ -169,10 +202,19 @@ static int run_sha256(tmx_ctx* ctx, const WitnessArgs& a, cudaStream_t st) {
     return TMX_OK;
 }
 
-static int run_ed25519(tmx_ctx* ctx, const WitnessArgs& a, cudaStream_t st) {
-    const size_t smem = 1024 * sizeof(ge_packed) + sizeof(EdShared);
-    TMX_CUDA(cudaFuncSetAttribute(ed25519_validator_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ed25519_validator_kernel<<<a.n_max, 512, smem, st>>>(a);
+size_t witness_points_bytes(uint32_t n_max) { return (size_t)n_max * 1024 * sizeof(ge_packed); }
+
+// phase 1 only (stream-ordered); points must hold witness_points_bytes(n_max)
+int run_ed25519_ladder(tmx_ctx* ctx, const WitnessArgs& a, void* points, cudaStream_t st) {
+    ed25519_ladder_kernel<<<a.n_max, 64, 0, st>>>(a, (ge_packed*)points);
+    ctx->launches++;
+    TMX_CUDA(cudaGetLastError());
+    return TMX_OK;
+}
+
+// phase 2 + padding rows of the SHA-512 and Ed25519 tables
+int run_ed25519_expand(tmx_ctx* ctx, const WitnessArgs& a, const void* points, cudaStream_t st) {
+    ed25519_expand_kernel<<<a.n_max, 512, 0, st>>>(a, (const ge_packed*)points);
     ctx->launches++;
     const size_t used512 = (size_t)a.n_max * S512_ROWS_PER_VALIDATOR;
     if (a.n512 > used512) {
@@ -189,6 +231,21 @@ static int run_ed25519(tmx_ctx* ctx, const WitnessArgs& a, cudaStream_t st) {
     TMX_CUDA(cudaGetLastError());
     return TMX_OK;
 }
+
+static int run_ed25519(tmx_ctx* ctx, const WitnessArgs& a, cudaStream_t st) {
+    void* points = nullptr;
+    int rc = ctx_scratch(ctx, 1, witness_points_bytes(a.n_max), &points);
+    if (rc) return rc;
+    rc = run_ed25519_ladder(ctx, a, points, st);
+    if (rc) return rc;
+    return run_ed25519_expand(ctx, a, points, st);
+}
+
+int witness_make_args(tmx_ctx* ctx, const uint8_t* d_blob, uint32_t kind, uint32_t n_max, uint64_t* t256, uint64_t* t512,
+                      uint64_t* ted, uint8_t* d_aux, WitnessArgs* a) {
+    return make_args(ctx, d_blob, kind, n_max, t256, t512, ted, d_aux, a);
+}
+int witness_run_sha256(tmx_ctx* ctx, const WitnessArgs& a, cudaStream_t st) { return run_sha256(ctx, a, st); }
 
 }  // namespace tmx
 

@@ -299,4 +299,19 @@ TMX_HD void ed_slot_prepare(const EdTriple& t, const uint8_t digest[64], EdSlot*
 // cofactorless check [s]B == R + [h]A on the two ladder results
 TMX_HD bool ed_slot_verdict(const EdSlot& e, const ge51& Ps, const ge51& Ph) { return e.ok && ge_equal51(Ps, ge_add51(Ph, e.R)); }
 
+
+}  // namespace tmx
+
+// host entry points of witness.cu used by the circuit driver (phase-split so the latency-bound Ed25519 ladders can
+// run on a second stream while the SHA-256 table is being proved)
+struct tmx_ctx;
+namespace tmx {
+#if defined(__CUDACC__)
+size_t witness_points_bytes(uint32_t n_max);
+int witness_make_args(tmx_ctx* ctx, const uint8_t* d_blob, uint32_t kind, uint32_t n_max, uint64_t* t256, uint64_t* t512,
+                      uint64_t* ted, uint8_t* d_aux, WitnessArgs* a);
+int witness_run_sha256(tmx_ctx* ctx, const WitnessArgs& a, cudaStream_t st);
+int run_ed25519_ladder(tmx_ctx* ctx, const WitnessArgs& a, void* points, cudaStream_t st);
+int run_ed25519_expand(tmx_ctx* ctx, const WitnessArgs& a, const void* points, cudaStream_t st);
+#endif
 }  // namespace tmx
