@@ -76,6 +76,9 @@ int tmx_poseidon_merkle(tmx_ctx *ctx, const uint64_t *d_cols, size_t n_cols, uns
 
 /* Poseidon permutation of n independent 12-element states (known-answer tests). */
 int tmx_poseidon_permute(tmx_ctx *ctx, uint64_t *d_states, size_t n, void *stream);
+/* Host-side self check (no GPU): the device permutation's arithmetic compiled for the CPU.
+ * variant 0 = plain formulation, 1 = the kernels' fast path (multiplier-free linear layer). */
+int tmx_host_poseidon_permute(uint64_t *states, size_t n, int variant);
 
 /* ------------------------------------------------------------------------------------------------
  * Witness tables (layout: include/tmx_trace.h).  They replace the trace generation that runs inside

@@ -90,62 +90,163 @@ TMX_HD void poseidon_permute_plain(gl s[12]) {
     }
 }
 
-#if defined(__CUDACC__)
-// ---- device fast path -------------------------------------------------------------------------------------------
-// Same permutation, fewer instructions (the kernels are bound by integer issue, not memory):
+// ---- fast path (device; also compiles for the host so CPU tests can pin it against the plain formulation) -------
+// Same permutation, fewer instructions:
 //   * lanes live in [0, 2^64) (not reduced below p) inside the permutation and are canonicalised once at the end;
-//   * the round constants of round r+1 seed the MDS accumulators of round r, so no separate modular additions;
-//   * the MDS sums the 32-bit halves of the lanes in 64-bit accumulators (constants < 2^6) and folds the result with
-//     2^64 = 2^32 - 1 using the carry flag instead of compare / select sequences.
-__device__ __forceinline__ gl gl_reduce128_nc(gl lo, gl hi) {  // result in [0, 2^64), congruent mod p
-    gl t0, t2, m;
+//   * the round constants of round r+1 are added inside the linear layer of round r;
+//   * reductions fold with 2^64 = 2^32 - 1 using the carry flag instead of compare / select sequences;
+//   * the linear layer uses no integer multiplies at all (see below).
+TMX_HD gl gl_add_carry(gl a, gl b, gl* carry) {  // a + b mod 2^64, *carry = 0 / 1
+#if defined(__CUDA_ARCH__)
+    gl s, c;
+    asm("add.cc.u64 %0, %2, %3;\n\taddc.u64 %1, 0, 0;" : "=l"(s), "=l"(c) : "l"(a), "l"(b));
+    *carry = c;
+    return s;
+#else
+    const gl s = a + b;
+    *carry = (gl)(s < a);
+    return s;
+#endif
+}
+TMX_HD gl gl_sub_borrow_mask(gl a, gl b, gl* mask) {  // a - b mod 2^64, *mask = borrow ? ~0 : 0
+#if defined(__CUDA_ARCH__)
+    gl d, m;
+    asm("sub.cc.u64 %0, %2, %3;\n\tsubc.u64 %1, 0, 0;" : "=l"(d), "=l"(m) : "l"(a), "l"(b));
+    *mask = m;
+    return d;
+#else
+    *mask = (gl)0 - (gl)(a < b);
+    return a - b;
+#endif
+}
+// 64 x 64 -> 128 schoolbook on 32-bit halves: four wide multiply-adds, no duplicated partial products (the
+// compiler's a * b plus __umul64hi(a, b) pair costs five wide and two narrow multiplies)
+TMX_HD void gl_mul128(gl a, gl b, gl* lo, gl* hi) {
+    const uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), b0 = (uint32_t)b, b1 = (uint32_t)(b >> 32);
+    const gl p0 = (gl)a0 * b0;
+    const gl t = (gl)a0 * b1 + (p0 >> 32);
+    const gl u = (gl)a1 * b0 + (uint32_t)t;
+    *hi = (gl)a1 * b1 + (t >> 32) + (u >> 32);
+    *lo = (u << 32) | (uint32_t)p0;
+}
+TMX_HD void gl_sqr128(gl a, gl* lo, gl* hi) {
+    const uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32);
+    const gl p0 = (gl)a0 * a0, m = (gl)a0 * a1;
+    const gl t = m + (p0 >> 32);          // < 2^64
+    const gl u = m + (uint32_t)t;         // < 2^64
+    *hi = (gl)a1 * a1 + (t >> 32) + (u >> 32);
+    *lo = (u << 32) | (uint32_t)p0;
+}
+TMX_HD gl gl_reduce128_nc(gl lo, gl hi) {  // result in [0, 2^64), congruent mod p
+    gl m, c;
     const gl hh = hi >> 32, hl = hi & GL_EPS;
-    asm("sub.cc.u64 %0, %2, %3;\n\tsubc.u64 %1, 0, 0;" : "=l"(t0), "=l"(m) : "l"(lo), "l"(hh));  // m = borrow ? ~0 : 0
+    gl t0 = gl_sub_borrow_mask(lo, hh, &m);
     t0 -= (m & GL_EPS);
     const gl t1 = (hl << 32) - hl;
-    asm("add.cc.u64 %0, %2, %3;\n\taddc.u64 %1, 0, 0;" : "=l"(t2), "=l"(m) : "l"(t0), "l"(t1));  // m = carry
-    return t2 + ((0 - m) & GL_EPS);
+    const gl t2 = gl_add_carry(t0, t1, &c);
+    return t2 + ((0 - c) & GL_EPS);
 }
-__device__ __forceinline__ gl gl_mul_nc(gl a, gl b) { return gl_reduce128_nc(a * b, __umul64hi(a, b)); }
-__device__ __forceinline__ gl poseidon_sbox_nc(gl x) {
-    const gl x2 = gl_mul_nc(x, x), x3 = gl_mul_nc(x2, x), x4 = gl_mul_nc(x2, x2);
+TMX_HD gl gl_mul_nc(gl a, gl b) {
+    gl lo, hi;
+    gl_mul128(a, b, &lo, &hi);
+    return gl_reduce128_nc(lo, hi);
+}
+TMX_HD gl gl_sqr_nc(gl a) {
+    gl lo, hi;
+    gl_sqr128(a, &lo, &hi);
+    return gl_reduce128_nc(lo, hi);
+}
+TMX_HD gl poseidon_sbox_nc(gl x) {
+    const gl x2 = gl_sqr_nc(x), x3 = gl_mul_nc(x2, x), x4 = gl_sqr_nc(x2);
     return gl_mul_nc(x3, x4);
 }
-// out[r] = sum_i s[(i+r)%12] C[i] + 8 s[0] [r == 0] + rc[rc_base + r]
-__device__ __forceinline__ void poseidon_mds_rc(gl s[12], int rc_base) {
-    const uint32_t C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
-    uint32_t lo[12], hi[12];
+TMX_HD gl poseidon_rc_padded(int i) {  // 30 rounds of constants followed by one all-zero round
+#if defined(__CUDA_ARCH__)
+    return d_poseidon_rc[i];
+#else
+    return i < POSEIDON_ROUNDS * POSEIDON_WIDTH ? h_poseidon_rc[i] : 0;
+#endif
+}
+// ---- multiplier-free MDS ----------------------------------------------------------------------------------------
+// ncu on the IMAD formulation above: the integer-multiply pipe (fmaheavy) is 89 % busy while the ALU pipe idles at
+// 42 %, and IMAD.WIDE issues at about 1.2 warp-instructions/clk/SM against 2.0 for IADD3/LEA/LOP3/SHF
+// (tools/lab/pipe_bench.cu).  So the linear layer moves off the multiplier: every lane is cut into 22/22/20-bit
+// pieces, each piece vector goes through a 12-point cyclic convolution done by the CRT split of Z[x]/(x^12 - 1)
+// over y = x^3 (y = 1: cyclic, y = -1: negacyclic, y = i: twisted by i), where all frequency-domain constants of
+// this particular circulant are powers of two ([16,32,16], [-1,-8,2], [(2,1),(-4,-1),(16,-1)] after folding the
+// 1/4 of the inverse transform), i.e. shifts and adds only.  Arithmetic is wrapping 32-bit and exact because every
+// output piece is < 264 * 2^22 < 2^31.  (plonky2's CPU code uses the same algebraic split on 32-bit halves with
+// 64-bit intermediates; the piece width here is chosen so that nothing leaves 32-bit registers.)
+TMX_HD void mds_conv12_pieces(const uint32_t s[12], uint32_t out[12]) {
+    uint32_t u0[3], u2[3], ur[3], ui[3];
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+        const uint32_t e = s[b] + s[6 + b], o = s[3 + b] + s[9 + b];
+        u0[b] = e + o;
+        u2[b] = e - o;
+        ur[b] = s[b] - s[6 + b];
+        ui[b] = s[3 + b] - s[9 + b];
+    }
+    // y = 1 (cyclic), constants 16 * [1, 2, 1]; the factor 16 is applied when the frequencies are merged
+    const uint32_t t = u0[0] + u0[1] + u0[2];
+    const uint32_t a0[3] = {t + u0[2], t + u0[0], t + u0[1]};
+    // y = -1 (negacyclic), constants [-1, -8, 2]
+    const uint32_t a2[3] = {(u2[2] << 3) - u2[0] - (u2[1] << 1), 0u - (u2[0] << 3) - u2[1] - (u2[2] << 1),
+                            (u2[0] << 1) - (u2[1] << 3) - u2[2]};
+    // y = i, constants k0 = 2 + i, k1 = -4 - i, k2 = 16 - i; product of (kr + i ki) with (ur + i ui)
+    //   z0 = k0 u0 + i (k2 u1 + k1 u2),  z1 = k1 u0 + k0 u1 + i k2 u2,  z2 = k2 u0 + k1 u1 + k0 u2
+    const uint32_t k0r[3] = {(ur[0] << 1) - ui[0], (ur[1] << 1) - ui[1], (ur[2] << 1) - ui[2]};
+    const uint32_t k0i[3] = {(ui[0] << 1) + ur[0], (ui[1] << 1) + ur[1], (ui[2] << 1) + ur[2]};
+    const uint32_t k1r[3] = {ui[0] - (ur[0] << 2), ui[1] - (ur[1] << 2), ui[2] - (ur[2] << 2)};
+    const uint32_t k1i[3] = {0u - (ui[0] << 2) - ur[0], 0u - (ui[1] << 2) - ur[1], 0u - (ui[2] << 2) - ur[2]};
+    const uint32_t k2r[3] = {(ur[0] << 4) + ui[0], (ur[1] << 4) + ui[1], (ur[2] << 4) + ui[2]};
+    const uint32_t k2i[3] = {(ui[0] << 4) - ur[0], (ui[1] << 4) - ur[1], (ui[2] << 4) - ur[2]};
+    const uint32_t zr[3] = {k0r[0] - k2i[1] - k1i[2], k1r[0] + k0r[1] - k2i[2], k2r[0] + k1r[1] + k0r[2]};
+    const uint32_t zi[3] = {k0i[0] + k2r[1] + k1r[2], k1i[0] + k0i[1] + k2r[2], k2i[0] + k1i[1] + k0i[2]};
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+        const uint32_t p = (a0[b] << 4) + a2[b], q = (a0[b] << 4) - a2[b];
+        out[b] = p + zr[b];
+        out[3 + b] = q + zi[b];
+        out[6 + b] = p - zr[b];
+        out[9 + b] = q - zi[b];
+    }
+}
+// out[r] = sum_i s[(i+r)%12] C[i] + 8 s[0] [r == 0] + rc[rc_base + r], lanes in [0, 2^64) in and out
+TMX_HD void poseidon_mds_rc_alu(gl s[12], int rc_base) {
+    uint32_t p0[12], p1[12], p2[12], o0[12], o1[12], o2[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) {
-        lo[i] = (uint32_t)s[i];
-        hi[i] = (uint32_t)(s[i] >> 32);
+        p0[i] = (uint32_t)s[i] & 0x3FFFFFu;
+        p1[i] = (uint32_t)(s[i] >> 22) & 0x3FFFFFu;
+        p2[i] = (uint32_t)(s[i] >> 44);
     }
+    mds_conv12_pieces(p0, o0);
+    mds_conv12_pieces(p1, o1);
+    mds_conv12_pieces(p2, o2);
+    o0[0] += p0[0] << 3;
+    o1[0] += p1[0] << 3;
+    o2[0] += p2[0] << 3;
 #pragma unroll
     for (int r = 0; r < 12; r++) {
-        const gl k = d_poseidon_rc[rc_base + r];
-        uint64_t al = (uint32_t)k, ah = k >> 32;
-#pragma unroll
-        for (int i = 0; i < 12; i++) {
-            al += (uint64_t)lo[(i + r) % 12] * C[i];
-            ah += (uint64_t)hi[(i + r) % 12] * C[i];
-        }
-        if (r == 0) {
-            al += (uint64_t)lo[0] * 8u;
-            ah += (uint64_t)hi[0] * 8u;
-        }
-        // value = al + ah * 2^32 with al, ah < 2^41:  al + (ah_low32 << 32) + (ah >> 32) * (2^32 - 1)
-        const uint64_t t = al + (ah >> 32) * GL_EPS;  // < 2^42
-        uint64_t v, c;
-        asm("add.cc.u64 %0, %2, %3;\n\taddc.u64 %1, 0, 0;" : "=l"(v), "=l"(c) : "l"(t), "l"(ah << 32));
+        // value = o0 + o1 2^22 + o2 2^44 + rc  (< 2^76) = A + (o2 << 12) 2^32 + rc with A = o0 + o1 2^22 < 2^54;
+        // the words above bit 64 (H >> 32, < 2^12) fold with 2^64 = 2^32 - 1
+        const gl A = (gl)o0[r] + ((gl)o1[r] << 22);
+        const gl H = (A >> 32) + ((gl)o2[r] << 12);
+        gl c;
+        const gl t2 = gl_add_carry((H << 32) | (uint32_t)A, poseidon_rc_padded(rc_base + r), &c);
+        const gl ov = (H >> 32) + c;
+        const gl v = gl_add_carry(t2, (ov << 32) - ov, &c);
         s[r] = v + ((0 - c) & GL_EPS);
     }
 }
+
 // One loop over the 30 rounds; the 11-lane S-box block only runs in the 8 full rounds.  Keeping a single copy of
-// the MDS / S-box code matters: the previous three-loop version was instruction-cache bound (ncu: no_instruction
+// the linear layer / S-box code matters: a three-loop version was instruction-cache bound (ncu: no_instruction
 // was the dominant stall with ~59 KB of straight-line code).
-__device__ __forceinline__ void poseidon_permute_dev(gl s[12]) {
+TMX_HD void poseidon_permute_fast(gl s[12]) {
 #pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = gl_add(s[i], d_poseidon_rc[i]);  // round 0 constants (inputs are canonical)
+    for (int i = 0; i < 12; i++) s[i] = gl_add(s[i], poseidon_rc_padded(i));  // round 0 constants (inputs are canonical)
 #pragma unroll 1
     for (int r = 0; r < POSEIDON_ROUNDS; r++) {
         s[0] = poseidon_sbox_nc(s[0]);
@@ -153,16 +254,15 @@ __device__ __forceinline__ void poseidon_permute_dev(gl s[12]) {
 #pragma unroll
             for (int i = 1; i < 12; i++) s[i] = poseidon_sbox_nc(s[i]);
         }
-        poseidon_mds_rc(s, 12 * (r + 1));  // + constants of round r + 1 (zeros after the last round)
+        poseidon_mds_rc_alu(s, 12 * (r + 1));  // + constants of round r + 1 (zeros after the last round)
     }
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = gl_canon(s[i]);
 }
-#endif
 
 TMX_HD void poseidon_permute(gl s[12]) {
 #if defined(__CUDA_ARCH__)
-    poseidon_permute_dev(s);
+    poseidon_permute_fast(s);
 #else
     poseidon_permute_plain(s);
 #endif

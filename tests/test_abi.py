@@ -46,3 +46,28 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 m = bad.search(txt)
                 assert m is None, (os.path.join(dirpath, f), m.group(0))
+
+
+def test_device_poseidon_fast_path_matches_plain_and_oracle_on_host():
+    """The kernels' permutation arithmetic (multiplier-free linear layer, unreduced lanes) compiled for the host
+    equals the plain formulation and the oracle on random, boundary and all-ones states."""
+    import ctypes
+
+    import numpy as np
+
+    import oracle
+    import tendermintx_b200 as tmx
+
+    P = 2**64 - 2**32 + 1
+    rng = np.random.default_rng(7)
+    states = [rng.integers(0, P, size=12, dtype=np.uint64) for _ in range(64)]
+    states += [np.zeros(12, dtype=np.uint64), np.full(12, P - 1, dtype=np.uint64), np.arange(12, dtype=np.uint64),
+               np.full(12, 2**32 - 1, dtype=np.uint64), np.full(12, 2**32, dtype=np.uint64)]
+    a = np.stack(states).copy()
+    b = a.copy()
+    lib = tmx.lib()
+    assert lib.tmx_host_poseidon_permute(a.ctypes.data_as(ctypes.c_void_p), len(states), 0) == 0
+    assert lib.tmx_host_poseidon_permute(b.ctypes.data_as(ctypes.c_void_p), len(states), 1) == 0
+    assert np.array_equal(a, b)
+    for i, s in enumerate(states):
+        assert np.array_equal(b[i], oracle.poseidon_permute(s))
