@@ -22,10 +22,17 @@ void poseidon_generate_constants();
 #if defined(__CUDACC__)
 // 30 rounds of constants plus one all-zero round (the fast path always adds "the next round's" constants)
 static __constant__ gl d_poseidon_rc[(POSEIDON_ROUNDS + 1) * POSEIDON_WIDTH];
+// the same constants cut into 22/22/20-bit pieces (x, y, z; w unused) for lanes that stay in piece form
+static __constant__ uint4 d_poseidon_rcp[(POSEIDON_ROUNDS + 1) * POSEIDON_WIDTH];
 static inline cudaError_t poseidon_upload_constants_tu() {
     poseidon_generate_constants();
     gl padded[(POSEIDON_ROUNDS + 1) * POSEIDON_WIDTH] = {0};
+    uint4 pieces[(POSEIDON_ROUNDS + 1) * POSEIDON_WIDTH];
     for (int i = 0; i < POSEIDON_ROUNDS * POSEIDON_WIDTH; i++) padded[i] = h_poseidon_rc[i];
+    for (int i = 0; i < (POSEIDON_ROUNDS + 1) * POSEIDON_WIDTH; i++)
+        pieces[i] = make_uint4((uint32_t)padded[i] & 0x3FFFFFu, (uint32_t)(padded[i] >> 22) & 0x3FFFFFu, (uint32_t)(padded[i] >> 44), 0u);
+    cudaError_t e = cudaMemcpyToSymbol(d_poseidon_rcp, pieces, sizeof(pieces));
+    if (e != cudaSuccess) return e;
     return cudaMemcpyToSymbol(d_poseidon_rc, padded, sizeof(padded));
 }
 #endif
@@ -119,23 +126,17 @@ TMX_HD gl gl_sub_borrow_mask(gl a, gl b, gl* mask) {  // a - b mod 2^64, *mask =
     return a - b;
 #endif
 }
-// 64 x 64 -> 128 schoolbook on 32-bit halves: four wide multiply-adds, no duplicated partial products (the
-// compiler's a * b plus __umul64hi(a, b) pair costs five wide and two narrow multiplies)
+// 64 x 64 -> 128: one mul.lo / mul.hi pair lets ptxas share the partial products (three IMAD.WIDE, one
+// IMAD.WIDE.X and four carry instructions); a * b next to __umul64hi(a, b) in C costs five wide and two narrow
+// multiplies, and a hand-written schoolbook on 32-bit halves pays for zero-extended register pairs.
 TMX_HD void gl_mul128(gl a, gl b, gl* lo, gl* hi) {
-    const uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), b0 = (uint32_t)b, b1 = (uint32_t)(b >> 32);
-    const gl p0 = (gl)a0 * b0;
-    const gl t = (gl)a0 * b1 + (p0 >> 32);
-    const gl u = (gl)a1 * b0 + (uint32_t)t;
-    *hi = (gl)a1 * b1 + (t >> 32) + (u >> 32);
-    *lo = (u << 32) | (uint32_t)p0;
-}
-TMX_HD void gl_sqr128(gl a, gl* lo, gl* hi) {
-    const uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32);
-    const gl p0 = (gl)a0 * a0, m = (gl)a0 * a1;
-    const gl t = m + (p0 >> 32);          // < 2^64
-    const gl u = m + (uint32_t)t;         // < 2^64
-    *hi = (gl)a1 * a1 + (t >> 32) + (u >> 32);
-    *lo = (u << 32) | (uint32_t)p0;
+#if defined(__CUDA_ARCH__)
+    asm("mul.lo.u64 %0, %2, %3;\n\tmul.hi.u64 %1, %2, %3;" : "=l"(*lo), "=l"(*hi) : "l"(a), "l"(b));
+#else
+    const unsigned __int128 m = (unsigned __int128)a * b;
+    *lo = (gl)m;
+    *hi = (gl)(m >> 64);
+#endif
 }
 TMX_HD gl gl_reduce128_nc(gl lo, gl hi) {  // result in [0, 2^64), congruent mod p
     gl m, c;
@@ -151,11 +152,7 @@ TMX_HD gl gl_mul_nc(gl a, gl b) {
     gl_mul128(a, b, &lo, &hi);
     return gl_reduce128_nc(lo, hi);
 }
-TMX_HD gl gl_sqr_nc(gl a) {
-    gl lo, hi;
-    gl_sqr128(a, &lo, &hi);
-    return gl_reduce128_nc(lo, hi);
-}
+TMX_HD gl gl_sqr_nc(gl a) { return gl_mul_nc(a, a); }
 TMX_HD gl poseidon_sbox_nc(gl x) {
     const gl x2 = gl_sqr_nc(x), x3 = gl_mul_nc(x2, x), x4 = gl_sqr_nc(x2);
     return gl_mul_nc(x3, x4);
@@ -212,52 +209,92 @@ TMX_HD void mds_conv12_pieces(const uint32_t s[12], uint32_t out[12]) {
         out[9 + b] = q - zi[b];
     }
 }
-// out[r] = sum_i s[(i+r)%12] C[i] + 8 s[0] [r == 0] + rc[rc_base + r], lanes in [0, 2^64) in and out
-TMX_HD void poseidon_mds_rc_alu(gl s[12], int rc_base) {
-    uint32_t p0[12], p1[12], p2[12], o0[12], o1[12], o2[12];
-#pragma unroll
-    for (int i = 0; i < 12; i++) {
-        p0[i] = (uint32_t)s[i] & 0x3FFFFFu;
-        p1[i] = (uint32_t)(s[i] >> 22) & 0x3FFFFFu;
-        p2[i] = (uint32_t)(s[i] >> 44);
-    }
-    mds_conv12_pieces(p0, o0);
-    mds_conv12_pieces(p1, o1);
-    mds_conv12_pieces(p2, o2);
-    o0[0] += p0[0] << 3;
-    o1[0] += p1[0] << 3;
-    o2[0] += p2[0] << 3;
-#pragma unroll
-    for (int r = 0; r < 12; r++) {
-        // value = o0 + o1 2^22 + o2 2^44 + rc  (< 2^76) = A + (o2 << 12) 2^32 + rc with A = o0 + o1 2^22 < 2^54;
-        // the words above bit 64 (H >> 32, < 2^12) fold with 2^64 = 2^32 - 1
-        const gl A = (gl)o0[r] + ((gl)o1[r] << 22);
-        const gl H = (A >> 32) + ((gl)o2[r] << 12);
-        gl c;
-        const gl t2 = gl_add_carry((H << 32) | (uint32_t)A, poseidon_rc_padded(rc_base + r), &c);
-        const gl ov = (H >> 32) + c;
-        const gl v = gl_add_carry(t2, (ov << 32) - ov, &c);
-        s[r] = v + ((0 - c) & GL_EPS);
-    }
+// Lanes that only pass through linear layers (1..11 during the 22 partial rounds) never leave piece form:
+//   lane = p0 + p1 2^22 + p2 2^44 (mod p),  p2 in [0, 2^20),  |p0|, |p1| < 2^22 + 2^19  (two's complement),
+// so a partial round splits and recombines one lane instead of twelve.  All piece arithmetic is signed wrapping
+// 32-bit with floor shifts; outputs of the convolution stay below 264 * (2^22 + 2^19) < 2^31 in magnitude.
+TMX_HD void poseidon_split(gl x, uint32_t* p0, uint32_t* p1, uint32_t* p2) {
+    *p0 = (uint32_t)x & 0x3FFFFFu;
+    *p1 = (uint32_t)(x >> 22) & 0x3FFFFFu;
+    *p2 = (uint32_t)(x >> 44);
+}
+// o0 + o1 2^22 + o2 2^44 + rc (0 <= value < 2^73, the o's signed) -> [0, 2^64), congruent mod p
+TMX_HD gl poseidon_recombine(uint32_t o0, uint32_t o1, uint32_t o2, gl rc) {
+    const int64_t A = (int64_t)(int32_t)o0 + ((int64_t)(int32_t)o1 << 22);
+    const gl H = (gl)((A >> 32) + ((int64_t)(int32_t)o2 << 12));  // >= 0: the words above bit 32
+    gl c;
+    const gl t = gl_add_carry((H << 32) | (uint32_t)A, rc, &c);
+    const gl ov = (H >> 32) + c;  // weight 2^64 = 2^32 - 1, ov < 2^12
+    const gl v = gl_add_carry(t, (ov << 32) - ov, &c);
+    return v + ((0 - c) & GL_EPS);
+}
+// the same value back in piece form (carry propagation; the part above bit 64 re-enters as ov 2^32 - ov)
+TMX_HD void poseidon_normalize(uint32_t o0, uint32_t o1, uint32_t o2, int rc_index, uint32_t* p0, uint32_t* p1, uint32_t* p2) {
+#if defined(__CUDA_ARCH__)
+    const uint4 k = d_poseidon_rcp[rc_index];
+    const uint32_t k0 = k.x, k1 = k.y, k2 = k.z;
+#else
+    const gl kk = rc_index < POSEIDON_ROUNDS * POSEIDON_WIDTH ? h_poseidon_rc[rc_index] : 0;
+    const uint32_t k0 = (uint32_t)kk & 0x3FFFFFu, k1 = (uint32_t)(kk >> 22) & 0x3FFFFFu, k2 = (uint32_t)(kk >> 44);
+#endif
+    const int32_t a0 = (int32_t)(o0 + k0);
+    const int32_t a1 = (int32_t)(o1 + k1) + (a0 >> 22);
+    const int32_t a2 = (int32_t)(o2 + k2) + (a1 >> 22);
+    const int32_t ov = a2 >> 20;
+    *p0 = (uint32_t)((a0 & 0x3FFFFF) - ov);
+    *p1 = (uint32_t)((a1 & 0x3FFFFF) + ov * 1024);
+    *p2 = (uint32_t)(a2 & 0xFFFFF);
 }
 
-// One loop over the 30 rounds; the 11-lane S-box block only runs in the 8 full rounds.  Keeping a single copy of
-// the linear layer / S-box code matters: a three-loop version was instruction-cache bound (ncu: no_instruction
-// was the dominant stall with ~59 KB of straight-line code).
+// One loop over the 30 rounds with a single copy of the S-box and convolution code (a three-loop version was
+// instruction-cache bound: ncu showed no_instruction as the dominant stall with ~59 KB of straight-line code).
+// Round r: S-boxes, then the linear layer, then the constants of round r + 1 (zeros after the last round).
+// The loop carries ONE register image of the state, w0/w1/w2[12]: in word form w0 = low word, w1 = high word
+// (w2 unused); in piece form w0/w1/w2 = p0/p1/p2.  (Carrying words and pieces side by side doubles the register
+// count and halves the occupancy.)
 TMX_HD void poseidon_permute_fast(gl s[12]) {
+    uint32_t w0[12], w1[12], w2[12], o0[12], o1[12], o2[12];
 #pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = gl_add(s[i], poseidon_rc_padded(i));  // round 0 constants (inputs are canonical)
+    for (int i = 0; i < 12; i++) {
+        const gl x = gl_add(s[i], poseidon_rc_padded(i));  // round 0 constants (inputs are canonical)
+        w0[i] = (uint32_t)x;
+        w1[i] = (uint32_t)(x >> 32);
+        w2[i] = 0;
+    }
 #pragma unroll 1
     for (int r = 0; r < POSEIDON_ROUNDS; r++) {
-        s[0] = poseidon_sbox_nc(s[0]);
-        if (r < POSEIDON_HALF_FULL || r >= POSEIDON_HALF_FULL + POSEIDON_PARTIAL) {
+        const bool full = r < POSEIDON_HALF_FULL || r >= POSEIDON_HALF_FULL + POSEIDON_PARTIAL;
+        // lanes 1..11 are needed as 64-bit words again when the next round is full (or the permutation ends)
+        const bool words_out = r + 1 < POSEIDON_HALF_FULL || r + 1 >= POSEIDON_HALF_FULL + POSEIDON_PARTIAL;
+        poseidon_split(poseidon_sbox_nc(((gl)w1[0] << 32) | w0[0]), &w0[0], &w1[0], &w2[0]);
+        if (full) {
 #pragma unroll
-            for (int i = 1; i < 12; i++) s[i] = poseidon_sbox_nc(s[i]);
+            for (int i = 1; i < 12; i++) poseidon_split(poseidon_sbox_nc(((gl)w1[i] << 32) | w0[i]), &w0[i], &w1[i], &w2[i]);
         }
-        poseidon_mds_rc_alu(s, 12 * (r + 1));  // + constants of round r + 1 (zeros after the last round)
+        mds_conv12_pieces(w0, o0);
+        mds_conv12_pieces(w1, o1);
+        mds_conv12_pieces(w2, o2);
+        o0[0] += w0[0] << 3;  // + diag(8, 0, ..., 0)
+        o1[0] += w1[0] << 3;
+        o2[0] += w2[0] << 3;
+        const int rc_base = 12 * (r + 1);
+        const gl x0 = poseidon_recombine(o0[0], o1[0], o2[0], poseidon_rc_padded(rc_base));
+        w0[0] = (uint32_t)x0;
+        w1[0] = (uint32_t)(x0 >> 32);
+        if (words_out) {
+#pragma unroll
+            for (int i = 1; i < 12; i++) {
+                const gl x = poseidon_recombine(o0[i], o1[i], o2[i], poseidon_rc_padded(rc_base + i));
+                w0[i] = (uint32_t)x;
+                w1[i] = (uint32_t)(x >> 32);
+            }
+        } else {
+#pragma unroll
+            for (int i = 1; i < 12; i++) poseidon_normalize(o0[i], o1[i], o2[i], rc_base + i, &w0[i], &w1[i], &w2[i]);
+        }
     }
 #pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = gl_canon(s[i]);
+    for (int i = 0; i < 12; i++) s[i] = gl_canon(((gl)w1[i] << 32) | w0[i]);
 }
 
 TMX_HD void poseidon_permute(gl s[12]) {
