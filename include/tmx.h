@@ -77,8 +77,14 @@ int tmx_poseidon_merkle(tmx_ctx *ctx, const uint64_t *d_cols, size_t n_cols, uns
 /* Poseidon permutation of n independent 12-element states (known-answer tests). */
 int tmx_poseidon_permute(tmx_ctx *ctx, uint64_t *d_states, size_t n, void *stream);
 /* Host-side self check (no GPU): the device permutation's arithmetic compiled for the CPU.
- * variant 0 = plain formulation, 1 = the kernels' fast path (multiplier-free linear layer). */
+ * variant 0 = plain formulation, 1 = the kernels' fast path (multiplier-free linear layer),
+ * 2 = the formulation the host transcript uses. */
 int tmx_host_poseidon_permute(uint64_t *states, size_t n, int variant);
+/* Host-side self check (no GPU) of the quotient kernel's factored Ed25519 constraint evaluation against the literal
+ * fold of the AIR on one (row, next row) pair of ED_COLS cells each:
+ * out = {literal(alpha[0]), literal(alpha[1]), factored(alpha[0]), factored(alpha[1])}. */
+int tmx_host_air_ed25519(const uint64_t *row_l, const uint64_t *row_n, uint64_t notend, const uint64_t alpha[2],
+                         uint64_t out[4]);
 
 /* ------------------------------------------------------------------------------------------------
  * Witness tables (layout: include/tmx_trace.h).  They replace the trace generation that runs inside

@@ -49,6 +49,7 @@ def load():
         "tmx_poseidon_merkle": (i32, [vp, u64p, sz, u32, u32, u64p, vp]),
         "tmx_poseidon_permute": (i32, [vp, u64p, sz, vp]),
         "tmx_host_poseidon_permute": (i32, [u64p, sz, i32]),
+        "tmx_host_air_ed25519": (i32, [u64p, u64p, c.c_uint64, u64p, u64p]),
         "tmx_trace_dims": (i32, [u32, u32, c.POINTER(sz)]),
         "tmx_witness_aux_bytes": (sz, [u32]),
         "tmx_sha256_trace": (i32, [vp, vp, u32, u32, u64p, vp, vp]),
@@ -84,7 +85,7 @@ def load():
 EXPORTED_SYMBOLS = [
     "tmx_last_error", "tmx_version", "tmx_ctx_create", "tmx_ctx_destroy", "tmx_ctx_sync",
     "tmx_ctx_stream", "tmx_ctx_launch_count", "tmx_ntt", "tmx_lde", "tmx_merkle_digest_count", "tmx_poseidon_merkle",
-    "tmx_poseidon_permute", "tmx_host_poseidon_permute", "tmx_trace_dims", "tmx_witness_aux_bytes", "tmx_sha256_trace", "tmx_ed25519_trace",
+    "tmx_poseidon_permute", "tmx_host_poseidon_permute", "tmx_host_air_ed25519", "tmx_trace_dims", "tmx_witness_aux_bytes", "tmx_sha256_trace", "tmx_ed25519_trace",
     "tmx_witness_generate", "tmx_quotient", "tmx_pow_grind", "tmx_circuit_build", "tmx_circuit_free", "tmx_circuit_digest",
     "tmx_circuit_save", "tmx_circuit_load", "tmx_prove", "tmx_last_check", "tmx_circuit_set_inputs", "tmx_header_hash_from_fixture", "tmx_skip_inputs_from_fixture",
     "tmx_step_inputs_from_fixture", "tmx_prove_fixture", "tmx_proof_size", "tmx_proof_bytes",

@@ -73,6 +73,65 @@ TMX_HD gl gl_root_of_unity(unsigned k) {
     return r;
 }
 
+// ---- lazily reduced arithmetic: values in [0, 2^64), congruent mod p (used inside Poseidon and the Horner chains
+// of the quotient kernel; canonicalise with gl_canon before a value leaves the kernel) ----
+TMX_HD gl gl_add_carry(gl a, gl b, gl* carry) {  // a + b mod 2^64, *carry = 0 / 1
+#if defined(__CUDA_ARCH__)
+    gl s, c;
+    asm("add.cc.u64 %0, %2, %3;\n\taddc.u64 %1, 0, 0;" : "=l"(s), "=l"(c) : "l"(a), "l"(b));
+    *carry = c;
+    return s;
+#else
+    const gl s = a + b;
+    *carry = (gl)(s < a);
+    return s;
+#endif
+}
+TMX_HD gl gl_sub_borrow_mask(gl a, gl b, gl* mask) {  // a - b mod 2^64, *mask = borrow ? ~0 : 0
+#if defined(__CUDA_ARCH__)
+    gl d, m;
+    asm("sub.cc.u64 %0, %2, %3;\n\tsubc.u64 %1, 0, 0;" : "=l"(d), "=l"(m) : "l"(a), "l"(b));
+    *mask = m;
+    return d;
+#else
+    *mask = (gl)0 - (gl)(a < b);
+    return a - b;
+#endif
+}
+// 64 x 64 -> 128: one mul.lo / mul.hi pair lets ptxas share the partial products (three IMAD.WIDE, one
+// IMAD.WIDE.X and four carry instructions); a * b next to __umul64hi(a, b) in C costs five wide and two narrow
+// multiplies, and a hand-written schoolbook on 32-bit halves pays for zero-extended register pairs.
+TMX_HD void gl_mul128(gl a, gl b, gl* lo, gl* hi) {
+#if defined(__CUDA_ARCH__)
+    asm("mul.lo.u64 %0, %2, %3;\n\tmul.hi.u64 %1, %2, %3;" : "=l"(*lo), "=l"(*hi) : "l"(a), "l"(b));
+#else
+    const unsigned __int128 m = (unsigned __int128)a * b;
+    *lo = (gl)m;
+    *hi = (gl)(m >> 64);
+#endif
+}
+TMX_HD gl gl_reduce128_nc(gl lo, gl hi) {  // result in [0, 2^64), congruent mod p
+    gl m, c;
+    const gl hh = hi >> 32, hl = hi & GL_EPS;
+    gl t0 = gl_sub_borrow_mask(lo, hh, &m);
+    t0 -= (m & GL_EPS);
+    const gl t1 = (hl << 32) - hl;
+    const gl t2 = gl_add_carry(t0, t1, &c);
+    return t2 + ((0 - c) & GL_EPS);
+}
+TMX_HD gl gl_mul_nc(gl a, gl b) {
+    gl lo, hi;
+    gl_mul128(a, b, &lo, &hi);
+    return gl_reduce128_nc(lo, hi);
+}
+// acc * a + x with one reduction (the 128-bit product cannot overflow when x is added: hi <= 2^64 - 2)
+TMX_HD gl gl_mac_nc(gl acc, gl a, gl x) {
+    gl lo, hi, c;
+    gl_mul128(acc, a, &lo, &hi);
+    lo = gl_add_carry(lo, x, &c);
+    return gl_reduce128_nc(lo, hi + c);
+}
+
 struct gl2 {
     gl a0, a1;
 };

@@ -193,13 +193,14 @@ extern "C" int tmx_pow_grind(tmx_ctx* ctx, const uint64_t state[12], int pos, un
 }
 
 // The arithmetic of the device fast path (multiplier-free linear layer, unreduced lanes) compiled for the HOST, so
-// the CPU test suite can pin it against the plain formulation without a GPU.  variant 0 = plain, 1 = fast path.
+// the CPU test suite can pin it against the plain formulation without a GPU.  variant 0 = plain, 1 = device fast path, 2 = the host transcript's formulation.
 extern "C" int tmx_host_poseidon_permute(uint64_t* states, size_t n, int variant) {
-    if (!states || variant < 0 || variant > 1) return fail(TMX_E_INPUT, "tmx_host_poseidon_permute: bad arguments");
+    if (!states || variant < 0 || variant > 2) return fail(TMX_E_INPUT, "tmx_host_poseidon_permute: bad arguments");
     poseidon_generate_constants();
     for (size_t i = 0; i < n; i++) {
         if (variant == 0) poseidon_permute_plain(states + 12 * i);
-        else poseidon_permute_fast(states + 12 * i);
+        else if (variant == 1) poseidon_permute_fast(states + 12 * i);
+        else poseidon_permute_host(states + 12 * i);
     }
     return TMX_OK;
 }

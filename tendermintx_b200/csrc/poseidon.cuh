@@ -103,55 +103,6 @@ TMX_HD void poseidon_permute_plain(gl s[12]) {
 //   * the round constants of round r+1 are added inside the linear layer of round r;
 //   * reductions fold with 2^64 = 2^32 - 1 using the carry flag instead of compare / select sequences;
 //   * the linear layer uses no integer multiplies at all (see below).
-TMX_HD gl gl_add_carry(gl a, gl b, gl* carry) {  // a + b mod 2^64, *carry = 0 / 1
-#if defined(__CUDA_ARCH__)
-    gl s, c;
-    asm("add.cc.u64 %0, %2, %3;\n\taddc.u64 %1, 0, 0;" : "=l"(s), "=l"(c) : "l"(a), "l"(b));
-    *carry = c;
-    return s;
-#else
-    const gl s = a + b;
-    *carry = (gl)(s < a);
-    return s;
-#endif
-}
-TMX_HD gl gl_sub_borrow_mask(gl a, gl b, gl* mask) {  // a - b mod 2^64, *mask = borrow ? ~0 : 0
-#if defined(__CUDA_ARCH__)
-    gl d, m;
-    asm("sub.cc.u64 %0, %2, %3;\n\tsubc.u64 %1, 0, 0;" : "=l"(d), "=l"(m) : "l"(a), "l"(b));
-    *mask = m;
-    return d;
-#else
-    *mask = (gl)0 - (gl)(a < b);
-    return a - b;
-#endif
-}
-// 64 x 64 -> 128: one mul.lo / mul.hi pair lets ptxas share the partial products (three IMAD.WIDE, one
-// IMAD.WIDE.X and four carry instructions); a * b next to __umul64hi(a, b) in C costs five wide and two narrow
-// multiplies, and a hand-written schoolbook on 32-bit halves pays for zero-extended register pairs.
-TMX_HD void gl_mul128(gl a, gl b, gl* lo, gl* hi) {
-#if defined(__CUDA_ARCH__)
-    asm("mul.lo.u64 %0, %2, %3;\n\tmul.hi.u64 %1, %2, %3;" : "=l"(*lo), "=l"(*hi) : "l"(a), "l"(b));
-#else
-    const unsigned __int128 m = (unsigned __int128)a * b;
-    *lo = (gl)m;
-    *hi = (gl)(m >> 64);
-#endif
-}
-TMX_HD gl gl_reduce128_nc(gl lo, gl hi) {  // result in [0, 2^64), congruent mod p
-    gl m, c;
-    const gl hh = hi >> 32, hl = hi & GL_EPS;
-    gl t0 = gl_sub_borrow_mask(lo, hh, &m);
-    t0 -= (m & GL_EPS);
-    const gl t1 = (hl << 32) - hl;
-    const gl t2 = gl_add_carry(t0, t1, &c);
-    return t2 + ((0 - c) & GL_EPS);
-}
-TMX_HD gl gl_mul_nc(gl a, gl b) {
-    gl lo, hi;
-    gl_mul128(a, b, &lo, &hi);
-    return gl_reduce128_nc(lo, hi);
-}
 TMX_HD gl gl_sqr_nc(gl a) { return gl_mul_nc(a, a); }
 TMX_HD gl poseidon_sbox_nc(gl x) {
     const gl x2 = gl_sqr_nc(x), x3 = gl_mul_nc(x2, x), x4 = gl_sqr_nc(x2);
@@ -297,11 +248,32 @@ TMX_HD void poseidon_permute_fast(gl s[12]) {
     for (int i = 0; i < 12; i++) s[i] = gl_canon(((gl)w1[i] << 32) | w0[i]);
 }
 
+// Host formulation for the transcript (the Fiat-Shamir challenger absorbs every opening on the CPU while the GPU
+// waits): 128-bit accumulators for the linear layer, no modulo in the inner loops.
+inline void poseidon_permute_host(gl s[12]) {
+    static const uint64_t C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+    gl t[24];
+    for (int r = 0; r < POSEIDON_ROUNDS; r++) {
+        const gl* rc = h_poseidon_rc + 12 * r;
+        for (int i = 0; i < 12; i++) t[i] = gl_add(s[i], rc[i]);
+        if (r < POSEIDON_HALF_FULL || r >= POSEIDON_HALF_FULL + POSEIDON_PARTIAL) {
+            for (int i = 0; i < 12; i++) t[i] = poseidon_sbox(t[i]);
+        } else
+            t[0] = poseidon_sbox(t[0]);
+        for (int i = 0; i < 12; i++) t[12 + i] = t[i];
+        for (int k = 0; k < 12; k++) {
+            unsigned __int128 acc = k == 0 ? (unsigned __int128)t[0] * 8u : 0;
+            for (int i = 0; i < 12; i++) acc += (unsigned __int128)t[k + i] * C[i];
+            s[k] = gl_reduce128((gl)acc, (gl)(acc >> 64));
+        }
+    }
+}
+
 TMX_HD void poseidon_permute(gl s[12]) {
 #if defined(__CUDA_ARCH__)
     poseidon_permute_fast(s);
 #else
-    poseidon_permute_plain(s);
+    poseidon_permute_host(s);
 #endif
 }
 

@@ -9,6 +9,7 @@
 // polynomial is formed pointwise on the LDE instead of dividing coefficient vectors, and FRI layers are folded by
 // a 16-point inverse NTT per coset instead of folding coefficients and re-running a coset FFT.
 #include "stark.cuh"
+#include "air_ed_fast.cuh"
 #include <cstring>
 #include <cstdio>
 #include <cstdlib>
@@ -72,6 +73,30 @@ __global__ void __launch_bounds__(128) quotient_kernel(QuotientArgs a) {
     const gl zi = a.zh_inv[j & ((1u << a.rate_bits) - 1)];
     a.out[j] = gl_mul(acc.acc0.v, zi);
     a.out[a.m + j] = gl_mul(acc.acc1.v, zi);
+}
+
+// Ed25519 table: factored evaluation (air_ed_fast.cuh), one thread per (LDE point, challenge); the two challenge
+// halves of a CTA read the same cells, so the second read is an L1 hit.
+struct QuotientEdArgs {
+    const gl* lde;
+    size_t m;
+    unsigned log_m, rate_bits;
+    const gl* pertab;  // [1][2P]: not_block_end
+    int P;
+    EdFastConsts k[2];
+    gl zh_inv[1 << 3];
+    gl* out;
+};
+__global__ void __launch_bounds__(128) quotient_ed25519_kernel(QuotientEdArgs a) {
+    const int which = threadIdx.x >> 6;
+    const size_t p = (size_t)blockIdx.x * 64 + (threadIdx.x & 63);
+    if (p >= a.m) return;
+    const uint32_t j = bitrev32((uint32_t)p, a.log_m);
+    const size_t pn = next_row_position(p, a.log_m - a.rate_bits);
+    LdeRow l{a.lde + p, a.m}, n{a.lde + pn, a.m};
+    const gl notend = a.pertab[j & (2 * a.P - 1)];
+    const gl v = ed25519_constraints_fast(l, n, notend, a.k[which]);
+    a.out[(size_t)which * a.m + j] = gl_mul(v, a.zh_inv[j & ((1u << a.rate_bits) - 1)]);
 }
 
 // after the inverse NTT of size m = 2n the buffer holds q_i * 7^i; chunk k of challenge c is coefficients
@@ -210,7 +235,17 @@ static int launch_quotient(tmx_ctx* ctx, int table, const QuotientArgs& qa, cuda
     const unsigned qblocks = (unsigned)((qa.m + 127) / 128);
     if (table == AIR_SHA256) quotient_kernel<AIR_SHA256><<<qblocks, 128, 0, st>>>(qa);
     else if (table == AIR_SHA512) quotient_kernel<AIR_SHA512><<<qblocks, 128, 0, st>>>(qa);
-    else quotient_kernel<AIR_ED25519><<<qblocks, 128, 0, st>>>(qa);
+    else if (getenv("TMX_QUOTIENT_LITERAL")) quotient_kernel<AIR_ED25519><<<qblocks, 128, 0, st>>>(qa);  // debugging aid
+    else {
+        QuotientEdArgs ea;
+        memset(&ea, 0, sizeof ea);
+        ea.lde = qa.lde; ea.m = qa.m; ea.log_m = qa.log_m; ea.rate_bits = qa.rate_bits; ea.pertab = qa.pertab; ea.P = qa.P;
+        ea.k[0] = ed_fast_consts(qa.alpha[0]);
+        ea.k[1] = ed_fast_consts(qa.alpha[1]);
+        memcpy(ea.zh_inv, qa.zh_inv, sizeof ea.zh_inv);
+        ea.out = qa.out;
+        quotient_ed25519_kernel<<<(unsigned)((qa.m + 63) / 64), 128, 0, st>>>(ea);
+    }
     ctx->launches++;
     TMX_CUDA(cudaGetLastError());
     return TMX_OK;
@@ -561,6 +596,28 @@ void TableProver::release() {
 }  // namespace tmx
 
 using namespace tmx;
+
+// Host-side self check (no GPU): the literal constraint fold of air_ed25519() and the factored evaluation used by the
+// quotient kernel on one (local row, next row) pair.  out = {literal(alpha0), literal(alpha1), fast(alpha0), fast(alpha1)}.
+struct HostRow {
+    const gl* p;
+    FB operator[](int c) const { return FB::mk(p[c]); }
+};
+extern "C" int tmx_host_air_ed25519(const uint64_t* row_l, const uint64_t* row_n, uint64_t notend, const uint64_t alpha[2],
+                                    uint64_t out[4]) {
+    if (!row_l || !row_n || !alpha || !out) return fail(TMX_E_INPUT, "tmx_host_air_ed25519: NULL argument");
+    HostRow l{row_l}, n{row_n};
+    const FB per[1] = {FB::mk(notend)};
+    ConstraintAcc<FB> acc;
+    acc.acc0 = FB::c(0); acc.acc1 = FB::c(0);
+    acc.alpha0 = FB::mk(alpha[0]); acc.alpha1 = FB::mk(alpha[1]);
+    air_ed25519<FB>(l, n, per, acc);
+    out[0] = acc.acc0.v;
+    out[1] = acc.acc1.v;
+    out[2] = ed25519_constraints_fast(l, n, notend, ed_fast_consts(alpha[0]));
+    out[3] = ed25519_constraints_fast(l, n, notend, ed_fast_consts(alpha[1]));
+    return TMX_OK;
+}
 
 // K5 as a kernel-level entry point (parity tests, ncu): constraint quotient of one table on its LDE coset.
 extern "C" int tmx_quotient(tmx_ctx* ctx, int table, const uint64_t* d_lde, unsigned log_n, const uint64_t alpha[2],

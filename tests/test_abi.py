@@ -69,5 +69,35 @@ def test_device_poseidon_fast_path_matches_plain_and_oracle_on_host():
     assert lib.tmx_host_poseidon_permute(a.ctypes.data_as(ctypes.c_void_p), len(states), 0) == 0
     assert lib.tmx_host_poseidon_permute(b.ctypes.data_as(ctypes.c_void_p), len(states), 1) == 0
     assert np.array_equal(a, b)
+    c = np.stack(states).copy()
+    assert lib.tmx_host_poseidon_permute(c.ctypes.data_as(ctypes.c_void_p), len(states), 2) == 0  # host transcript formulation
+    assert np.array_equal(a, c)
     for i, s in enumerate(states):
         assert np.array_equal(b[i], oracle.poseidon_permute(s))
+
+
+def test_factored_ed25519_constraint_fold_equals_literal_fold_on_host():
+    """K5 fast path: the factored evaluation of the Ed25519 table's constraint combination is the same field element
+    as the literal Horner fold of air_ed25519(), on random cells (the identity is polynomial, not witness-dependent),
+    on small 16-bit cells, and for notend = 0 / 1 / random."""
+    import ctypes
+
+    import numpy as np
+
+    import tendermintx_b200 as tmx
+
+    P = 2**64 - 2**32 + 1
+    ED_COLS = 1217
+    rng = np.random.default_rng(11)
+    lib = tmx.lib()
+    for trial in range(6):
+        hi = P if trial % 2 == 0 else 1 << 16
+        l = rng.integers(0, hi, size=ED_COLS, dtype=np.uint64)
+        n = rng.integers(0, hi, size=ED_COLS, dtype=np.uint64)
+        notend = [0, 1, int(rng.integers(0, P, dtype=np.uint64))][trial % 3]
+        alpha = rng.integers(0, P, size=2, dtype=np.uint64)
+        out = np.zeros(4, dtype=np.uint64)
+        vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        assert lib.tmx_host_air_ed25519(vp(l), vp(n), notend, vp(alpha), vp(out)) == 0
+        assert out[0] == out[2] and out[1] == out[3], (trial, out)
+        assert out[0] != 0
