@@ -78,26 +78,15 @@ static int upload(tmx_ctx* ctx, const std::vector<gl>& h, gl** out) {
     return TMX_OK;
 }
 
-// base^e for e < 2^log_size, optionally every entry of the hi table scaled by `hi_scale`
-static int build_pow_table(tmx_ctx* ctx, gl base, unsigned log_size, gl hi_scale, PowTable* t) {
-    t->log_size = log_size;
-    t->klo = (log_size + 1) / 2;
-    const size_t nlo = (size_t)1 << t->klo, nhi = (size_t)1 << (log_size - t->klo);
-    std::vector<gl> lo(nlo), hi(nhi);
-    gl cur = 1;
-    for (size_t i = 0; i < nlo; i++) {
-        lo[i] = cur;
+// scale * base^e for e < 2^log_size
+static int build_pow_table(tmx_ctx* ctx, gl base, unsigned log_size, gl scale, gl** out) {
+    std::vector<gl> t((size_t)1 << log_size);
+    gl cur = scale;
+    for (size_t i = 0; i < t.size(); i++) {
+        t[i] = cur;
         cur = gl_mul(cur, base);
     }
-    gl step = cur;  // base^(2^klo)
-    cur = hi_scale;
-    for (size_t i = 0; i < nhi; i++) {
-        hi[i] = cur;
-        cur = gl_mul(cur, step);
-    }
-    int rc = upload(ctx, lo, &t->lo);
-    if (rc) return rc;
-    return upload(ctx, hi, &t->hi);
+    return upload(ctx, t, out);
 }
 
 int ctx_ntt_tables(tmx_ctx* ctx, unsigned log_n, bool inverse, const NttTables** out) {
@@ -110,35 +99,25 @@ int ctx_ntt_tables(tmx_ctx* ctx, unsigned log_n, bool inverse, const NttTables**
     NttTables t;
     gl w = gl_root_of_unity(log_n);
     if (inverse) w = gl_inv(w);
-    if (log_n >= 1 && log_n <= 10) {
-        const size_t half = (size_t)1 << (log_n - 1);
-        std::vector<gl> s(half);
-        gl cur = 1;
-        for (size_t i = 0; i < half; i++) {
-            s[i] = cur;
-            cur = gl_mul(cur, w);
-        }
-        int rc = upload(ctx, s, &t.small);
-        if (rc) return rc;
-    }
-    int rc = build_pow_table(ctx, w, log_n, 1, &t.big);
+    int rc = build_pow_table(ctx, w, log_n, 1, &t.full);
     if (rc) return rc;
+    t.small = t.full;  // the first half of the full table is exactly w^e, e < 2^(k-1)
     auto ins = cache.emplace(log_n, t);
     *out = &ins.first->second;
     return TMX_OK;
 }
 
-int ctx_coset_scale(tmx_ctx* ctx, unsigned log_n, const PowTable** out) {
+int ctx_coset_scale(tmx_ctx* ctx, unsigned log_n, const gl** out) {
     auto it = ctx->coset_scale.find(log_n);
     if (it != ctx->coset_scale.end()) {
-        *out = &it->second;
+        *out = it->second;
         return TMX_OK;
     }
-    PowTable t;
+    gl* t = nullptr;
     int rc = build_pow_table(ctx, GL_GEN, log_n, gl_inv((gl)((uint64_t)1 << log_n)), &t);
     if (rc) return rc;
-    auto ins = ctx->coset_scale.emplace(log_n, t);
-    *out = &ins.first->second;
+    ctx->coset_scale.emplace(log_n, t);
+    *out = t;
     return TMX_OK;
 }
 

@@ -19,17 +19,12 @@ int fail(int code, const std::string& msg);
             return ::tmx::fail(TMX_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
     } while (0)
 
-// Two-level power table: base^e = lo[e & ((1<<klo)-1)] * hi[e >> klo]
-struct PowTable {
-    gl* lo = nullptr;
-    gl* hi = nullptr;
-    unsigned klo = 0;
-    unsigned log_size = 0;  // table covers exponents < 2^log_size
-};
-
+// Twiddle tables are flat (at most 2^18 entries of 8 bytes for the tables proved here: L2-resident).  A two-level
+// table saves memory but costs a second load and an extra field multiplication per use, and the transforms are
+// bound by integer issue, not by memory.
 struct NttTables {
-    gl* small = nullptr;  // w_L^e, e < L/2 (L = 2^k)
-    PowTable big;         // w_{2^k}^e, e < 2^k
+    gl* small = nullptr;  // w_L^e, e < L/2 (L = 2^k, k <= 10)
+    gl* full = nullptr;   // w_{2^k}^e, e < 2^k
 };
 
 }  // namespace tmx
@@ -40,7 +35,7 @@ struct tmx_ctx {
     uint64_t launches = 0;
     int sm_count = 148;
     std::map<unsigned, tmx::NttTables> fwd, inv;      // keyed by log size
-    std::map<unsigned, tmx::PowTable> coset_scale;    // keyed by log n: 7^i / n
+    std::map<unsigned, tmx::gl*> coset_scale;         // keyed by log n: 7^i / n, i < n
     // grow-only scratch buffers
     void* scratch[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t scratch_bytes[4] = {0, 0, 0, 0};
@@ -51,7 +46,7 @@ namespace tmx {
 
 int ctx_scratch(tmx_ctx* ctx, int slot, size_t bytes, void** out);
 int ctx_ntt_tables(tmx_ctx* ctx, unsigned log_n, bool inverse, const NttTables** out);
-int ctx_coset_scale(tmx_ctx* ctx, unsigned log_n, const PowTable** out);
+int ctx_coset_scale(tmx_ctx* ctx, unsigned log_n, const gl** out);
 inline cudaStream_t pick_stream(tmx_ctx* ctx, void* stream) { return stream ? (cudaStream_t)stream : ctx->stream; }
 
 // internal cross-file entry points

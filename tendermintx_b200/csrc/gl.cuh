@@ -24,57 +24,9 @@ constexpr gl GL_EPS = 0xFFFFFFFFULL;  // 2^64 mod p
 constexpr gl GL_GEN = 7ULL;           // multiplicative generator, also the LDE coset shift
 constexpr gl GL_ROOT_2_32 = 1753635133440165772ULL;
 
-// Branch-free on purpose: on the host (transcript, verifier) data-dependent branches on random field elements
-// mispredict half the time; on the device the compiler turns these into selects either way.
-TMX_HD gl gl_canon(gl a) { return a - (GL_P & (0 - (gl)(a >= GL_P))); }
-
-TMX_HD gl gl_add(gl a, gl b) {
-    const gl s = a + b;
-    const gl over = (gl)(s < a) | (gl)(s >= GL_P);  // wrapped past 2^64, or landed in [p, 2^64)
-    return s - (GL_P & (0 - over));                 // s - p (mod 2^64) is right in both cases (a, b < p)
-}
-TMX_HD gl gl_sub(gl a, gl b) { return (a - b) + (GL_P & (0 - (gl)(a < b))); }
-TMX_HD gl gl_neg(gl a) { return a ? GL_P - a : 0; }
-
-// x = lo + 2^64*hi with 2^64 = 2^32-1, 2^96 = -1  (mod p)
-TMX_HD gl gl_reduce128(gl lo, gl hi) {
-    const gl hh = hi >> 32, hl = hi & GL_EPS;
-    gl t0 = lo - hh;
-    t0 -= GL_EPS & (0 - (gl)(lo < hh));
-    const gl t1 = hl * GL_EPS;
-    gl t2 = t0 + t1;
-    t2 += GL_EPS & (0 - (gl)(t2 < t1));
-    return gl_canon(t2);
-}
-
-TMX_HD gl gl_mul(gl a, gl b) {
-#if defined(__CUDA_ARCH__)
-    return gl_reduce128(a * b, __umul64hi(a, b));
-#else
-    unsigned __int128 m = (unsigned __int128)a * b;
-    return gl_reduce128((gl)m, (gl)(m >> 64));
-#endif
-}
-TMX_HD gl gl_sqr(gl a) { return gl_mul(a, a); }
-
-TMX_HD gl gl_pow(gl b, uint64_t e) {
-    gl r = 1;
-    while (e) {
-        if (e & 1) r = gl_mul(r, b);
-        b = gl_sqr(b);
-        e >>= 1;
-    }
-    return r;
-}
-TMX_HD gl gl_inv(gl a) { return gl_pow(a, GL_P - 2); }
-TMX_HD gl gl_root_of_unity(unsigned k) {
-    gl r = GL_ROOT_2_32;
-    for (unsigned i = k; i < 32; i++) r = gl_sqr(r);
-    return r;
-}
-
-// ---- lazily reduced arithmetic: values in [0, 2^64), congruent mod p (used inside Poseidon and the Horner chains
-// of the quotient kernel; canonicalise with gl_canon before a value leaves the kernel) ----
+// Host versions are branch-free on purpose (transcript, verifier: data-dependent branches on random field elements
+// mispredict half the time).  Device versions use the carry flag: the compare / select formulation costs about
+// twice the instructions there (ncu on the NTT: SEL + ISETP were a quarter of all issued instructions).
 TMX_HD gl gl_add_carry(gl a, gl b, gl* carry) {  // a + b mod 2^64, *carry = 0 / 1
 #if defined(__CUDA_ARCH__)
     gl s, c;
@@ -98,6 +50,53 @@ TMX_HD gl gl_sub_borrow_mask(gl a, gl b, gl* mask) {  // a - b mod 2^64, *mask =
     return a - b;
 #endif
 }
+
+TMX_HD gl gl_canon(gl a) {  // [0, 2^64) -> [0, p)
+#if defined(__CUDA_ARCH__)
+    gl c;
+    const gl t = gl_add_carry(a, GL_EPS, &c);  // a - p mod 2^64; carries exactly when a >= p
+    return c ? t : a;
+#else
+    return a - (GL_P & (0 - (gl)(a >= GL_P)));
+#endif
+}
+
+TMX_HD gl gl_add(gl a, gl b) {
+#if defined(__CUDA_ARCH__)
+    gl c1, c2;
+    const gl s = gl_add_carry(a, b, &c1);
+    const gl t = gl_add_carry(s, GL_EPS, &c2);  // s - p mod 2^64
+    return (c1 | c2) ? t : s;
+#else
+    const gl s = a + b;
+    const gl over = (gl)(s < a) | (gl)(s >= GL_P);  // wrapped past 2^64, or landed in [p, 2^64)
+    return s - (GL_P & (0 - over));                 // s - p (mod 2^64) is right in both cases (a, b < p)
+#endif
+}
+TMX_HD gl gl_sub(gl a, gl b) {
+#if defined(__CUDA_ARCH__)
+    gl m;
+    const gl d = gl_sub_borrow_mask(a, b, &m);
+    return d - (m & GL_EPS);  // + p mod 2^64 on borrow (a, b < p: no second borrow)
+#else
+    return (a - b) + (GL_P & (0 - (gl)(a < b)));
+#endif
+}
+TMX_HD gl gl_neg(gl a) { return a ? GL_P - a : 0; }
+
+// x = lo + 2^64*hi with 2^64 = 2^32-1, 2^96 = -1  (mod p)
+TMX_HD gl gl_reduce128(gl lo, gl hi) {
+    const gl hh = hi >> 32, hl = hi & GL_EPS;
+    gl t0 = lo - hh;
+    t0 -= GL_EPS & (0 - (gl)(lo < hh));
+    const gl t1 = hl * GL_EPS;
+    gl t2 = t0 + t1;
+    t2 += GL_EPS & (0 - (gl)(t2 < t1));
+    return gl_canon(t2);
+}
+
+// ---- lazily reduced arithmetic: values in [0, 2^64), congruent mod p (used inside Poseidon and the Horner chains
+// of the quotient kernel; canonicalise with gl_canon before a value leaves the kernel) ----
 // 64 x 64 -> 128: one mul.lo / mul.hi pair lets ptxas share the partial products (three IMAD.WIDE, one
 // IMAD.WIDE.X and four carry instructions); a * b next to __umul64hi(a, b) in C costs five wide and two narrow
 // multiplies, and a hand-written schoolbook on 32-bit halves pays for zero-extended register pairs.
@@ -130,6 +129,32 @@ TMX_HD gl gl_mac_nc(gl acc, gl a, gl x) {
     gl_mul128(acc, a, &lo, &hi);
     lo = gl_add_carry(lo, x, &c);
     return gl_reduce128_nc(lo, hi + c);
+}
+
+TMX_HD gl gl_mul(gl a, gl b) {
+#if defined(__CUDA_ARCH__)
+    return gl_canon(gl_mul_nc(a, b));
+#else
+    unsigned __int128 m = (unsigned __int128)a * b;
+    return gl_reduce128((gl)m, (gl)(m >> 64));
+#endif
+}
+TMX_HD gl gl_sqr(gl a) { return gl_mul(a, a); }
+
+TMX_HD gl gl_pow(gl b, uint64_t e) {
+    gl r = 1;
+    while (e) {
+        if (e & 1) r = gl_mul(r, b);
+        b = gl_sqr(b);
+        e >>= 1;
+    }
+    return r;
+}
+TMX_HD gl gl_inv(gl a) { return gl_pow(a, GL_P - 2); }
+TMX_HD gl gl_root_of_unity(unsigned k) {
+    gl r = GL_ROOT_2_32;
+    for (unsigned i = k; i < 32; i++) r = gl_sqr(r);
+    return r;
 }
 
 struct gl2 {

@@ -30,25 +30,21 @@ struct PassArgs {
     unsigned log_n;      // column length 2^log_n
     unsigned log_block;  // this pass runs inside blocks of 2^log_block consecutive elements
     const gl* tw_small;  // w_L^e, e < L/2
-    // inter-pass twiddle w_{2^tw.log_size}^(e << tw_shift)
-    PowTable tw;
+    // inter-pass twiddle w_N^(e << tw_shift), flat table of N = 2^log_n entries
+    const gl* tw;
     unsigned tw_shift;
-    // optional pre-scale of element i by base^(ps_mult * i mod 2^ps.log_size)
-    PowTable ps;
-    uint64_t ps_mult;
+    // optional pre-scale of element i by ps[(ps_mult * i) & ps_mask] (coset selection of the LDE)
+    const gl* ps;
+    uint64_t ps_mult, ps_mask;
     // contiguous pass only: scatter to natural order (bit reversal of the in-place position) and optional
     // post-scale of natural index j by os[j]
     int scatter_natural;
-    PowTable os;
+    const gl* os;
 };
 
-TMX_D gl pow2level(const PowTable& t, uint64_t e) {
-    gl a = t.lo[e & ((1ull << t.klo) - 1)];
-    gl b = t.hi[e >> t.klo];
-    return gl_mul(a, b);
-}
-
 // r consecutive DIF stages starting at `stage0` of an L-point vector held point-major in shared memory.
+// Twiddles equal to one (the whole last stage of a transform, and the first butterfly of every group in the last
+// round) are not multiplied.
 template <int LOG_L, int R_LOG, int STAGE0>
 TMX_D void dif_round(gl* tile, const gl* tws, int tid, int nthreads) {
     constexpr int L = 1 << LOG_L;
@@ -71,10 +67,11 @@ TMX_D void dif_round(gl* tile, const gl* tws, int tid, int nthreads) {
 #pragma unroll
             for (int m = 0; m < R; m++) {
                 if ((m & hm) == 0) {
-                    const int e = ((m % hm) * rs + lo) * tw_step;
-                    gl a = x[m], b = x[m + hm];
+                    const gl a = x[m], b = x[m + hm];
                     x[m] = gl_add(a, b);
-                    x[m + hm] = gl_mul(gl_sub(a, b), tws[e]);
+                    const gl d = gl_sub(a, b);
+                    if (rs == 1 && (m % hm) == 0) x[m + hm] = d;  // exponent 0 at compile time
+                    else x[m + hm] = gl_mul(d, tws[((m % hm) * rs + lo) * tw_step]);
                 }
             }
         }
@@ -86,18 +83,19 @@ TMX_D void dif_round(gl* tile, const gl* tws, int tid, int nthreads) {
 template <int LOG_L>
 TMX_D void dif_vector(gl* tile, const gl* tws, int tid, int nthreads) {
     constexpr int full = LOG_L / 4, rem = LOG_L % 4;
+    // the short round goes first so that the last round (stride 1, compile-time unit twiddles) is a full radix-16
+    if constexpr (rem == 3) dif_round<LOG_L, 3, 0>(tile, tws, tid, nthreads);
+    if constexpr (rem == 2) dif_round<LOG_L, 2, 0>(tile, tws, tid, nthreads);
+    if constexpr (rem == 1) dif_round<LOG_L, 1, 0>(tile, tws, tid, nthreads);
+    if constexpr (rem != 0) __syncthreads();
     if constexpr (full >= 1) {
-        dif_round<LOG_L, 4, 0>(tile, tws, tid, nthreads);
+        dif_round<LOG_L, 4, rem>(tile, tws, tid, nthreads);
         __syncthreads();
     }
     if constexpr (full >= 2) {
-        dif_round<LOG_L, 4, 4>(tile, tws, tid, nthreads);
+        dif_round<LOG_L, 4, rem + 4>(tile, tws, tid, nthreads);
         __syncthreads();
     }
-    if constexpr (rem == 3) dif_round<LOG_L, 3, 4 * full>(tile, tws, tid, nthreads);
-    if constexpr (rem == 2) dif_round<LOG_L, 2, 4 * full>(tile, tws, tid, nthreads);
-    if constexpr (rem == 1) dif_round<LOG_L, 1, 4 * full>(tile, tws, tid, nthreads);
-    if constexpr (rem != 0) __syncthreads();
 }
 
 template <int LOG_L>
@@ -105,6 +103,8 @@ constexpr int pass_threads() {
     return (1 << LOG_L) < 32 ? 32 : ((1 << LOG_L) > 512 ? 512 : (1 << LOG_L));
 }
 
+// All sizes are powers of two: every index split below is a shift / mask (the first version divided 64-bit indices
+// by runtime values, which cost more instructions than the butterflies).
 template <int LOG_L, bool STRIDED>
 __global__ void __launch_bounds__(pass_threads<LOG_L>()) ntt_pass_kernel(PassArgs a) {
     constexpr int L = 1 << LOG_L;
@@ -113,55 +113,52 @@ __global__ void __launch_bounds__(pass_threads<LOG_L>()) ntt_pass_kernel(PassArg
     gl* tws = sm + L * TILE_TS;
     const int tid = threadIdx.x, nthreads = blockDim.x;
     for (int i = tid; i < L / 2; i += nthreads) tws[i] = a.tw_small[i];
-    const size_t n = (size_t)1 << a.log_n;
 
     if constexpr (STRIDED) {
-        const unsigned log_s = a.log_block - LOG_L;
+        const unsigned log_s = a.log_block - LOG_L;  // >= 4: S = 2^log_s elements between the points of a vector
         const size_t S = (size_t)1 << log_s;
-        const size_t tiles_per_block = S / TILE_T;
-        const size_t blocks_per_col = n >> a.log_block;
-        size_t t = blockIdx.x;
-        const size_t lo0 = (t % tiles_per_block) * TILE_T;
-        t /= tiles_per_block;
-        const size_t hi = t % blocks_per_col;
-        const size_t col = t / blocks_per_col;
+        const unsigned log_tiles = log_s - 4;                  // tiles per block
+        const unsigned log_blocks = a.log_n - a.log_block;     // blocks per column
+        const size_t t = blockIdx.x;
+        const size_t lo0 = (t & (((size_t)1 << log_tiles) - 1)) << 4;
+        const size_t hi = (t >> log_tiles) & (((size_t)1 << log_blocks) - 1);
+        const size_t col = t >> (log_tiles + log_blocks);
         const size_t off = (hi << a.log_block) + lo0;
         const gl* src = a.in + col * a.in_col_stride + off;
         gl* dst = a.out + col * a.out_col_stride + off;
         for (int idx = tid; idx < L * TILE_T; idx += nthreads) {
-            const int v = idx % TILE_T, m = idx / TILE_T;
-            gl x = src[(size_t)m * S + v];
-            if (a.ps.lo) {
-                const uint64_t i = off + (uint64_t)m * S + v;
-                x = gl_mul(x, pow2level(a.ps, (i * a.ps_mult) & ((1ull << a.ps.log_size) - 1)));
+            const int v = idx & (TILE_T - 1), m = idx >> 4;
+            gl x = src[((size_t)m << log_s) + v];
+            if (a.ps) {
+                const uint64_t i = off + ((uint64_t)m << log_s) + v;
+                x = gl_mul(x, a.ps[(i * a.ps_mult) & a.ps_mask]);
             }
             tile[m * TILE_TS + v] = x;
         }
         __syncthreads();
         dif_vector<LOG_L>(tile, tws, tid, nthreads);
         for (int idx = tid; idx < L * TILE_T; idx += nthreads) {
-            const int v = idx % TILE_T, p = idx / TILE_T;
+            const int v = idx & (TILE_T - 1), p = idx >> 4;
             gl x = tile[p * TILE_TS + v];
-            const uint64_t j1 = bitrev32((uint32_t)p, LOG_L);
-            const uint64_t e = ((lo0 + v) * j1) << a.tw_shift;
-            x = gl_mul(x, pow2level(a.tw, e));
-            dst[(size_t)p * S + v] = x;
+            const uint32_t j1 = bitrev32((uint32_t)p, LOG_L);
+            if (j1) x = gl_mul(x, a.tw[((lo0 + v) * j1) << a.tw_shift]);
+            dst[((size_t)p << log_s) + v] = x;
         }
     } else {
-        const size_t vecs_per_col = n >> LOG_L;
-        const size_t total_vecs = vecs_per_col * a.n_cols;
+        const unsigned log_vecs = a.log_n - LOG_L;  // vectors per column
+        const size_t vec_mask = ((size_t)1 << log_vecs) - 1;
+        const size_t total_vecs = a.n_cols << log_vecs;
         const size_t gid0 = (size_t)blockIdx.x * TILE_T;
-        const unsigned log_vecs = a.log_n - LOG_L;
         for (int idx = tid; idx < L * TILE_T; idx += nthreads) {
-            const int m = idx % L, v = idx / L;
+            const int m = idx & (L - 1), v = idx >> LOG_L;
             const size_t gid = gid0 + v;
             gl x = 0;
             if (gid < total_vecs) {
-                const size_t col = gid / vecs_per_col, c = gid % vecs_per_col;
+                const size_t col = gid >> log_vecs, c = gid & vec_mask;
                 const size_t hi = a.scatter_natural ? bitrev32((uint32_t)c, log_vecs) : c;
-                const uint64_t i = hi * L + m;
+                const uint64_t i = (hi << LOG_L) + m;
                 x = a.in[col * a.in_col_stride + i];
-                if (a.ps.lo) x = gl_mul(x, pow2level(a.ps, (i * a.ps_mult) & ((1ull << a.ps.log_size) - 1)));
+                if (a.ps) x = gl_mul(x, a.ps[(i * a.ps_mult) & a.ps_mask]);
             }
             tile[m * TILE_TS + v] = x;
         }
@@ -169,23 +166,23 @@ __global__ void __launch_bounds__(pass_threads<LOG_L>()) ntt_pass_kernel(PassArg
         dif_vector<LOG_L>(tile, tws, tid, nthreads);
         if (a.scatter_natural) {
             for (int idx = tid; idx < L * TILE_T; idx += nthreads) {
-                const int v = idx % TILE_T, p = idx / TILE_T;
+                const int v = idx & (TILE_T - 1), p = idx >> 4;
                 const size_t gid = gid0 + v;
                 if (gid < total_vecs) {
-                    const size_t col = gid / vecs_per_col, c = gid % vecs_per_col;
-                    const uint64_t j = (uint64_t)bitrev32((uint32_t)p, LOG_L) * vecs_per_col + c;
+                    const size_t col = gid >> log_vecs, c = gid & vec_mask;
+                    const uint64_t j = ((uint64_t)bitrev32((uint32_t)p, LOG_L) << log_vecs) + c;
                     gl x = tile[p * TILE_TS + v];
-                    if (a.os.lo) x = gl_mul(x, pow2level(a.os, j));
+                    if (a.os) x = gl_mul(x, a.os[j]);
                     a.out[col * a.out_col_stride + j] = x;
                 }
             }
         } else {
             for (int idx = tid; idx < L * TILE_T; idx += nthreads) {
-                const int p = idx % L, v = idx / L;
+                const int p = idx & (L - 1), v = idx >> LOG_L;
                 const size_t gid = gid0 + v;
                 if (gid < total_vecs) {
-                    const size_t col = gid / vecs_per_col, c = gid % vecs_per_col;
-                    a.out[col * a.out_col_stride + c * L + p] = tile[p * TILE_TS + v];
+                    const size_t col = gid >> log_vecs, c = gid & vec_mask;
+                    a.out[col * a.out_col_stride + (c << LOG_L) + p] = tile[p * TILE_TS + v];
                 }
             }
         }
@@ -251,9 +248,9 @@ struct XformDesc {
     unsigned log_n;
     bool inverse;
     bool natural_out;
-    PowTable ps;  // pre-scale (first pass)
-    uint64_t ps_mult;
-    PowTable os;  // post-scale (last pass, natural_out only)
+    const gl* ps;  // pre-scale table (first pass): element i times ps[(ps_mult * i) & ps_mask]
+    uint64_t ps_mult, ps_mask;
+    const gl* os;  // post-scale (last pass, natural_out only), indexed by the natural output index
 };
 
 static int run_xform(tmx_ctx* ctx, const XformDesc& d, cudaStream_t st) {
@@ -279,15 +276,16 @@ static int run_xform(tmx_ctx* ctx, const XformDesc& d, cudaStream_t st) {
         a.log_n = d.log_n;
         a.log_block = log_block;
         a.tw_small = T->small;
-        a.tw = Tn->big;
+        a.tw = Tn->full;
         a.tw_shift = d.log_n - log_block;
-        if (i == 0 && d.ps.lo) {
+        if (i == 0 && d.ps) {
             a.ps = d.ps;
             a.ps_mult = d.ps_mult;
+            a.ps_mask = d.ps_mask;
         }
         if (last) {
             a.scatter_natural = d.natural_out ? 1 : 0;
-            if (d.natural_out && d.os.lo) a.os = d.os;
+            if (d.natural_out && d.os) a.os = d.os;
             a.out = d.out;
             a.out_col_stride = d.out_col_stride;
             if (d.natural_out && (const gl*)a.out == a.in) return fail(TMX_E_INPUT, "ntt: scatter pass cannot run in place");
@@ -341,8 +339,6 @@ extern "C" int tmx_ntt(tmx_ctx* ctx, uint64_t* d_data, size_t n_cols, unsigned l
     d.log_n = log_n;
     d.inverse = inverse != 0;
     d.natural_out = true;
-    PowTable ninv;
-    memset(&ninv, 0, sizeof ninv);
     if (multi) {
         // data -> tmpa (strided passes) -> data (scatter)
         d.in = d_data;
@@ -393,8 +389,9 @@ int lde_forward_cosets(tmx_ctx* ctx, const gl* coeffs, gl* d_out, size_t n_cols,
         f.inverse = false;
         f.natural_out = false;
         if (s != 0) {
-            f.ps = Tm->big;
+            f.ps = Tm->full;
             f.ps_mult = s;
+            f.ps_mask = m - 1;
         }
         rc = run_xform(ctx, f, st);
         if (rc) return rc;
@@ -418,7 +415,7 @@ extern "C" int tmx_lde(tmx_ctx* ctx, const uint64_t* d_values, uint64_t* d_out, 
         if (rc) return rc;
         coeffs = (gl*)p;
     }
-    const PowTable* cs = nullptr;
+    const gl* cs = nullptr;
     int rc = ctx_coset_scale(ctx, log_n, &cs);
     if (rc) return rc;
     // 1. inverse transform: values -> (region 0 of out as intermediate) -> coeffs, natural order,
@@ -435,7 +432,7 @@ extern "C" int tmx_lde(tmx_ctx* ctx, const uint64_t* d_values, uint64_t* d_out, 
     d.log_n = log_n;
     d.inverse = true;
     d.natural_out = true;
-    d.os = *cs;
+    d.os = cs;
     rc = run_xform(ctx, d, st);
     if (rc) return rc;
     return lde_forward_cosets(ctx, coeffs, d_out, n_cols, log_n, rate_bits, st);

@@ -109,3 +109,64 @@ def test_full_size_skip_n128_celestia(ctx):
     with pytest.raises(tmx.TmxError):
         circuit.verify(bytes(bad), pub, out)
     circuit.close()
+
+
+def _celestia_case(name):
+    root = os.path.join(HERE, "golden", "celestia")
+    with open(os.path.join(root, "index.json")) as f:
+        idx = json.load(f)[name]
+    return os.path.join(root, name), idx
+
+
+def _full_size_roundtrip(ctx, kind_name, name, n_max):
+    """prove from the fixture directory at full size, check the output header against the fixture's block hash, the
+    product verifier, reproducibility and tamper rejection (size-independent properties; the byte-level comparison
+    with the oracle is test_skip_n128_proof_bytes_equal_oracle and bench.py's cpu_baseline leg)."""
+    import tendermintx_b200 as tmx
+
+    path, idx = _celestia_case(name)
+    kind = tmx.KIND_SKIP if kind_name == "skip" else tmx.KIND_STEP
+    th = bytes.fromhex(idx["trusted_hash"])
+    pub = idx["trusted"].to_bytes(8, "big") + th + (idx["target"].to_bytes(8, "big") if kind_name == "skip" else b"")
+    circuit = tmx.Circuit.build(ctx, kind, n_max, tmx.CelestiaConfig)
+    proof, out = circuit.prove_fixture(pub, path)
+    assert out.hex() == idx["target_hash"]
+    circuit.verify(proof, pub, out)
+    tmx.verify_proof(kind, n_max, tmx.CelestiaConfig, proof, pub, out)
+    proof2, _ = circuit.prove_fixture(pub, path)
+    assert proof2 == proof
+    bad = bytearray(proof)
+    bad[len(bad) // 3] ^= 4
+    with pytest.raises(tmx.TmxError):
+        circuit.verify(bytes(bad), pub, out)
+    circuit.close()
+    return proof
+
+
+def test_full_size_step_n128_celestia(ctx):
+    """BASELINE config 3: step circuit, VALIDATOR_SET_SIZE_MAX = 128, consecutive headers."""
+    _full_size_roundtrip(ctx, "step", "step_n128_seed0", 128)
+
+
+def test_full_size_skip_n256(ctx):
+    """BASELINE config 4: skip circuit, VALIDATOR_SET_SIZE_MAX = 256 (dYdX-class validator set)."""
+    _full_size_roundtrip(ctx, "skip", "skip_n256_seed0", 256)
+
+
+def test_skip_n128_proof_bytes_equal_oracle(ctx, oracle):
+    """BASELINE config 2, bit-exact: the 2.17 MB GPU proof of the 128-validator skip equals the CPU oracle's."""
+    import tendermintx_b200 as tmx
+    from oracle import tm_inputs as ti
+
+    path, idx = _celestia_case("skip_n128_seed1")
+    th = bytes.fromhex(idx["trusted_hash"])
+    src = ti.FixtureSource(path)
+    blob = ti.skip_inputs(src, 128, idx["trusted"], th, idx["target"])
+    pub = ti.skip_public_input(idx["trusted"], th, idx["target"])
+    circuit = tmx.Circuit.build(ctx, tmx.KIND_SKIP, 128, tmx.CelestiaConfig)
+    proof, out = circuit.prove(pub, blob)
+    status, want, want_out = oracle.prove(pub, blob, "celestia")
+    assert status == "OK" and want_out == out and out.hex() == idx["target_hash"]
+    got = np.frombuffer(proof, dtype=np.uint64)
+    assert got.size == want.size and np.array_equal(got, want), f"first differing word {_first_diff(got, want)} of {want.size}"
+    circuit.close()
