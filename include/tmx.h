@@ -142,6 +142,10 @@ int tmx_circuit_load(tmx_ctx *ctx, const char *path, tmx_circuit **out);
  * reference's witness generation would panic.  out32 = the proven target / next header hash. */
 int tmx_prove(tmx_circuit *circuit, const uint8_t *input, size_t input_len, const uint8_t *blob, size_t blob_len,
               tmx_proof **proof, uint8_t out32[32]);
+/* Device time (CUDA events on the proving stream) of the trace commitments inside the last tmx_prove of this circuit,
+ * milliseconds: {LDE (K1) table 0, Merkle (K2) table 0, LDE 1, Merkle 1, LDE 2, Merkle 2}.  Measurement aid for the
+ * roofline figures; no reference counterpart. */
+int tmx_circuit_last_phase_ms(const tmx_circuit *c, float out[6]);
 int tmx_last_check(void);
 /* keep one proof's off-chain inputs resident in HBM; tmx_prove(..., blob = NULL, 0, ...) then proves from them */
 int tmx_circuit_set_inputs(tmx_circuit *circuit, const uint8_t *blob, size_t blob_len);

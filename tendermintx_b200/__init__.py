@@ -10,7 +10,7 @@ import ctypes
 from . import _lib
 from ._lib import TmxError
 
-__all__ = ["Context", "TmxError", "lib"]
+__all__ = ["Context", "Circuit", "ProverPool", "InputDataFetcher", "TmxError", "lib"]
 
 _LIB = None
 
@@ -214,10 +214,25 @@ class Circuit:
     def save(self, path):
         _check(lib().tmx_circuit_save(self._h, path.encode()))
 
+    @classmethod
+    def load(cls, ctx, path, kind, n_max, config):
+        """`<bin> prove` side of the CLI contract: load ./build/main.circuit written by `build` [REF succinct.json:8-9]."""
+        h = ctypes.c_void_p()
+        _check(lib().tmx_circuit_load(ctx.handle, str(path).encode(), ctypes.byref(h)))
+        c = cls.__new__(cls)
+        c.ctx, c.kind, c.n_max, c.config, c._h = ctx, kind, n_max, config, h
+        return c
+
     def set_inputs(self, blob):
         """Upload the off-chain inputs once; prove(public_input, None) then runs from the HBM-resident copy."""
         blob = bytes(blob)
         _check(lib().tmx_circuit_set_inputs(self._h, blob, len(blob)))
+
+    def last_phase_ms(self):
+        """Device time of the trace commitments inside the last prove(): [(lde_ms, merkle_ms)] per table."""
+        out = (ctypes.c_float * 6)()
+        _check(lib().tmx_circuit_last_phase_ms(self._h, out))
+        return [(out[2 * t], out[2 * t + 1]) for t in range(3)]
 
     def prove(self, public_input, blob):
         """Returns (proof bytes, output header bytes).  Raises TmxError(TMX_E_UNSAT) with `.check` set to the name
@@ -257,3 +272,59 @@ class Circuit:
     def verify(self, proof, public_input, output):
         proof, public_input, output = bytes(proof), bytes(public_input), bytes(output)
         _check(lib().tmx_verify(self._h, proof, len(proof), public_input, len(public_input), output))
+
+
+class ProverPool:
+    """Several provers in flight on ONE GPU.
+
+    A proof is a chain of kernels interleaved with Fiat-Shamir round trips to the host (cap -> challenge -> next
+    kernel), so a single prover leaves the GPU idle for about a sixth of the proof.  Proofs are independent
+    (SURVEY section 8e), so a service keeps `in_flight` of them going, each with its own tmx_ctx (stream, scratch)
+    and circuit buffers, driven by its own host thread (ctypes releases the GIL during the C call): the gaps of one
+    are filled by the kernels of the others.  Nothing is shared between the provers and no proof changes.
+    """
+
+    def __init__(self, device, kind, n_max, config, in_flight=3, artefact=None):
+        self.device, self.kind, self.n_max, self.config = device, kind, n_max, config
+        self.ctxs = [Context(device) for _ in range(in_flight)]
+        if artefact is None:
+            self.circuits = [Circuit.build(c, kind, n_max, config) for c in self.ctxs]
+        else:
+            self.circuits = [Circuit.load(c, artefact, kind, n_max, config) for c in self.ctxs]
+
+    def launch_count(self):
+        return sum(c.launch_count() for c in self.ctxs)
+
+    def set_inputs(self, blob):
+        for c in self.circuits:
+            c.set_inputs(blob)
+
+    def prove_many(self, statements):
+        """statements: list of (public_input, blob or None).  Returns the list of (proof, output) in order.
+        Statement j runs on prover j mod in_flight; the first exception (e.g. TMX_E_UNSAT) is re-raised."""
+        import threading
+
+        results = [None] * len(statements)
+        errors = []
+
+        def work(k):
+            try:
+                for j in range(k, len(statements), len(self.circuits)):
+                    results[j] = self.circuits[k].prove(*statements[j])
+            except Exception as e:  # noqa: BLE001 - re-raised below on the caller's thread
+                errors.append(e)
+
+        threads = [threading.Thread(target=work, args=(k,)) for k in range(min(len(self.circuits), len(statements)))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        return results
+
+    def close(self):
+        for c in self.circuits:
+            c.close()
+        for c in self.ctxs:
+            c.close()

@@ -64,6 +64,7 @@ def load():
         "tmx_circuit_load": (i32, [vp, c.c_char_p, c.POINTER(vp)]),
         "tmx_prove": (i32, [vp, vp, sz, vp, sz, c.POINTER(vp), vp]),
         "tmx_last_check": (i32, []),
+        "tmx_circuit_last_phase_ms": (i32, [vp, vp]),
         "tmx_circuit_set_inputs": (i32, [vp, vp, sz]),
         "tmx_header_hash_from_fixture": (i32, [c.c_char_p, c.c_uint64, vp]),
         "tmx_skip_inputs_from_fixture": (i32, [c.c_char_p, u32, c.c_uint64, vp, c.c_uint64, vp, sz]),
@@ -87,7 +88,7 @@ EXPORTED_SYMBOLS = [
     "tmx_ctx_stream", "tmx_ctx_launch_count", "tmx_ntt", "tmx_lde", "tmx_merkle_digest_count", "tmx_poseidon_merkle",
     "tmx_poseidon_permute", "tmx_host_poseidon_permute", "tmx_host_air_ed25519", "tmx_trace_dims", "tmx_witness_aux_bytes", "tmx_sha256_trace", "tmx_ed25519_trace",
     "tmx_witness_generate", "tmx_quotient", "tmx_pow_grind", "tmx_circuit_build", "tmx_circuit_free", "tmx_circuit_digest",
-    "tmx_circuit_save", "tmx_circuit_load", "tmx_prove", "tmx_last_check", "tmx_circuit_set_inputs", "tmx_header_hash_from_fixture", "tmx_skip_inputs_from_fixture",
+    "tmx_circuit_save", "tmx_circuit_load", "tmx_prove", "tmx_last_check", "tmx_circuit_last_phase_ms", "tmx_circuit_set_inputs", "tmx_header_hash_from_fixture", "tmx_skip_inputs_from_fixture",
     "tmx_step_inputs_from_fixture", "tmx_prove_fixture", "tmx_proof_size", "tmx_proof_bytes",
     "tmx_proof_free", "tmx_verify", "tmx_verify_params",
 ]

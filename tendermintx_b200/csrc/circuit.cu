@@ -33,6 +33,7 @@ struct tmx_circuit {
     std::vector<uint8_t> h_blob;  // host copy of the resident inputs (tmx_circuit_set_inputs)
     bool resident = false;
     TableProver prover;
+    float phase_ms[6] = {0, 0, 0, 0, 0, 0};  // per table of the last proof: LDE (K1), trace Merkle tree (K2), device time
 };
 
 struct tmx_proof {
@@ -372,6 +373,8 @@ extern "C" int tmx_prove(tmx_circuit* c, const uint8_t* input, size_t input_len,
         delete p;
         return rc;
     }
+    c->phase_ms[0] = c->prover.last_lde_ms;
+    c->phase_ms[1] = c->prover.last_merkle_ms;
     // join: phase 2 of the Ed25519 / SHA-512 tables, then the gadget checks that need the kernels' digests
     TMX_CUDA(cudaStreamWaitEvent(st, c->ev_ladder, 0));
     rc = run_ed25519_expand(ctx, wa, c->d_points, st);
@@ -399,8 +402,18 @@ extern "C" int tmx_prove(tmx_circuit* c, const uint8_t* input, size_t input_len,
             delete p;
             return rc;
         }
+        c->phase_ms[2 * t] = c->prover.last_lde_ms;
+        c->phase_ms[2 * t + 1] = c->prover.last_merkle_ms;
     }
     *proof_out = p;
+    return TMX_OK;
+}
+
+// Device time (CUDA events on the proving stream) of the trace commitments inside the LAST tmx_prove of this circuit:
+// out = {LDE table 0, Merkle table 0, LDE table 1, Merkle table 1, LDE table 2, Merkle table 2} in milliseconds.
+extern "C" int tmx_circuit_last_phase_ms(const tmx_circuit* c, float out[6]) {
+    if (!c || !out) return fail(TMX_E_INPUT, "tmx_circuit_last_phase_ms: NULL argument");
+    for (int i = 0; i < 6; i++) out[i] = c->phase_ms[i];
     return TMX_OK;
 }
 

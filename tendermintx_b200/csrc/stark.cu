@@ -321,12 +321,17 @@ int TableProver::prove(tmx_ctx* ctx, int table, const gl* d_trace, unsigned log_
     rc = reserve(ctx, C, n, m, dig_t);
     if (rc) return rc;
     PhaseTimer pt(st);
+    for (int i = 0; i < 3; i++)
+        if (!ev_phase[i]) TMX_CUDA(cudaEventCreate(&ev_phase[i]));
     // ---- 1. trace commitment ----
+    TMX_CUDA(cudaEventRecord(ev_phase[0], st));
     rc = tmx_lde(ctx, d_trace, d_lde, d_coeffs, C, log_n, STARK_RATE_BITS, st);
     if (rc) return rc;
+    TMX_CUDA(cudaEventRecord(ev_phase[1], st));
     pt.tick("lde");
     rc = merkle_generic(ctx, d_lde, C, 1, m, km, cap_h, d_dig_t, st);
     if (rc) return rc;
+    TMX_CUDA(cudaEventRecord(ev_phase[2], st));
     pt.tick("trace merkle");
     std::vector<gl> cap;
     rc = d2h(cap, d_dig_t + 4 * (dig_t - cap_n), 4 * cap_n, st);
@@ -515,6 +520,9 @@ int TableProver::prove(tmx_ctx* ctx, int table, const gl* d_trace, unsigned log_
     if (rc) return rc;
     proof.insert(proof.end(), qd.begin(), qd.end());
     pt.tick("queries");
+    // the stream has been synchronised by the copy above: the stamps of this table's commitment are complete
+    TMX_CUDA(cudaEventElapsedTime(&last_lde_ms, ev_phase[0], ev_phase[1]));
+    TMX_CUDA(cudaEventElapsedTime(&last_merkle_ms, ev_phase[1], ev_phase[2]));
     (void)host_poly_eval_ext;
     return TMX_OK;
 }
@@ -585,6 +593,8 @@ int TableProver::periodic_tables(tmx_ctx* ctx, int table, unsigned log_n, const 
 }
 
 void TableProver::release() {
+    for (int i = 0; i < 3; i++)
+        if (ev_phase[i]) cudaEventDestroy(ev_phase[i]);
     void* ps[] = {d_lde, d_coeffs, d_dig_t, d_dig_q, d_dig_fri, d_qv, d_qcoef, d_qlde, d_ypa, d_open, d_apow, d_idx, d_fri_base, d_query};
     for (void* p : ps)
         if (p) cudaFree(p);

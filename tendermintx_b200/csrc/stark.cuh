@@ -40,6 +40,9 @@ struct TableProver {
     gl2* d_fri[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     gl* d_query = nullptr; size_t sz_query = 0;
     std::map<uint64_t, gl*> pertabs;
+    // device-time stamps of the trace commitment of the last prove(): LDE start, LDE end = Merkle start, Merkle end
+    cudaEvent_t ev_phase[3] = {nullptr, nullptr, nullptr};
+    float last_lde_ms = 0.f, last_merkle_ms = 0.f;
 
     // Appends this table's proof to `proof` and advances the transcript.
     int prove(tmx_ctx* ctx, int table, const gl* d_trace, unsigned log_n, Challenger& ch, std::vector<gl>& proof, cudaStream_t st);

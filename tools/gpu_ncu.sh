@@ -2,19 +2,15 @@
 # exported on the box because the merged gpurun_out/ is capped at 64 MiB.
 set -x
 mkdir -p gpurun_out/ncu
+rm -f gpurun_out/ncu/*
 cap() {  # name regex skip count
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:"$2" -s $3 -c $4 -f -o gpurun_out/ncu/$1 python tools/profile_prove.py 1 > gpurun_out/ncu/$1.log 2>&1
   ncu -i gpurun_out/ncu/$1.ncu-rep --page raw --csv > gpurun_out/ncu/$1.raw.csv 2>/dev/null
-  ncu -i gpurun_out/ncu/$1.ncu-rep --page details --csv > gpurun_out/ncu/$1.details.csv 2>/dev/null
   ncu -i gpurun_out/ncu/$1.ncu-rep --page source --csv > gpurun_out/ncu/$1.source.csv 2>/dev/null
-  ls -la gpurun_out/ncu/$1.ncu-rep
-  if [ $(stat -c %s gpurun_out/ncu/$1.ncu-rep) -gt 12000000 ]; then rm gpurun_out/ncu/$1.ncu-rep; fi
+  if [ $(stat -c %s gpurun_out/ncu/$1.ncu-rep) -gt 9000000 ]; then rm gpurun_out/ncu/$1.ncu-rep; fi
 }
 cap leaf_hash leaf_hash_kernel 10 1
 cap ntt ntt_pass_kernel 24 6
-cap quotient quotient_kernel 2 1
-cap ladder ed25519_ladder 0 1
-cap fri_batch fri_batch_kernel 2 1
-cap eval_columns eval_columns_kernel 4 1
-cap subtree merkle_subtree_kernel 10 1
+cap quotient_ed quotient_ed25519_kernel 0 1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_2proofs.csv python tools/profile_prove.py 2 > gpurun_out/launches.log 2>&1
 du -sh gpurun_out
