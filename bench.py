@@ -84,6 +84,12 @@ class ClockSampler:
 
 
 def run_reference(args):
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm must use all the host threads it can
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())
+    _run_reference(args)
+
+
+def _run_reference(args):
     """The CPU implementation of the path on the box's host cores: the repo's deterministic oracle prover (the
     Rust reference cannot be built here: no cargo, un-vendored dependencies), all OpenMP threads, same workload."""
     rank = int(os.environ.get("RANK", "0"))
@@ -292,10 +298,12 @@ def run_ours(args):
                      "traffic": NCU_K1_TRAFFIC_BYTES, "traffic_note": "dram read+write of the six K1 launches of the Ed25519 table, "
                      "ncu --set full (profiles/); algorithmic bytes of that table alone: %d" % (8 * rows * cols * 3),
                      "peak_source": peak_src, "algorithmic_bytes": alg_bytes, "ms": lde_ms,
+                     "ms_per_table": [p[0] / args.steps for p in phase],
                      "share_of_step": lde_ms / (lat_ms / args.steps),
                      "note": "K1 is bound by 64-bit modular-arithmetic issue (ncu: ALU pipe ~80 % busy, DRAM < 20 %), so the HBM "
                              "fraction is low by construction; see DESIGN.md section 4"},
         "kernels": {"k2_poseidon_merkle_ms_per_proof": merkle_ms, "k2_Mperm_per_s": perms / merkle_ms / 1e3,
+                    "k2_ms_per_table": [p[1] / args.steps for p in phase],
                     "k2_share_of_step": merkle_ms / (lat_ms / args.steps),
                     "k2_note": "dominant kernel by time; bound by integer issue (ncu: ~1 % DRAM), 22.5 k instructions per permutation",
                     "isolated_ed25519_table": {"lde_ms": iso[0], "lde_GBps": 8 * rows * cols * 3 / iso[0] / 1e6,
