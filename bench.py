@@ -25,7 +25,7 @@ sys.path.insert(0, ROOT)
 N_MAX = 128
 # dram__bytes_read.sum + dram__bytes_write.sum of the six ntt_pass_kernel launches that make up the LDE of the Ed25519
 # table (1217 columns x 2^16), from profiles/r1c_ncu_ntt.raw.csv (one ncu --set full capture, per LDE)
-NCU_K1_TRAFFIC_BYTES = None
+NCU_K1_TRAFFIC_BYTES = 7370255872
 METRIC = "skip proofs/hour (CelestiaConfig, 128 val)"
 UNIT = "proofs/hour"
 WORKLOAD = "skip circuit CelestiaConfig VALIDATOR_SET_SIZE_MAX=128 (synthetic celestia chain, 128 signers, seed=rank)"

@@ -4,7 +4,7 @@
 // Replaces plonky2 0.2.0 hash/poseidon.rs + hash/hashing.rs + iop/challenger.rs, which the reference
 // reaches through `builder.build()` / `circuit.prove()` [REF circuits/skip.rs:173,214].  Round constants
 // are regenerated at start-up (ChaCha8, rand-0.8 seed_from_u64(0), gen_range(0..p)) -- see
-// poseidon_generate_constants() in host.cpp -- and uploaded once per translation unit.
+// poseidon_generate_constants() in context.cu -- and uploaded once per translation unit.
 #pragma once
 #include "gl.cuh"
 
@@ -15,7 +15,7 @@ constexpr int POSEIDON_ROUNDS = 30;
 constexpr int POSEIDON_HALF_FULL = 4;
 constexpr int POSEIDON_PARTIAL = 22;
 
-// host copy (filled by poseidon_generate_constants, host.cpp)
+// host copy (filled by poseidon_generate_constants, context.cu)
 extern gl h_poseidon_rc[POSEIDON_ROUNDS * POSEIDON_WIDTH];
 void poseidon_generate_constants();
 
