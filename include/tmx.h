@@ -159,6 +159,13 @@ int tmx_skip_inputs_from_fixture(const char *fixture_dir, uint32_t n_max, uint64
                                  const uint8_t trusted_hash[32], uint64_t target_block, uint8_t *blob, size_t cap);
 int tmx_step_inputs_from_fixture(const char *fixture_dir, uint32_t n_max, uint64_t prev_block, const uint8_t prev_hash[32],
                                  uint8_t *blob, size_t cap);
+/* Operator-side search [circuits/input/mod.rs:158-186 find_block_to_request; circuits/input/tendermint_utils.rs:444-482
+ * is_valid_skip]: is a skip from start_block to target_block possible (more than 1/3 of the target set's voting power is
+ * held by start-set validators present in the target commit), and the highest block <= max_end_block reachable from
+ * start_block by halving the distance (start_block + 1 = "request a step instead").  Missing fixtures -> TMX_E_IO, as
+ * the reference's `expect` would abort. */
+int tmx_is_valid_skip_from_fixture(const char *fixture_dir, uint64_t start_block, uint64_t target_block, int *valid);
+int tmx_find_block_to_request(const char *fixture_dir, uint64_t start_block, uint64_t max_end_block, uint64_t *block);
 /* tmx_prove with the off-chain inputs fetched from a fixture directory (the complete `prove input.json` path) */
 int tmx_prove_fixture(tmx_circuit *circuit, const uint8_t *input, size_t input_len, const char *fixture_dir,
                       tmx_proof **proof, uint8_t out32[32]);

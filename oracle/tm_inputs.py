@@ -397,3 +397,36 @@ class SignedBlockSource:
 
     def validators(self, height):
         return self._load(height)["validator_set"]["validators"]
+
+
+# ---- operator-side search ----
+def is_valid_skip(src, start_block, target_block):
+    """REF circuits/input/tendermint_utils.rs:444-482.  `validator_address()` is Some for block_id_flag 2 (commit) and
+    3 (nil), None for 1 (absent); the comparison is done in f64 exactly like the reference."""
+    start, target = src.validators(start_block), src.validators(target_block)
+    sigs = src.signed_header(target_block)["commit"]["signatures"]
+    threshold = 1.0 / 3.0
+    total = sum(int(v["voting_power"]) for v in target)
+    by_addr = {}
+    for v in target:
+        by_addr.setdefault(v["address"].upper(), v)
+    shared, idx = 0, 0
+    while float(total) * threshold > float(shared) and idx < len(start):
+        tv = by_addr.get(start[idx]["address"].upper())
+        if tv is not None:
+            for s in sigs:
+                if int(s["block_id_flag"]) in (2, 3) and s["validator_address"].upper() == tv["address"].upper():
+                    shared += int(tv["voting_power"])
+        idx += 1
+    return float(total) * threshold <= float(shared)
+
+
+def find_block_to_request(src, start_block, max_end_block):
+    """REF circuits/input/mod.rs:158-186."""
+    cur = max_end_block
+    while True:
+        if cur - start_block == 1:
+            return cur
+        if is_valid_skip(src, start_block, cur):
+            return cur
+        cur = (cur + start_block) // 2

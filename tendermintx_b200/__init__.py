@@ -175,6 +175,18 @@ class InputDataFetcher:
                                                   buf, len(buf)))
         return bytes(buf)
 
+    def is_valid_skip(self, start_block, target_block):
+        """REF circuits/input/tendermint_utils.rs:444-482."""
+        v = ctypes.c_int()
+        _check(lib().tmx_is_valid_skip_from_fixture(self.fixture_path, start_block, target_block, ctypes.byref(v)))
+        return bool(v.value)
+
+    def find_block_to_request(self, start_block, max_end_block):
+        """REF circuits/input/mod.rs:158-186: highest block to request a skip to (start_block + 1 = request a step)."""
+        b = ctypes.c_uint64()
+        _check(lib().tmx_find_block_to_request(self.fixture_path, start_block, max_end_block, ctypes.byref(b)))
+        return int(b.value)
+
     def get_step_inputs(self, n_max, prev_block, prev_hash):
         buf = (ctypes.c_uint8 * blob_size(KIND_STEP, n_max))()
         _check(lib().tmx_step_inputs_from_fixture(self.fixture_path, n_max, prev_block, bytes(prev_hash), buf, len(buf)))

@@ -69,6 +69,8 @@ def load():
         "tmx_header_hash_from_fixture": (i32, [c.c_char_p, c.c_uint64, vp]),
         "tmx_skip_inputs_from_fixture": (i32, [c.c_char_p, u32, c.c_uint64, vp, c.c_uint64, vp, sz]),
         "tmx_step_inputs_from_fixture": (i32, [c.c_char_p, u32, c.c_uint64, vp, vp, sz]),
+        "tmx_is_valid_skip_from_fixture": (i32, [c.c_char_p, c.c_uint64, c.c_uint64, c.POINTER(c.c_int)]),
+        "tmx_find_block_to_request": (i32, [c.c_char_p, c.c_uint64, c.c_uint64, c.POINTER(c.c_uint64)]),
         "tmx_prove_fixture": (i32, [vp, vp, sz, c.c_char_p, c.POINTER(vp), vp]),
         "tmx_proof_size": (sz, [vp]),
         "tmx_proof_bytes": (i32, [vp, vp, sz]),
@@ -89,6 +91,6 @@ EXPORTED_SYMBOLS = [
     "tmx_poseidon_permute", "tmx_host_poseidon_permute", "tmx_host_air_ed25519", "tmx_trace_dims", "tmx_witness_aux_bytes", "tmx_sha256_trace", "tmx_ed25519_trace",
     "tmx_witness_generate", "tmx_quotient", "tmx_pow_grind", "tmx_circuit_build", "tmx_circuit_free", "tmx_circuit_digest",
     "tmx_circuit_save", "tmx_circuit_load", "tmx_prove", "tmx_last_check", "tmx_circuit_last_phase_ms", "tmx_circuit_set_inputs", "tmx_header_hash_from_fixture", "tmx_skip_inputs_from_fixture",
-    "tmx_step_inputs_from_fixture", "tmx_prove_fixture", "tmx_proof_size", "tmx_proof_bytes",
+    "tmx_step_inputs_from_fixture", "tmx_is_valid_skip_from_fixture", "tmx_find_block_to_request", "tmx_prove_fixture", "tmx_proof_size", "tmx_proof_bytes",
     "tmx_proof_free", "tmx_verify", "tmx_verify_params",
 ]

@@ -522,6 +522,48 @@ int build_step(const FixtureSource& src, uint32_t n_max, uint64_t prev, const ui
     return TMX_OK;
 }
 
+// REF tendermint_utils.rs:444-482 (is_valid_skip): voting power of the target set held by validators of the start set
+// that appear in the target commit with a validator address (tendermint-rs CommitSig::validator_address(): flag 2
+// "commit" and flag 3 "nil" carry one, flag 1 "absent" does not), compared in f64 against one third of the target
+// set's total power exactly as the reference does (1_f64 / 3_f64, >, <=).
+bool is_valid_skip(const FixtureSource& src, uint64_t start_block, uint64_t target_block) {
+    const std::vector<Validator> start = src.validators(start_block), target = src.validators(target_block);
+    const Json sh = src.signed_header(target_block);
+    const auto& sigs = need(need(sh, "commit"), "signatures").arr;
+    const double threshold = 1.0 / 3.0;
+    uint64_t total = 0, shared = 0;
+    for (const Validator& v : target) total += v.power;
+    size_t idx = 0;
+    while ((double)total * threshold > (double)shared && idx < start.size()) {
+        const Validator* tv = nullptr;
+        for (const Validator& v : target)
+            if (v.address == start[idx].address) {
+                tv = &v;
+                break;
+            }
+        if (tv) {
+            for (const Json& sig : sigs) {
+                const uint64_t flag = as_u64(need(sig, "block_id_flag"));
+                if (flag != 2 && flag != 3) continue;
+                if (from_hex(as_str(need(sig, "validator_address"))) == tv->address) shared += tv->power;
+            }
+        }
+        idx++;
+    }
+    return (double)total * threshold <= (double)shared;
+}
+
+// REF input/mod.rs:158-186 (find_block_to_request): halve the distance until a skip is possible; start + 1 means "step"
+uint64_t find_block_to_request(const FixtureSource& src, uint64_t start_block, uint64_t max_end_block) {
+    if (max_end_block <= start_block) bad("find_block_to_request: max_end_block must be above start_block");
+    uint64_t cur = max_end_block;
+    for (;;) {
+        if (cur - start_block == 1) return cur;
+        if (is_valid_skip(src, start_block, cur)) return cur;
+        cur = (cur + start_block) / 2;
+    }
+}
+
 template <class Fn>
 int guarded(Fn&& fn) {
     try {
@@ -545,6 +587,22 @@ extern "C" int tmx_header_hash_from_fixture(const char* fixture_dir, uint64_t bl
         const Json sh = src.signed_header(block);
         const HeaderProofs hp = prove_header(need(sh, "header"));
         memcpy(out, hp.root.data(), 32);
+        return (int)TMX_OK;
+    });
+}
+
+extern "C" int tmx_is_valid_skip_from_fixture(const char* fixture_dir, uint64_t start_block, uint64_t target_block, int* valid) {
+    if (!fixture_dir || !valid) return fail(TMX_E_INPUT, "tmx_is_valid_skip_from_fixture: NULL argument");
+    return guarded([&] {
+        *valid = is_valid_skip(FixtureSource{fixture_dir}, start_block, target_block) ? 1 : 0;
+        return (int)TMX_OK;
+    });
+}
+
+extern "C" int tmx_find_block_to_request(const char* fixture_dir, uint64_t start_block, uint64_t max_end_block, uint64_t* block) {
+    if (!fixture_dir || !block) return fail(TMX_E_INPUT, "tmx_find_block_to_request: NULL argument");
+    return guarded([&] {
+        *block = find_block_to_request(FixtureSource{fixture_dir}, start_block, max_end_block);
         return (int)TMX_OK;
     });
 }

@@ -170,3 +170,27 @@ def test_skip_n128_proof_bytes_equal_oracle(ctx, oracle):
     got = np.frombuffer(proof, dtype=np.uint64)
     assert got.size == want.size and np.array_equal(got, want), f"first differing word {_first_diff(got, want)} of {want.size}"
     circuit.close()
+
+
+def test_prover_pool_three_in_flight(ctx):
+    """ProverPool: independent proofs in flight on one GPU give the same bytes as one prover, in order, and a failing
+    statement surfaces as the reference's witness-generation panic would (TMX_E_UNSAT)."""
+    import tendermintx_b200 as tmx
+
+    cases = _cases()
+    a, b = cases["skip_3000_3100_n4"], cases["skip_10000_10500_n4"]
+    stm = [(bytes.fromhex(c["input"]), bytes.fromhex(c["blob"])) for c in (a, b)]
+    single = tmx.Circuit.build(ctx, tmx.KIND_SKIP, 4, tmx.Mocha4Config)
+    want = [single.prove(*s) for s in stm]
+    pool = tmx.ProverPool(0, tmx.KIND_SKIP, 4, tmx.Mocha4Config, in_flight=3)
+    got = pool.prove_many([stm[i % 2] for i in range(8)])
+    for i, (proof, out) in enumerate(got):
+        assert proof == want[i % 2][0] and out == want[i % 2][1]
+        assert out.hex() == (a, b)[i % 2]["expected_output"]
+    bad = bytearray(stm[0][1])
+    bad[920 + 32 + 3] ^= 0x40
+    with pytest.raises(tmx.TmxError) as e:
+        pool.prove_many([stm[0], (stm[0][0], bytes(bad)), stm[1]])
+    assert e.value.code == 2
+    pool.close()
+    single.close()
