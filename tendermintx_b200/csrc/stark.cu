@@ -123,12 +123,20 @@ __global__ void __launch_bounds__(256) eval_columns_kernel(const gl* __restrict_
                                                             gl2* __restrict__ out_b) {
     __shared__ gl2 red[2][256];
     const gl* c = coeffs + (size_t)blockIdx.x * n;
-    gl2 sa = gl2_from(0), sb = gl2_from(0);
+    // exact field sums, order irrelevant: 192-bit accumulators, one reduction per thread
+    gl_acc192 a0 = gl_acc_zero(), a1 = gl_acc_zero(), b0 = gl_acc_zero(), b1 = gl_acc_zero();
     for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
         const gl v = c[i];
-        sa = gl2_add(sa, gl2_scale(ypa[i], v));
-        if (ypb) sb = gl2_add(sb, gl2_scale(ypb[i], v));
+        const gl2 ya = ypa[i];
+        gl_acc_mac(a0, ya.a0, v);
+        gl_acc_mac(a1, ya.a1, v);
+        if (ypb) {
+            const gl2 yb = ypb[i];
+            gl_acc_mac(b0, yb.a0, v);
+            gl_acc_mac(b1, yb.a1, v);
+        }
     }
+    const gl2 sa = gl2_make(gl_acc_reduce(a0), gl_acc_reduce(a1)), sb = gl2_make(gl_acc_reduce(b0), gl_acc_reduce(b1));
     red[0][threadIdx.x] = sa;
     red[1][threadIdx.x] = sb;
     __syncthreads();
@@ -162,9 +170,16 @@ struct FriBatchArgs {
 __global__ void __launch_bounds__(128) fri_batch_kernel(FriBatchArgs a) {
     const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= a.m) return;
-    gl2 s1 = gl2_from(0);
+    // S1 = sum_j alpha^j col_j (extension times base, component-wise): 192-bit accumulators, reduced once
+    gl_acc192 u0 = gl_acc_zero(), u1 = gl_acc_zero();
     const gl* col = a.lde_t + p;
-    for (size_t j = 0; j < a.C; j++) s1 = gl2_add(s1, gl2_scale(a.apow[j], col[j * a.m]));
+    for (size_t j = 0; j < a.C; j++) {
+        const gl v = col[j * a.m];
+        const gl2 w = a.apow[j];
+        gl_acc_mac(u0, w.a0, v);
+        gl_acc_mac(u1, w.a1, v);
+    }
+    const gl2 s1 = gl2_make(gl_acc_reduce(u0), gl_acc_reduce(u1));
     gl2 s0 = s1;
     for (size_t q = 0; q < 4; q++) s0 = gl2_add(s0, gl2_scale(a.apow[a.C + q], a.lde_q[q * a.m + p]));
     const gl x = gl_mul(GL_GEN, gl_pow(a.w_m, bitrev32((uint32_t)p, a.log_m)));
