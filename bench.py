@@ -330,7 +330,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--in-flight", type=int, default=3, help="independent proofs in flight per GPU (ProverPool)")
+    ap.add_argument("--in-flight", type=int, default=4, help="independent proofs in flight per GPU (ProverPool)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -170,10 +170,11 @@ TMX_HD void poseidon_split(gl x, uint32_t* p0, uint32_t* p1, uint32_t* p2) {
     *p1 = (uint32_t)(x >> 22) & 0x3FFFFFu;
     *p2 = (uint32_t)(x >> 44);
 }
-// o0 + o1 2^22 + o2 2^44 + rc (0 <= value < 2^73, the o's signed) -> [0, 2^64), congruent mod p
+// o0 + o1 2^22 + o2 2^44 + rc (0 <= value < 2^73) -> [0, 2^64), congruent mod p.  Only o0 can be negative: p1 and p2 of
+// every lane are non-negative (see poseidon_normalize), so their convolutions are too.
 TMX_HD gl poseidon_recombine(uint32_t o0, uint32_t o1, uint32_t o2, gl rc) {
-    const int64_t A = (int64_t)(int32_t)o0 + ((int64_t)(int32_t)o1 << 22);
-    const gl H = (gl)((A >> 32) + ((int64_t)(int32_t)o2 << 12));  // >= 0: the words above bit 32
+    const int64_t A = (int64_t)(int32_t)o0 + (int64_t)((gl)o1 << 22);
+    const gl H = (gl)(A >> 32) + ((gl)o2 << 12);  // >= 0: the words above bit 32
     gl c;
     const gl t = gl_add_carry((H << 32) | (uint32_t)A, rc, &c);
     const gl ov = (H >> 32) + c;  // weight 2^64 = 2^32 - 1, ov < 2^12

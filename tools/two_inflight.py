@@ -8,7 +8,7 @@ f = tmx.InputDataFetcher(f"{root}/skip_n128_seed0")
 th = bytes.fromhex(idx["trusted_hash"])
 blob = f.get_skip_inputs(128, idx["trusted"], th, idx["target"])
 pub = idx["trusted"].to_bytes(8, "big") + th + idx["target"].to_bytes(8, "big")
-for T in (1, 2, 3):
+for T in (1, 2, 3, 4):
     ctxs = [tmx.Context(0) for _ in range(T)]
     cs = [tmx.Circuit.build(c, tmx.KIND_SKIP, 128, tmx.CelestiaConfig) for c in ctxs]
     for c in cs:
