@@ -194,3 +194,33 @@ def test_prover_pool_three_in_flight(ctx):
     assert e.value.code == 2
     pool.close()
     single.close()
+
+
+@pytest.mark.parametrize("seed,kw,n,n_max", [(22, {"absent_frac": 0.3}, 13, 16), (21, {"absent_frac": 0.3}, 13, 16), (21, {"rnd": 3}, 16, 16),
+                                             (22, {"absent_frac": 0.25, "step": True}, 7, 8), (21, {"absent_frac": 0.25, "step": True}, 7, 8)])
+def test_ragged_validator_sets_equal_oracle(ctx, oracle, seed, kw, n, n_max):
+    """Edge cases of the domain: absent signers (dummy signature slots), padding slots (n < n_max), non-zero round
+    (longer sign-bytes), step linkage -- GPU proof bytes equal the oracle's."""
+    import tendermintx_b200 as tmx
+    from oracle import tm_inputs as ti
+
+    step = kw.get("step", False)
+    src, t, g = ti.synthetic_source(seed=seed, n_validators=n, **kw)  # seed 22: 6 / 1 absent signers, still above the
+    th = ti.header_hash(src.signed_header(t)["header"])              # thresholds; seed 21: too much power absent -> UNSAT
+    if step:
+        blob, pub, kind = ti.step_inputs(src, n_max, t, th), ti.step_public_input(t, th), tmx.KIND_STEP
+    else:
+        blob, pub, kind = ti.skip_inputs(src, n_max, t, th, g), ti.skip_public_input(t, th, g), tmx.KIND_SKIP
+    circuit = tmx.Circuit.build(ctx, kind, n_max, tmx.CelestiaConfig)
+    status, want, want_out = oracle.prove(pub, blob, "celestia")
+    assert (status == "OK") == (seed == 22 or "rnd" in kw)
+    if status != "OK":  # too much voting power absent: both sides must name the same failing check
+        with pytest.raises(tmx.TmxError) as e:
+            circuit.prove(pub, blob)
+        assert e.value.code == 2 and e.value.check == status
+    else:
+        proof, out = circuit.prove(pub, blob)
+        assert out == want_out == ti.header_hash(src.signed_header(g)["header"])
+        assert np.array_equal(np.frombuffer(proof, dtype=np.uint64), want)
+        circuit.verify(proof, pub, out)
+    circuit.close()
