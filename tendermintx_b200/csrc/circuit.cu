@@ -344,13 +344,20 @@ extern "C" int tmx_prove(tmx_circuit* c, const uint8_t* input, size_t input_len,
     WitnessArgs wa;
     int rc = witness_make_args(ctx, c->d_blob, c->kind, c->n_max, c->d_trace[0], c->d_trace[1], c->d_trace[2], c->d_aux, &wa);
     if (rc) return rc;
-    // side stream: Ed25519 phase 1 (sequential ladders, ~7 ms of latency, few threads) runs while the main stream
-    // fills and proves the SHA-256 table
+    // side stream: Ed25519 phase 1 (sequential ladders, ~6 ms of latency, two warps per validator) overlaps with the
+    // latency-bound part of the SHA-256 table's proof (quotient, openings, FRI: small kernels and host round trips).  It is
+    // started only after that table's commitment: run next to the LDE it kept the NTT tiles off its 128 SMs (the LDE
+    // took 6.8 ms instead of 1.5), and next to the leaf hashing its 11 k registers per SM push one hashing CTA per SM
+    // into a second wave.
     TMX_CUDA(cudaEventRecord(c->ev_inputs, st));
-    TMX_CUDA(cudaStreamWaitEvent(c->side, c->ev_inputs, 0));
-    rc = run_ed25519_ladder(ctx, wa, c->d_points, c->side);
-    if (rc) return rc;
-    TMX_CUDA(cudaEventRecord(c->ev_ladder, c->side));
+    auto start_ladders = [&](cudaEvent_t committed) -> int {
+        TMX_CUDA(cudaStreamWaitEvent(c->side, c->ev_inputs, 0));
+        TMX_CUDA(cudaStreamWaitEvent(c->side, committed, 0));
+        int r = run_ed25519_ladder(ctx, wa, c->d_points, c->side);
+        if (r) return r;
+        TMX_CUDA(cudaEventRecord(c->ev_ladder, c->side));
+        return TMX_OK;
+    };
     rc = witness_run_sha256(ctx, wa, st);
     if (rc) return rc;
     memcpy(out32, h->header, 32);
@@ -368,7 +375,7 @@ extern "C" int tmx_prove(tmx_circuit* c, const uint8_t* input, size_t input_len,
     }
     Challenger ch;
     transcript_init(c, input, input_len, out32, ch);
-    rc = c->prover.prove(ctx, 0, c->d_trace[0], ilog2(c->dims[0]), ch, w, st);
+    rc = c->prover.prove(ctx, 0, c->d_trace[0], ilog2(c->dims[0]), ch, w, st, start_ladders);
     if (rc) {
         delete p;
         return rc;

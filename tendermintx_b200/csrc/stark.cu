@@ -324,7 +324,7 @@ struct PhaseTimer {
 };
 
 int TableProver::prove(tmx_ctx* ctx, int table, const gl* d_trace, unsigned log_n, Challenger& ch, std::vector<gl>& proof,
-                       cudaStream_t st) {
+                       cudaStream_t st, const std::function<int(cudaEvent_t)>& on_trace_committed) {
     const size_t n = (size_t)1 << log_n, m = n << STARK_RATE_BITS;
     const unsigned km = log_n + STARK_RATE_BITS;
     const size_t C = (size_t)air_cols(table);
@@ -347,6 +347,10 @@ int TableProver::prove(tmx_ctx* ctx, int table, const gl* d_trace, unsigned log_
     rc = merkle_generic(ctx, d_lde, C, 1, m, km, cap_h, d_dig_t, st);
     if (rc) return rc;
     TMX_CUDA(cudaEventRecord(ev_phase[2], st));
+    if (on_trace_committed) {
+        rc = on_trace_committed(ev_phase[2]);
+        if (rc) return rc;
+    }
     pt.tick("trace merkle");
     std::vector<gl> cap;
     rc = d2h(cap, d_dig_t + 4 * (dig_t - cap_n), 4 * cap_n, st);
