@@ -36,45 +36,6 @@ __global__ void __launch_bounds__(128) merkle_level_kernel(const gl* __restrict_
     reinterpret_cast<ulonglong2*>(parents + 4 * i)[1] = make_ulonglong2(out[2], out[3]);
 }
 
-// Upper part of the tree in ONE launch: a CTA loads `width` (<= 1024) sibling digests of one subtree into shared
-// memory and reduces `levels` levels there; grid = number of such subtrees.  Used once the level is small enough that
-// per-level launches would be latency-bound (the tree has log2(rows) - cap levels, most of them tiny).
-__global__ void __launch_bounds__(256) merkle_subtree_kernel(const gl* __restrict__ level_in, gl* __restrict__ levels_out,
-                                                             unsigned width_log, unsigned levels, size_t n_in) {
-    extern __shared__ gl sm[];  // ping-pong: width * 4 + width * 2 words
-    const size_t width = (size_t)1 << width_log;
-    gl* cur_buf = sm;
-    gl* nxt_buf = sm + width * 4;
-    const size_t base = (size_t)blockIdx.x * width;
-    for (size_t i = threadIdx.x; i < width * 4; i += blockDim.x) cur_buf[i] = level_in[4 * base + i];
-    __syncthreads();
-    // level l (1-based, relative to level_in) has n_in >> l nodes and starts out_off digests into levels_out
-    size_t out_off = 0, cur = width;
-    for (unsigned l = 1; l <= levels; l++) {
-        cur >>= 1;
-        for (size_t i = threadIdx.x; i < cur; i += blockDim.x) {
-            gl a[4], b[4], o[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                a[k] = cur_buf[8 * i + k];
-                b[k] = cur_buf[8 * i + 4 + k];
-            }
-            poseidon_two_to_one(a, b, o);
-            gl* dst = levels_out + 4 * (out_off + (size_t)blockIdx.x * cur + i);
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                dst[k] = o[k];
-                nxt_buf[4 * i + k] = o[k];
-            }
-        }
-        __syncthreads();
-        gl* t = cur_buf;
-        cur_buf = nxt_buf;
-        nxt_buf = t;
-        out_off += n_in >> l;
-    }
-}
-
 __global__ void poseidon_permute_kernel(gl* states, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -112,25 +73,19 @@ int merkle_generic(tmx_ctx* ctx, const gl* base, size_t leaf_len, size_t row_str
     TMX_CUDA(cudaGetLastError());
     gl* lvl = d_digests;
     size_t m = n;
-    unsigned l = 0;
-    // big levels: one launch each
-    while (l + cap_height < log_rows && (m >> cap_height) > 512) {
+    // One launch per level.  Large levels are throughput work (128-thread CTAs); small ones are latency work: a
+    // permutation is ~23 k instructions, so a warp that shares its SM sub-partition with another one takes twice as
+    // long.  Below 16 Ki parents the level is spread one warp per CTA over as many SMs as possible (the first version
+    // reduced the last nine levels inside one 256-thread CTA per cap subtree: 16 busy SMs, 0.3 - 0.45 ms per tree,
+    // fifteen trees per proof).
+    for (unsigned l = 0; l + cap_height < log_rows; l++) {
         gl* nxt = lvl + 4 * m;
         m >>= 1;
-        merkle_level_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(lvl, nxt, m);
+        const unsigned threads = m >= 16384 ? 128 : 32;
+        merkle_level_kernel<<<(unsigned)((m + threads - 1) / threads), threads, 0, st>>>(lvl, nxt, m);
         ctx->launches++;
         TMX_CUDA(cudaGetLastError());
         lvl = nxt;
-        l++;
-    }
-    // remaining levels (each cap subtree <= 512 digests wide): one launch, one CTA per cap subtree
-    if (l + cap_height < log_rows) {
-        const unsigned levels = log_rows - cap_height - l;       // levels still to build
-        const unsigned width_log = levels;                       // each cap digest covers 2^levels nodes of this level
-        const unsigned grid = (unsigned)(m >> width_log);        // = 2^cap_height
-        merkle_subtree_kernel<<<grid, 256, ((size_t)6 << width_log) * sizeof(gl), st>>>(lvl, lvl + 4 * m, width_log, levels, m);
-        ctx->launches++;
-        TMX_CUDA(cudaGetLastError());
     }
     return TMX_OK;
 }

@@ -292,10 +292,20 @@ unsigned fri_num_layers(unsigned degree_bits) {
     return l;
 }
 
-static int d2h(std::vector<gl>& dst, const gl* src, size_t n, cudaStream_t st) {
-    dst.resize(n);
-    TMX_CUDA(cudaMemcpyAsync(dst.data(), src, n * sizeof(gl), cudaMemcpyDeviceToHost, st));
+// device -> host through a pinned staging buffer owned by the prover (pageable destinations make every one of the
+// ~12 transcript round trips per table a staged, driver-synchronised copy)
+int TableProver::d2h(std::vector<gl>& dst, const gl* src, size_t n, cudaStream_t st) {
+    if (sz_pinned < n) {
+        if (h_pinned) cudaFreeHost(h_pinned);
+        h_pinned = nullptr;
+        sz_pinned = 0;
+        const size_t want = std::max<size_t>(n + n / 4, 1 << 16);
+        TMX_CUDA(cudaMallocHost((void**)&h_pinned, want * sizeof(gl)));
+        sz_pinned = want;
+    }
+    TMX_CUDA(cudaMemcpyAsync(h_pinned, src, n * sizeof(gl), cudaMemcpyDeviceToHost, st));
     TMX_CUDA(cudaStreamSynchronize(st));
+    dst.assign(h_pinned, h_pinned + n);
     return TMX_OK;
 }
 
@@ -614,6 +624,7 @@ int TableProver::periodic_tables(tmx_ctx* ctx, int table, unsigned log_n, const 
 void TableProver::release() {
     for (int i = 0; i < 3; i++)
         if (ev_phase[i]) cudaEventDestroy(ev_phase[i]);
+    if (h_pinned) cudaFreeHost(h_pinned);
     void* ps[] = {d_lde, d_coeffs, d_dig_t, d_dig_q, d_dig_fri, d_qv, d_qcoef, d_qlde, d_ypa, d_open, d_apow, d_idx, d_fri_base, d_query};
     for (void* p : ps)
         if (p) cudaFree(p);

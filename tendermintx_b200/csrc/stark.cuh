@@ -44,12 +44,14 @@ struct TableProver {
     // device-time stamps of the trace commitment of the last prove(): LDE start, LDE end = Merkle start, Merkle end
     cudaEvent_t ev_phase[3] = {nullptr, nullptr, nullptr};
     float last_lde_ms = 0.f, last_merkle_ms = 0.f;
+    gl* h_pinned = nullptr; size_t sz_pinned = 0;  // pinned staging buffer for the transcript's device -> host copies
 
     // Appends this table's proof to `proof` and advances the transcript.  `on_trace_committed` (optional) is called once
     // the trace commitment has been enqueued and its completion event recorded: the caller uses it to start
     // work on another stream that should overlap with the latency-bound rest of this table's proof.
     int prove(tmx_ctx* ctx, int table, const gl* d_trace, unsigned log_n, Challenger& ch, std::vector<gl>& proof, cudaStream_t st,
               const std::function<int(cudaEvent_t)>& on_trace_committed = nullptr);
+    int d2h(std::vector<gl>& dst, const gl* src, size_t n, cudaStream_t st);
     int reserve(tmx_ctx* ctx, size_t C, size_t n, size_t m, size_t dig_t);
     int reserve_queries(tmx_ctx* ctx, size_t n);
     int periodic_tables(tmx_ctx* ctx, int table, unsigned log_n, const gl** out);
