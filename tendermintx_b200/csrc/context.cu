@@ -72,7 +72,11 @@ void poseidon_generate_constants() {
 static int upload(tmx_ctx* ctx, const std::vector<gl>& h, gl** out) {
     void* d = nullptr;
     TMX_CUDA(cudaMalloc(&d, h.size() * sizeof(gl)));
+    // cudaMemcpy from pageable memory returns once the data is STAGED; the DMA runs in the legacy stream, which the
+    // provers' non-blocking streams do not wait for.  With several provers in flight a kernel could read a table before
+    // it had landed (seen as a wrong quotient cap in the first proof of a fresh context).  Wait for the DMA.
     TMX_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(gl), cudaMemcpyHostToDevice));
+    TMX_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
     ctx->owned.push_back(d);
     *out = (gl*)d;
     return TMX_OK;

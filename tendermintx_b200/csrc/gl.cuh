@@ -53,33 +53,39 @@ TMX_HD gl gl_sub_borrow_mask(gl a, gl b, gl* mask) {  // a - b mod 2^64, *mask =
 
 TMX_HD gl gl_canon(gl a) {  // [0, 2^64) -> [0, p)
 #if defined(__CUDA_ARCH__)
-    gl c;
-    const gl t = gl_add_carry(a, GL_EPS, &c);  // a - p mod 2^64; carries exactly when a >= p
-    return c ? t : a;
+    gl t;
+    // a - p = a + (2^32 - 1) mod 2^64 carries exactly when a >= p; the carry goes straight into a predicate
+    asm("{\n\t.reg .u32 al, ah, tl, th, c;\n\t.reg .pred q;\n\tmov.b64 {al, ah}, %1;\n\t"
+        "add.cc.u32 tl, al, 0xffffffff;\n\taddc.cc.u32 th, ah, 0;\n\taddc.u32 c, 0, 0;\n\t"
+        "setp.ne.u32 q, c, 0;\n\tselp.u32 tl, tl, al, q;\n\tselp.u32 th, th, ah, q;\n\tmov.b64 %0, {tl, th};\n\t}"
+        : "=l"(t) : "l"(a));
+    return t;
 #else
     return a - (GL_P & (0 - (gl)(a >= GL_P)));
 #endif
 }
 
+TMX_HD gl gl_sub(gl a, gl b) {  // a, b < p (b = p is also fine: used by gl_add)
+#if defined(__CUDA_ARCH__)
+    gl d;
+    // on borrow add p, i.e. subtract 2^32 - 1 from the wrapped difference: the borrow word (0 / 0xffffffff) IS that
+    // constant.  No second borrow: a - b + 2^64 >= 2^64 - p + 1 = 2^32.
+    asm("{\n\t.reg .u32 al, ah, bl, bh, dl, dh, m;\n\tmov.b64 {al, ah}, %1;\n\tmov.b64 {bl, bh}, %2;\n\t"
+        "sub.cc.u32 dl, al, bl;\n\tsubc.cc.u32 dh, ah, bh;\n\tsubc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 dl, dl, m;\n\tsubc.u32 dh, dh, 0;\n\tmov.b64 %0, {dl, dh};\n\t}"
+        : "=l"(d) : "l"(a), "l"(b));
+    return d;
+#else
+    return (a - b) + (GL_P & (0 - (gl)(a < b)));
+#endif
+}
 TMX_HD gl gl_add(gl a, gl b) {
 #if defined(__CUDA_ARCH__)
-    gl c1, c2;
-    const gl s = gl_add_carry(a, b, &c1);
-    const gl t = gl_add_carry(s, GL_EPS, &c2);  // s - p mod 2^64
-    return (c1 | c2) ? t : s;
+    return gl_sub(a, GL_P - b);  // a - (p - b): seven instructions against ten for add / compare / select
 #else
     const gl s = a + b;
     const gl over = (gl)(s < a) | (gl)(s >= GL_P);  // wrapped past 2^64, or landed in [p, 2^64)
     return s - (GL_P & (0 - over));                 // s - p (mod 2^64) is right in both cases (a, b < p)
-#endif
-}
-TMX_HD gl gl_sub(gl a, gl b) {
-#if defined(__CUDA_ARCH__)
-    gl m;
-    const gl d = gl_sub_borrow_mask(a, b, &m);
-    return d - (m & GL_EPS);  // + p mod 2^64 on borrow (a, b < p: no second borrow)
-#else
-    return (a - b) + (GL_P & (0 - (gl)(a < b)));
 #endif
 }
 TMX_HD gl gl_neg(gl a) { return a ? GL_P - a : 0; }

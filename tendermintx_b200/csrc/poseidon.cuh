@@ -33,7 +33,9 @@ static inline cudaError_t poseidon_upload_constants_tu() {
         pieces[i] = make_uint4((uint32_t)padded[i] & 0x3FFFFFu, (uint32_t)(padded[i] >> 22) & 0x3FFFFFu, (uint32_t)(padded[i] >> 44), 0u);
     cudaError_t e = cudaMemcpyToSymbol(d_poseidon_rcp, pieces, sizeof(pieces));
     if (e != cudaSuccess) return e;
-    return cudaMemcpyToSymbol(d_poseidon_rc, padded, sizeof(padded));
+    e = cudaMemcpyToSymbol(d_poseidon_rc, padded, sizeof(padded));
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(cudaStreamLegacy);  // staged copies: wait for the DMA (the provers' streams are non-blocking)
 }
 #endif
 

@@ -615,6 +615,7 @@ int TableProver::periodic_tables(tmx_ctx* ctx, int table, unsigned log_n, const 
     void* d = nullptr;
     TMX_CUDA(cudaMalloc(&d, tab.size() * sizeof(gl)));
     TMX_CUDA(cudaMemcpy(d, tab.data(), tab.size() * sizeof(gl), cudaMemcpyHostToDevice));
+    TMX_CUDA(cudaStreamSynchronize(cudaStreamLegacy));  // staged copy: the DMA must land before kernels on other streams read it
     pertabs[key] = (gl*)d;
     *out = (gl*)d;
     (void)ctx;

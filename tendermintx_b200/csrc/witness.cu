@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(256) ed25519_padding_kernel(WitnessArgs a, siz
 
 int witness_tu_init() {
     TMX_CUDA(cudaMemcpyToSymbol(d_DUMMY_SIGNATURE, DUMMY_SIGNATURE, 64));
+    TMX_CUDA(cudaStreamSynchronize(cudaStreamLegacy));  // staged copy, see context.cu upload()
     return TMX_OK;
 }
 

@@ -224,3 +224,24 @@ def test_ragged_validator_sets_equal_oracle(ctx, oracle, seed, kw, n, n_max):
         assert np.array_equal(np.frombuffer(proof, dtype=np.uint64), want)
         circuit.verify(proof, pub, out)
     circuit.close()
+
+
+def test_fresh_provers_in_flight_first_proofs_are_exact(ctx):
+    """Regression: lookup tables are uploaded on first use (staged cudaMemcpy); with several fresh provers racing through
+    their first proofs a kernel once read a table before the DMA had landed (wrong quotient cap, proof rejected)."""
+    import tendermintx_b200 as tmx
+
+    path, idx = _celestia_case("skip_n128_seed2")
+    f = tmx.InputDataFetcher(path)
+    th = bytes.fromhex(idx["trusted_hash"])
+    blob = f.get_skip_inputs(128, idx["trusted"], th, idx["target"])
+    pub = idx["trusted"].to_bytes(8, "big") + th + idx["target"].to_bytes(8, "big")
+    single = tmx.Circuit.build(ctx, tmx.KIND_SKIP, 128, tmx.CelestiaConfig)
+    want, out = single.prove(pub, blob)
+    single.verify(want, pub, out)
+    for _ in range(4):
+        pool = tmx.ProverPool(0, tmx.KIND_SKIP, 128, tmx.CelestiaConfig, in_flight=4)
+        res = pool.prove_many([(pub, blob)] * 8)
+        pool.close()
+        assert all(p == want and o == out for p, o in res)
+    single.close()
