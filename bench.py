@@ -24,8 +24,8 @@ sys.path.insert(0, ROOT)
 
 N_MAX = 128
 # dram__bytes_read.sum + dram__bytes_write.sum of the six ntt_pass_kernel launches that make up the LDE of the Ed25519
-# table (1217 columns x 2^16), from profiles/r1c_ncu_ntt.raw.csv (one ncu --set full capture, per LDE)
-NCU_K1_TRAFFIC_BYTES = 7370255872
+# table (1217 columns x 2^16), from profiles/r1d_ncu_ntt.raw.csv (one ncu --set full capture, per LDE)
+NCU_K1_TRAFFIC_BYTES = 7370145280
 METRIC = "skip proofs/hour (CelestiaConfig, 128 val)"
 UNIT = "proofs/hour"
 WORKLOAD = "skip circuit CelestiaConfig VALIDATOR_SET_SIZE_MAX=128 (synthetic celestia chain, 128 signers, seed=rank)"
@@ -300,18 +300,18 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": "ntt_pass_kernel family (K1: iNTT + coset LDE, rate 1/2, of the Ed25519 trace table, 1217 x 2^16, "
                      "six launches per proof, CUDA events recorded by the prover inside the timed proofs)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_K1_TRAFFIC_BYTES, "traffic_note": "dram read+write of the six K1 launches of the Ed25519 table, "
-                     "ncu --set full (profiles/r1c_ncu_ntt.raw.csv), per proof like achieved",
+                     "ncu --set full (profiles/r1d_ncu_ntt.raw.csv), per proof like achieved",
                      "peak_source": peak_src, "algorithmic_bytes": alg_bytes, "ms": lde_ms,
                      "ms_per_table": [p[0] / args.steps for p in phase],
                      "all_tables": {"algorithmic_bytes": alg_bytes_all, "ms": lde_ms_all,
                                     "achieved": alg_bytes_all / (lde_ms_all / 1e3) / 1e9},
                      "share_of_step": lde_ms_all / (lat_ms / args.steps),
-                     "note": "K1 is bound by 64-bit modular-arithmetic issue (ncu: ALU pipe ~80 % busy, DRAM < 20 %), so the HBM "
+                     "note": "K1 is bound by 64-bit modular-arithmetic issue and tile-load latency (ncu: ALU pipe ~70 % busy, DRAM ~20 %), so the HBM "
                              "fraction is low by construction; see DESIGN.md section 4"},
         "kernels": {"k2_poseidon_merkle_ms_per_proof": merkle_ms, "k2_Mperm_per_s": perms / merkle_ms / 1e3,
                     "k2_ms_per_table": [p[1] / args.steps for p in phase],
                     "k2_share_of_step": merkle_ms / (lat_ms / args.steps),
-                    "k2_note": "dominant kernel by time; bound by integer issue (ncu: ~1 % DRAM), 22.5 k instructions per permutation",
+                    "k2_note": "dominant kernel by time; bound by integer issue (ncu: < 1 % DRAM, busiest pipe 84 %), 22.7 k instructions per permutation",
                     "isolated_ed25519_table": {"lde_ms": iso[0], "lde_GBps": 8 * rows * cols * 3 / iso[0] / 1e6,
                                                "poseidon_merkle_ms": iso[1]}},
         "proof_bytes": len(proof),
