@@ -6,21 +6,29 @@
 //
 // Design (not a port of the CPU algorithm): an N = 2^k transform is split into 1..3 passes; pass i covers
 // l_i <= 10 butterfly stages of an in-place decimation-in-frequency network.  Each CTA stages a tile of
-// 16 vectors x 2^l points in shared memory (point-major, stride 17 so both the strided and the transposing
+// 8 vectors x 2^l points in shared memory (point-major, stride 9 so both the strided and the transposing
 // access patterns are bank-conflict free), runs the stages as radix-16 register blocks with twiddles from a
-// shared-memory table, applies the inter-pass twiddle w_N^(lo * bitrev(p)) from a two-level power table and
-// writes the tile back with >= 128-byte coalesced segments.  In-place DIF leaves the result bit-reversed,
+// shared-memory table, applies the inter-pass twiddle w_N^(lo * bitrev(p)) from a flat L2-resident table and
+// writes the tile back in 64-byte (strided passes) or full-row (contiguous pass) segments.  In-place DIF leaves the result bit-reversed,
 // which is exactly the Merkle-leaf order plonky2 wants for LDE values, so the forward transform never
 // reorders; the inverse transform folds the bit-reversal, the 1/n factor and the coset shift 7^i into the
-// scatter of its last pass.  HBM-bound integer work: no tensor cores.
+// scatter of its last pass.  HBM-shaped integer work that is in fact bound by 64-bit modular-arithmetic issue (see
+// profiles/r1_ncu_summary.md): no tensor cores.
 #include "ctx.cuh"
 #include <algorithm>
 #include <cstring>
 
 namespace tmx {
 
-constexpr int TILE_T = 16;   // vectors per tile
-constexpr int TILE_TS = 17;  // padded stride
+// Vectors per tile.  Measured on the Ed25519 table's LDE (1217 x 2^16): 16 vectors 4.42 ms, 8 vectors 4.13 ms, 4 vectors
+// 4.35 ms.  Narrower tiles mean smaller CTAs (128 threads, 19 KB of shared memory, < 60 registers): more CTAs per SM in
+// different phases, so tile loads overlap better with butterflies; below 64-byte rows the global accesses get too short.
+#ifndef TMX_NTT_TILE_LOG
+#define TMX_NTT_TILE_LOG 3
+#endif
+constexpr int TILE_LOG = TMX_NTT_TILE_LOG;
+constexpr int TILE_T = 1 << TILE_LOG;  // vectors per tile
+constexpr int TILE_TS = TILE_T + 1;    // padded stride
 
 struct PassArgs {
     const gl* in;
@@ -100,7 +108,9 @@ TMX_D void dif_vector(gl* tile, const gl* tws, int tid, int nthreads) {
 
 template <int LOG_L>
 constexpr int pass_threads() {
-    return (1 << LOG_L) < 32 ? 32 : ((1 << LOG_L) > 512 ? 512 : (1 << LOG_L));
+    // one thread per radix-16 register block of the tile
+    constexpr int t = ((1 << LOG_L) * TILE_T) / 16;
+    return t < 32 ? 32 : (t > 512 ? 512 : t);
 }
 
 // All sizes are powers of two: every index split below is a shift / mask (the first version divided 64-bit indices
@@ -115,19 +125,19 @@ __global__ void __launch_bounds__(pass_threads<LOG_L>()) ntt_pass_kernel(PassArg
     for (int i = tid; i < L / 2; i += nthreads) tws[i] = a.tw_small[i];
 
     if constexpr (STRIDED) {
-        const unsigned log_s = a.log_block - LOG_L;  // >= 4: S = 2^log_s elements between the points of a vector
+        const unsigned log_s = a.log_block - LOG_L;  // >= TILE_LOG: S = 2^log_s elements between the points of a vector
         const size_t S = (size_t)1 << log_s;
-        const unsigned log_tiles = log_s - 4;                  // tiles per block
+        const unsigned log_tiles = log_s - TILE_LOG;                  // tiles per block
         const unsigned log_blocks = a.log_n - a.log_block;     // blocks per column
         const size_t t = blockIdx.x;
-        const size_t lo0 = (t & (((size_t)1 << log_tiles) - 1)) << 4;
+        const size_t lo0 = (t & (((size_t)1 << log_tiles) - 1)) << TILE_LOG;
         const size_t hi = (t >> log_tiles) & (((size_t)1 << log_blocks) - 1);
         const size_t col = t >> (log_tiles + log_blocks);
         const size_t off = (hi << a.log_block) + lo0;
         const gl* src = a.in + col * a.in_col_stride + off;
         gl* dst = a.out + col * a.out_col_stride + off;
         for (int idx = tid; idx < L * TILE_T; idx += nthreads) {
-            const int v = idx & (TILE_T - 1), m = idx >> 4;
+            const int v = idx & (TILE_T - 1), m = idx >> TILE_LOG;
             gl x = src[((size_t)m << log_s) + v];
             if (a.ps) {
                 const uint64_t i = off + ((uint64_t)m << log_s) + v;
@@ -138,7 +148,7 @@ __global__ void __launch_bounds__(pass_threads<LOG_L>()) ntt_pass_kernel(PassArg
         __syncthreads();
         dif_vector<LOG_L>(tile, tws, tid, nthreads);
         for (int idx = tid; idx < L * TILE_T; idx += nthreads) {
-            const int v = idx & (TILE_T - 1), p = idx >> 4;
+            const int v = idx & (TILE_T - 1), p = idx >> TILE_LOG;
             gl x = tile[p * TILE_TS + v];
             const uint32_t j1 = bitrev32((uint32_t)p, LOG_L);
             if (j1) x = gl_mul(x, a.tw[((lo0 + v) * j1) << a.tw_shift]);
@@ -166,7 +176,7 @@ __global__ void __launch_bounds__(pass_threads<LOG_L>()) ntt_pass_kernel(PassArg
         dif_vector<LOG_L>(tile, tws, tid, nthreads);
         if (a.scatter_natural) {
             for (int idx = tid; idx < L * TILE_T; idx += nthreads) {
-                const int v = idx & (TILE_T - 1), p = idx >> 4;
+                const int v = idx & (TILE_T - 1), p = idx >> TILE_LOG;
                 const size_t gid = gid0 + v;
                 if (gid < total_vecs) {
                     const size_t col = gid >> log_vecs, c = gid & vec_mask;
