@@ -1,0 +1,64 @@
+"""CPU-side parity of the witness kernels' per-thread logic: tendermintx_b200/csrc/witness_jobs.cuh + witness.cuh are
+header code shared by the CUDA kernels and a host build (tools/hostsim.cpp, TEST TOOL: compiled here with g++ into
+tests/_build, never part of libtmx.so).  The tables it fills must equal the oracle's cell for cell, so a logic error in
+the SHA-256 / SHA-512 / Ed25519 row expansion shows up in the authoring container, without a GPU."""
+import ctypes
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+@pytest.fixture(scope="module")
+def hostsim():
+    out = os.path.join(HERE, "_build", "libhostsim.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    src = os.path.join(ROOT, "tools", "hostsim.cpp")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", out, src])
+    return ctypes.CDLL(out)
+
+
+def _cases():
+    with open(os.path.join(HERE, "golden", "fixture_vectors.json")) as f:
+        return {c["name"]: c for c in json.load(f)["cases"]}
+
+
+@pytest.mark.parametrize("name", ["step_10000_n2", "skip_3000_3100_n4", "step_10500_n4_with_dummy"])
+def test_kernel_row_logic_equals_oracle_tables(hostsim, oracle, name):
+    c = _cases()[name]
+    blob = bytes.fromhex(c["blob"])
+    want = oracle.build_traces(blob)
+    kind = 1 if c["kind"] == "skip" else 0
+    dims = oracle.trace_dims(kind, c["n_max"])
+    got = [np.zeros((cols, rows), dtype=np.uint64) for rows, cols in dims]
+    aux = np.zeros(4096, dtype=np.uint8)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rc = hostsim.hostsim_build_traces(blob, p(got[0]), ctypes.c_size_t(dims[0][0]), p(got[1]), ctypes.c_size_t(dims[1][0]),
+                                      p(got[2]), ctypes.c_size_t(dims[2][0]), p(aux))
+    assert rc == 0
+    for t, (g, w) in enumerate(zip(got, want)):
+        assert g.shape == w.shape
+        bad = np.argwhere(g != w)
+        assert bad.size == 0, f"table {t}: first differing (column, row) {bad[0]} of {len(bad)}"
+
+
+def test_synthetic_chain_with_absent_signers(hostsim, oracle):
+    from oracle import tm_inputs as ti
+
+    src, t, g = ti.synthetic_source(seed=22, n_validators=6, absent_frac=0.3)
+    th = ti.header_hash(src.signed_header(t)["header"])
+    blob = ti.skip_inputs(src, 8, t, th, g)
+    want = oracle.build_traces(blob)
+    dims = oracle.trace_dims(1, 8)
+    got = [np.zeros((cols, rows), dtype=np.uint64) for rows, cols in dims]
+    aux = np.zeros(4096, dtype=np.uint8)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    assert hostsim.hostsim_build_traces(blob, p(got[0]), ctypes.c_size_t(dims[0][0]), p(got[1]), ctypes.c_size_t(dims[1][0]),
+                                        p(got[2]), ctypes.c_size_t(dims[2][0]), p(aux)) == 0
+    for g_, w in zip(got, want):
+        assert np.array_equal(g_, w)
