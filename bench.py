@@ -158,7 +158,8 @@ def run_ours(args):
             with open(path, "wb") as fh:
                 fh.write(blob_bytes)
         pool = tmx.ProverPool(local_rank, tmx.KIND_SKIP, N_MAX, cfg, in_flight=args.in_flight, artefact=path)
-    circuit, ctx = pool.circuits[0], pool.ctxs[0]
+        ctx = tmx.Context(local_rank)  # a plain prover beside the pool: verification and the one-proof-at-a-time pass
+        circuit = tmx.Circuit.load(ctx, path, tmx.KIND_SKIP, N_MAX, cfg)
 
     # ---- inputs: host-side assembly from the fixture directory (C++), kept in host memory ----
     fixture, idx = load_case(rank)
@@ -190,14 +191,15 @@ def run_ours(args):
 
     # ---- warm-up on every prover (also the correctness gate: output header and CPU verification) ----
     warm = max(args.warmup, 1)
-    res = pool.prove_many([(pub, blob)] * (warm * args.in_flight))
+    res = pool.prove_many([(pub, blob)] * (warm * args.in_flight)) + [circuit.prove(pub, blob) for _ in range(warm)]
     proof, out = res[-1]
     assert all(r[1].hex() == idx["target_hash"] for r in res), "proved header differs from the fixture's block hash"
     assert all(r[0] == proof for r in res), "provers in flight disagree on the proof bytes"
     circuit.verify(proof, pub, out)
 
     pool.set_inputs(blob)
-    launches0 = pool.launch_count()
+    circuit.set_inputs(blob)
+    launches0 = ctx.launch_count()
     phase = [[0.0, 0.0] for _ in range(3)]  # per table: LDE (K1) and trace Merkle (K2) device ms summed over the proofs
 
     def one_at_a_time():
@@ -210,7 +212,7 @@ def run_ours(args):
     with ClockSampler(local_rank) as clocks:
         # (1) one proof at a time, HBM-resident inputs: per-proof latency and clean per-kernel timings for the roofline
         lat_ms, _ = timed(one_at_a_time)
-        launches = pool.launch_count() - launches0
+        launches = ctx.launch_count() - launches0
         # (2) value: K proofs, `in_flight` provers on this GPU, HBM-resident inputs
         launches1 = pool.launch_count()
         dev_ms, _ = timed(lambda: pool.prove_many([(pub, None)] * args.steps))

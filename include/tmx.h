@@ -174,6 +174,27 @@ size_t tmx_proof_size(const tmx_proof *proof);
 int tmx_proof_bytes(const tmx_proof *proof, uint8_t *buf, size_t cap);
 void tmx_proof_free(tmx_proof *proof);
 
+/* ------------------------------------------------------------------------------------------------
+ * Prover pool: `in_flight` independent provers on one GPU (own tmx_ctx, circuit buffers and host thread each), fed from
+ * one FIFO queue.  The Fiat-Shamir host round trips of one proof are filled by the kernels of the others (+25 % proofs
+ * per hour on a B200 at in_flight = 4); proofs are byte-identical to tmx_prove's.  Upstream this role is played by the
+ * proving platform dispatching `prove` requests to workers [bin/tendermintx.rs:169-223].  submit / wait may be called
+ * from any thread; wait returns the job's tmx_prove status (TMX_E_UNSAT + tmx_last_check() on the calling thread) and
+ * hands over the proof (free it with tmx_proof_free).  blob = NULL proves from the inputs of tmx_pool_set_inputs. */
+typedef struct tmx_pool tmx_pool;
+int tmx_pool_create(int device, uint32_t kind, uint32_t n_max, const char *chain_id, size_t chain_id_len, uint64_t skip_max,
+                    unsigned in_flight, tmx_pool **pool);
+/* the same with every prover loading the `build` artefact (./build/main.circuit) instead of building the circuit */
+int tmx_pool_create_from_artefact(int device, const char *path, unsigned in_flight, tmx_pool **pool);
+void tmx_pool_destroy(tmx_pool *pool);
+int tmx_pool_set_inputs(tmx_pool *pool, const uint8_t *blob, size_t blob_len);
+int tmx_pool_submit(tmx_pool *pool, const uint8_t *input, size_t input_len, const uint8_t *blob, size_t blob_len,
+                    uint64_t *ticket);
+int tmx_pool_wait(tmx_pool *pool, uint64_t ticket, tmx_proof **proof, uint8_t out32[32]);
+unsigned tmx_pool_in_flight(const tmx_pool *pool);
+uint64_t tmx_pool_launch_count(const tmx_pool *pool);
+int tmx_pool_last_phase_ms(const tmx_pool *pool, unsigned prover, float out[6]);
+
 /* `circuit.verify(&proof, &input, &output)` [circuits/skip.rs:247]: CPU verifier, 0 = accepted. */
 int tmx_verify(const tmx_circuit *circuit, const uint8_t *proof, size_t proof_len, const uint8_t *input,
                size_t input_len, const uint8_t out32[32]);

@@ -287,56 +287,84 @@ class Circuit:
 
 
 class ProverPool:
-    """Several provers in flight on ONE GPU.
+    """Several provers in flight on ONE GPU (`tmx_pool_*`, native: one tmx_ctx + circuit + host thread per prover, one
+    FIFO queue).
 
     A proof is a chain of kernels interleaved with Fiat-Shamir round trips to the host (cap -> challenge -> next
     kernel), so a single prover leaves the GPU idle for about a sixth of the proof.  Proofs are independent
-    (SURVEY section 8e), so a service keeps `in_flight` of them going, each with its own tmx_ctx (stream, scratch)
-    and circuit buffers, driven by its own host thread (ctypes releases the GIL during the C call): the gaps of one
-    are filled by the kernels of the others.  Nothing is shared between the provers and no proof changes.
+    (SURVEY section 8e), so a service keeps `in_flight` of them going: the gaps of one are filled by the kernels of the
+    others.  Nothing is shared between the provers and no proof changes.
     """
 
-    def __init__(self, device, kind, n_max, config, in_flight=3, artefact=None):
+    def __init__(self, device, kind, n_max, config, in_flight=4, artefact=None):
         self.device, self.kind, self.n_max, self.config = device, kind, n_max, config
-        self.ctxs = [Context(device) for _ in range(in_flight)]
+        self._h = ctypes.c_void_p()
         if artefact is None:
-            self.circuits = [Circuit.build(c, kind, n_max, config) for c in self.ctxs]
+            _check(lib().tmx_pool_create(device, kind, n_max, config.chain_id, len(config.chain_id), config.skip_max, in_flight,
+                                         ctypes.byref(self._h)))
         else:
-            self.circuits = [Circuit.load(c, artefact, kind, n_max, config) for c in self.ctxs]
+            _check(lib().tmx_pool_create_from_artefact(device, str(artefact).encode(), in_flight, ctypes.byref(self._h)))
+        self.in_flight = int(lib().tmx_pool_in_flight(self._h))
 
     def launch_count(self):
-        return sum(c.launch_count() for c in self.ctxs)
+        return int(lib().tmx_pool_launch_count(self._h))
+
+    def last_phase_ms(self, prover=0):
+        """Device time of the trace commitments inside prover `prover`'s last proof: [(lde_ms, merkle_ms)] per table."""
+        out = (ctypes.c_float * 6)()
+        _check(lib().tmx_pool_last_phase_ms(self._h, prover, out))
+        return [(out[2 * t], out[2 * t + 1]) for t in range(3)]
 
     def set_inputs(self, blob):
-        for c in self.circuits:
-            c.set_inputs(blob)
+        blob = bytes(blob)
+        _check(lib().tmx_pool_set_inputs(self._h, blob, len(blob)))
+
+    def submit(self, public_input, blob):
+        """Queue one proof (blob None = the resident inputs).  Returns a ticket for wait()."""
+        t = ctypes.c_uint64()
+        public_input = bytes(public_input)
+        blob = bytes(blob) if blob is not None else None
+        _check(lib().tmx_pool_submit(self._h, public_input, len(public_input), blob, len(blob) if blob is not None else 0,
+                                     ctypes.byref(t)))
+        return int(t.value)
+
+    def wait(self, ticket):
+        """Returns (proof bytes, output header bytes) of a submitted proof; raises TmxError as Circuit.prove would."""
+        p = ctypes.c_void_p()
+        out = (ctypes.c_uint8 * 32)()
+        rc = lib().tmx_pool_wait(self._h, ticket, ctypes.byref(p), out)
+        if rc != 0:
+            err = TmxError(rc, lib().tmx_last_error().decode())
+            err.check = CHECK_NAMES[lib().tmx_last_check()]
+            raise err
+        n = lib().tmx_proof_size(p)
+        buf = (ctypes.c_uint8 * n)()
+        _check(lib().tmx_proof_bytes(p, buf, n))
+        lib().tmx_proof_free(p)
+        return bytes(buf), bytes(out)
 
     def prove_many(self, statements):
-        """statements: list of (public_input, blob or None).  Returns the list of (proof, output) in order.
-        Statement j runs on prover j mod in_flight; the first exception (e.g. TMX_E_UNSAT) is re-raised."""
-        import threading
-
-        results = [None] * len(statements)
-        errors = []
-
-        def work(k):
+        """statements: list of (public_input, blob or None).  Returns the list of (proof, output) in order; the first
+        failing statement (e.g. TMX_E_UNSAT) raises after every queued proof has finished."""
+        tickets = [self.submit(p, b) for p, b in statements]
+        results, first_error = [], None
+        for t in tickets:
             try:
-                for j in range(k, len(statements), len(self.circuits)):
-                    results[j] = self.circuits[k].prove(*statements[j])
-            except Exception as e:  # noqa: BLE001 - re-raised below on the caller's thread
-                errors.append(e)
-
-        threads = [threading.Thread(target=work, args=(k,)) for k in range(min(len(self.circuits), len(statements)))]
-        for t in threads:
-            t.start()
-        for t in threads:
-            t.join()
-        if errors:
-            raise errors[0]
+                results.append(self.wait(t))
+            except TmxError as e:
+                results.append(None)
+                first_error = first_error or e
+        if first_error is not None:
+            raise first_error
         return results
 
     def close(self):
-        for c in self.circuits:
-            c.close()
-        for c in self.ctxs:
-            c.close()
+        if self._h:
+            lib().tmx_pool_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -71,6 +71,15 @@ def load():
         "tmx_step_inputs_from_fixture": (i32, [c.c_char_p, u32, c.c_uint64, vp, vp, sz]),
         "tmx_is_valid_skip_from_fixture": (i32, [c.c_char_p, c.c_uint64, c.c_uint64, c.POINTER(c.c_int)]),
         "tmx_find_block_to_request": (i32, [c.c_char_p, c.c_uint64, c.c_uint64, c.POINTER(c.c_uint64)]),
+        "tmx_pool_create": (i32, [i32, u32, u32, c.c_char_p, sz, c.c_uint64, u32, c.POINTER(vp)]),
+        "tmx_pool_create_from_artefact": (i32, [i32, c.c_char_p, u32, c.POINTER(vp)]),
+        "tmx_pool_destroy": (None, [vp]),
+        "tmx_pool_set_inputs": (i32, [vp, vp, sz]),
+        "tmx_pool_submit": (i32, [vp, vp, sz, vp, sz, c.POINTER(c.c_uint64)]),
+        "tmx_pool_wait": (i32, [vp, c.c_uint64, c.POINTER(vp), vp]),
+        "tmx_pool_in_flight": (u32, [vp]),
+        "tmx_pool_launch_count": (c.c_uint64, [vp]),
+        "tmx_pool_last_phase_ms": (i32, [vp, u32, vp]),
         "tmx_prove_fixture": (i32, [vp, vp, sz, c.c_char_p, c.POINTER(vp), vp]),
         "tmx_proof_size": (sz, [vp]),
         "tmx_proof_bytes": (i32, [vp, vp, sz]),
@@ -91,6 +100,8 @@ EXPORTED_SYMBOLS = [
     "tmx_poseidon_permute", "tmx_host_poseidon_permute", "tmx_host_air_ed25519", "tmx_trace_dims", "tmx_witness_aux_bytes", "tmx_sha256_trace", "tmx_ed25519_trace",
     "tmx_witness_generate", "tmx_quotient", "tmx_pow_grind", "tmx_circuit_build", "tmx_circuit_free", "tmx_circuit_digest",
     "tmx_circuit_save", "tmx_circuit_load", "tmx_prove", "tmx_last_check", "tmx_circuit_last_phase_ms", "tmx_circuit_set_inputs", "tmx_header_hash_from_fixture", "tmx_skip_inputs_from_fixture",
-    "tmx_step_inputs_from_fixture", "tmx_is_valid_skip_from_fixture", "tmx_find_block_to_request", "tmx_prove_fixture", "tmx_proof_size", "tmx_proof_bytes",
+    "tmx_step_inputs_from_fixture", "tmx_is_valid_skip_from_fixture", "tmx_find_block_to_request", "tmx_prove_fixture",
+    "tmx_pool_create", "tmx_pool_create_from_artefact", "tmx_pool_destroy", "tmx_pool_set_inputs", "tmx_pool_submit", "tmx_pool_wait", "tmx_pool_in_flight",
+    "tmx_pool_launch_count", "tmx_pool_last_phase_ms", "tmx_proof_size", "tmx_proof_bytes",
     "tmx_proof_free", "tmx_verify", "tmx_verify_params",
 ]

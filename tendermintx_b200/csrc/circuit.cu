@@ -206,6 +206,9 @@ static int check_statement(const tmx_circuit* c, const uint8_t* input, const uin
 }  // namespace tmx
 
 extern "C" int tmx_last_check(void) { return g_last_check; }
+namespace tmx {
+void set_last_check(int check) { g_last_check = check; }  // pool.cu hands a worker's verdict to the waiting thread
+}
 extern "C" int tmx_verify(const tmx_circuit* c, const uint8_t* proof, size_t proof_len, const uint8_t* input, size_t input_len,
                           const uint8_t out32[32]);
 
