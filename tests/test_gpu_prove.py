@@ -245,3 +245,22 @@ def test_fresh_provers_in_flight_first_proofs_are_exact(ctx):
         pool.close()
         assert all(p == want and o == out for p, o in res)
     single.close()
+
+
+def test_reference_default_size_n100_equals_oracle(ctx, oracle):
+    """The reference ships VALIDATOR_SET_SIZE_MAX = 100 [REF circuits/consts.rs:4, bin/skip.rs:25]: not a power of two
+    (Merkle shape 128, tables padded to 2^16 / 2^14 / 2^16 rows).  GPU proof bytes equal the oracle's."""
+    import tendermintx_b200 as tmx
+    from oracle import tm_inputs as ti
+
+    src, t, g = ti.synthetic_source(seed=5, n_validators=100)
+    th = ti.header_hash(src.signed_header(t)["header"])
+    blob, pub = ti.skip_inputs(src, 100, t, th, g), ti.skip_public_input(t, th, g)
+    circuit = tmx.Circuit.build(ctx, tmx.KIND_SKIP, 100, tmx.CelestiaConfig)
+    proof, out = circuit.prove(pub, blob)
+    assert out == ti.header_hash(src.signed_header(g)["header"])
+    circuit.verify(proof, pub, out)
+    status, want, want_out = oracle.prove(pub, blob, "celestia")
+    assert status == "OK" and want_out == out
+    assert np.array_equal(np.frombuffer(proof, dtype=np.uint64), want)
+    circuit.close()
