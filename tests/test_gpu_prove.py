@@ -264,3 +264,24 @@ def test_reference_default_size_n100_equals_oracle(ctx, oracle):
     assert status == "OK" and want_out == out
     assert np.array_equal(np.frombuffer(proof, dtype=np.uint64), want)
     circuit.close()
+
+
+@pytest.mark.parametrize("name,compare_oracle", [("step_157000_n128", True), ("skip_15000_50000_n128", False)])
+def test_real_mocha4_large_cases(ctx, oracle, name, compare_oracle):
+    """Real mocha-4 data at full table size: step 157000 -> 157001 with 100 validators and skip
+    15000 -> 50000 (34 trusted / 100 target validators, 47 signers, 97.6 % overlap), N_MAX = 128, Mocha4Config.  The expected
+    output is the block hash recorded in the fixture; one of them is also compared byte for byte with the oracle."""
+    import tendermintx_b200 as tmx
+
+    c = _cases()[name]
+    pub, blob = bytes.fromhex(c["input"]), bytes.fromhex(c["blob"])
+    kind = tmx.KIND_SKIP if c["kind"] == "skip" else tmx.KIND_STEP
+    circuit = tmx.Circuit.build(ctx, kind, c["n_max"], tmx.Mocha4Config)
+    proof, out = circuit.prove(pub, blob)
+    assert out.hex() == c["expected_output"]
+    circuit.verify(proof, pub, out)
+    if compare_oracle:
+        status, want, want_out = oracle.prove(pub, blob, "mocha-4")
+        assert status == "OK" and want_out == out
+        assert np.array_equal(np.frombuffer(proof, dtype=np.uint64), want)
+    circuit.close()
