@@ -33,7 +33,11 @@
 #define S256_COLS 371
 #define S256_ROUNDS 64
 
-/* ---------------- SHA-512: one row per round, 80 rows per 128-byte chunk, 2 chunks per validator -------- */
+/* ---------------- SHA-512: one row per round, 128 rows per 128-byte chunk, 2 chunks per validator --------
+ * Rows 0..79 of a chunk are the 80 rounds; rows 80..127 CONTINUE the round function and the message schedule with
+ * round constant 0.  They cost nothing (the table was padded from 80 to a power of two anyway) and make the chunk
+ * period a power of two, so the round constants and the selectors are periodic columns and every round / schedule
+ * relation is enforced in the proof; the digest is taken on row 79. */
 #define S512_A 0      /* 64 bits each */
 #define S512_B 64
 #define S512_C 128
@@ -53,9 +57,11 @@
 #define S512_CW 704   /* 2 + 2 bits */
 #define S512_DG 708   /* 8 words x (lo, hi), last round only */
 #define S512_DC 724   /* 8 words x (carry lo, carry hi), last round only */
-#define S512_COLS 740
+#define S512_WS 740   /* lo, hi of the schedule sum; equals the next row's w[15] on rows 15..126 */
+#define S512_COLS 742
 #define S512_ROUNDS 80
-#define S512_ROWS_PER_VALIDATOR 160
+#define S512_ROWS_PER_CHUNK 128
+#define S512_ROWS_PER_VALIDATOR 256
 
 /* ---------------- Ed25519: one row per double-and-add step, 2 x 256 rows per validator ---------------- */
 #define ED_BIT 0

@@ -70,8 +70,8 @@ void tm_trace_dims(uint32_t kind, uint32_t n_max, size_t dims[6]);
 
 enum { T_SHA256 = 0, T_SHA512 = 1, T_ED = 2, N_TABLES = 3 };
 static const int TABLE_COLS[3] = {S256_COLS, S512_COLS, ED_COLS};
-static const int TABLE_NPER[3] = {4, 0, 1};
-static const int TABLE_PERIOD[3] = {64, 1, 256};
+static const int TABLE_NPER[3] = {4, 6, 1};
+static const int TABLE_PERIOD[3] = {64, S512_ROWS_PER_CHUNK, 256};
 
 /* periodic pattern value of column pc at row r (r < period) */
 static gl_t periodic_pattern(int table, int pc, int r) {
@@ -81,6 +81,16 @@ static gl_t periodic_pattern(int table, int pc, int r) {
             case 1: return r == 63;
             case 2: return r != 63;
             default: return r >= 15 && r <= 62;
+        }
+    }
+    if (table == T_SHA512) {
+        switch (pc) {
+            case 0: return r < 80 ? (uint32_t)SHA512_K[r] : 0;
+            case 1: return r < 80 ? SHA512_K[r] >> 32 : 0;
+            case 2: return r == 79;
+            case 3: return r != 79;
+            case 4: return r != S512_ROWS_PER_CHUNK - 1;
+            default: return r >= 15 && r <= S512_ROWS_PER_CHUNK - 2;
         }
     }
     return r != 255; /* ED NOTEND */

@@ -237,15 +237,34 @@ static void put_halves(trace_t *t, int col, size_t row, uint64_t v) {
     CELL(t, col + 1, row) = v >> 32;
 }
 
-/* rows [row0, row0 + nrows) of one compression; nrows < 80 only for the truncated last padding chunk */
+/* rows [row0, row0 + nrows) of one compression: 80 rounds, then 48 continuation rounds with round constant 0
+ * (include/tmx_trace.h); nrows < 128 only for a truncated last padding chunk */
 static void sha512_rows(trace_t *t, size_t row0, size_t nrows, const uint64_t cv[8], const uint8_t blk[128], uint64_t out_state[8]) {
-    sha512_round_t r[80];
+    sha512_round_t r[S512_ROWS_PER_CHUNK];
     uint64_t st[8];
     memcpy(st, cv, sizeof st);
     sha512_compress(st, blk, r);
     if (out_state) memcpy(out_state, st, sizeof st);
-    uint64_t W[80];
+    uint64_t W[S512_ROWS_PER_CHUNK];
     for (int i = 0; i < 80; i++) W[i] = r[i].w;
+    for (int i = 80; i < S512_ROWS_PER_CHUNK; i++) {
+        uint64_t s0 = ror64(W[i - 15], 1) ^ ror64(W[i - 15], 8) ^ (W[i - 15] >> 7);
+        uint64_t s1 = ror64(W[i - 2], 19) ^ ror64(W[i - 2], 61) ^ (W[i - 2] >> 6);
+        W[i] = W[i - 16] + s0 + W[i - 7] + s1;
+    }
+    {   /* working variables entering rounds 80..127 */
+        uint64_t v[8];
+        memcpy(v, r[79].v, sizeof v);
+        for (int i = 79; i < S512_ROWS_PER_CHUNK - 1; i++) {
+            uint64_t a = v[0], bb = v[1], c = v[2], d = v[3], e = v[4], f = v[5], g = v[6], hh = v[7];
+            uint64_t S1 = ror64(e, 14) ^ ror64(e, 18) ^ ror64(e, 41), ch = (e & f) ^ (~e & g);
+            uint64_t S0 = ror64(a, 28) ^ ror64(a, 34) ^ ror64(a, 39), mj = (a & bb) ^ (a & c) ^ (bb & c);
+            uint64_t t1 = hh + S1 + ch + (i < 80 ? SHA512_K[i] : 0) + W[i], t2 = S0 + mj;
+            v[7] = g; v[6] = f; v[5] = e; v[4] = d + t1; v[3] = c; v[2] = bb; v[1] = a; v[0] = t1 + t2;
+            memcpy(r[i + 1].v, v, sizeof v);
+            r[i + 1].w = W[i + 1];
+        }
+    }
     for (size_t i = 0; i < nrows; i++) {
         size_t row = row0 + i;
         const uint64_t *v = r[i].v;
@@ -257,7 +276,7 @@ static void sha512_rows(trace_t *t, size_t row0, size_t nrows, const uint64_t cv
         uint64_t a = v[0], bb = v[1], c = v[2], d = v[3], e = v[4], f = v[5], g = v[6], hh = v[7];
         uint64_t S1 = ror64(e, 14) ^ ror64(e, 18) ^ ror64(e, 41), ch = (e & f) ^ (~e & g);
         uint64_t S0 = ror64(a, 28) ^ ror64(a, 34) ^ ror64(a, 39), mj = (a & bb) ^ (a & c) ^ (bb & c);
-        uint64_t K = SHA512_K[i], w = W[i];
+        uint64_t K = i < 80 ? SHA512_K[i] : 0, w = W[i];
 #define LO(x) ((uint64_t)(uint32_t)(x))
 #define HI(x) ((uint64_t)((x) >> 32))
         uint64_t t1lo = LO(hh) + LO(S1) + LO(ch) + LO(K) + LO(w);
@@ -288,19 +307,20 @@ static void sha512_rows(trace_t *t, size_t row0, size_t nrows, const uint64_t cv
             CELL(t, S512_WB1 + b, row) = (w1 >> b) & 1;
         }
         for (int j = 0; j < 8; j++) put_halves(t, S512_CV + 2 * j, row, cv[j]);
-        uint64_t cwlo = 0, cwhi = 0;
-        if (i >= 15 && i <= 78) {
-            uint64_t x = W[i - 1], y = W[i - 14];
+        {   /* schedule sum of the row's window: sigma1(w[14]) + w[9] + sigma0(w[1]) + w[0], zeros before the block starts */
+            uint64_t x = w14, y = w1, w9 = i >= 6 ? W[i - 6] : 0, w0 = i >= 15 ? W[i - 15] : 0;
             uint64_t s1 = ror64(x, 19) ^ ror64(x, 61) ^ (x >> 6), s0 = ror64(y, 1) ^ ror64(y, 8) ^ (y >> 7);
-            uint64_t lo = LO(s1) + LO(W[i - 6]) + LO(s0) + LO(W[i - 15]);
-            cwlo = lo >> 32;
-            uint64_t hi = HI(s1) + HI(W[i - 6]) + HI(s0) + HI(W[i - 15]) + cwlo;
-            cwhi = hi >> 32;
+            uint64_t lo = LO(s1) + LO(w9) + LO(s0) + LO(w0);
+            uint64_t cwlo = lo >> 32;
+            uint64_t hi = HI(s1) + HI(w9) + HI(s0) + HI(w0) + cwlo;
+            uint64_t cwhi = hi >> 32;
+            CELL(t, S512_CW, row) = cwlo & 1;
+            CELL(t, S512_CW + 1, row) = (cwlo >> 1) & 1;
+            CELL(t, S512_CW + 2, row) = cwhi & 1;
+            CELL(t, S512_CW + 3, row) = (cwhi >> 1) & 1;
+            CELL(t, S512_WS, row) = LO(lo);
+            CELL(t, S512_WS + 1, row) = LO(hi);
         }
-        CELL(t, S512_CW, row) = cwlo & 1;
-        CELL(t, S512_CW + 1, row) = (cwlo >> 1) & 1;
-        CELL(t, S512_CW + 2, row) = cwhi & 1;
-        CELL(t, S512_CW + 3, row) = (cwhi >> 1) & 1;
         for (int j = 0; j < 8; j++) {
             uint64_t dlo = 0, dhi = 0, clo = 0, chi = 0;
             if (i == 79) {
@@ -354,16 +374,16 @@ static void build_sha512(trace_t *t, const tmx_offchain_head *h, const tmx_valid
         size_t row = i * S512_ROWS_PER_VALIDATOR;
         for (size_t b = 0; b < 2; b++) {
             if (b < nb) {
-                sha512_rows(t, row + 80 * b, 80, st, buf + 128 * b, nxt);
+                sha512_rows(t, row + S512_ROWS_PER_CHUNK * b, S512_ROWS_PER_CHUNK, st, buf + 128 * b, nxt);
                 memcpy(st, nxt, sizeof st);
             } else
-                sha512_rows(t, row + 80 * b, 80, SHA512_IV, zero, NULL); /* unused second slot */
+                sha512_rows(t, row + S512_ROWS_PER_CHUNK * b, S512_ROWS_PER_CHUNK, SHA512_IV, zero, NULL); /* unused second slot */
         }
         for (int k = 0; k < 8; k++)
             for (int j = 0; j < 8; j++) hdigest[i][8 * k + j] = (uint8_t)(st[k] >> (56 - 8 * j));
     }
-    for (size_t row = (size_t)h->n_max * S512_ROWS_PER_VALIDATOR; row < t->n_rows; row += 80) {
-        size_t nr = t->n_rows - row < 80 ? t->n_rows - row : 80;
+    for (size_t row = (size_t)h->n_max * S512_ROWS_PER_VALIDATOR; row < t->n_rows; row += S512_ROWS_PER_CHUNK) {
+        size_t nr = t->n_rows - row < S512_ROWS_PER_CHUNK ? t->n_rows - row : S512_ROWS_PER_CHUNK;
         sha512_rows(t, row, nr, SHA512_IV, zero, NULL);
     }
 }

@@ -61,8 +61,8 @@ TMX_HD F pack_bits(const Row& r, int col0, int nbits) {
 
 constexpr int AIR_SHA256 = 0, AIR_SHA512 = 1, AIR_ED25519 = 2;
 TMX_HD int air_cols(int t) { return t == AIR_SHA256 ? S256_COLS : (t == AIR_SHA512 ? S512_COLS : ED_COLS); }
-TMX_HD int air_n_periodic(int t) { return t == AIR_SHA256 ? 4 : (t == AIR_SHA512 ? 0 : 1); }
-TMX_HD int air_period(int t) { return t == AIR_SHA256 ? 64 : (t == AIR_SHA512 ? 1 : 256); }
+TMX_HD int air_n_periodic(int t) { return t == AIR_SHA256 ? 4 : (t == AIR_SHA512 ? 6 : 1); }
+TMX_HD int air_period(int t) { return t == AIR_SHA256 ? 64 : (t == AIR_SHA512 ? S512_ROWS_PER_CHUNK : 256); }
 
 // ------------------------------------------------------------------------------------------ SHA-256
 // per = {K_t, is_last_round, not_last_round, schedule_active (rounds 15..62)}
@@ -132,19 +132,99 @@ TMX_HD void air_sha256(const Row& l, const Row& n, const Per& per, Emit& emit) {
 }
 
 // ------------------------------------------------------------------------------------------ SHA-512
+// per = {K_t low half, K_t high half, is_round_79, not_round_79, not_chunk_end, schedule_active (rows 15..126)}, period 128.
+// 64-bit words are (lo, hi) pairs of 32-bit field elements with an explicit carry from lo to hi.  Rows 80..127 of a chunk
+// continue the round function with round constant 0 (include/tmx_trace.h), so only what reads the next row, the digest
+// and the schedule hand-over need a selector.
 template <class F, class Row, class Per, class Emit>
 TMX_HD void air_sha512(const Row& l, const Row& n, const Per& per, Emit& emit) {
-    (void)n;
-    (void)per;
+    const F KLO = per[0], KHI = per[1], LAST = per[2], NOTLAST = per[3], NOTEND = per[4], SCHED = per[5];
+    const F two32 = F::c(1ULL << 32);
     for (int i = S512_A; i < S512_D; i++) emit(is_bool<F>(l[i]));
     for (int i = S512_AN; i < S512_W; i++) emit(is_bool<F>(l[i]));
     for (int i = S512_WB14; i < S512_CV; i++) emit(is_bool<F>(l[i]));
     for (int i = S512_CA; i < S512_DG; i++) emit(is_bool<F>(l[i]));
     for (int i = 0; i < 16; i++) emit(is_bool<F>(l[S512_DC + i]));
+    // round function
+    F S1[2] = {F::c(0), F::c(0)}, CH[2] = {F::c(0), F::c(0)}, S0[2] = {F::c(0), F::c(0)}, MJ[2] = {F::c(0), F::c(0)};
+    for (int i = 63; i >= 0; i--) {
+        const int h = i >> 5;
+        const F ei = l[S512_E + i], fi = l[S512_F + i], gi = l[S512_G + i];
+        const F ai = l[S512_A + i], bi = l[S512_B + i], ci = l[S512_C + i];
+        const F s1 = xor3<F>(l[S512_E + ((i + 14) & 63)], l[S512_E + ((i + 18) & 63)], l[S512_E + ((i + 41) & 63)]);
+        const F ch = ei * fi + (F::c(1) - ei) * gi;
+        const F s0 = xor3<F>(l[S512_A + ((i + 28) & 63)], l[S512_A + ((i + 34) & 63)], l[S512_A + ((i + 39) & 63)]);
+        const F ab = ai * bi;
+        const F mj = (ab + ai * ci + bi * ci) - F::c(2) * (ab * ci);
+        S1[h] = S1[h] + S1[h] + s1;
+        CH[h] = CH[h] + CH[h] + ch;
+        S0[h] = S0[h] + S0[h] + s0;
+        MJ[h] = MJ[h] + MJ[h] + mj;
+    }
+    const F T1lo = l[S512_H] + S1[0] + (CH[0] + KLO) + l[S512_W + 30];
+    const F T1hi = l[S512_H + 1] + S1[1] + (CH[1] + KHI) + l[S512_W + 31];
+    const F an[2] = {pack_bits<F>(l, S512_AN, 32), pack_bits<F>(l, S512_AN + 32, 32)};
+    const F en[2] = {pack_bits<F>(l, S512_EN, 32), pack_bits<F>(l, S512_EN + 32, 32)};
+    const F ca[2] = {pack_bits<F>(l, S512_CA, 3), pack_bits<F>(l, S512_CA + 3, 3)};
+    const F ce[2] = {pack_bits<F>(l, S512_CE, 3), pack_bits<F>(l, S512_CE + 3, 3)};
+    const F cw[2] = {pack_bits<F>(l, S512_CW, 2), pack_bits<F>(l, S512_CW + 2, 2)};
+    emit((an[0] + two32 * ca[0]) - (T1lo + (S0[0] + MJ[0])));
+    emit((an[1] + two32 * ca[1]) - ((T1hi + (S0[1] + MJ[1])) + ca[0]));
+    emit((en[0] + two32 * ce[0]) - (l[S512_D] + T1lo));
+    emit((en[1] + two32 * ce[1]) - ((l[S512_D + 1] + T1hi) + ce[0]));
+    // shift registers (not across the chunk boundary)
+    for (int i = 0; i < 64; i++) {
+        emit(NOTEND * (n[S512_A + i] - l[S512_AN + i]));
+        emit(NOTEND * (n[S512_B + i] - l[S512_A + i]));
+        emit(NOTEND * (n[S512_C + i] - l[S512_B + i]));
+        emit(NOTEND * (n[S512_E + i] - l[S512_EN + i]));
+        emit(NOTEND * (n[S512_F + i] - l[S512_E + i]));
+        emit(NOTEND * (n[S512_G + i] - l[S512_F + i]));
+    }
+    const F pc[2] = {pack_bits<F>(l, S512_C, 32), pack_bits<F>(l, S512_C + 32, 32)};
+    const F pg[2] = {pack_bits<F>(l, S512_G, 32), pack_bits<F>(l, S512_G + 32, 32)};
+    for (int h = 0; h < 2; h++) {
+        emit(NOTEND * (n[S512_D + h] - pc[h]));
+        emit(NOTEND * (n[S512_H + h] - pg[h]));
+    }
+    for (int j = 0; j < 30; j++) emit(NOTEND * (n[S512_W + j] - l[S512_W + j + 2]));
+    for (int j = 0; j < 16; j++) emit(NOTEND * (n[S512_CV + j] - l[S512_CV + j]));
+    // message schedule
     emit(pack_bits<F>(l, S512_WB14, 32) - l[S512_W + 28]);
     emit(pack_bits<F>(l, S512_WB14 + 32, 32) - l[S512_W + 29]);
     emit(pack_bits<F>(l, S512_WB1, 32) - l[S512_W + 2]);
     emit(pack_bits<F>(l, S512_WB1 + 32, 32) - l[S512_W + 3]);
+    F s1[2] = {F::c(0), F::c(0)}, s0[2] = {F::c(0), F::c(0)};
+    for (int i = 63; i >= 0; i--) {
+        const int h = i >> 5;
+        const F hi1 = i + 6 < 64 ? l[S512_WB14 + i + 6] : F::c(0);
+        const F hi0 = i + 7 < 64 ? l[S512_WB1 + i + 7] : F::c(0);
+        s1[h] = s1[h] + s1[h] + xor3<F>(l[S512_WB14 + ((i + 19) & 63)], l[S512_WB14 + ((i + 61) & 63)], hi1);
+        s0[h] = s0[h] + s0[h] + xor3<F>(l[S512_WB1 + ((i + 1) & 63)], l[S512_WB1 + ((i + 8) & 63)], hi0);
+    }
+    emit((l[S512_WS] + two32 * cw[0]) - ((s1[0] + l[S512_W + 18]) + (s0[0] + l[S512_W])));
+    emit((l[S512_WS + 1] + two32 * cw[1]) - (((s1[1] + l[S512_W + 19]) + (s0[1] + l[S512_W + 1])) + cw[0]));
+    emit(SCHED * (n[S512_W + 30] - l[S512_WS]));
+    emit(SCHED * (n[S512_W + 31] - l[S512_WS + 1]));
+    // digest words on round 79, zero elsewhere
+    const F fin[8][2] = {{an[0], an[1]},
+                         {pack_bits<F>(l, S512_A, 32), pack_bits<F>(l, S512_A + 32, 32)},
+                         {pack_bits<F>(l, S512_B, 32), pack_bits<F>(l, S512_B + 32, 32)},
+                         {pc[0], pc[1]},
+                         {en[0], en[1]},
+                         {pack_bits<F>(l, S512_E, 32), pack_bits<F>(l, S512_E + 32, 32)},
+                         {pack_bits<F>(l, S512_F, 32), pack_bits<F>(l, S512_F + 32, 32)},
+                         {pg[0], pg[1]}};
+    for (int j = 0; j < 8; j++) {
+        const F lo = l[S512_DG + 2 * j] + two32 * l[S512_DC + 2 * j];
+        const F hi = l[S512_DG + 2 * j + 1] + two32 * l[S512_DC + 2 * j + 1];
+        emit(LAST * (lo - (l[S512_CV + 2 * j] + fin[j][0])));
+        emit(LAST * (hi - ((l[S512_CV + 2 * j + 1] + fin[j][1]) + l[S512_DC + 2 * j])));
+        for (int k = 0; k < 2; k++) {
+            emit(NOTLAST * l[S512_DG + 2 * j + k]);
+            emit(NOTLAST * l[S512_DC + 2 * j + k]);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------ Ed25519
@@ -254,12 +334,20 @@ TMX_HD void air_eval(int table, const Row& l, const Row& n, const Per& per, Emit
 }
 
 // periodic pattern of column pc at row r of its period
-TMX_HD uint64_t air_periodic_pattern(int table, int pc, int r, const uint32_t* k256_table) {
+TMX_HD uint64_t air_periodic_pattern(int table, int pc, int r, const uint32_t* k256_table, const uint64_t* k512_table) {
     if (table == AIR_SHA256) {
         if (pc == 0) return k256_table[r];
         if (pc == 1) return r == 63;
         if (pc == 2) return r != 63;
         return r >= 15 && r <= 62;
+    }
+    if (table == AIR_SHA512) {
+        if (pc == 0) return r < S512_ROUNDS ? (uint32_t)k512_table[r] : 0;
+        if (pc == 1) return r < S512_ROUNDS ? k512_table[r] >> 32 : 0;
+        if (pc == 2) return r == S512_ROUNDS - 1;
+        if (pc == 3) return r != S512_ROUNDS - 1;
+        if (pc == 4) return r != S512_ROWS_PER_CHUNK - 1;
+        return r >= 15 && r <= S512_ROWS_PER_CHUNK - 2;
     }
     return r != 255;
 }
@@ -267,7 +355,7 @@ TMX_HD uint64_t air_periodic_pattern(int table, int pc, int r, const uint32_t* k
 // Host: values of the periodic columns on the LDE coset, [nper][2P], indexed by (natural LDE index mod 2P).
 // Column pc is the interpolant s of its one-period pattern composed with x -> x^(n/P); on the coset
 // x_j = 7 w_m^j this only depends on j mod 2P: s(7^(n/P) w_2P^j).
-inline std::vector<gl> air_periodic_lde_table(int table, unsigned log_n, const uint32_t* k256_table) {
+inline std::vector<gl> air_periodic_lde_table(int table, unsigned log_n, const uint32_t* k256_table, const uint64_t* k512_table) {
     const int nper = air_n_periodic(table), P = air_period(table);
     const size_t n = (size_t)1 << log_n;
     std::vector<gl> tab((size_t)nper * 2 * P);
@@ -279,7 +367,7 @@ inline std::vector<gl> air_periodic_lde_table(int table, unsigned log_n, const u
         for (int k = 0; k < P; k++) {
             gl acc = 0;
             for (int r = 0; r < P; r++)
-                acc = gl_add(acc, gl_mul((gl)air_periodic_pattern(table, pc, r, k256_table), gl_pow(wPi, ((uint64_t)r * k) % P)));
+                acc = gl_add(acc, gl_mul((gl)air_periodic_pattern(table, pc, r, k256_table, k512_table), gl_pow(wPi, ((uint64_t)r * k) % P)));
             coef[k] = gl_mul(acc, Pinv);
         }
         for (int j = 0; j < 2 * P; j++) {

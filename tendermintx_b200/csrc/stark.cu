@@ -611,7 +611,7 @@ int TableProver::periodic_tables(tmx_ctx* ctx, int table, unsigned log_n, const 
         *out = it->second;
         return TMX_OK;
     }
-    std::vector<gl> tab = air_periodic_lde_table(table, log_n, h_K256);
+    std::vector<gl> tab = air_periodic_lde_table(table, log_n, h_K256, h_K512);
     void* d = nullptr;
     TMX_CUDA(cudaMalloc(&d, tab.size() * sizeof(gl)));
     TMX_CUDA(cudaMemcpy(d, tab.data(), tab.size() * sizeof(gl), cudaMemcpyHostToDevice));

@@ -113,7 +113,7 @@ int verify_table(int table, size_t n, const gl* proof, size_t proof_len, size_t*
     // constraint identity at zeta: (chunk0 + zeta^n chunk1) * (zeta^n - 1) == sum_i alpha^(M-1-i) C_i(zeta)
     {
         const int nper = air_n_periodic(table), P = air_period(table);
-        FE per[4] = {FE::c(0), FE::c(0), FE::c(0), FE::c(0)};
+        FE per[8] = {FE::c(0), FE::c(0), FE::c(0), FE::c(0), FE::c(0), FE::c(0), FE::c(0), FE::c(0)};
         const gl2 y = gl2_pow(zeta, n / P);
         const gl wPi = gl_inv(gl_root_of_unity(ilog2(P))), Pinv = gl_inv((gl)P);
         for (int pc = 0; pc < nper; pc++) {
@@ -121,7 +121,7 @@ int verify_table(int table, size_t n, const gl* proof, size_t proof_len, size_t*
             for (int kk = 0; kk < P; kk++) {
                 gl acc = 0;
                 for (int rr = 0; rr < P; rr++)
-                    acc = gl_add(acc, gl_mul((gl)air_periodic_pattern(table, pc, rr, h_K256), gl_pow(wPi, ((uint64_t)rr * kk) % P)));
+                    acc = gl_add(acc, gl_mul((gl)air_periodic_pattern(table, pc, rr, h_K256, h_K512), gl_pow(wPi, ((uint64_t)rr * kk) % P)));
                 coef[kk] = gl2_from(gl_mul(acc, Pinv));
             }
             per[pc] = FE::mk(ext_horner(coef.data(), P, y));

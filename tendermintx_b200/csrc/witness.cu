@@ -14,7 +14,7 @@
 //     ladder; the two 256-step ladders ([s]B and [h]A) run on two warps with 5 x 51-bit-limb field arithmetic in
 //     registers and park the canonical (res, temp) of every step in a 128 KB-per-validator scratch.  Phase 2 (512
 //     threads): each thread expands one ladder row into its 1217 cells (17 multiplication gadgets: product limbs,
-//     quotient, carries) and the 160 SHA-512 round rows are written.
+//     quotient, carries) and the 2 x 128 SHA-512 rows are written.
 //   Integer / bit work, HBM-write bound at best: no tensor cores.
 #include "ctx.cuh"
 #include "witness_jobs.cuh"
@@ -69,8 +69,8 @@ __global__ void __launch_bounds__(128) sha512_padding_kernel(WitnessArgs a, size
     __shared__ Sha512Hist hs;
     if (threadIdx.x == 0) sha512_padding_prepare(&hs);
     __syncthreads();
-    const size_t row = first_row + (size_t)blockIdx.x * 80 + threadIdx.x;
-    if (threadIdx.x < 80 && row < a.n512) sha512_row_cells(a.t512, a.n512, row, threadIdx.x, &hs);
+    const size_t row = first_row + (size_t)blockIdx.x * S512_ROWS_PER_CHUNK + threadIdx.x;
+    if (row < a.n512) sha512_row_cells(a.t512, a.n512, row, threadIdx.x, &hs);
 }
 
 struct LadderShared {
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(64) ed25519_ladder_kernel(WitnessArgs a, ge_pa
     if (tid == 0) a.aux[AUX_SIG_OK + i] = (sh.ok_r && ed_slot_verdict(sh.slot, sh.Ps, sh.Ph)) ? 1 : 0;
 }
 
-// Phase 2 (throughput): one thread per trace row -- 160 SHA-512 rounds and 512 ladder steps per validator.
+// Phase 2 (throughput): one thread per trace row -- 2 x 128 SHA-512 rows and 512 ladder steps per validator.
 __global__ void __launch_bounds__(512) ed25519_expand_kernel(WitnessArgs a, const ge_packed* __restrict__ points) {
     __shared__ Sha512Hist h5[2];
     __shared__ uint64_t sc[2][4];
@@ -129,7 +129,8 @@ __global__ void __launch_bounds__(512) ed25519_expand_kernel(WitnessArgs a, cons
         sc_reduce512(digest, sc[1]);
     }
     __syncthreads();
-    if (tid < 160) sha512_row_cells(a.t512, a.n512, (size_t)i * S512_ROWS_PER_VALIDATOR + tid, tid % 80, &h5[tid / 80]);
+    if (tid < S512_ROWS_PER_VALIDATOR)
+        sha512_row_cells(a.t512, a.n512, (size_t)i * S512_ROWS_PER_VALIDATOR + tid, tid % S512_ROWS_PER_CHUNK, &h5[tid / S512_ROWS_PER_CHUNK]);
     const uint64_t* s = sc[tid >> 8];
     const int bit = (int)((s[(tid & 255) >> 6] >> (tid & 63)) & 1);
     const ge_packed* res = points + (size_t)i * 1024;
@@ -223,7 +224,7 @@ int run_ed25519_expand(tmx_ctx* ctx, const WitnessArgs& a, const void* points, c
     ctx->launches++;
     const size_t used512 = (size_t)a.n_max * S512_ROWS_PER_VALIDATOR;
     if (a.n512 > used512) {
-        sha512_padding_kernel<<<(unsigned)((a.n512 - used512 + 79) / 80), 128, 0, st>>>(a, used512);
+        sha512_padding_kernel<<<(unsigned)((a.n512 - used512 + S512_ROWS_PER_CHUNK - 1) / S512_ROWS_PER_CHUNK), S512_ROWS_PER_CHUNK, 0, st>>>(a, used512);
         ctx->launches++;
     }
     const size_t used_ed = (size_t)a.n_max * ED_ROWS_PER_VALIDATOR;

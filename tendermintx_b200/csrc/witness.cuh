@@ -188,8 +188,9 @@ TMX_HD void validator_leaf_message(const uint8_t pk[32], uint64_t power, uint8_t
 }
 
 // ------------------------------------------------------------------------------------------- SHA-512
+// history of one chunk: the 80 rounds and the 48 continuation rounds with round constant 0 (include/tmx_trace.h)
 struct Sha512Hist {
-    uint64_t ah[84], eh[84], W[80], cv[8];
+    uint64_t ah[S512_ROWS_PER_CHUNK + 4], eh[S512_ROWS_PER_CHUNK + 4], W[S512_ROWS_PER_CHUNK], cv[8];
 };
 
 TMX_HD void sha512_compress_hist(const uint64_t cv[8], const uint8_t* blk, Sha512Hist* hs, uint64_t out[8]) {
@@ -199,7 +200,7 @@ TMX_HD void sha512_compress_hist(const uint64_t cv[8], const uint8_t* blk, Sha51
         for (int j = 0; j < 8; j++) x = (x << 8) | blk[8 * i + j];
         W[i] = x;
     }
-    for (int i = 16; i < 80; i++) {
+    for (int i = 16; i < S512_ROWS_PER_CHUNK; i++) {
         uint64_t x = W[i - 15], y = W[i - 2];
         W[i] = W[i - 16] + (rotr64(x, 1) ^ rotr64(x, 8) ^ (x >> 7)) + W[i - 7] + (rotr64(y, 19) ^ rotr64(y, 61) ^ (y >> 6));
     }
@@ -207,15 +208,17 @@ TMX_HD void sha512_compress_hist(const uint64_t cv[8], const uint8_t* blk, Sha51
     uint64_t a = cv[0], b = cv[1], c = cv[2], d = cv[3], e = cv[4], f = cv[5], g = cv[6], h = cv[7];
     hs->ah[0] = d; hs->ah[1] = c; hs->ah[2] = b; hs->ah[3] = a;
     hs->eh[0] = h; hs->eh[1] = g; hs->eh[2] = f; hs->eh[3] = e;
-    for (int t = 0; t < 80; t++) {
-        uint64_t t1 = h + (rotr64(e, 14) ^ rotr64(e, 18) ^ rotr64(e, 41)) + ((e & f) ^ (~e & g)) + k512(t) + W[t];
+    for (int t = 0; t < S512_ROWS_PER_CHUNK; t++) {
+        if (t == S512_ROUNDS) {  // the digest is the state after round 79; the rows beyond only keep the table periodic
+            uint64_t fin[8] = {a, b, c, d, e, f, g, h};
+            for (int i = 0; i < 8; i++) out[i] = hs->cv[i] + fin[i];
+        }
+        uint64_t t1 = h + (rotr64(e, 14) ^ rotr64(e, 18) ^ rotr64(e, 41)) + ((e & f) ^ (~e & g)) + (t < S512_ROUNDS ? k512(t) : 0) + W[t];
         uint64_t t2 = (rotr64(a, 28) ^ rotr64(a, 34) ^ rotr64(a, 39)) + ((a & b) ^ (a & c) ^ (b & c));
         h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
         hs->ah[t + 4] = a;
         hs->eh[t + 4] = e;
     }
-    uint64_t fin[8] = {a, b, c, d, e, f, g, h};
-    for (int i = 0; i < 8; i++) out[i] = hs->cv[i] + fin[i];
 }
 
 TMX_HD void sha512_row_cells(gl* trace, size_t n_rows, size_t row, int t, const Sha512Hist* hs) {
@@ -242,7 +245,7 @@ TMX_HD void sha512_row_cells(gl* trace, size_t n_rows, size_t row, int t, const 
     p[(size_t)(S512_H + 1) * n_rows] = TMX_HI(h);
     const uint64_t S1 = rotr64(e, 14) ^ rotr64(e, 18) ^ rotr64(e, 41), ch = (e & f) ^ (~e & g);
     const uint64_t S0 = rotr64(a, 28) ^ rotr64(a, 34) ^ rotr64(a, 39), mj = (a & b) ^ (a & c) ^ (b & c);
-    const uint64_t K = k512(t), w = hs->W[t];
+    const uint64_t K = t < S512_ROUNDS ? k512(t) : 0, w = hs->W[t];
     const uint64_t t1lo = TMX_LO(h) + TMX_LO(S1) + TMX_LO(ch) + TMX_LO(K) + TMX_LO(w);
     const uint64_t t1hi = TMX_HI(h) + TMX_HI(S1) + TMX_HI(ch) + TMX_HI(K) + TMX_HI(w);
     const uint64_t calo = (t1lo + TMX_LO(S0) + TMX_LO(mj)) >> 32;
@@ -271,13 +274,15 @@ TMX_HD void sha512_row_cells(gl* trace, size_t n_rows, size_t row, int t, const 
         p[(size_t)(S512_CV + 2 * j) * n_rows] = TMX_LO(hs->cv[j]);
         p[(size_t)(S512_CV + 2 * j + 1) * n_rows] = TMX_HI(hs->cv[j]);
     }
-    uint64_t cwlo = 0, cwhi = 0;
-    if (t >= 15 && t <= 78) {
-        const uint64_t x = hs->W[t - 1], y = hs->W[t - 14];
-        const uint64_t s1 = rotr64(x, 19) ^ rotr64(x, 61) ^ (x >> 6), s0 = rotr64(y, 1) ^ rotr64(y, 8) ^ (y >> 7);
-        cwlo = (TMX_LO(s1) + TMX_LO(hs->W[t - 6]) + TMX_LO(s0) + TMX_LO(hs->W[t - 15])) >> 32;
-        cwhi = (TMX_HI(s1) + TMX_HI(hs->W[t - 6]) + TMX_HI(s0) + TMX_HI(hs->W[t - 15]) + cwlo) >> 32;
-    }
+    // schedule sum of the row's window: sigma1(w[14]) + w[9] + sigma0(w[1]) + w[0], zeros before the block starts
+    const uint64_t w9 = t >= 6 ? hs->W[t - 6] : 0, w0 = t >= 15 ? hs->W[t - 15] : 0;
+    const uint64_t sg1 = rotr64(w14, 19) ^ rotr64(w14, 61) ^ (w14 >> 6), sg0 = rotr64(w1, 1) ^ rotr64(w1, 8) ^ (w1 >> 7);
+    const uint64_t wslo = TMX_LO(sg1) + TMX_LO(w9) + TMX_LO(sg0) + TMX_LO(w0);
+    const uint64_t cwlo = wslo >> 32;
+    const uint64_t wshi = TMX_HI(sg1) + TMX_HI(w9) + TMX_HI(sg0) + TMX_HI(w0) + cwlo;
+    const uint64_t cwhi = wshi >> 32;
+    p[(size_t)S512_WS * n_rows] = TMX_LO(wslo);
+    p[(size_t)(S512_WS + 1) * n_rows] = TMX_LO(wshi);
     p[(size_t)S512_CW * n_rows] = cwlo & 1;
     p[(size_t)(S512_CW + 1) * n_rows] = (cwlo >> 1) & 1;
     p[(size_t)(S512_CW + 2) * n_rows] = cwhi & 1;

@@ -68,7 +68,8 @@ extern "C" int hostsim_build_traces(const uint8_t* blob, uint64_t* t256, size_t 
         effective_triple(blob_validators(blob) + i, &t);
         uint8_t digest[64];
         sha512_validator_prepare(t, h5, digest);
-        for (int r = 0; r < 160; r++) sha512_row_cells(a.t512, a.n512, (size_t)i * 160 + r, r % 80, &h5[r / 80]);
+        for (int r = 0; r < S512_ROWS_PER_VALIDATOR; r++)
+            sha512_row_cells(a.t512, a.n512, (size_t)i * S512_ROWS_PER_VALIDATOR + r, r % S512_ROWS_PER_CHUNK, &h5[r / S512_ROWS_PER_CHUNK]);
         EdSlot e;
         ed_slot_prepare(t, digest, &e);
         ge51 Ps = ed_ladder(e.s, ge_base51(), res.data(), tmp.data());
@@ -81,7 +82,8 @@ extern "C" int hostsim_build_traces(const uint8_t* blob, uint64_t* t256, size_t 
         }
     }
     sha512_padding_prepare(&h5[0]);
-    for (size_t row = (size_t)a.n_max * 160; row < n512; row++) sha512_row_cells(a.t512, a.n512, row, (int)((row - (size_t)a.n_max * 160) % 80), &h5[0]);
+    for (size_t row = (size_t)a.n_max * S512_ROWS_PER_VALIDATOR; row < n512; row++)
+        sha512_row_cells(a.t512, a.n512, row, (int)((row - (size_t)a.n_max * S512_ROWS_PER_VALIDATOR) % S512_ROWS_PER_CHUNK), &h5[0]);
     if ((size_t)a.n_max * 512 < ned) {
         uint64_t zero[4] = {0, 0, 0, 0};
         ed_ladder(zero, ge_base51(), res.data(), tmp.data());
@@ -99,7 +101,7 @@ struct HostRow {
 extern "C" void hostsim_quotient(int table, const uint64_t* lde, size_t n, const uint64_t alpha[2], uint64_t* out) {
     const unsigned log_n = log2u((uint32_t)n), log_m = log_n + 1;
     const size_t m = n << 1;
-    std::vector<gl> tab = air_periodic_lde_table(table, log_n, h_K256);
+    std::vector<gl> tab = air_periodic_lde_table(table, log_n, h_K256, h_K512);
     const int P = air_period(table);
     const gl gn = gl_pow(GL_GEN, n);
     const gl zh_inv[2] = {gl_inv(gl_sub(gn, 1)), gl_inv(gl_sub(gl_neg(gn), 1))};
