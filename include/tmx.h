@@ -81,9 +81,9 @@ int tmx_poseidon_permute(tmx_ctx *ctx, uint64_t *d_states, size_t n, void *strea
  * 2 = the formulation the host transcript uses. */
 int tmx_host_poseidon_permute(uint64_t *states, size_t n, int variant);
 /* Host-side self check (no GPU) of the quotient kernel's factored Ed25519 constraint evaluation against the literal
- * fold of the AIR on one (row, next row) pair of ED_COLS cells each:
+ * fold of the AIR on one (row, next row) pair of ED_COLS cells each and the three periodic column values:
  * out = {literal(alpha[0]), literal(alpha[1]), factored(alpha[0]), factored(alpha[1])}. */
-int tmx_host_air_ed25519(const uint64_t *row_l, const uint64_t *row_n, uint64_t notend, const uint64_t alpha[2],
+int tmx_host_air_ed25519(const uint64_t *row_l, const uint64_t *row_n, const uint64_t periodic[3], const uint64_t alpha[2],
                          uint64_t out[4]);
 
 /* ------------------------------------------------------------------------------------------------

@@ -75,5 +75,10 @@
 #define ED_COLS (ED_MUL + ED_N_MUL * ED_MUL_STRIDE) /* 1217 */
 #define ED_W_OFFSET (1 << 22)
 #define ED_ROWS_PER_VALIDATOR 512
+/* Row 0 of every 256-row ladder starts from res = O = (0, 1, 1, 0); the first ladder of a validator ([s]B, rows 0..255)
+ * doubles the base point B = (BX, BY, 1, BX*BY), the second ([h]A, rows 256..511) an affine point (Z = 1).  16-bit limbs. */
+#define ED_BASE_X_LIMBS {0xd51a, 0x8f25, 0x2d60, 0xc956, 0xa7b2, 0x9525, 0xc760, 0x692c, 0xdc5c, 0xfdd6, 0xe231, 0xc0a4, 0x53fe, 0xcd6e, 0x36d3, 0x2169}
+#define ED_BASE_Y_LIMBS {0x6658, 0x6666, 0x6666, 0x6666, 0x6666, 0x6666, 0x6666, 0x6666, 0x6666, 0x6666, 0x6666, 0x6666, 0x6666, 0x6666, 0x6666, 0x6666}
+#define ED_BASE_T_LIMBS {0xdda3, 0xa5b7, 0x8ab3, 0x6dde, 0x52f5, 0x7751, 0x9f80, 0x20f0, 0xe37d, 0x64ab, 0x4e8e, 0x66ea, 0x7665, 0xd78b, 0x5f0f, 0x6787}
 
 #endif

@@ -70,8 +70,8 @@ void tm_trace_dims(uint32_t kind, uint32_t n_max, size_t dims[6]);
 
 enum { T_SHA256 = 0, T_SHA512 = 1, T_ED = 2, N_TABLES = 3 };
 static const int TABLE_COLS[3] = {S256_COLS, S512_COLS, ED_COLS};
-static const int TABLE_NPER[3] = {4, 6, 1};
-static const int TABLE_PERIOD[3] = {64, S512_ROWS_PER_CHUNK, 256};
+static const int TABLE_NPER[3] = {4, 7, 3};
+static const int TABLE_PERIOD[3] = {64, S512_ROWS_PER_VALIDATOR, ED_ROWS_PER_VALIDATOR};
 
 /* periodic pattern value of column pc at row r (r < period) */
 static gl_t periodic_pattern(int table, int pc, int r) {
@@ -84,16 +84,22 @@ static gl_t periodic_pattern(int table, int pc, int r) {
         }
     }
     if (table == T_SHA512) {
+        const int rr = r % S512_ROWS_PER_CHUNK; /* row inside the chunk; r inside the validator's two-chunk slot */
         switch (pc) {
-            case 0: return r < 80 ? (uint32_t)SHA512_K[r] : 0;
-            case 1: return r < 80 ? SHA512_K[r] >> 32 : 0;
-            case 2: return r == 79;
-            case 3: return r != 79;
-            case 4: return r != S512_ROWS_PER_CHUNK - 1;
-            default: return r >= 15 && r <= S512_ROWS_PER_CHUNK - 2;
+            case 0: return rr < 80 ? (uint32_t)SHA512_K[rr] : 0;
+            case 1: return rr < 80 ? SHA512_K[rr] >> 32 : 0;
+            case 2: return rr == 79;
+            case 3: return rr != 79;
+            case 4: return rr != S512_ROWS_PER_CHUNK - 1;
+            case 5: return rr >= 15 && rr <= S512_ROWS_PER_CHUNK - 2;
+            default: return r == 0;
         }
     }
-    return r != 255; /* ED NOTEND */
+    switch (pc) { /* Ed25519 */
+        case 0: return (r & 255) != 255;
+        case 1: return r == 0;
+        default: return r == 256;
+    }
 }
 
 /* ------------------------------------------------------------------ small utilities */
@@ -543,7 +549,7 @@ static int verify_table(int table, size_t n, rbuf_t *r, challenger_t *ch) {
         gl2_t per[8];
         gl2_t y = gl2_pow(zeta, n / P);
         for (int pc = 0; pc < nper; pc++) {
-            gl_t pat[256];
+            gl_t pat[512];
             for (int rr = 0; rr < P; rr++) pat[rr] = periodic_pattern(table, pc, rr);
             ntt_inverse(pat, P);
             per[pc] = base_poly_eval(pat, P, y);

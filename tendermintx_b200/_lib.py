@@ -49,7 +49,7 @@ def load():
         "tmx_poseidon_merkle": (i32, [vp, u64p, sz, u32, u32, u64p, vp]),
         "tmx_poseidon_permute": (i32, [vp, u64p, sz, vp]),
         "tmx_host_poseidon_permute": (i32, [u64p, sz, i32]),
-        "tmx_host_air_ed25519": (i32, [u64p, u64p, c.c_uint64, u64p, u64p]),
+        "tmx_host_air_ed25519": (i32, [u64p, u64p, u64p, u64p, u64p]),
         "tmx_trace_dims": (i32, [u32, u32, c.POINTER(sz)]),
         "tmx_witness_aux_bytes": (sz, [u32]),
         "tmx_sha256_trace": (i32, [vp, vp, u32, u32, u64p, vp, vp]),

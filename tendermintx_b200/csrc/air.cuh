@@ -61,8 +61,8 @@ TMX_HD F pack_bits(const Row& r, int col0, int nbits) {
 
 constexpr int AIR_SHA256 = 0, AIR_SHA512 = 1, AIR_ED25519 = 2;
 TMX_HD int air_cols(int t) { return t == AIR_SHA256 ? S256_COLS : (t == AIR_SHA512 ? S512_COLS : ED_COLS); }
-TMX_HD int air_n_periodic(int t) { return t == AIR_SHA256 ? 4 : (t == AIR_SHA512 ? 6 : 1); }
-TMX_HD int air_period(int t) { return t == AIR_SHA256 ? 64 : (t == AIR_SHA512 ? S512_ROWS_PER_CHUNK : 256); }
+TMX_HD int air_n_periodic(int t) { return t == AIR_SHA256 ? 4 : (t == AIR_SHA512 ? 7 : 3); }
+TMX_HD int air_period(int t) { return t == AIR_SHA256 ? 64 : (t == AIR_SHA512 ? S512_ROWS_PER_VALIDATOR : ED_ROWS_PER_VALIDATOR); }
 
 // ------------------------------------------------------------------------------------------ SHA-256
 // per = {K_t, is_last_round, not_last_round, schedule_active (rounds 15..62)}
@@ -132,7 +132,8 @@ TMX_HD void air_sha256(const Row& l, const Row& n, const Per& per, Emit& emit) {
 }
 
 // ------------------------------------------------------------------------------------------ SHA-512
-// per = {K_t low half, K_t high half, is_round_79, not_round_79, not_chunk_end, schedule_active (rows 15..126)}, period 128.
+// per = {K_t low half, K_t high half, is_round_79, not_round_79, not_chunk_end, schedule_active (rows 15..126),
+// first_row_of_the_validator_slot}, period 256 (two 128-row chunks).
 // 64-bit words are (lo, hi) pairs of 32-bit field elements with an explicit carry from lo to hi.  Rows 80..127 of a chunk
 // continue the round function with round constant 0 (include/tmx_trace.h), so only what reads the next row, the digest
 // and the schedule hand-over need a selector.
@@ -225,6 +226,13 @@ TMX_HD void air_sha512(const Row& l, const Row& n, const Per& per, Emit& emit) {
             emit(NOTLAST * l[S512_DC + 2 * j + k]);
         }
     }
+    // the first chunk of every validator slot starts from the IV
+    const uint64_t IV[8] = {0x6a09e667f3bcc908ULL, 0xbb67ae8584caa73bULL, 0x3c6ef372fe94f82bULL, 0xa54ff53a5f1d36f1ULL,
+                            0x510e527fade682d1ULL, 0x9b05688c2b3e6c1fULL, 0x1f83d9abfb41bd6bULL, 0x5be0cd19137e2179ULL};
+    for (int j = 0; j < 8; j++) {
+        emit(per[6] * (l[S512_CV + 2 * j] - F::c((uint32_t)IV[j])));
+        emit(per[6] * (l[S512_CV + 2 * j + 1] - F::c(IV[j] >> 32)));
+    }
 }
 
 // ------------------------------------------------------------------------------------------ Ed25519
@@ -257,7 +265,8 @@ TMX_HD void ed_mul_gadget(const F U[16], const F V[16], const Row& l, int g0, Em
     }
 }
 
-// per = {not_block_end} (period 256)
+// per = {not_block_end (row % 256 != 255), first row of the [s]B ladder (row == 0), first row of the [h]A ladder (row == 256)},
+// period 512
 template <class F, class Row, class Per, class Emit>
 TMX_HD void air_ed25519(const Row& l, const Row& n, const Per& per, Emit& emit) {
     const F NOTEND = per[0];
@@ -324,6 +333,19 @@ TMX_HD void air_ed25519(const Row& l, const Row& n, const Per& per, Emit& emit) 
             emit(NOTEND * (n[ED_RES + 16 * co + i] - (r + bit * (s - r))));
             emit(NOTEND * (n[ED_TMP + 16 * co + i] - l[G(dbl_slot[co]) + i]));
         }
+    // block initialisation: res = O at the start of both ladders, temp = B at the start of [s]B, temp.Z = 1 at the start of [h]A
+    const uint64_t BXL[16] = ED_BASE_X_LIMBS, BYL[16] = ED_BASE_Y_LIMBS, BTL[16] = ED_BASE_T_LIMBS;
+    const F S0 = per[1], H0 = per[2];
+    for (int co = 0; co < 4; co++)
+        for (int i = 0; i < 16; i++) emit(S0 * (l[ED_RES + 16 * co + i] - F::c((co == 1 || co == 2) && i == 0 ? 1 : 0)));
+    for (int co = 0; co < 4; co++)
+        for (int i = 0; i < 16; i++) {
+            const uint64_t want = co == 0 ? BXL[i] : (co == 1 ? BYL[i] : (co == 2 ? (uint64_t)(i == 0) : BTL[i]));
+            emit(S0 * (l[ED_TMP + 16 * co + i] - F::c(want)));
+        }
+    for (int co = 0; co < 4; co++)
+        for (int i = 0; i < 16; i++) emit(H0 * (l[ED_RES + 16 * co + i] - F::c((co == 1 || co == 2) && i == 0 ? 1 : 0)));
+    for (int i = 0; i < 16; i++) emit(H0 * (l[ED_TMP + 32 + i] - F::c(i == 0 ? 1 : 0)));
 }
 
 template <class F, class Row, class Per, class Emit>
@@ -342,14 +364,18 @@ TMX_HD uint64_t air_periodic_pattern(int table, int pc, int r, const uint32_t* k
         return r >= 15 && r <= 62;
     }
     if (table == AIR_SHA512) {
-        if (pc == 0) return r < S512_ROUNDS ? (uint32_t)k512_table[r] : 0;
-        if (pc == 1) return r < S512_ROUNDS ? k512_table[r] >> 32 : 0;
-        if (pc == 2) return r == S512_ROUNDS - 1;
-        if (pc == 3) return r != S512_ROUNDS - 1;
-        if (pc == 4) return r != S512_ROWS_PER_CHUNK - 1;
-        return r >= 15 && r <= S512_ROWS_PER_CHUNK - 2;
+        const int rr = r % S512_ROWS_PER_CHUNK;  // row inside the chunk; r is the row inside the validator's two-chunk slot
+        if (pc == 0) return rr < S512_ROUNDS ? (uint32_t)k512_table[rr] : 0;
+        if (pc == 1) return rr < S512_ROUNDS ? k512_table[rr] >> 32 : 0;
+        if (pc == 2) return rr == S512_ROUNDS - 1;
+        if (pc == 3) return rr != S512_ROUNDS - 1;
+        if (pc == 4) return rr != S512_ROWS_PER_CHUNK - 1;
+        if (pc == 5) return rr >= 15 && rr <= S512_ROWS_PER_CHUNK - 2;
+        return r == 0;
     }
-    return r != 255;
+    if (pc == 0) return (r & 255) != 255;
+    if (pc == 1) return r == 0;
+    return r == 256;
 }
 
 // Host: values of the periodic columns on the LDE coset, [nper][2P], indexed by (natural LDE index mod 2P).

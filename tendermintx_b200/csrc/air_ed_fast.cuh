@@ -1,6 +1,6 @@
 // Factored evaluation of the Ed25519 table's random-linear-combination of constraints (K5 fast path).
 //
-// air_ed25519() in air.cuh is the definition: 1 + 17 * 32 + 128 constraints folded by Horner's rule in the
+// air_ed25519() in air.cuh is the definition: 1 + 17 * 32 + 128 + 208 constraints folded by Horner's rule in the
 // challenge alpha.  Evaluated literally that costs ~9,000 field multiplications per LDE point, almost all of them
 // the limb products U_i V_j and q_i p_j of the 17 multiplication gadgets.  Because the 32 limb equations of a
 // gadget carry CONSECUTIVE powers of alpha, their combination is a product of two polynomial evaluations:
@@ -21,7 +21,8 @@
 namespace tmx {
 
 struct EdFastConsts {
-    gl a, a16, a32, a128;
+    gl a, a15, a16, a32, a48, a64, a128;
+    gl base_tilde[4];  // tildes of the base point's X, Y, Z (= 1), T limbs: the start of every [s]B ladder
     gl p_tilde;      // sum_j p_j a^(15-j), p = 2^255 - 19 in 16-bit limbs
     gl twod_tilde;   // same for the curve constant 2d
     gl w_off;        // ED_W_OFFSET * sum_{e<=30} a^e
@@ -33,9 +34,25 @@ inline EdFastConsts ed_fast_consts(gl a) {
                                       0xD130, 0xEEF3, 0x80F2, 0x198E, 0xFCE7, 0x56DF, 0xD9DC, 0x2406};
     EdFastConsts k;
     k.a = a;
+    k.a15 = gl_pow(a, 15);
     k.a16 = gl_pow(a, 16);
     k.a32 = gl_pow(a, 32);
+    k.a48 = gl_pow(a, 48);
+    k.a64 = gl_pow(a, 64);
     k.a128 = gl_pow(a, 128);
+    {
+        static const uint64_t BXL[16] = ED_BASE_X_LIMBS, BYL[16] = ED_BASE_Y_LIMBS, BTL[16] = ED_BASE_T_LIMBS;
+        gl bx = 0, by = 0, bt = 0;
+        for (int i = 0; i < 16; i++) {
+            bx = gl_add(gl_mul(bx, a), (gl)BXL[i]);
+            by = gl_add(gl_mul(by, a), (gl)BYL[i]);
+            bt = gl_add(gl_mul(bt, a), (gl)BTL[i]);
+        }
+        k.base_tilde[0] = bx;
+        k.base_tilde[1] = by;
+        k.base_tilde[2] = k.a15;  // limbs (1, 0, ..., 0)
+        k.base_tilde[3] = bt;
+    }
     gl pt = 0, tt = 0, s = 0;
     for (int i = 0; i < 16; i++) {
         pt = gl_add(gl_mul(pt, a), (gl)p25519_limb(i));
@@ -49,9 +66,11 @@ inline EdFastConsts ed_fast_consts(gl a) {
     return k;
 }
 
-// Row: operator[](int col) -> FB (canonical cell).  Returns the Horner-folded constraint value for challenge k.a.
+// Row: operator[](int col) -> FB (canonical cell).  per = {not_block_end, first row of [s]B, first row of [h]A}.
+// Returns the Horner-folded constraint value for challenge k.a.
 template <class Row>
-TMX_HD gl ed25519_constraints_fast(const Row& l, const Row& n, gl notend, const EdFastConsts& k) {
+TMX_HD gl ed25519_constraints_fast(const Row& l, const Row& n, const gl per[3], const EdFastConsts& k) {
+    const gl notend = per[0], s0 = per[1], h0 = per[2];
     const gl a = k.a;
     auto G = [](int m) { return ED_MUL + m * ED_MUL_STRIDE; };
     const gl bit = l[ED_BIT].v;
@@ -128,7 +147,23 @@ TMX_HD gl ed25519_constraints_fast(const Row& l, const Row& n, gl notend, const 
         gadget(Fq, Gq, 16, true, Cd[2]);
     }
     // ---- the 128 transition constraints share the periodic selector ----
-    return gl_add(gl_mul(acc, k.a128), gl_mul(notend, gl_canon(T)));
+    acc = gl_add(gl_mul(acc, k.a128), gl_mul(notend, gl_canon(T)));
+    // ---- block initialisation: 64 limbs of res - O, 64 of temp - B (both on S0), 64 of res - O and 16 of temp.Z - 1 (H0);
+    //      sum over (co, i) of a^(63 - 16 co - i) x = sum over co of a^(48 - 16 co) tilde(x_co) ----
+    const gl zero = 0;
+    const gl o_tilde[4] = {zero, k.a15, k.a15, zero};  // O = (0, 1, 1, 0), the limbs of 1 are (1, 0, ..., 0)
+    const gl wgt[4] = {k.a48, k.a32, k.a16, 1};
+    gl res_o = 0, tmp_b = 0;
+#pragma unroll
+    for (int co = 0; co < 4; co++) {
+        res_o = gl_add(res_o, gl_mul(wgt[co], gl_sub(R[co], o_tilde[co])));
+        tmp_b = gl_add(tmp_b, gl_mul(wgt[co], gl_sub(S[co], k.base_tilde[co])));
+    }
+    acc = gl_add(gl_mul(acc, k.a64), gl_mul(s0, res_o));
+    acc = gl_add(gl_mul(acc, k.a64), gl_mul(s0, tmp_b));
+    acc = gl_add(gl_mul(acc, k.a64), gl_mul(h0, res_o));
+    acc = gl_add(gl_mul(acc, k.a16), gl_mul(h0, gl_sub(S[2], k.a15)));
+    return acc;
 }
 
 }  // namespace tmx

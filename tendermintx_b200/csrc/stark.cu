@@ -81,7 +81,7 @@ struct QuotientEdArgs {
     const gl* lde;
     size_t m;
     unsigned log_m, rate_bits;
-    const gl* pertab;  // [1][2P]: not_block_end
+    const gl* pertab;  // [3][2P]: not_block_end, first row of [s]B, first row of [h]A
     int P;
     EdFastConsts k[2];
     gl zh_inv[1 << 3];
@@ -94,8 +94,9 @@ __global__ void __launch_bounds__(128) quotient_ed25519_kernel(QuotientEdArgs a)
     const uint32_t j = bitrev32((uint32_t)p, a.log_m);
     const size_t pn = next_row_position(p, a.log_m - a.rate_bits);
     LdeRow l{a.lde + p, a.m}, n{a.lde + pn, a.m};
-    const gl notend = a.pertab[j & (2 * a.P - 1)];
-    const gl v = ed25519_constraints_fast(l, n, notend, a.k[which]);
+    const uint32_t jp = j & (2 * a.P - 1);
+    const gl per[3] = {a.pertab[jp], a.pertab[2 * a.P + jp], a.pertab[4 * a.P + jp]};
+    const gl v = ed25519_constraints_fast(l, n, per, a.k[which]);
     a.out[(size_t)which * a.m + j] = gl_mul(v, a.zh_inv[j & ((1u << a.rate_bits) - 1)]);
 }
 
@@ -644,19 +645,19 @@ struct HostRow {
     const gl* p;
     FB operator[](int c) const { return FB::mk(p[c]); }
 };
-extern "C" int tmx_host_air_ed25519(const uint64_t* row_l, const uint64_t* row_n, uint64_t notend, const uint64_t alpha[2],
+extern "C" int tmx_host_air_ed25519(const uint64_t* row_l, const uint64_t* row_n, const uint64_t periodic[3], const uint64_t alpha[2],
                                     uint64_t out[4]) {
-    if (!row_l || !row_n || !alpha || !out) return fail(TMX_E_INPUT, "tmx_host_air_ed25519: NULL argument");
+    if (!row_l || !row_n || !periodic || !alpha || !out) return fail(TMX_E_INPUT, "tmx_host_air_ed25519: NULL argument");
     HostRow l{row_l}, n{row_n};
-    const FB per[1] = {FB::mk(notend)};
+    const FB per[3] = {FB::mk(periodic[0]), FB::mk(periodic[1]), FB::mk(periodic[2])};
     ConstraintAcc<FB> acc;
     acc.acc0 = FB::c(0); acc.acc1 = FB::c(0);
     acc.alpha0 = FB::mk(alpha[0]); acc.alpha1 = FB::mk(alpha[1]);
     air_ed25519<FB>(l, n, per, acc);
     out[0] = acc.acc0.v;
     out[1] = acc.acc1.v;
-    out[2] = ed25519_constraints_fast(l, n, notend, ed_fast_consts(alpha[0]));
-    out[3] = ed25519_constraints_fast(l, n, notend, ed_fast_consts(alpha[1]));
+    out[2] = ed25519_constraints_fast(l, n, periodic, ed_fast_consts(alpha[0]));
+    out[3] = ed25519_constraints_fast(l, n, periodic, ed_fast_consts(alpha[1]));
     return TMX_OK;
 }
 

@@ -79,7 +79,7 @@ def test_device_poseidon_fast_path_matches_plain_and_oracle_on_host():
 def test_factored_ed25519_constraint_fold_equals_literal_fold_on_host():
     """K5 fast path: the factored evaluation of the Ed25519 table's constraint combination is the same field element
     as the literal Horner fold of air_ed25519(), on random cells (the identity is polynomial, not witness-dependent),
-    on small 16-bit cells, and for notend = 0 / 1 / random."""
+    on small 16-bit cells, and for 0 / 1 / random values of the three periodic columns."""
     import ctypes
 
     import numpy as np
@@ -94,10 +94,11 @@ def test_factored_ed25519_constraint_fold_equals_literal_fold_on_host():
         hi = P if trial % 2 == 0 else 1 << 16
         l = rng.integers(0, hi, size=ED_COLS, dtype=np.uint64)
         n = rng.integers(0, hi, size=ED_COLS, dtype=np.uint64)
-        notend = [0, 1, int(rng.integers(0, P, dtype=np.uint64))][trial % 3]
+        per = [np.array([0, 1, 0], dtype=np.uint64), np.array([1, 0, 1], dtype=np.uint64),
+               rng.integers(0, P, size=3, dtype=np.uint64)][trial % 3]  # {not_block_end, first row of [s]B, first row of [h]A}
         alpha = rng.integers(0, P, size=2, dtype=np.uint64)
         out = np.zeros(4, dtype=np.uint64)
         vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
-        assert lib.tmx_host_air_ed25519(vp(l), vp(n), notend, vp(alpha), vp(out)) == 0
+        assert lib.tmx_host_air_ed25519(vp(l), vp(n), vp(per), vp(alpha), vp(out)) == 0
         assert out[0] == out[2] and out[1] == out[3], (trial, out)
         assert out[0] != 0
