@@ -111,9 +111,10 @@ int tmx_witness_generate(tmx_ctx *ctx, const uint8_t *d_blob, uint32_t kind, uin
 
 /* K5: constraint quotient of one witness table (0 = SHA-256, 1 = SHA-512, 2 = Ed25519) evaluated on its LDE coset
  * (rate_bits 1): d_lde = [cols][2n] bit-reversed as produced by tmx_lde; d_out = [2][2n] in NATURAL order, one row per
- * constraint challenge alpha[i]: sum_k alpha^(M-1-k) C_k(x) / (x^n - 1). */
-int tmx_quotient(tmx_ctx *ctx, int table, const uint64_t *d_lde, unsigned log_n, const uint64_t alpha[2], uint64_t *d_out,
-                 void *stream);
+ * constraint challenge alpha[i]: sum_k alpha^(M-1-k) C_k(x) / (x^n - 1).  kind / n_max: the circuit shape (the SHA-256
+ * table's public message-boundary columns depend on it). */
+int tmx_quotient(tmx_ctx *ctx, uint32_t kind, uint32_t n_max, int table, const uint64_t *d_lde, unsigned log_n,
+                 const uint64_t alpha[2], uint64_t *d_out, void *stream);
 
 /* K9: proof-of-work grind: the SMALLEST w such that Poseidon(state with state[pos] = w)[7] has `bits` leading
  * zero bits (plonky2 fri_proof_of_work uses rayon find_any, i.e. any witness).  `state` is a host pointer. */

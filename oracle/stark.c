@@ -70,17 +70,50 @@ void tm_trace_dims(uint32_t kind, uint32_t n_max, size_t dims[6]);
 
 enum { T_SHA256 = 0, T_SHA512 = 1, T_ED = 2, N_TABLES = 3 };
 static const int TABLE_COLS[3] = {S256_COLS, S512_COLS, ED_COLS};
-static const int TABLE_NPER[3] = {4, 7, 3};
-static const int TABLE_PERIOD[3] = {64, S512_ROWS_PER_VALIDATOR, ED_ROWS_PER_VALIDATOR};
+static const int TABLE_NPER[3] = {6, 7, 3};
+/* The SHA-256 table's last two "periodic" columns are not periodic: which chunk starts a message (chaining value = IV)
+ * and which chunk continues one (chaining value = previous digest) is fixed by the circuit shape (kind, n_max), see
+ * sha256_chunk_continues().  They are public columns of full length: the prover evaluates them on the LDE coset, the
+ * verifier evaluates their interpolant at zeta itself.  So the "period" of that table is its length. */
+static __thread uint32_t g_kind, g_n_max; /* shape of the circuit being proved / verified (set by the entry points) */
+static size_t table_period(int table, size_t n) {
+    return table == 0 ? n : (table == 1 ? S512_ROWS_PER_VALIDATOR : ED_ROWS_PER_VALIDATOR);
+}
+/* Does 64-row chunk c of the SHA-256 table continue the message of chunk c - 1?  Layout (oracle/trace.c build_sha256):
+ * per validator set n_max one-chunk leaf hashes, then np - 1 two-chunk inner nodes; then the header proofs, each a leaf
+ * (two chunks for the 72-byte last-block-id leaf of the step circuit, else one) and four two-chunk inner nodes; then
+ * one-chunk padding messages. */
+static int sha256_chunk_continues(uint32_t kind, uint32_t n_max, size_t c) {
+    size_t np = 1;
+    while (np < n_max) np *= 2;
+    const size_t set_chunks = n_max + 2 * (np - 1), sets = kind == TMX_KIND_SKIP ? 2 : 1;
+    if (c < sets * set_chunks) {
+        const size_t local = c % set_chunks;
+        return local >= n_max && ((local - n_max) & 1);
+    }
+    size_t h = c - sets * set_chunks;
+    const int n_proofs = kind == TMX_KIND_SKIP ? 4 : 5;
+    for (int k = 0; k < n_proofs; k++) {
+        const size_t leaf = (kind == TMX_KIND_STEP && k == 3) ? 2 : 1, len = leaf + 8;
+        if (h < len) return h < leaf ? h == 1 : ((h - leaf) & 1);
+        h -= len;
+    }
+    return 0;
+}
 
 /* periodic pattern value of column pc at row r (r < period) */
-static gl_t periodic_pattern(int table, int pc, int r) {
+static gl_t periodic_pattern(int table, int pc, size_t row) {
+    const int r = (int)(row & 511);
     if (table == T_SHA256) {
+        const int rr = (int)(row & 63);
+        const size_t chunk = row >> 6;
         switch (pc) {
-            case 0: return SHA256_K[r];
-            case 1: return r == 63;
-            case 2: return r != 63;
-            default: return r >= 15 && r <= 62;
+            case 0: return SHA256_K[rr];
+            case 1: return rr == 63;
+            case 2: return rr != 63;
+            case 3: return rr >= 15 && rr <= 62;
+            case 4: return rr == 0 && !sha256_chunk_continues(g_kind, g_n_max, chunk);      /* FIRST: chaining value = IV */
+            default: return rr == 63 && sha256_chunk_continues(g_kind, g_n_max, chunk + 1); /* LINK: next chunk chains */
         }
     }
     if (table == T_SHA512) {
@@ -294,14 +327,15 @@ static void prove_table(int table, const trace_t *tr, challenger_t *ch, wbuf_t *
     gl_t alpha[NUM_CHALLENGES];
     for (int i = 0; i < NUM_CHALLENGES; i++) alpha[i] = challenger_get(ch);
     /* 3. quotient on the LDE coset */
-    const int nper = TABLE_NPER[table], P = TABLE_PERIOD[table];
+    const int nper = TABLE_NPER[table];
+    const size_t P = table_period(table, n);
     gl_t *pertab = NULL; /* [nper][2P] values at natural LDE index mod 2P */
     if (nper) {
         pertab = (gl_t *)malloc((size_t)nper * 2 * P * sizeof(gl_t));
         gl_t shift = gl_pow(GL_GENERATOR, n / P);
         for (int pc = 0; pc < nper; pc++) {
             gl_t *t = pertab + (size_t)pc * 2 * P;
-            for (int r = 0; r < P; r++) t[r] = periodic_pattern(table, pc, r);
+            for (size_t r = 0; r < P; r++) t[r] = periodic_pattern(table, pc, r);
             ntt_inverse(t, P);
             memset(t + P, 0, P * sizeof(gl_t));
             ntt_coset_forward(t, 2 * P, shift);
@@ -499,6 +533,8 @@ int tm_prove(const uint8_t *input, size_t input_len, const uint8_t *blob, size_t
     if (rc) return rc;
     challenger_t ch;
     transcript_init(&ch, h->kind, h->n_max, chain_id, chain_id_len, skip_max, input, input_len, out32);
+    g_kind = h->kind;
+    g_n_max = h->n_max;
     wbuf_t w = {0};
     wb_push(&w, PROOF_MAGIC);
     wb_push(&w, h->kind);
@@ -545,15 +581,17 @@ static int verify_table(int table, size_t n, rbuf_t *r, challenger_t *ch) {
     for (size_t c = 0; c < C && !bad; c++) observe_ext(ch, op_next[c]);
     /* constraint identity at zeta */
     if (!bad) {
-        const int nper = TABLE_NPER[table], P = TABLE_PERIOD[table];
+        const int nper = TABLE_NPER[table];
+        const size_t P = table_period(table, n);
         gl2_t per[8];
         gl2_t y = gl2_pow(zeta, n / P);
+        gl_t *pat = (gl_t *)malloc(P * sizeof(gl_t));
         for (int pc = 0; pc < nper; pc++) {
-            gl_t pat[512];
-            for (int rr = 0; rr < P; rr++) pat[rr] = periodic_pattern(table, pc, rr);
+            for (size_t rr = 0; rr < P; rr++) pat[rr] = periodic_pattern(table, pc, rr);
             ntt_inverse(pat, P);
             per[pc] = base_poly_eval(pat, P, y);
         }
+        free(pat);
         acc_e_t a;
         for (int i = 0; i < NUM_CHALLENGES; i++) {
             a.acc[i] = gl2_from(0);
@@ -674,6 +712,8 @@ int tm_verify_proof(const uint64_t *proof, size_t proof_len, const uint8_t *inpu
     transcript_init(&ch, kind, n_max, chain_id, chain_id_len, skip_max, input, input_len, out32);
     size_t dims[6];
     tm_trace_dims(kind, n_max, dims);
+    g_kind = kind;
+    g_n_max = n_max;
     for (int t = 0; t < N_TABLES; t++) {
         int rc = verify_table(t, dims[2 * t], &r, &ch);
         if (rc) return 10 * (t + 1) + rc;
@@ -682,7 +722,12 @@ int tm_verify_proof(const uint64_t *proof, size_t proof_len, const uint8_t *inpu
     return 0;
 }
 
-/* debug / test hook: LDE of a trace and the quotient values on the LDE coset in natural order, [2][m] */
+void tm_debug_set_shape(uint32_t kind, uint32_t n_max) {
+    g_kind = kind;
+    g_n_max = n_max;
+}
+
+/* debug / test hook (shape from tm_debug_set_shape): LDE of a trace and the quotient values on the LDE coset in natural order, [2][m] */
 void tm_debug_quotient(int table, const uint64_t *trace, size_t n, size_t C, const uint64_t alpha[2], uint64_t *lde_out,
                        uint64_t *qv_out) {
     const size_t m = n << RATE_BITS;
@@ -690,12 +735,13 @@ void tm_debug_quotient(int table, const uint64_t *trace, size_t n, size_t C, con
     gl_t *coeffs = (gl_t *)malloc(C * n * sizeof(gl_t));
     ntt_lde_batch(trace, C, n, RATE_BITS, lde_out, coeffs);
     free(coeffs);
-    const int nper = TABLE_NPER[table], P = TABLE_PERIOD[table];
+    const int nper = TABLE_NPER[table];
+    const size_t P = table_period(table, n);
     gl_t *pertab = (gl_t *)calloc((size_t)(nper ? nper : 1) * 2 * P, sizeof(gl_t));
     gl_t shift = gl_pow(GL_GENERATOR, n / P);
     for (int pc = 0; pc < nper; pc++) {
         gl_t *t = pertab + (size_t)pc * 2 * P;
-        for (int r = 0; r < P; r++) t[r] = periodic_pattern(table, pc, r);
+        for (size_t r = 0; r < P; r++) t[r] = periodic_pattern(table, pc, r);
         ntt_inverse(t, P);
         memset(t + P, 0, P * sizeof(gl_t));
         ntt_coset_forward(t, 2 * P, shift);

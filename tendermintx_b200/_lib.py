@@ -55,7 +55,7 @@ def load():
         "tmx_sha256_trace": (i32, [vp, vp, u32, u32, u64p, vp, vp]),
         "tmx_ed25519_trace": (i32, [vp, vp, u32, u32, u64p, u64p, vp, vp]),
         "tmx_witness_generate": (i32, [vp, vp, u32, u32, u64p, u64p, u64p, vp, vp]),
-        "tmx_quotient": (i32, [vp, i32, u64p, u32, vp, u64p, vp]),
+        "tmx_quotient": (i32, [vp, u32, u32, i32, u64p, u32, vp, u64p, vp]),
         "tmx_pow_grind": (i32, [vp, vp, i32, u32, c.POINTER(c.c_uint64), vp]),
         "tmx_circuit_build": (i32, [vp, u32, u32, c.c_char_p, sz, c.c_uint64, c.POINTER(vp)]),
         "tmx_circuit_free": (None, [vp]),

@@ -10,6 +10,7 @@
 #include "gl.cuh"
 #include "../../include/tmx_trace.h"
 #include <vector>
+#include <algorithm>
 
 namespace tmx {
 
@@ -61,11 +62,42 @@ TMX_HD F pack_bits(const Row& r, int col0, int nbits) {
 
 constexpr int AIR_SHA256 = 0, AIR_SHA512 = 1, AIR_ED25519 = 2;
 TMX_HD int air_cols(int t) { return t == AIR_SHA256 ? S256_COLS : (t == AIR_SHA512 ? S512_COLS : ED_COLS); }
-TMX_HD int air_n_periodic(int t) { return t == AIR_SHA256 ? 4 : (t == AIR_SHA512 ? 7 : 3); }
-TMX_HD int air_period(int t) { return t == AIR_SHA256 ? 64 : (t == AIR_SHA512 ? S512_ROWS_PER_VALIDATOR : ED_ROWS_PER_VALIDATOR); }
+// Circuit shape the SHA-256 table's public columns depend on.
+struct AirShape {
+    uint32_t kind, n_max;
+};
+TMX_HD int air_n_periodic(int t) { return t == AIR_SHA256 ? 6 : (t == AIR_SHA512 ? 7 : 3); }
+// The last two columns of the SHA-256 table are not periodic: which chunk starts a message and which continues one is
+// fixed by the circuit shape (sha256_chunk_continues).  They are public columns of full length -- the prover evaluates
+// them on the LDE coset once per circuit, the verifier evaluates their interpolant at zeta itself -- so that table's
+// "period" is its length n.
+TMX_HD size_t air_period(int t, size_t n) { return t == AIR_SHA256 ? n : (t == AIR_SHA512 ? S512_ROWS_PER_VALIDATOR : ED_ROWS_PER_VALIDATOR); }
+
+// Does 64-row chunk c of the SHA-256 table continue the message of chunk c - 1?  Layout (witness_jobs.cuh): per
+// validator set n_max one-chunk leaf hashes, then np - 1 two-chunk inner nodes; then the header proofs, each a leaf (two
+// chunks for the 72-byte last-block-id leaf of the step circuit, else one) and four two-chunk inner nodes; then one-chunk
+// padding messages.
+TMX_HD bool sha256_chunk_continues(AirShape sh, size_t c) {
+    size_t np = 1;
+    while (np < sh.n_max) np *= 2;
+    const size_t set_chunks = sh.n_max + 2 * (np - 1), sets = sh.kind == 1 /* TMX_KIND_SKIP */ ? 2 : 1;
+    if (c < sets * set_chunks) {
+        const size_t local = c % set_chunks;
+        return local >= sh.n_max && ((local - sh.n_max) & 1);
+    }
+    size_t h = c - sets * set_chunks;
+    const int n_proofs = sh.kind == 1 ? 4 : 5;
+    for (int k = 0; k < n_proofs; k++) {
+        const size_t leaf = (sh.kind == 0 && k == 3) ? 2 : 1, len = leaf + 8;
+        if (h < len) return h < leaf ? h == 1 : ((h - leaf) & 1) != 0;
+        h -= len;
+    }
+    return false;
+}
 
 // ------------------------------------------------------------------------------------------ SHA-256
-// per = {K_t, is_last_round, not_last_round, schedule_active (rounds 15..62)}
+// per = {K_t, is_last_round, not_last_round, schedule_active (rounds 15..62)} with period 64, then the two public
+// full-length columns {FIRST: row 0 of a chunk that starts a message, LINK: row 63 of a chunk whose successor continues it}
 template <class F, class Row, class Per, class Emit>
 TMX_HD void air_sha256(const Row& l, const Row& n, const Per& per, Emit& emit) {
     const F K = per[0], LAST = per[1], NOTLAST = per[2], SCHED = per[3];
@@ -129,6 +161,10 @@ TMX_HD void air_sha256(const Row& l, const Row& n, const Per& per, Emit& emit) {
         emit(NOTLAST * l[S256_DG + j]);
         emit(NOTLAST * l[S256_DC + j]);
     }
+    // message chaining: a message starts from the IV, a continuation chunk from the previous chunk's digest
+    const uint32_t IV[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
+    for (int j = 0; j < 8; j++) emit(per[4] * (l[S256_CV + j] - F::c(IV[j])));
+    for (int j = 0; j < 8; j++) emit(per[5] * (n[S256_CV + j] - l[S256_DG + j]));
 }
 
 // ------------------------------------------------------------------------------------------ SHA-512
@@ -356,12 +392,17 @@ TMX_HD void air_eval(int table, const Row& l, const Row& n, const Per& per, Emit
 }
 
 // periodic pattern of column pc at row r of its period
-TMX_HD uint64_t air_periodic_pattern(int table, int pc, int r, const uint32_t* k256_table, const uint64_t* k512_table) {
+TMX_HD uint64_t air_periodic_pattern(int table, int pc, size_t row, const uint32_t* k256_table, const uint64_t* k512_table,
+                                     AirShape shape) {
+    const int r = (int)(row & 511);
     if (table == AIR_SHA256) {
-        if (pc == 0) return k256_table[r];
-        if (pc == 1) return r == 63;
-        if (pc == 2) return r != 63;
-        return r >= 15 && r <= 62;
+        const int r64 = (int)(row & 63);
+        if (pc == 0) return k256_table[r64];
+        if (pc == 1) return r64 == 63;
+        if (pc == 2) return r64 != 63;
+        if (pc == 3) return r64 >= 15 && r64 <= 62;
+        if (pc == 4) return r64 == 0 && !sha256_chunk_continues(shape, row >> 6);
+        return r64 == 63 && sha256_chunk_continues(shape, (row >> 6) + 1);
     }
     if (table == AIR_SHA512) {
         const int rr = r % S512_ROWS_PER_CHUNK;  // row inside the chunk; r is the row inside the validator's two-chunk slot
@@ -378,30 +419,62 @@ TMX_HD uint64_t air_periodic_pattern(int table, int pc, int r, const uint32_t* k
     return r == 256;
 }
 
+// Host NTT (in place, natural order in and out) for the public columns: iterative radix-2, O(n log n).
+inline void air_host_ntt(std::vector<gl>& a, bool inverse) {
+    const size_t n = a.size();
+    const unsigned lg = ilog2(n);
+    for (size_t i = 0; i < n; i++) {
+        const size_t j = bitrev32((uint32_t)i, lg);
+        if (i < j) std::swap(a[i], a[j]);
+    }
+    for (unsigned s = 1; s <= lg; s++) {
+        const size_t half = (size_t)1 << (s - 1);
+        gl w = gl_root_of_unity(s);
+        if (inverse) w = gl_inv(w);
+        std::vector<gl> tw(half);
+        tw[0] = 1;
+        for (size_t k = 1; k < half; k++) tw[k] = gl_mul(tw[k - 1], w);
+        for (size_t base = 0; base < n; base += 2 * half)
+            for (size_t k = 0; k < half; k++) {
+                const gl u = a[base + k], v = gl_mul(a[base + k + half], tw[k]);
+                a[base + k] = gl_add(u, v);
+                a[base + k + half] = gl_sub(u, v);
+            }
+    }
+    if (inverse) {
+        const gl ninv = gl_inv((gl)n);
+        for (auto& x : a) x = gl_mul(x, ninv);
+    }
+}
+
+// coefficients of the interpolant of periodic / public column pc over one period (P values)
+inline std::vector<gl> air_periodic_coeffs(int table, int pc, size_t P, const uint32_t* k256_table, const uint64_t* k512_table,
+                                           AirShape shape) {
+    std::vector<gl> c(P);
+    for (size_t r = 0; r < P; r++) c[r] = (gl)air_periodic_pattern(table, pc, r, k256_table, k512_table, shape);
+    air_host_ntt(c, true);
+    return c;
+}
+
 // Host: values of the periodic columns on the LDE coset, [nper][2P], indexed by (natural LDE index mod 2P).
 // Column pc is the interpolant s of its one-period pattern composed with x -> x^(n/P); on the coset
 // x_j = 7 w_m^j this only depends on j mod 2P: s(7^(n/P) w_2P^j).
-inline std::vector<gl> air_periodic_lde_table(int table, unsigned log_n, const uint32_t* k256_table, const uint64_t* k512_table) {
-    const int nper = air_n_periodic(table), P = air_period(table);
-    const size_t n = (size_t)1 << log_n;
+inline std::vector<gl> air_periodic_lde_table(int table, unsigned log_n, const uint32_t* k256_table, const uint64_t* k512_table,
+                                              AirShape shape) {
+    const size_t n = (size_t)1 << log_n, P = air_period(table, n);
+    const int nper = air_n_periodic(table);
     std::vector<gl> tab((size_t)nper * 2 * P);
-    const unsigned lgP = ilog2(P);
-    const gl wPi = gl_inv(gl_root_of_unity(lgP)), Pinv = gl_inv((gl)P);
-    const gl w2P = gl_root_of_unity(lgP + 1), sh = gl_pow(GL_GEN, n / P);
+    const gl sh = gl_pow(GL_GEN, n / P);
     for (int pc = 0; pc < nper; pc++) {
-        std::vector<gl> coef(P);
-        for (int k = 0; k < P; k++) {
-            gl acc = 0;
-            for (int r = 0; r < P; r++)
-                acc = gl_add(acc, gl_mul((gl)air_periodic_pattern(table, pc, r, k256_table, k512_table), gl_pow(wPi, ((uint64_t)r * k) % P)));
-            coef[k] = gl_mul(acc, Pinv);
+        std::vector<gl> coef = air_periodic_coeffs(table, pc, P, k256_table, k512_table, shape);
+        coef.resize(2 * P, 0);
+        gl s = 1;
+        for (size_t k = 0; k < P; k++) {  // s(sh * x): scale coefficient k by sh^k, then a plain NTT of size 2P
+            coef[k] = gl_mul(coef[k], s);
+            s = gl_mul(s, sh);
         }
-        for (int j = 0; j < 2 * P; j++) {
-            const gl x = gl_mul(sh, gl_pow(w2P, j));
-            gl acc = 0;
-            for (int k = P - 1; k >= 0; k--) acc = gl_add(gl_mul(acc, x), coef[k]);
-            tab[(size_t)pc * 2 * P + j] = acc;
-        }
+        air_host_ntt(coef, false);
+        for (size_t j = 0; j < 2 * P; j++) tab[(size_t)pc * 2 * P + j] = coef[j];
     }
     return tab;
 }

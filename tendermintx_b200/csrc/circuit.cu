@@ -378,6 +378,7 @@ extern "C" int tmx_prove(tmx_circuit* c, const uint8_t* input, size_t input_len,
     }
     Challenger ch;
     transcript_init(c, input, input_len, out32, ch);
+    c->prover.shape = AirShape{c->kind, c->n_max};
     rc = c->prover.prove(ctx, 0, c->d_trace[0], ilog2(c->dims[0]), ch, w, st, start_ladders);
     if (rc) {
         delete p;
@@ -489,7 +490,7 @@ extern "C" int tmx_verify(const tmx_circuit* c, const uint8_t* proof, size_t pro
     transcript_init(c, input, input_len, out32, ch);
     size_t pos = 8;
     for (int t = 0; t < STARK_N_TABLES; t++) {
-        const int rc = verify_table(t, c->dims[2 * t], w.data(), w.size(), &pos, ch);
+        const int rc = verify_table(t, c->dims[2 * t], AirShape{c->kind, c->n_max}, w.data(), w.size(), &pos, ch);
         if (rc) return fail(TMX_E_VERIFY, "tmx_verify: table " + std::to_string(t) + " rejected (code " + std::to_string(rc) + ")");
     }
     if (pos != w.size()) return fail(TMX_E_VERIFY, "tmx_verify: trailing data");

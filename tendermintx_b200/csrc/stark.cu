@@ -373,7 +373,7 @@ int TableProver::prove(tmx_ctx* ctx, int table, const gl* d_trace, unsigned log_
     QuotientArgs qa;
     memset(&qa, 0, sizeof qa);
     qa.lde = d_lde; qa.m = m; qa.log_m = km; qa.rate_bits = STARK_RATE_BITS;
-    qa.nper = air_n_periodic(table); qa.P = air_period(table);
+    qa.nper = air_n_periodic(table); qa.P = (int)air_period(table, n);
     qa.alpha[0] = ch.get();
     qa.alpha[1] = ch.get();
     fill_zh_inv(qa, n);
@@ -606,13 +606,13 @@ int TableProver::reserve_queries(tmx_ctx* ctx, size_t n) {
 }
 
 int TableProver::periodic_tables(tmx_ctx* ctx, int table, unsigned log_n, const gl** out) {
-    const uint64_t key = ((uint64_t)table << 8) | log_n;
+    const uint64_t key = ((uint64_t)shape.kind << 48) | ((uint64_t)shape.n_max << 16) | ((uint64_t)table << 8) | log_n;
     auto it = pertabs.find(key);
     if (it != pertabs.end()) {
         *out = it->second;
         return TMX_OK;
     }
-    std::vector<gl> tab = air_periodic_lde_table(table, log_n, h_K256, h_K512);
+    std::vector<gl> tab = air_periodic_lde_table(table, log_n, h_K256, h_K512, shape);
     void* d = nullptr;
     TMX_CUDA(cudaMalloc(&d, tab.size() * sizeof(gl)));
     TMX_CUDA(cudaMemcpy(d, tab.data(), tab.size() * sizeof(gl), cudaMemcpyHostToDevice));
@@ -662,16 +662,17 @@ extern "C" int tmx_host_air_ed25519(const uint64_t* row_l, const uint64_t* row_n
 }
 
 // K5 as a kernel-level entry point (parity tests, ncu): constraint quotient of one table on its LDE coset.
-extern "C" int tmx_quotient(tmx_ctx* ctx, int table, const uint64_t* d_lde, unsigned log_n, const uint64_t alpha[2],
-                            uint64_t* d_out, void* stream) {
+extern "C" int tmx_quotient(tmx_ctx* ctx, uint32_t kind, uint32_t n_max, int table, const uint64_t* d_lde, unsigned log_n,
+                            const uint64_t alpha[2], uint64_t* d_out, void* stream) {
     if (!ctx || !d_lde || !alpha || !d_out || table < 0 || table > 2 || log_n < 8 || log_n > 28)
         return fail(TMX_E_INPUT, "tmx_quotient: bad arguments");
     static thread_local TableProver tp;  // only its periodic-table cache is used
+    tp.shape = AirShape{kind, n_max};
     QuotientArgs qa;
     memset(&qa, 0, sizeof qa);
     const size_t n = (size_t)1 << log_n;
     qa.lde = d_lde; qa.m = n << STARK_RATE_BITS; qa.log_m = log_n + STARK_RATE_BITS; qa.rate_bits = STARK_RATE_BITS;
-    qa.nper = air_n_periodic(table); qa.P = air_period(table);
+    qa.nper = air_n_periodic(table); qa.P = (int)air_period(table, n);
     qa.alpha[0] = alpha[0]; qa.alpha[1] = alpha[1];
     fill_zh_inv(qa, n);
     if (qa.nper) {

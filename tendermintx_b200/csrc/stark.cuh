@@ -41,6 +41,7 @@ struct TableProver {
     gl2* d_fri[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     gl* d_query = nullptr; size_t sz_query = 0;
     std::map<uint64_t, gl*> pertabs;
+    AirShape shape = {0, 0};  // circuit shape (kind, n_max): the SHA-256 table's public columns depend on it
     // device-time stamps of the trace commitment of the last prove(): LDE start, LDE end = Merkle start, Merkle end
     cudaEvent_t ev_phase[3] = {nullptr, nullptr, nullptr};
     float last_lde_ms = 0.f, last_merkle_ms = 0.f;
@@ -59,6 +60,6 @@ struct TableProver {
 };
 
 // host verifier of one table proof; returns 0 or a diagnostic code
-int verify_table(int table, size_t n, const gl* proof, size_t proof_len, size_t* pos, Challenger& ch);
+int verify_table(int table, size_t n, AirShape shape, const gl* proof, size_t proof_len, size_t* pos, Challenger& ch);
 
 }  // namespace tmx

@@ -84,7 +84,7 @@ gl2 fold_coset(gl x, unsigned within, const gl2 evals[16], gl2 beta) {
 
 }  // namespace
 
-int verify_table(int table, size_t n, const gl* proof, size_t proof_len, size_t* pos, Challenger& ch) {
+int verify_table(int table, size_t n, AirShape shape, const gl* proof, size_t proof_len, size_t* pos, Challenger& ch) {
     Reader r{proof, proof_len, *pos, false};
     const size_t C = (size_t)air_cols(table), m = n << STARK_RATE_BITS;
     const unsigned k = ilog2(n), km = k + STARK_RATE_BITS;
@@ -112,18 +112,15 @@ int verify_table(int table, size_t n, const gl* proof, size_t proof_len, size_t*
     for (size_t c = 0; c < C; c++) ch.observe_ext(nxt[c].v);
     // constraint identity at zeta: (chunk0 + zeta^n chunk1) * (zeta^n - 1) == sum_i alpha^(M-1-i) C_i(zeta)
     {
-        const int nper = air_n_periodic(table), P = air_period(table);
+        const int nper = air_n_periodic(table);
+        const size_t P = air_period(table, n);
         FE per[8] = {FE::c(0), FE::c(0), FE::c(0), FE::c(0), FE::c(0), FE::c(0), FE::c(0), FE::c(0)};
         const gl2 y = gl2_pow(zeta, n / P);
-        const gl wPi = gl_inv(gl_root_of_unity(ilog2(P))), Pinv = gl_inv((gl)P);
         for (int pc = 0; pc < nper; pc++) {
+            // interpolant of the column's one-period pattern (for the SHA-256 table's public columns: of the whole column)
+            const std::vector<gl> cb = air_periodic_coeffs(table, pc, P, h_K256, h_K512, shape);
             std::vector<gl2> coef(P);
-            for (int kk = 0; kk < P; kk++) {
-                gl acc = 0;
-                for (int rr = 0; rr < P; rr++)
-                    acc = gl_add(acc, gl_mul((gl)air_periodic_pattern(table, pc, rr, h_K256, h_K512), gl_pow(wPi, ((uint64_t)rr * kk) % P)));
-                coef[kk] = gl2_from(gl_mul(acc, Pinv));
-            }
+            for (size_t kk = 0; kk < P; kk++) coef[kk] = gl2_from(cb[kk]);
             per[pc] = FE::mk(ext_horner(coef.data(), P, y));
         }
         ConstraintAcc<FE> acc;

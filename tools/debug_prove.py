@@ -15,6 +15,7 @@ alpha = np.array([123456789123, 987654321987], dtype=np.uint64)
 vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
 dev = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).cuda()
 host = lambda t: t.cpu().numpy().view(np.uint64)
+O.tm_debug_set_shape(ctypes.c_uint32(0), ctypes.c_uint32(c["n_max"]))  # step circuit: the SHA-256 public columns depend on the shape
 for t in range(3):
     C, n = tr[t].shape
     lg = n.bit_length() - 1
@@ -23,7 +24,7 @@ for t in range(3):
     d_lde = ctx.lde(dev(tr[t]), lg, 1)
     print("table", t, "lde equal", np.array_equal(host(d_lde), lde))
     d_q = torch.zeros((2, 2 * n), dtype=torch.int64, device="cuda")
-    rc = tmx.lib().tmx_quotient(ctx.handle, t, ctypes.c_void_p(d_lde.data_ptr()), lg, vp(alpha), ctypes.c_void_p(d_q.data_ptr()), ctx._stream())
+    rc = tmx.lib().tmx_quotient(ctx.handle, 0, c["n_max"], t, ctypes.c_void_p(d_lde.data_ptr()), lg, vp(alpha), ctypes.c_void_p(d_q.data_ptr()), ctx._stream())
     torch.cuda.synchronize()
     got = host(d_q)
     print("  quotient rc", rc, "equal", np.array_equal(got, qv), "mismatch count", int((got != qv).sum()))

@@ -98,11 +98,12 @@ struct HostRow {
     size_t stride;
     FB operator[](int c) const { return FB::mk(base[(size_t)c * stride]); }
 };
-extern "C" void hostsim_quotient(int table, const uint64_t* lde, size_t n, const uint64_t alpha[2], uint64_t* out) {
+extern "C" void hostsim_quotient(uint32_t kind, uint32_t n_max, int table, const uint64_t* lde, size_t n, const uint64_t alpha[2],
+                                 uint64_t* out) {
     const unsigned log_n = log2u((uint32_t)n), log_m = log_n + 1;
     const size_t m = n << 1;
-    std::vector<gl> tab = air_periodic_lde_table(table, log_n, h_K256, h_K512);
-    const int P = air_period(table);
+    std::vector<gl> tab = air_periodic_lde_table(table, log_n, h_K256, h_K512, AirShape{kind, n_max});
+    const size_t P = air_period(table, n);
     const gl gn = gl_pow(GL_GEN, n);
     const gl zh_inv[2] = {gl_inv(gl_sub(gn, 1)), gl_inv(gl_sub(gl_neg(gn), 1))};
     for (size_t p = 0; p < m; p++) {
