@@ -24,8 +24,8 @@ sys.path.insert(0, ROOT)
 
 N_MAX = 128
 # dram__bytes_read.sum + dram__bytes_write.sum of the six ntt_pass_kernel launches that make up the LDE of the Ed25519
-# table (1217 columns x 2^16), from profiles/r1d_ncu_ntt.raw.csv (one ncu --set full capture, per LDE)
-NCU_K1_TRAFFIC_BYTES = 7370145280
+# table (1217 columns x 2^16), from profiles/r1e_ncu_ntt.raw.csv (one ncu --set full capture, per LDE)
+NCU_K1_TRAFFIC_BYTES = 7383291392
 METRIC = "skip proofs/hour (CelestiaConfig, 128 val)"
 UNIT = "proofs/hour"
 WORKLOAD = "skip circuit CelestiaConfig VALIDATOR_SET_SIZE_MAX=128 (synthetic celestia chain, 128 signers, seed=rank)"
@@ -302,7 +302,7 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": "ntt_pass_kernel family (K1: iNTT + coset LDE, rate 1/2, of the Ed25519 trace table, 1217 x 2^16, "
                      "six launches per proof, CUDA events recorded by the prover inside the timed proofs)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_K1_TRAFFIC_BYTES, "traffic_note": "dram read+write of the six K1 launches of the Ed25519 table, "
-                     "ncu --set full (profiles/r1d_ncu_ntt.raw.csv), per proof like achieved",
+                     "ncu --set full (profiles/r1e_ncu_ntt.raw.csv), per proof like achieved",
                      "peak_source": peak_src, "algorithmic_bytes": alg_bytes, "ms": lde_ms,
                      "ms_per_table": [p[0] / args.steps for p in phase],
                      "all_tables": {"algorithmic_bytes": alg_bytes_all, "ms": lde_ms_all,
