@@ -15,6 +15,8 @@
 #include <cstdlib>
 #include <ctime>
 #include <algorithm>
+#include <memory>
+#include <mutex>
 
 namespace tmx {
 
@@ -612,7 +614,19 @@ int TableProver::periodic_tables(tmx_ctx* ctx, int table, unsigned log_n, const 
         *out = it->second;
         return TMX_OK;
     }
-    std::vector<gl> tab = air_periodic_lde_table(table, log_n, h_K256, h_K512, shape);
+    // the host-side values depend on (shape, table, log_n) only: computed once per process (the SHA-256 table's public
+    // columns cost six NTTs of the table length), shared by every prover / context
+    static std::mutex cache_mutex;
+    static std::map<uint64_t, std::shared_ptr<const std::vector<gl>>> cache;
+    std::shared_ptr<const std::vector<gl>> host;
+    {
+        std::lock_guard<std::mutex> lk(cache_mutex);
+        auto hit = cache.find(key);
+        if (hit == cache.end())
+            hit = cache.emplace(key, std::make_shared<const std::vector<gl>>(air_periodic_lde_table(table, log_n, h_K256, h_K512, shape))).first;
+        host = hit->second;
+    }
+    const std::vector<gl>& tab = *host;
     void* d = nullptr;
     TMX_CUDA(cudaMalloc(&d, tab.size() * sizeof(gl)));
     TMX_CUDA(cudaMemcpy(d, tab.data(), tab.size() * sizeof(gl), cudaMemcpyHostToDevice));

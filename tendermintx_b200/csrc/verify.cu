@@ -5,6 +5,8 @@
 // client or the next recursion layer runs); independent of the GPU prover's code paths.
 #include "stark.cuh"
 #include <algorithm>
+#include <memory>
+#include <mutex>
 
 namespace tmx {
 
@@ -49,6 +51,18 @@ bool merkle_check(const gl* leaf, size_t leaf_len, size_t index, const gl* sib, 
     for (int i = 0; i < 4; i++)
         if (cur[i] != cap[4 * index + i]) return false;
     return true;
+}
+
+// interpolants of the periodic / public columns depend on (table, column, length, shape) only: computed once per process
+static const std::vector<gl>& cached_periodic_coeffs(int table, int pc, size_t P, AirShape shape) {
+    static std::mutex m;
+    static std::map<std::vector<uint64_t>, std::shared_ptr<const std::vector<gl>>> cache;
+    const std::vector<uint64_t> key = {(uint64_t)table, (uint64_t)pc, (uint64_t)P, shape.kind, shape.n_max};
+    std::lock_guard<std::mutex> lk(m);
+    auto hit = cache.find(key);
+    if (hit == cache.end())
+        hit = cache.emplace(key, std::make_shared<const std::vector<gl>>(air_periodic_coeffs(table, pc, P, h_K256, h_K512, shape))).first;
+    return *hit->second;  // entries are never erased
 }
 
 gl2 ext_horner(const gl2* c, size_t n, gl2 x) {
@@ -118,7 +132,7 @@ int verify_table(int table, size_t n, AirShape shape, const gl* proof, size_t pr
         const gl2 y = gl2_pow(zeta, n / P);
         for (int pc = 0; pc < nper; pc++) {
             // interpolant of the column's one-period pattern (for the SHA-256 table's public columns: of the whole column)
-            const std::vector<gl> cb = air_periodic_coeffs(table, pc, P, h_K256, h_K512, shape);
+            const std::vector<gl>& cb = cached_periodic_coeffs(table, pc, P, shape);
             std::vector<gl2> coef(P);
             for (size_t kk = 0; kk < P; kk++) coef[kk] = gl2_from(cb[kk]);
             per[pc] = FE::mk(ext_horner(coef.data(), P, y));
