@@ -55,10 +55,12 @@
 #define S512_CA 692   /* 3 bits carry of the low half, then 3 bits carry of the high half */
 #define S512_CE 698
 #define S512_CW 704   /* 2 + 2 bits */
-#define S512_DG 708   /* 8 words x (lo, hi), last round only */
+#define S512_DG 708   /* 8 digest words x (lo, hi): zero before round 79, the digest from row 79 to the end of the chunk */
 #define S512_DC 724   /* 8 words x (carry lo, carry hi), last round only */
 #define S512_WS 740   /* lo, hi of the schedule sum; equals the next row's w[15] on rows 15..126 */
-#define S512_COLS 742
+#define S512_TWO 742  /* 1 on all 256 rows of a validator slot whose message has two blocks (the second chunk chains from the
+                         first); 0 when the second chunk is an unused compression from the IV */
+#define S512_COLS 743
 #define S512_ROUNDS 80
 #define S512_ROWS_PER_CHUNK 128
 #define S512_ROWS_PER_VALIDATOR 256

@@ -70,7 +70,7 @@ void tm_trace_dims(uint32_t kind, uint32_t n_max, size_t dims[6]);
 
 enum { T_SHA256 = 0, T_SHA512 = 1, T_ED = 2, N_TABLES = 3 };
 static const int TABLE_COLS[3] = {S256_COLS, S512_COLS, ED_COLS};
-static const int TABLE_NPER[3] = {6, 7, 3};
+static const int TABLE_NPER[3] = {6, 11, 3};
 /* The SHA-256 table's last two "periodic" columns are not periodic: which chunk starts a message (chaining value = IV)
  * and which chunk continues one (chaining value = previous digest) is fixed by the circuit shape (kind, n_max), see
  * sha256_chunk_continues().  They are public columns of full length: the prover evaluates them on the LDE coset, the
@@ -125,7 +125,11 @@ static gl_t periodic_pattern(int table, int pc, size_t row) {
             case 3: return rr != 79;
             case 4: return rr != S512_ROWS_PER_CHUNK - 1;
             case 5: return rr >= 15 && rr <= S512_ROWS_PER_CHUNK - 2;
-            default: return r == 0;
+            case 6: return r == 0;
+            case 7: return rr < 79;
+            case 8: return rr >= 79 && rr <= S512_ROWS_PER_CHUNK - 2;
+            case 9: return r == S512_ROWS_PER_CHUNK - 1;
+            default: return r != S512_ROWS_PER_VALIDATOR - 1;
         }
     }
     switch (pc) { /* Ed25519 */
@@ -347,7 +351,7 @@ static void prove_table(int table, const trace_t *tr, challenger_t *ch, wbuf_t *
 #pragma omp parallel
     {
         gl_t *loc = (gl_t *)malloc(C * sizeof(gl_t)), *nxt = (gl_t *)malloc(C * sizeof(gl_t));
-        gl_t per[8];
+        gl_t per[16];
 #pragma omp for schedule(static)
         for (size_t j = 0; j < m; j++) {
             size_t p = tmx_bitrev(j, km), p2 = tmx_bitrev((j + (1u << RATE_BITS)) & (m - 1), km);
@@ -583,7 +587,7 @@ static int verify_table(int table, size_t n, rbuf_t *r, challenger_t *ch) {
     if (!bad) {
         const int nper = TABLE_NPER[table];
         const size_t P = table_period(table, n);
-        gl2_t per[8];
+        gl2_t per[16];
         gl2_t y = gl2_pow(zeta, n / P);
         gl_t *pat = (gl_t *)malloc(P * sizeof(gl_t));
         for (int pc = 0; pc < nper; pc++) {
@@ -755,7 +759,7 @@ void tm_debug_quotient(int table, const uint64_t *trace, size_t n, size_t C, con
             loc[c] = lde_out[c * m + p];
             nxt[c] = lde_out[c * m + p2];
         }
-        gl_t per[8];
+        gl_t per[16];
         for (int pc = 0; pc < nper; pc++) per[pc] = pertab[(size_t)pc * 2 * P + (j & (2 * P - 1))];
         acc_b_t a;
         for (int i = 0; i < 2; i++) { a.acc[i] = 0; a.alpha[i] = alpha[i]; }

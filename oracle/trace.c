@@ -239,7 +239,8 @@ static void put_halves(trace_t *t, int col, size_t row, uint64_t v) {
 
 /* rows [row0, row0 + nrows) of one compression: 80 rounds, then 48 continuation rounds with round constant 0
  * (include/tmx_trace.h); nrows < 128 only for a truncated last padding chunk */
-static void sha512_rows(trace_t *t, size_t row0, size_t nrows, const uint64_t cv[8], const uint8_t blk[128], uint64_t out_state[8]) {
+static void sha512_rows(trace_t *t, size_t row0, size_t nrows, const uint64_t cv[8], const uint8_t blk[128], uint64_t out_state[8],
+                        int two) {
     sha512_round_t r[S512_ROWS_PER_CHUNK];
     uint64_t st[8];
     memcpy(st, cv, sizeof st);
@@ -323,12 +324,18 @@ static void sha512_rows(trace_t *t, size_t row0, size_t nrows, const uint64_t cv
         }
         for (int j = 0; j < 8; j++) {
             uint64_t dlo = 0, dhi = 0, clo = 0, chi = 0;
-            if (i == 79) {
-                const uint64_t fin[8] = {an, v[0], v[1], v[2], en, v[4], v[5], v[6]};
+            if (i >= 79) { /* the digest stays on the rows 79..127 so that the next chunk can chain from it; carries on row 79 only */
+                const uint64_t *v79 = r[79].v;
+                uint64_t a79 = v79[0], b79 = v79[1], c79 = v79[2], d79 = v79[3], e79 = v79[4], f79 = v79[5], g79 = v79[6], h79 = v79[7];
+                uint64_t t1 = h79 + (ror64(e79, 14) ^ ror64(e79, 18) ^ ror64(e79, 41)) + ((e79 & f79) ^ (~e79 & g79)) + SHA512_K[79] + W[79];
+                uint64_t t2 = (ror64(a79, 28) ^ ror64(a79, 34) ^ ror64(a79, 39)) + ((a79 & b79) ^ (a79 & c79) ^ (b79 & c79));
+                const uint64_t fin[8] = {t1 + t2, a79, b79, c79, d79 + t1, e79, f79, g79};
                 uint64_t lo = LO(cv[j]) + LO(fin[j]);
-                clo = lo >> 32;
-                uint64_t hi = HI(cv[j]) + HI(fin[j]) + clo;
-                chi = hi >> 32;
+                uint64_t hi = HI(cv[j]) + HI(fin[j]) + (lo >> 32);
+                if (i == 79) {
+                    clo = lo >> 32;
+                    chi = hi >> 32;
+                }
                 dlo = LO(lo);
                 dhi = LO(hi);
             }
@@ -337,6 +344,7 @@ static void sha512_rows(trace_t *t, size_t row0, size_t nrows, const uint64_t cv
             CELL(t, S512_DC + 2 * j, row) = clo;
             CELL(t, S512_DC + 2 * j + 1, row) = chi;
         }
+        CELL(t, S512_TWO, row) = (uint64_t)(two != 0);
 #undef LO
 #undef HI
     }
@@ -374,17 +382,17 @@ static void build_sha512(trace_t *t, const tmx_offchain_head *h, const tmx_valid
         size_t row = i * S512_ROWS_PER_VALIDATOR;
         for (size_t b = 0; b < 2; b++) {
             if (b < nb) {
-                sha512_rows(t, row + S512_ROWS_PER_CHUNK * b, S512_ROWS_PER_CHUNK, st, buf + 128 * b, nxt);
+                sha512_rows(t, row + S512_ROWS_PER_CHUNK * b, S512_ROWS_PER_CHUNK, st, buf + 128 * b, nxt, nb == 2);
                 memcpy(st, nxt, sizeof st);
             } else
-                sha512_rows(t, row + S512_ROWS_PER_CHUNK * b, S512_ROWS_PER_CHUNK, SHA512_IV, zero, NULL); /* unused second slot */
+                sha512_rows(t, row + S512_ROWS_PER_CHUNK * b, S512_ROWS_PER_CHUNK, SHA512_IV, zero, NULL, 0); /* unused second slot */
         }
         for (int k = 0; k < 8; k++)
             for (int j = 0; j < 8; j++) hdigest[i][8 * k + j] = (uint8_t)(st[k] >> (56 - 8 * j));
     }
     for (size_t row = (size_t)h->n_max * S512_ROWS_PER_VALIDATOR; row < t->n_rows; row += S512_ROWS_PER_CHUNK) {
         size_t nr = t->n_rows - row < S512_ROWS_PER_CHUNK ? t->n_rows - row : S512_ROWS_PER_CHUNK;
-        sha512_rows(t, row, nr, SHA512_IV, zero, NULL);
+        sha512_rows(t, row, nr, SHA512_IV, zero, NULL, 0);
     }
 }
 

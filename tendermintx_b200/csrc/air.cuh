@@ -66,7 +66,8 @@ TMX_HD int air_cols(int t) { return t == AIR_SHA256 ? S256_COLS : (t == AIR_SHA5
 struct AirShape {
     uint32_t kind, n_max;
 };
-TMX_HD int air_n_periodic(int t) { return t == AIR_SHA256 ? 6 : (t == AIR_SHA512 ? 7 : 3); }
+TMX_HD int air_n_periodic(int t) { return t == AIR_SHA256 ? 6 : (t == AIR_SHA512 ? 11 : 3); }
+constexpr int AIR_MAX_PERIODIC = 16;
 // The last two columns of the SHA-256 table are not periodic: which chunk starts a message and which continues one is
 // fixed by the circuit shape (sha256_chunk_continues).  They are public columns of full length -- the prover evaluates
 // them on the LDE coset once per circuit, the verifier evaluates their interpolant at zeta itself -- so that table's
@@ -169,7 +170,10 @@ TMX_HD void air_sha256(const Row& l, const Row& n, const Per& per, Emit& emit) {
 
 // ------------------------------------------------------------------------------------------ SHA-512
 // per = {K_t low half, K_t high half, is_round_79, not_round_79, not_chunk_end, schedule_active (rows 15..126),
-// first_row_of_the_validator_slot}, period 256 (two 128-row chunks).
+// first_row_of_the_validator_slot, before_round_79, rows_79_to_126 (digest carried), last_row_of_the_first_chunk,
+// not_last_row_of_the_slot}, period 256 (two 128-row chunks).  The digest columns are zero before round 79 and constant
+// from row 79 to the end of the chunk, so the slot's second chunk can chain from them: its chaining value is the first
+// chunk's digest when the slot's TWO flag is set (two-block message), else the IV (unused second compression).
 // 64-bit words are (lo, hi) pairs of 32-bit field elements with an explicit carry from lo to hi.  Rows 80..127 of a chunk
 // continue the round function with round constant 0 (include/tmx_trace.h), so only what reads the next row, the digest
 // and the schedule hand-over need a selector.
@@ -258,17 +262,23 @@ TMX_HD void air_sha512(const Row& l, const Row& n, const Per& per, Emit& emit) {
         emit(LAST * (lo - (l[S512_CV + 2 * j] + fin[j][0])));
         emit(LAST * (hi - ((l[S512_CV + 2 * j + 1] + fin[j][1]) + l[S512_DC + 2 * j])));
         for (int k = 0; k < 2; k++) {
-            emit(NOTLAST * l[S512_DG + 2 * j + k]);
+            emit(per[7] * l[S512_DG + 2 * j + k]);                                  // zero before round 79
+            emit(per[8] * (n[S512_DG + 2 * j + k] - l[S512_DG + 2 * j + k]));       // carried to the end of the chunk
             emit(NOTLAST * l[S512_DC + 2 * j + k]);
         }
     }
-    // the first chunk of every validator slot starts from the IV
+    // chaining inside a validator slot: first chunk from the IV, second chunk from the first one's digest iff TWO
     const uint64_t IV[8] = {0x6a09e667f3bcc908ULL, 0xbb67ae8584caa73bULL, 0x3c6ef372fe94f82bULL, 0xa54ff53a5f1d36f1ULL,
                             0x510e527fade682d1ULL, 0x9b05688c2b3e6c1fULL, 0x1f83d9abfb41bd6bULL, 0x5be0cd19137e2179ULL};
-    for (int j = 0; j < 8; j++) {
-        emit(per[6] * (l[S512_CV + 2 * j] - F::c((uint32_t)IV[j])));
-        emit(per[6] * (l[S512_CV + 2 * j + 1] - F::c(IV[j] >> 32)));
-    }
+    const F two = l[S512_TWO];
+    emit(is_bool<F>(two));
+    emit(per[10] * (n[S512_TWO] - two));
+    for (int j = 0; j < 8; j++)
+        for (int k = 0; k < 2; k++) {
+            const F iv = F::c(k ? IV[j] >> 32 : (uint64_t)(uint32_t)IV[j]);
+            emit(per[6] * (l[S512_CV + 2 * j + k] - iv));
+            emit(per[9] * (n[S512_CV + 2 * j + k] - (iv + two * (l[S512_DG + 2 * j + k] - iv))));
+        }
 }
 
 // ------------------------------------------------------------------------------------------ Ed25519
@@ -412,7 +422,11 @@ TMX_HD uint64_t air_periodic_pattern(int table, int pc, size_t row, const uint32
         if (pc == 3) return rr != S512_ROUNDS - 1;
         if (pc == 4) return rr != S512_ROWS_PER_CHUNK - 1;
         if (pc == 5) return rr >= 15 && rr <= S512_ROWS_PER_CHUNK - 2;
-        return r == 0;
+        if (pc == 6) return r == 0;
+        if (pc == 7) return rr < S512_ROUNDS - 1;
+        if (pc == 8) return rr >= S512_ROUNDS - 1 && rr <= S512_ROWS_PER_CHUNK - 2;
+        if (pc == 9) return r == S512_ROWS_PER_CHUNK - 1;
+        return r != S512_ROWS_PER_VALIDATOR - 1;
     }
     if (pc == 0) return (r & 255) != 255;
     if (pc == 1) return r == 0;

@@ -128,7 +128,8 @@ int verify_table(int table, size_t n, AirShape shape, const gl* proof, size_t pr
     {
         const int nper = air_n_periodic(table);
         const size_t P = air_period(table, n);
-        FE per[8] = {FE::c(0), FE::c(0), FE::c(0), FE::c(0), FE::c(0), FE::c(0), FE::c(0), FE::c(0)};
+        FE per[AIR_MAX_PERIODIC];
+        for (int i = 0; i < AIR_MAX_PERIODIC; i++) per[i] = FE::c(0);
         const gl2 y = gl2_pow(zeta, n / P);
         for (int pc = 0; pc < nper; pc++) {
             // interpolant of the column's one-period pattern (for the SHA-256 table's public columns: of the whole column)

@@ -191,6 +191,8 @@ TMX_HD void validator_leaf_message(const uint8_t pk[32], uint64_t power, uint8_t
 // history of one chunk: the 80 rounds and the 48 continuation rounds with round constant 0 (include/tmx_trace.h)
 struct Sha512Hist {
     uint64_t ah[S512_ROWS_PER_CHUNK + 4], eh[S512_ROWS_PER_CHUNK + 4], W[S512_ROWS_PER_CHUNK], cv[8];
+    uint64_t digest[8];  // chaining value + state after round 79 (stays on rows 79..127 of the chunk)
+    uint64_t two;        // 1 when the validator slot's message has two blocks (S512_TWO)
 };
 
 TMX_HD void sha512_compress_hist(const uint64_t cv[8], const uint8_t* blk, Sha512Hist* hs, uint64_t out[8]) {
@@ -211,7 +213,7 @@ TMX_HD void sha512_compress_hist(const uint64_t cv[8], const uint8_t* blk, Sha51
     for (int t = 0; t < S512_ROWS_PER_CHUNK; t++) {
         if (t == S512_ROUNDS) {  // the digest is the state after round 79; the rows beyond only keep the table periodic
             uint64_t fin[8] = {a, b, c, d, e, f, g, h};
-            for (int i = 0; i < 8; i++) out[i] = hs->cv[i] + fin[i];
+            for (int i = 0; i < 8; i++) out[i] = hs->digest[i] = hs->cv[i] + fin[i];
         }
         uint64_t t1 = h + (rotr64(e, 14) ^ rotr64(e, 18) ^ rotr64(e, 41)) + ((e & f) ^ (~e & g)) + (t < S512_ROUNDS ? k512(t) : 0) + W[t];
         uint64_t t2 = (rotr64(a, 28) ^ rotr64(a, 34) ^ rotr64(a, 39)) + ((a & b) ^ (a & c) ^ (b & c));
@@ -295,14 +297,17 @@ TMX_HD void sha512_row_cells(gl* trace, size_t n_rows, size_t row, int t, const 
             clo = lo >> 32;
             const uint64_t hi = TMX_HI(hs->cv[j]) + TMX_HI(fin[j]) + clo;
             chi = hi >> 32;
-            dlo = TMX_LO(lo);
-            dhi = TMX_LO(hi);
+        }
+        if (t >= 79) {  // the digest stays on rows 79..127 so that the slot's second chunk can chain from it
+            dlo = TMX_LO(hs->digest[j]);
+            dhi = TMX_HI(hs->digest[j]);
         }
         p[(size_t)(S512_DG + 2 * j) * n_rows] = dlo;
         p[(size_t)(S512_DG + 2 * j + 1) * n_rows] = dhi;
         p[(size_t)(S512_DC + 2 * j) * n_rows] = clo;
         p[(size_t)(S512_DC + 2 * j + 1) * n_rows] = chi;
     }
+    p[(size_t)S512_TWO * n_rows] = hs->two;
 #undef TMX_LO
 #undef TMX_HI
 }

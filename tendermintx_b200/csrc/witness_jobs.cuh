@@ -236,6 +236,7 @@ TMX_HD void sha512_padding_prepare(Sha512Hist* hs) {
     uint64_t cv[8], st[8];
     for (int k = 0; k < 8; k++) cv[k] = iv512(k);
     sha512_compress_hist(cv, zero, hs, st);
+    hs->two = 0;
 }
 
 // ---- validator slot i: the triple the Ed25519 gadget verifies (REF conversion.rs:79-134: unsigned slots carry
@@ -272,6 +273,7 @@ TMX_HD void sha512_validator_prepare(const EdTriple& t, Sha512Hist hs[2], uint8_
         sha512_compress_hist(st, buf + 128, &hs[1], st);
     else
         sha512_padding_prepare(&hs[1]);
+    hs[0].two = hs[1].two = (nb == 2);
     for (int k = 0; k < 8; k++)
         for (int j = 0; j < 8; j++) digest[8 * k + j] = (uint8_t)(st[k] >> (56 - 8 * j));
 }
