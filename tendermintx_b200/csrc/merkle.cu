@@ -14,7 +14,7 @@
 
 namespace tmx {
 
-__global__ void __launch_bounds__(128, 8) leaf_hash_kernel(const gl* __restrict__ base, size_t leaf_len, size_t row_stride,
+__global__ void __launch_bounds__(128, 7) leaf_hash_kernel(const gl* __restrict__ base, size_t leaf_len, size_t row_stride,
                                                          size_t elem_stride, size_t n_rows, gl* __restrict__ digests) {
     const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_rows) return;
