@@ -10,13 +10,16 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
+# TMX_ORACLE_LIB: run the same tests against another build of the same sources (the ASan / UBSan one, `make san`)
+LIB_PATH = os.environ.get("TMX_ORACLE_LIB") or os.path.join(_HERE, "_build", "liboracle.so")
 P = 2**64 - 2**32 + 1
 
 _LIB = None
 
 
 def build(force=False):
+    if os.environ.get("TMX_ORACLE_LIB"):
+        return LIB_PATH
     if force or not os.path.exists(LIB_PATH) or _stale():
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return LIB_PATH

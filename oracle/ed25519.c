@@ -66,7 +66,7 @@ static void reduce_to_canonical(const int64_t *t, int n, int64_t c[16]) {
     for (int k = 0; k < nd; k++) {
         int64_t s = (k < n ? t[k] : 0) + carry;
         carry = floordiv16(s);
-        d[k] = s - (carry << 16);
+        d[k] = s - carry * 65536;
     }
     /* fold digits >= 16 down with 2^256 = 38 (mod p) until they vanish */
     for (;;) {
@@ -80,7 +80,7 @@ static void reduce_to_canonical(const int64_t *t, int n, int64_t c[16]) {
         for (int k = 0; k < nd; k++) {
             int64_t s = e[k] + carry;
             carry = floordiv16(s);
-            d[k] = s - (carry << 16);
+            d[k] = s - carry * 65536;
         }
     }
     /* value < 2^256 = 2p + 38: subtract p while >= p */
@@ -95,7 +95,7 @@ static void reduce_to_canonical(const int64_t *t, int n, int64_t c[16]) {
         for (int k = 0; k < 16; k++) {
             int64_t s = d[k] - P_LIMBS[k] + borrow;
             borrow = floordiv16(s);
-            d[k] = s - (borrow << 16);
+            d[k] = s - borrow * 65536;
         }
     }
     for (int k = 0; k < 16; k++) c[k] = d[k];

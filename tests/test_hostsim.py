@@ -16,10 +16,13 @@ ROOT = os.path.dirname(HERE)
 
 @pytest.fixture(scope="module")
 def hostsim():
-    out = os.path.join(HERE, "_build", "libhostsim.so")
+    # TMX_HOSTSIM_SAN=1 (tools/oracle_sanitize.sh): the kernels' per-thread logic under ASan + UBSan on the host
+    san = os.environ.get("TMX_HOSTSIM_SAN") == "1"
+    out = os.path.join(HERE, "_build", "libhostsim_san.so" if san else "libhostsim.so")
     os.makedirs(os.path.dirname(out), exist_ok=True)
     src = os.path.join(ROOT, "tools", "hostsim.cpp")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", out, src])
+    flags = ["-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer"] if san else ["-O2"]
+    subprocess.check_call(["g++", *flags, "-std=c++17", "-shared", "-fPIC", "-o", out, src])
     return ctypes.CDLL(out)
 
 
