@@ -213,6 +213,21 @@ def build_traces(blob):
     return out
 
 
+def constraints_at_rows(table, trace, rows, kind, n_max, alpha=(0x123456789ABCDEF, 0xFEDCBA987654321)):
+    """Folded constraint values (two challenges) of the transitions row -> row + 1 (cyclic) of `trace` ([n_cols, n_rows])
+    on the trace domain; [len(rows), 2] uint64, all zero for a satisfying trace."""
+    trace = np.ascontiguousarray(trace, dtype=np.uint64)
+    C, n = trace.shape
+    rows = np.ascontiguousarray(rows, dtype=np.uint64)
+    a = np.array(alpha, dtype=np.uint64)
+    out = np.zeros((rows.size, 2), dtype=np.uint64)
+    vp = lambda x: x.ctypes.data_as(ctypes.c_void_p)
+    lib().tm_debug_set_shape(ctypes.c_uint32(kind), ctypes.c_uint32(n_max))
+    lib().tm_debug_constraints_at_rows(ctypes.c_int(table), vp(trace), ctypes.c_size_t(n), ctypes.c_size_t(C), vp(a), vp(rows),
+                                       ctypes.c_size_t(rows.size), vp(out))
+    return out
+
+
 def prove(public_input, blob, chain_id, skip_max=100800):
     """CPU oracle prover.  Returns (status, proof as uint64 array or None, output32 or None)."""
     cid = chain_id.encode() if isinstance(chain_id, str) else chain_id

@@ -768,3 +768,28 @@ void tm_debug_quotient(int table, const uint64_t *trace, size_t n, size_t C, con
     }
     free(loc); free(nxt); free(pertab);
 }
+
+/* debug / test hook (shape from tm_debug_set_shape): the folded constraint values (two challenges) of the transitions
+ * rows[i] -> rows[i] + 1 (cyclic) evaluated on the TRACE domain itself; all zero for a satisfying trace.  trace is
+ * column-major [C][n]; out is [n_rows][2]. */
+void tm_debug_constraints_at_rows(int table, const uint64_t *trace, size_t n, size_t C, const uint64_t alpha[2], const uint64_t *rows,
+                                  size_t n_rows, uint64_t *out) {
+    const int nper = TABLE_NPER[table];
+    const size_t P = table_period(table, n);
+    gl_t *loc = (gl_t *)malloc(C * sizeof(gl_t)), *nxt = (gl_t *)malloc(C * sizeof(gl_t));
+    for (size_t i = 0; i < n_rows; i++) {
+        const size_t r = rows[i] % n, r2 = (r + 1) % n;
+        for (size_t c = 0; c < C; c++) {
+            loc[c] = trace[c * n + r];
+            nxt[c] = trace[c * n + r2];
+        }
+        gl_t per[16];
+        for (int pc = 0; pc < nper; pc++) per[pc] = periodic_pattern(table, pc, r % P);
+        acc_b_t a;
+        for (int k = 0; k < 2; k++) { a.acc[k] = 0; a.alpha[k] = alpha[k]; }
+        air_eval_b(table, loc, nxt, per, &a);
+        out[2 * i] = a.acc[0];
+        out[2 * i + 1] = a.acc[1];
+    }
+    free(loc); free(nxt);
+}
