@@ -526,6 +526,16 @@ static void transcript_init(challenger_t *ch, uint32_t kind, uint32_t n_max, con
     challenger_observe_many(ch, ph, 4);
 }
 
+/* debug / test hook: the NEXT tm_prove() on this thread adds one to cell (col, row) of `table` after witness generation,
+ * i.e. it plays a prover that commits to an invalid witness; the verifiers must reject what it outputs. */
+static _Thread_local struct { int active, table; size_t col, row; } g_corrupt;
+void tm_debug_corrupt_next_proof(int table, size_t col, size_t row) {
+    g_corrupt.active = 1;
+    g_corrupt.table = table;
+    g_corrupt.col = col;
+    g_corrupt.row = row;
+}
+
 /* proof = header (8 u64), then the three table proofs.  Returns a TMX_CHECK id (0 = ok). */
 int tm_prove(const uint8_t *input, size_t input_len, const uint8_t *blob, size_t blob_len, const uint8_t *chain_id,
              size_t chain_id_len, uint64_t skip_max, uint64_t **proof_out, size_t *proof_len, uint8_t out32[32]) {
@@ -535,6 +545,12 @@ int tm_prove(const uint8_t *input, size_t input_len, const uint8_t *blob, size_t
     trace_t tr[3];
     rc = tm_build_traces(blob, blob_len, tr);
     if (rc) return rc;
+    if (g_corrupt.active) {
+        trace_t *t = &tr[g_corrupt.table];
+        uint64_t *cell = &t->data[(g_corrupt.col % t->n_cols) * t->n_rows + g_corrupt.row % t->n_rows];
+        *cell = gl_add(*cell, 1);
+        g_corrupt.active = 0;
+    }
     challenger_t ch;
     transcript_init(&ch, h->kind, h->n_max, chain_id, chain_id_len, skip_max, input, input_len, out32);
     g_kind = h->kind;

@@ -62,3 +62,26 @@ def test_unsatisfied_statement_is_not_provable(oracle, proved):
     b[920 + 32 + 3] ^= 0x40
     status, p, _ = oracle.prove(pub, bytes(b), "mocha-4")
     assert status == "SIGNATURE" and p is None
+
+
+@pytest.mark.parametrize("table", [0, 1, 2])
+def test_cheating_prover_with_one_bad_cell_is_rejected(oracle, proved, table):
+    """Soundness end to end: a prover that commits to a witness with ONE wrong cell (after witness generation, so no
+    assertion stops it) still emits a well-formed proof; the constraint identity at the out-of-domain point no longer
+    holds and both verifiers reject it."""
+    import ctypes
+
+    import tendermintx_b200 as tmx
+
+    c, pub, blob, proof, out = proved
+    rng = np.random.default_rng(7 + table)
+    for _ in range(3):
+        col, row = int(rng.integers(0, 2000)), int(rng.integers(0, 1 << 20))
+        oracle.lib().tm_debug_corrupt_next_proof(ctypes.c_int(table), ctypes.c_size_t(col), ctypes.c_size_t(row))
+        status, bad, out2 = oracle.prove(pub, blob, "mocha-4")
+        assert status == "OK" and out2 == out and bad.size == proof.size and not np.array_equal(bad, proof)
+        assert oracle.verify_proof(bad, pub, "mocha-4", 0, 2, out) != 0, (table, col, row)
+        with pytest.raises(tmx.TmxError):
+            tmx.verify_proof(tmx.KIND_STEP, 2, tmx.Mocha4Config, bad.tobytes(), pub, out)
+    # and the hook is one-shot: the next proof is the honest one again
+    assert np.array_equal(oracle.prove(pub, blob, "mocha-4")[1], proof)
