@@ -69,12 +69,13 @@
 #define ED_BIT 0
 #define ED_RES 1      /* X, Y, Z, T of the accumulator, 16 x 16-bit limbs each */
 #define ED_TMP 65     /* X, Y, Z, T of the running double */
-#define ED_MUL 129    /* 17 multiplication gadgets x 64 columns: c[16], q[17], w[31] (w stored + ED_W_OFFSET) */
-#define ED_MUL_STRIDE 64
+#define ED_MUL 129    /* 17 multiplication gadgets x 48 columns: c[16], q[17], w'[15] (stored + ED_W_OFFSET) */
+#define ED_MUL_STRIDE 48
 #define ED_MUL_Q 16
 #define ED_MUL_W 33
+#define ED_MUL_NW 15  /* the limb equations are checked in pairs: w'_k = carry out of limb 2k + 1, w'_15 = 0 */
 #define ED_N_MUL 17
-#define ED_COLS (ED_MUL + ED_N_MUL * ED_MUL_STRIDE) /* 1217 */
+#define ED_COLS (ED_MUL + ED_N_MUL * ED_MUL_STRIDE) /* 945 */
 #define ED_W_OFFSET (1 << 22)
 #define ED_ROWS_PER_VALIDATOR 512
 /* Row 0 of every 256-row ladder starts from res = O = (0, 1, 1, 0); the first ladder of a validator ([s]B, rows 0..255)

@@ -287,25 +287,31 @@ TMX_HD uint64_t p25519_limb(int i) { return i == 0 ? 0xFFEDULL : (i == 15 ? 0x7F
 // U * V = c + q * p with carries: 32 limb equations of one multiplication gadget whose cells start at column g0
 template <class F, class Row, class Emit>
 TMX_HD void ed_mul_gadget(const F U[16], const F V[16], const Row& l, int g0, Emit& emit) {
-    const F off = F::c(ED_W_OFFSET), two16 = F::c(1 << 16);
+    const F off = F::c(ED_W_OFFSET), two16 = F::c(1 << 16), two32 = F::c(1ULL << 32);
     F q[17];
     for (int i = 0; i < 17; i++) q[i] = l[g0 + ED_MUL_Q + i];
     F wprev = F::c(0);
-    for (int k = 0; k < 32; k++) {
+    // limb equations in pairs: e_2K + 2^16 e_2K+1 + w'_{K-1} = 2^32 w'_K  (every term < 2^54: no wrap in F_p)
+    for (int K = 0; K < 16; K++) {
         F s = F::c(0);
-        for (int i = 0; i < 16; i++) {
-            const int j = k - i;
-            if (j >= 0 && j < 16) s = s + U[i] * V[j];
+        for (int h = 0; h < 2; h++) {
+            const int k = 2 * K + h;
+            F e = F::c(0);
+            for (int i = 0; i < 16; i++) {
+                const int j = k - i;
+                if (j >= 0 && j < 16) e = e + U[i] * V[j];
+            }
+            if (k < 16) e = e - l[g0 + k];
+            for (int i = 0; i < 17; i++) {
+                const int j = k - i;
+                if (j >= 0 && j < 16) e = e - q[i] * F::c(p25519_limb(j));
+            }
+            s = h ? s + two16 * e : e;
         }
-        if (k < 16) s = s - l[g0 + k];
-        for (int i = 0; i < 17; i++) {
-            const int j = k - i;
-            if (j >= 0 && j < 16) s = s - q[i] * F::c(p25519_limb(j));
-        }
-        if (k >= 1) s = s + wprev;
-        if (k < 31) {
-            wprev = l[g0 + ED_MUL_W + k] - off;
-            s = s - two16 * wprev;
+        if (K >= 1) s = s + wprev;
+        if (K < ED_MUL_NW) {
+            wprev = l[g0 + ED_MUL_W + K] - off;
+            s = s - two32 * wprev;
         }
         emit(s);
     }

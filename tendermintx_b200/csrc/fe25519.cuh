@@ -350,7 +350,7 @@ TMX_HD void mul_gadget_cells(const int32_t U[16], const int32_t V[16], gl* cells
             cells[(size_t)(ED_MUL_Q + k) * stride] = (gl)qk;
         }
         carry = s >> 16;
-        if (k < 31) cells[(size_t)(ED_MUL_W + k) * stride] = (gl)(carry + ED_W_OFFSET);
+        if ((k & 1) && k < 31) cells[(size_t)(ED_MUL_W + (k >> 1)) * stride] = (gl)(carry + ED_W_OFFSET);
     }
 }
 

@@ -87,7 +87,7 @@ def test_factored_ed25519_constraint_fold_equals_literal_fold_on_host():
     import tendermintx_b200 as tmx
 
     P = 2**64 - 2**32 + 1
-    ED_COLS = 1217
+    ED_COLS = 945
     rng = np.random.default_rng(11)
     lib = tmx.lib()
     for trial in range(6):
