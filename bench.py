@@ -24,8 +24,11 @@ sys.path.insert(0, ROOT)
 
 N_MAX = 128
 # dram__bytes_read.sum + dram__bytes_write.sum of the six ntt_pass_kernel launches that make up the LDE of the Ed25519
-# table (1217 columns x 2^16), from profiles/r1e_ncu_ntt.raw.csv (one ncu --set full capture, per LDE)
-NCU_K1_TRAFFIC_BYTES = 7383291392
+# table, from profiles/r1e_ncu_ntt.raw.csv (one ncu --set full capture, per LDE).  The capture was taken when the table
+# had 1217 columns (7,383,291,392 bytes); the carry packing of the last commit of the round narrowed it to 945 and
+# left the kernel untouched.  Every pass moves every column exactly once, so the figure is scaled by 945 / 1217 until
+# the capture is retaken (first item of the next round).
+NCU_K1_TRAFFIC_BYTES = 7383291392 * 945 // 1217
 NCU_K2_WARP_INSTR_PER_PERM = 14.21e9 / 20.05e6  # = 709 (22.7 k thread instructions per permutation)
 METRIC = "skip proofs/hour (CelestiaConfig, 128 val)"
 UNIT = "proofs/hour"
@@ -347,10 +350,11 @@ def run_ours(args):
         "one_proof_at_a_time": {"ms_per_proof": lat_ms / args.steps, "proofs_per_hour": world * args.steps / (lat_ms / 1e3) * 3600.0,
                                 "gpu_launches_per_proof": launches / args.steps},
         "gpu_launches": launches_value,
-        "roofline": {"bound": "hbm", "kernel": "ntt_pass_kernel family (K1: iNTT + coset LDE, rate 1/2, of the Ed25519 trace table, 1217 x 2^16, "
+        "roofline": {"bound": "hbm", "kernel": "ntt_pass_kernel family (K1: iNTT + coset LDE, rate 1/2, of the Ed25519 trace table, 945 x 2^16, "
                      "six launches per proof, CUDA events recorded by the prover inside the timed proofs)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_K1_TRAFFIC_BYTES, "traffic_note": "dram read+write of the six K1 launches of the Ed25519 table, "
-                     "ncu --set full (profiles/r1e_ncu_ntt.raw.csv), per proof like achieved",
+                     "ncu --set full (profiles/r1e_ncu_ntt.raw.csv), per proof like achieved; captured at 1217 columns and scaled "
+                     "by 945/1217 (same kernel, every pass moves every column once); re-capture pending",
                      "peak_source": peak_src, "algorithmic_bytes": alg_bytes, "ms": lde_ms,
                      "ms_per_table": [p[0] / args.steps for p in phase],
                      "all_tables": {"algorithmic_bytes": alg_bytes_all, "ms": lde_ms_all,

@@ -284,7 +284,7 @@ TMX_HD void air_sha512(const Row& l, const Row& n, const Per& per, Emit& emit) {
 // ------------------------------------------------------------------------------------------ Ed25519
 TMX_HD uint64_t p25519_limb(int i) { return i == 0 ? 0xFFEDULL : (i == 15 ? 0x7FFFULL : 0xFFFFULL); }
 
-// U * V = c + q * p with carries: 32 limb equations of one multiplication gadget whose cells start at column g0
+// U * V = c + q * p with carries: the 32 limb equations of one multiplication gadget (cells from column g0), in 16 pairs
 template <class F, class Row, class Emit>
 TMX_HD void ed_mul_gadget(const F U[16], const F V[16], const Row& l, int g0, Emit& emit) {
     const F off = F::c(ED_W_OFFSET), two16 = F::c(1 << 16), two32 = F::c(1ULL << 32);

@@ -276,7 +276,7 @@ TMX_HD void sc_reduce512(const uint8_t in[64], uint64_t out[4]) {
 }
 
 // ---- multiplication gadget witness on 16-bit limbs ----
-// U, V: signed limb vectors (|limb| < 2^19); writes the 64 cells (c[16], q[17], w[31] + offset) of one gadget with
+// U, V: signed limb vectors (|limb| < 2^19); writes the 48 cells (c[16], q[17], the 15 odd carries + offset) of one gadget with
 // stride `stride` starting at `cells`; returns c limbs in c_out.
 TMX_HD void mul_gadget_cells(const int32_t U[16], const int32_t V[16], gl* cells, size_t stride, int32_t c_out[16]) {
     int64_t t[31];

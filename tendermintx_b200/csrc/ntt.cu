@@ -20,7 +20,7 @@
 
 namespace tmx {
 
-// Vectors per tile.  Measured on the Ed25519 table's LDE (1217 x 2^16): 16 vectors 4.42 ms, 8 vectors 4.13 ms, 4 vectors
+// Vectors per tile.  Measured on the Ed25519 table's LDE (then 1217 x 2^16): 16 vectors 4.42 ms, 8 vectors 4.13 ms, 4 vectors
 // 4.35 ms.  Narrower tiles mean smaller CTAs (128 threads, 19 KB of shared memory, < 60 registers): more CTAs per SM in
 // different phases, so tile loads overlap better with butterflies; below 64-byte rows the global accesses get too short.
 #ifndef TMX_NTT_TILE_LOG

@@ -13,7 +13,7 @@
 //     the SMs with another stream's kernels): h = SHA-512(R || A || M) is reduced mod l on the SM and feeds the [h]A
 //     ladder; the two 256-step ladders ([s]B and [h]A) run on two warps with 5 x 51-bit-limb field arithmetic in
 //     registers and park the canonical (res, temp) of every step in a 128 KB-per-validator scratch.  Phase 2 (512
-//     threads): each thread expands one ladder row into its 1217 cells (17 multiplication gadgets: product limbs,
+//     threads): each thread expands one ladder row into its 945 cells (17 multiplication gadgets: product limbs,
 //     quotient, carries) and the 2 x 128 SHA-512 rows are written.
 //   Integer / bit work, HBM-write bound at best: no tensor cores.
 #include "ctx.cuh"

@@ -154,7 +154,7 @@ def test_full_size_skip_n256(ctx):
 
 
 def test_skip_n128_proof_bytes_equal_oracle(ctx, oracle):
-    """BASELINE config 2, bit-exact: the 2.17 MB GPU proof of the 128-validator skip equals the CPU oracle's."""
+    """BASELINE config 2, bit-exact: the 1.98 MB GPU proof of the 128-validator skip equals the CPU oracle's."""
     import tendermintx_b200 as tmx
     from oracle import tm_inputs as ti
 
