@@ -418,6 +418,7 @@ static void ed_ladder_rows(trace_t *t, size_t row0, const uint8_t scalar[32], co
             int base = ED_MUL + m * ED_MUL_STRIDE;
             for (int k = 0; k < 16; k++) CELL(t, base + k, row) = (uint64_t)wit[m].c[k];
             for (int k = 0; k < 17; k++) CELL(t, base + ED_MUL_Q + k, row) = (uint64_t)wit[m].q[k];
+            /* the limb equations are checked in pairs (air.inc), so only the carries out of the odd limbs are committed */
             for (int k = 0; k < ED_MUL_NW; k++) CELL(t, base + ED_MUL_W + k, row) = (uint64_t)(wit[m].w[2 * k + 1] + ED_W_OFFSET);
         }
         if (bit) res = sum;
