@@ -291,7 +291,7 @@ TMX_HD void ed_mul_gadget(const F U[16], const F V[16], const Row& l, int g0, Em
     F q[17];
     for (int i = 0; i < 17; i++) q[i] = l[g0 + ED_MUL_Q + i];
     F wprev = F::c(0);
-    // limb equations in pairs: e_2K + 2^16 e_2K+1 + w'_{K-1} = 2^32 w'_K  (every term < 2^54: no wrap in F_p)
+    // limb equations in pairs: e_2K + 2^16 e_2K+1 + w'_{K-1} = 2^32 w'_K  (|operand limbs| < 2^19, so every term is below 2^58: no wrap in F_p)
     for (int K = 0; K < 16; K++) {
         F s = F::c(0);
         for (int h = 0; h < 2; h++) {
