@@ -80,12 +80,6 @@ int tmx_poseidon_permute(tmx_ctx *ctx, uint64_t *d_states, size_t n, void *strea
  * variant 0 = plain formulation, 1 = the kernels' fast path (multiplier-free linear layer),
  * 2 = the formulation the host transcript uses. */
 int tmx_host_poseidon_permute(uint64_t *states, size_t n, int variant);
-/* Host-side self check (no GPU) of the quotient kernel's factored Ed25519 constraint evaluation against the literal
- * fold of the AIR on one (row, next row) pair of ED_COLS cells each and the three periodic column values:
- * out = {literal(alpha[0]), literal(alpha[1]), factored(alpha[0]), factored(alpha[1])}. */
-int tmx_host_air_ed25519(const uint64_t *row_l, const uint64_t *row_n, const uint64_t periodic[3], const uint64_t alpha[2],
-                         uint64_t out[4]);
-
 /* ------------------------------------------------------------------------------------------------
  * Witness tables (layout: include/tmx_trace.h).  They replace the trace generation that runs inside
  * `curta_sha256_variable`, the Tendermint Merkle gadgets and `curta_eddsa_verify_sigs_conditional` when the
@@ -102,19 +96,21 @@ size_t tmx_witness_aux_bytes(uint32_t n_max);
 /* K6: SHA-256 table (validator leaves, validator-set trees, header inclusion proofs) */
 int tmx_sha256_trace(tmx_ctx *ctx, const uint8_t *d_blob, uint32_t kind, uint32_t n_max, uint64_t *d_t256,
                      uint8_t *d_aux, void *stream);
-/* K7 + K8 fused, one validator per CTA: SHA-512(R || A || M) table and the Ed25519 double-and-add table */
+/* K7 alone: SHA-512(R || A || M) table of every validator slot */
+int tmx_sha512_trace(tmx_ctx *ctx, const uint8_t *d_blob, uint32_t kind, uint32_t n_max, uint64_t *d_t512, void *stream);
+/* K7 + K8 fused, one validator per CTA: SHA-512(R || A || M) table and the Ed25519 table (joint evaluation of
+ * [s]B + [h](-A), one row per scalar-bit pair) */
 int tmx_ed25519_trace(tmx_ctx *ctx, const uint8_t *d_blob, uint32_t kind, uint32_t n_max, uint64_t *d_t512,
                       uint64_t *d_ted, uint8_t *d_aux, void *stream);
 /* all three tables */
 int tmx_witness_generate(tmx_ctx *ctx, const uint8_t *d_blob, uint32_t kind, uint32_t n_max, uint64_t *d_t256,
                          uint64_t *d_t512, uint64_t *d_ted, uint8_t *d_aux, void *stream);
 
-/* K5: constraint quotient of one witness table (0 = SHA-256, 1 = SHA-512, 2 = Ed25519) evaluated on its LDE coset
- * (rate_bits 1): d_lde = [cols][2n] bit-reversed as produced by tmx_lde; d_out = [2][2n] in NATURAL order, one row per
- * constraint challenge alpha[i]: sum_k alpha^(M-1-k) C_k(x) / (x^n - 1).  kind / n_max: the circuit shape (the SHA-256
- * table's public message-boundary columns depend on it). */
-int tmx_quotient(tmx_ctx *ctx, uint32_t kind, uint32_t n_max, int table, const uint64_t *d_lde, unsigned log_n,
-                 const uint64_t alpha[2], uint64_t *d_out, void *stream);
+/* K3 (fold): one arity-16 FRI folding step in evaluation space [plonky2 fri/prover.rs fri_committed_trees, one layer].
+ * d_in: 16 << log_cosets extension elements (interleaved (a0, a1), bit-reversed order) on the coset shift * <w>;
+ * d_out: 1 << log_cosets folded values (bit-reversed) on shift^16 * <w^16>. */
+int tmx_fri_fold(tmx_ctx *ctx, const uint64_t *d_in, unsigned log_cosets, uint64_t shift, const uint64_t beta[2],
+                 uint64_t *d_out, void *stream);
 
 /* K9: proof-of-work grind: the SMALLEST w such that Poseidon(state with state[pos] = w)[7] has `bits` leading
  * zero bits (plonky2 fri_proof_of_work uses rayon find_any, i.e. any witness).  `state` is a host pointer. */
@@ -136,6 +132,30 @@ int tmx_circuit_digest(const tmx_circuit *circuit, uint64_t out[4]);
 /* the `build` artefact (./build/main.circuit in succinct.json:8,15) */
 int tmx_circuit_save(const tmx_circuit *circuit, const char *path);
 int tmx_circuit_load(tmx_ctx *ctx, const char *path, tmx_circuit **out);
+
+/* The build artefact as u64 words WITHOUT a GPU (host-only: symbolic run of the constraint templates, constant columns and
+ * their commitment, digest): returns the word count and copies at most `cap` words to `out` (may be NULL). */
+size_t tmx_circuit_artefact(uint32_t kind, uint32_t n_max, const char *chain_id, size_t chain_id_len, uint64_t skip_max,
+                            uint64_t *out, size_t cap);
+/* shape of table t (TMX_T_* in tmx_trace.h): {rows, first-round columns, constant columns, second-round columns}; rows = 0
+ * when the table is absent from the circuit */
+int tmx_circuit_table_shape(const tmx_circuit *circuit, int table, size_t out[4]);
+
+/* Kernel-level entry points that need a circuit's constant / periodic columns (parity tests, ncu):
+ * tmx_bus_count   histogram of the range lookups of one table's first-round trace (d_trace: [cols][rows], device):
+ *                 d_hist[2^16 + 2^11 + 2^8] u32 (16-, 11-, 8-bit tables); *bad is set when a value is outside its table.
+ * tmx_bus_aux     second commitment round of one table: helper columns of its bus interactions and the running sum for the
+ *                 given bus challenges (extension elements as two u64); d_aux: [second-round columns][rows]; total: the
+ *                 table's bus contribution.
+ * tmx_quotient    K5: constraint quotient of one table on its LDE coset (rate_bits 1).  d_lde_main / d_lde_aux: LDEs
+ *                 ([cols][2 rows], bit-reversed rows, as tmx_lde produces them) of the first- and second-round traces;
+ *                 d_out = [2][2 rows] in NATURAL order, one row per constraint challenge alpha[i]:
+ *                 sum_k alpha^(M-1-k) C_k(x) / (x^n - 1) over table, helper-column and running-sum constraints. */
+int tmx_bus_count(tmx_circuit *circuit, int table, const uint64_t *d_trace, uint32_t *d_hist, int *bad, void *stream);
+int tmx_bus_aux(tmx_circuit *circuit, int table, const uint64_t *d_trace, const uint64_t beta[2], const uint64_t gamma[2],
+                uint64_t *d_aux, uint64_t total[2], void *stream);
+int tmx_quotient(tmx_circuit *circuit, int table, const uint64_t *d_lde_main, const uint64_t *d_lde_aux, const uint64_t total[2],
+                 const uint64_t beta[2], const uint64_t gamma[2], const uint64_t alpha[2], uint64_t *d_out, void *stream);
 
 /* `circuit.prove(&input)` [circuits/skip.rs:213-214,238-244]: input = 48 (skip) / 40 (step) bytes in the
  * abi.encodePacked layout of circuits/skip.rs:120-122; blob = the off-chain inputs the async hint would fetch

@@ -65,23 +65,99 @@
 #define S512_ROWS_PER_CHUNK 128
 #define S512_ROWS_PER_VALIDATOR 256
 
-/* ---------------- Ed25519: one row per double-and-add step, 2 x 256 rows per validator ---------------- */
-#define ED_BIT 0
-#define ED_RES 1      /* X, Y, Z, T of the accumulator, 16 x 16-bit limbs each */
-#define ED_TMP 65     /* X, Y, Z, T of the running double */
-#define ED_MUL 129    /* 17 multiplication gadgets x 48 columns: c[16], q[17], w'[15] (stored + ED_W_OFFSET) */
-#define ED_MUL_STRIDE 48
-#define ED_MUL_Q 16
-#define ED_MUL_W 33
-#define ED_MUL_NW 15  /* the limb equations are checked in pairs: w'_k = carry out of limb 2k + 1, w'_15 = 0 */
-#define ED_N_MUL 17
-#define ED_COLS (ED_MUL + ED_N_MUL * ED_MUL_STRIDE) /* 945 */
+/* ---------------- Ed25519: one row per scalar-bit PAIR, 256 rows per validator ----------------
+ * Joint (Straus) evaluation of Q = [s]B + [h](-A), most significant bits first:
+ *     acc' = 2 * acc + T[bs + 2 bh],   T = {O, B, -A, B - A}  (affine, cached as (y + x, y - x, 2 d x y))
+ * The addend of the row is looked up on the bus (ED_BUS_ADDEND: validator id, selector, 48 limbs) from the four
+ * entries the logic table provides per validator.  dbl-2008-hwcd (8 multiplications, T3 kept for the addition) then
+ * add-2008-hwcd-3 with Z2 = 1 and no T output (6 multiplications): 14 multiplication gadgets per row.
+ * Every gadget cell is range checked on the bus: c, q, wlo in [0, 2^16), whi in [0, 2^11).
+ * Field elements are 16 x 16-bit limbs, little endian. */
+#define ED_BS 0       /* bit of s */
+#define ED_BH 1       /* bit of h */
+#define ED_SACC_S 2   /* bits of s seen so far inside the current 16-row group (MSB first); 0 on the group's first row */
+#define ED_SACC_H 3
+#define ED_ACC 4      /* X, Y, Z of the accumulator BEFORE the row's step */
+#define ED_ADD 52     /* the row's addend: y + x, y - x, 2 d x y */
+#define ED_MUL 100    /* 14 multiplication gadgets x 63 columns */
+#define ED_MUL_STRIDE 63
+#define ED_MUL_Q 16   /* q[17] */
+#define ED_MUL_WLO 33 /* low 16 bits of (carry + ED_W_OFFSET), 15 carries (the limb equations are checked in pairs) */
+#define ED_MUL_WHI 48 /* high bits of the same, below 2^11 */
+#define ED_MUL_NW 15
+#define ED_N_MUL 14
+#define ED_COLS (ED_MUL + ED_N_MUL * ED_MUL_STRIDE) /* 982 */
 #define ED_W_OFFSET (1 << 22)
-#define ED_ROWS_PER_VALIDATOR 512
-/* Row 0 of every 256-row ladder starts from res = O = (0, 1, 1, 0); the first ladder of a validator ([s]B, rows 0..255)
- * doubles the base point B = (BX, BY, 1, BX*BY), the second ([h]A, rows 256..511) an affine point (Z = 1).  16-bit limbs. */
+#define ED_ROWS_PER_VALIDATOR 256
+/* gadget slots */
+#define ED_G_A 0   /* X * X */
+#define ED_G_B 1   /* Y * Y */
+#define ED_G_CZ 2  /* Z * Z */
+#define ED_G_S 3   /* (X + Y)^2 */
+#define ED_G_X3 4  /* E * F  (doubled point) */
+#define ED_G_Y3 5  /* G * H */
+#define ED_G_T3 6  /* E * H */
+#define ED_G_Z3 7  /* F * G */
+#define ED_G_AA 8  /* (Y3 - X3) * (y - x) */
+#define ED_G_BB 9  /* (Y3 + X3) * (y + x) */
+#define ED_G_CC 10 /* T3 * 2dxy */
+#define ED_G_X4 11 /* E' * F' */
+#define ED_G_Y4 12 /* G' * H' */
+#define ED_G_Z4 13 /* F' * G' */
+/* constant (preprocessed) columns of the Ed25519 table, fixed by the circuit shape */
+#define EDK_VID 0     /* validator slot of the row (row / 256) */
+#define EDK_ACTIVE 1  /* 1 on the rows of slots < n_max */
+#define EDK_SEND16 2  /* active and last row of a 16-row group: a scalar limb is complete */
+#define EDK_LIMB 3    /* index of the scalar limb of the row's group: 15 - (row % 256) / 16 */
+#define EDK_LAST 4    /* active and last row of the slot: the result leaves on the bus */
+#define EDK_COLS 5
 #define ED_BASE_X_LIMBS {0xd51a, 0x8f25, 0x2d60, 0xc956, 0xa7b2, 0x9525, 0xc760, 0x692c, 0xdc5c, 0xfdd6, 0xe231, 0xc0a4, 0x53fe, 0xcd6e, 0x36d3, 0x2169}
 #define ED_BASE_Y_LIMBS {0x6658, 0x6666, 0x6666, 0x6666, 0x6666, 0x6666, 0x6666, 0x6666, 0x6666, 0x6666, 0x6666, 0x6666, 0x6666, 0x6666, 0x6666, 0x6666}
 #define ED_BASE_T_LIMBS {0xdda3, 0xa5b7, 0x8ab3, 0x6dde, 0x52f5, 0x7751, 0x9f80, 0x20f0, 0xe37d, 0x64ab, 0x4e8e, 0x66ea, 0x7665, 0xd78b, 0x5f0f, 0x6787}
+
+/* constant columns of the SHA-256 table */
+#define S256K_FIRST 0  /* row 0 of a chunk that starts a message: chaining value = IV */
+#define S256K_LINK 1   /* row 63 of a chunk whose successor continues the message: next chaining value = this digest */
+#define S256K_CID 2    /* chunk index (row / 64) */
+#define S256K_MSG 3    /* used chunk, row 15: the 16 message words are received from the bus */
+#define S256K_DIG 4    /* used chunk, row 63: the digest is sent on the bus */
+#define S256K_COLS 5
+/* constant columns of the SHA-512 table */
+#define S512K_VID 0    /* validator slot (row / 256) */
+#define S512K_CHUNK 1  /* 0 / 1: chunk inside the slot */
+#define S512K_MSG 2    /* active slot, row 15 of a chunk */
+#define S512K_DIG0 3   /* active slot, row 79 of the first chunk */
+#define S512K_DIG1 4   /* active slot, row 79 of the second chunk */
+#define S512K_COLS 5
+
+/* ---------------- range table: 2^16 rows, row t provides the value t ---------------- */
+#define RG_M16 0  /* multiplicity of t among the 16-bit lookups */
+#define RG_M11 1  /* ... among the 11-bit lookups (zero on rows >= 2^11) */
+#define RG_M8 2   /* ... among the 8-bit lookups (zero on rows >= 2^8) */
+#define RG_COLS 3
+#define RGK_T 0
+#define RGK_S11 1
+#define RGK_S8 2
+#define RGK_COLS 3
+#define RG_LOG_ROWS 16
+
+/* ---------------- bus tags (first element of every message fingerprint) ---------------- */
+#define BUS_R16 1      /* (v) */
+#define BUS_R11 2      /* (v) */
+#define BUS_R8 3       /* (v) */
+#define BUS_MSG256 4   /* (chunk, w0..w15) */
+#define BUS_DIG256 5   /* (chunk, d0..d7) */
+#define BUS_MSG512 6   /* (slot, chunk, two, 32 halves) */
+#define BUS_DIG512 7   /* (slot, chunk, 16 halves) */
+#define BUS_ADDEND 8   /* (slot, selector, 48 limbs) */
+#define BUS_SCALAR 9   /* (slot, which, limb index, limb) */
+#define BUS_EDRES 10   /* (slot, X[16], Y[16], Z[16]) */
+
+#define TMX_N_TABLES 5
+#define TMX_T_SHA256 0
+#define TMX_T_SHA512 1
+#define TMX_T_ED 2
+#define TMX_T_LOGIC 3
+#define TMX_T_RANGE 4
 
 #endif

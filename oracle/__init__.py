@@ -193,6 +193,10 @@ class _Trace(ctypes.Structure):
     _fields_ = [("n_rows", ctypes.c_size_t), ("n_cols", ctypes.c_size_t), ("data", ctypes.POINTER(ctypes.c_uint64))]
 
 
+N_TABLES = 5
+T_SHA256, T_SHA512, T_ED, T_LOGIC, T_RANGE = range(5)
+
+
 def trace_dims(kind, n_max):
     d = (ctypes.c_size_t * 6)()
     lib().tm_trace_dims(ctypes.c_uint32(kind), ctypes.c_uint32(n_max), d)
@@ -213,29 +217,111 @@ def build_traces(blob):
     return out
 
 
-def constraints_at_rows(table, trace, rows, kind, n_max, alpha=(0x123456789ABCDEF, 0xFEDCBA987654321)):
-    """Folded constraint values (two challenges) of the transitions row -> row + 1 (cyclic) of `trace` ([n_cols, n_rows])
-    on the trace domain; [len(rows), 2] uint64, all zero for a satisfying trace."""
-    trace = np.ascontiguousarray(trace, dtype=np.uint64)
-    C, n = trace.shape
-    rows = np.ascontiguousarray(rows, dtype=np.uint64)
-    a = np.array(alpha, dtype=np.uint64)
-    out = np.zeros((rows.size, 2), dtype=np.uint64)
-    vp = lambda x: x.ctypes.data_as(ctypes.c_void_p)
-    lib().tm_debug_set_shape(ctypes.c_uint32(kind), ctypes.c_uint32(n_max))
-    lib().tm_debug_constraints_at_rows(ctypes.c_int(table), vp(trace), ctypes.c_size_t(n), ctypes.c_size_t(C), vp(a), vp(rows),
-                                       ctypes.c_size_t(rows.size), vp(out))
-    return out
+# ---------------------------------------------------------------- circuits (build artefacts) and proofs
+_PRODUCT_LIB = None
+_CIRCUITS = {}
 
 
-def prove(public_input, blob, chain_id, skip_max=100800):
-    """CPU oracle prover.  Returns (status, proof as uint64 array or None, output32 or None)."""
+def _product_lib():
+    """libtmx.so, loaded directly (not through the product's Python package): the oracle takes the circuit DEFINITION -- the
+    build artefact, pure data -- from the product's host-side builder and nothing else."""
+    global _PRODUCT_LIB
+    if _PRODUCT_LIB is None:
+        path = os.path.join(os.path.dirname(_HERE), "tendermintx_b200", "libtmx.so")
+        _PRODUCT_LIB = ctypes.CDLL(path)
+        _PRODUCT_LIB.tmx_circuit_artefact.restype = ctypes.c_size_t
+        _PRODUCT_LIB.tmx_circuit_artefact.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_uint64,
+                                                      ctypes.c_void_p, ctypes.c_size_t]
+    return _PRODUCT_LIB
+
+
+def artefact_words(kind, n_max, chain_id, skip_max=100800):
     cid = chain_id.encode() if isinstance(chain_id, str) else chain_id
+    n = _product_lib().tmx_circuit_artefact(kind, n_max, cid, len(cid), skip_max, None, 0)
+    if n == 0:
+        raise RuntimeError("tmx_circuit_artefact failed")
+    w = np.zeros(n, dtype=np.uint64)
+    _product_lib().tmx_circuit_artefact(kind, n_max, cid, len(cid), skip_max, w.ctypes.data_as(ctypes.c_void_p), n)
+    return w
+
+
+class Circuit:
+    """A parsed build artefact.  Parsing recomputes the digest and re-commits the constant columns with the oracle's own code."""
+
+    def __init__(self, words):
+        words = np.ascontiguousarray(words, dtype=np.uint64)
+        rc = ctypes.c_int(0)
+        lib().tm_circuit_load.restype = ctypes.c_void_p
+        self.handle = lib().tm_circuit_load(words.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(words.size), ctypes.byref(rc))
+        if not self.handle:
+            raise ValueError(f"tm_circuit_load: code {rc.value}")
+        self.words = words
+
+    def digest(self):
+        out = np.zeros(4, dtype=np.uint64)
+        lib().tm_circuit_digest(ctypes.c_void_p(self.handle), out.ctypes.data_as(ctypes.c_void_p))
+        return out
+
+    def table_shapes(self):
+        """[(present, log_n, n_main, n_const, n_per, period, n_helpers, n_constraints)] per table, read from the words."""
+        w = self.words
+        pos, out = 20, []
+        for _ in range(N_TABLES):
+            present = int(w[pos]); pos += 1
+            if not present:
+                out.append((0,) * 8)
+                continue
+            f = [int(x) for x in w[pos:pos + 10]]; pos += 10
+            out.append((1, f[0], f[1], f[2], f[3], f[4], f[5], f[6]))
+            pos += f[3] * f[4] + (f[2] << f[0]) + f[7] + 2 * f[8] + f[9]
+        return out
+
+
+    def table_data(self, table):
+        """(periodic [n_per, period], constants [n_const, n]) of a table, read from the words."""
+        w = self.words
+        pos = 20
+        for t in range(N_TABLES):
+            present = int(w[pos]); pos += 1
+            if not present:
+                if t == table:
+                    return None
+                continue
+            f = [int(x) for x in w[pos:pos + 10]]; pos += 10
+            n_per, n_cst = f[3] * f[4], f[2] << f[0]
+            if t == table:
+                per = np.array(w[pos:pos + n_per]).reshape(f[3], f[4]) if f[3] else np.zeros((0, f[4]), dtype=np.uint64)
+                cst = np.array(w[pos + n_per:pos + n_per + n_cst]).reshape(f[2], 1 << f[0])
+                return np.ascontiguousarray(per), np.ascontiguousarray(cst)
+            pos += n_per + n_cst + f[7] + 2 * f[8] + f[9]
+        return None
+
+
+def circuit(kind, n_max, chain_id, skip_max=100800):
+    key = (kind, n_max, chain_id if isinstance(chain_id, str) else chain_id.decode(), skip_max)
+    if key not in _CIRCUITS:
+        _CIRCUITS[key] = Circuit(artefact_words(kind, n_max, chain_id, skip_max))
+    return _CIRCUITS[key]
+
+
+def _blob_shape(blob):
+    kind, n_max = np.frombuffer(bytes(blob[4:12]), dtype=np.uint32)
+    return int(kind), int(n_max)
+
+
+def prove(public_input, blob, chain_id, skip_max=100800, logic_trace=None):
+    """CPU oracle prover.  Returns (status, proof as uint64 array or None, output32 or None)."""
+    kind, n_max = _blob_shape(blob)
+    c = circuit(kind, n_max, chain_id, skip_max)
     p = ctypes.POINTER(ctypes.c_uint64)()
     n = ctypes.c_size_t(0)
     out = (ctypes.c_uint8 * 32)()
-    rc = lib().tm_prove(_buf(public_input), ctypes.c_size_t(len(public_input)), _buf(blob), ctypes.c_size_t(len(blob)),
-                        _buf(cid), ctypes.c_size_t(len(cid)), ctypes.c_uint64(skip_max), ctypes.byref(p), ctypes.byref(n), out)
+    lt = None
+    if logic_trace is not None:
+        lt = np.ascontiguousarray(logic_trace, dtype=np.uint64)
+    rc = lib().tm_prove(ctypes.c_void_p(c.handle), _buf(public_input), ctypes.c_size_t(len(public_input)), _buf(blob),
+                        ctypes.c_size_t(len(blob)), lt.ctypes.data_as(ctypes.c_void_p) if lt is not None else ctypes.c_void_p(0),
+                        ctypes.byref(p), ctypes.byref(n), out)
     if rc != 0:
         return CHECK_NAMES[rc], None, None
     proof = np.ctypeslib.as_array(p, shape=(n.value,)).copy()
@@ -245,8 +331,69 @@ def prove(public_input, blob, chain_id, skip_max=100800):
 
 def verify_proof(proof, public_input, chain_id, kind, n_max, output32, skip_max=100800):
     """Returns 0 when the proof verifies; a non-zero diagnostic code otherwise."""
-    cid = chain_id.encode() if isinstance(chain_id, str) else chain_id
+    c = circuit(kind, n_max, chain_id, skip_max)
     proof = np.ascontiguousarray(proof, dtype=np.uint64)
-    return lib().tm_verify_proof(proof.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(proof.size), _buf(public_input),
-                                 ctypes.c_size_t(len(public_input)), _buf(cid), ctypes.c_size_t(len(cid)),
-                                 ctypes.c_uint64(skip_max), ctypes.c_uint32(kind), ctypes.c_uint32(n_max), _buf(output32))
+    return lib().tm_verify_proof(ctypes.c_void_p(c.handle), proof.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(proof.size),
+                                 _buf(public_input), ctypes.c_size_t(len(public_input)), _buf(output32))
+
+
+def all_traces(blob, chain_id, skip_max=100800, logic_trace=None):
+    """First-round traces of all tables (None where a table is absent), [n_cols, n_rows] each."""
+    kind, n_max = _blob_shape(blob)
+    c = circuit(kind, n_max, chain_id, skip_max)
+    shapes = c.table_shapes()
+    arrs, ptrs = [], (ctypes.c_void_p * N_TABLES)()
+    for t, sh in enumerate(shapes):
+        if sh[0]:
+            a = np.zeros((sh[2], 1 << sh[1]), dtype=np.uint64)
+            arrs.append(a)
+            ptrs[t] = a.ctypes.data_as(ctypes.c_void_p)
+        else:
+            arrs.append(None)
+            ptrs[t] = None
+    lt = np.ascontiguousarray(logic_trace, dtype=np.uint64) if logic_trace is not None else None
+    rc = lib().tm_debug_traces(ctypes.c_void_p(c.handle), _buf(blob), ctypes.c_size_t(len(blob)),
+                               lt.ctypes.data_as(ctypes.c_void_p) if lt is not None else ctypes.c_void_p(0), ptrs)
+    if rc != 0:
+        raise ValueError(f"tm_debug_traces: {CHECK_NAMES[rc]}")
+    return arrs
+
+
+def aux_trace(circ, table, trace, beta, gamma):
+    """Second-round trace [2 (H + 1), n] and the table's bus total for given challenges (pairs of u64)."""
+    sh = circ.table_shapes()[table]
+    trace = np.ascontiguousarray(trace, dtype=np.uint64)
+    aux = np.zeros((2 * (sh[6] + 1), 1 << sh[1]), dtype=np.uint64)
+    total = np.zeros(2, dtype=np.uint64)
+    b, g = np.array(beta, dtype=np.uint64), np.array(gamma, dtype=np.uint64)
+    vp = lambda x: x.ctypes.data_as(ctypes.c_void_p)
+    lib().tm_debug_aux(ctypes.c_void_p(circ.handle), ctypes.c_int(table), vp(trace), vp(b), vp(g), vp(aux), vp(total))
+    return aux, total
+
+
+def quotient(circ, table, trace, aux, total, beta, gamma, alpha):
+    """LDEs of both traces (bit-reversed rows) and the quotient values on the LDE coset, natural order [2, m]."""
+    sh = circ.table_shapes()[table]
+    m = 2 << sh[1]
+    trace, aux = np.ascontiguousarray(trace, dtype=np.uint64), np.ascontiguousarray(aux, dtype=np.uint64)
+    lde_m, lde_a, qv = np.zeros((sh[2], m), dtype=np.uint64), np.zeros((aux.shape[0], m), dtype=np.uint64), np.zeros((2, m), dtype=np.uint64)
+    arr = lambda x: np.array(x, dtype=np.uint64)
+    t, b, g, a = arr(total), arr(beta), arr(gamma), arr(alpha)
+    vp = lambda x: x.ctypes.data_as(ctypes.c_void_p)
+    lib().tm_debug_quotient(ctypes.c_void_p(circ.handle), ctypes.c_int(table), vp(trace), vp(aux), vp(t), vp(b), vp(g), vp(a), vp(lde_m),
+                            vp(lde_a), vp(qv))
+    return lde_m, lde_a, qv
+
+
+def constraints_at_rows(circ, table, trace, aux, total, beta, gamma, rows, alpha=(0x123456789ABCDEF, 0xFEDCBA987654321)):
+    """Folded constraint values (two challenges) of the transitions row -> row + 1 (cyclic) on the trace domain, second-round
+    columns included; [len(rows), 2] uint64, all zero for a satisfying pair of traces."""
+    trace, aux = np.ascontiguousarray(trace, dtype=np.uint64), np.ascontiguousarray(aux, dtype=np.uint64)
+    rows = np.ascontiguousarray(rows, dtype=np.uint64)
+    arr = lambda x: np.array(x, dtype=np.uint64)
+    t, b, g, a = arr(total), arr(beta), arr(gamma), arr(alpha)
+    out = np.zeros((rows.size, 2), dtype=np.uint64)
+    vp = lambda x: x.ctypes.data_as(ctypes.c_void_p)
+    lib().tm_debug_constraints_at_rows(ctypes.c_void_p(circ.handle), ctypes.c_int(table), vp(trace), vp(aux), vp(t), vp(b), vp(g), vp(a),
+                                       vp(rows), ctypes.c_size_t(rows.size), vp(out))
+    return out

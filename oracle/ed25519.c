@@ -289,6 +289,119 @@ void ge_ladder_row(const ge_t *res, const ge_t *temp, ge_t *sum, ge_t *dbl, fe_m
     fe_mul_gadget(F, G, &wit[16]); wit_out(&dbl->Z, &wit[16]);
 }
 
+/* ---- joint (Straus) evaluation of [s]B + [h](-A), the row structure of the Ed25519 table (include/tmx_trace.h) ---- */
+static void fe_invert(fe_t *r, const fe_t *a) { /* a^(p-2), p - 2 = 2^255 - 21 */
+    fe_t acc = FE_ONE;
+    for (int i = 254; i >= 0; i--) {
+        fe_sqr(&acc, &acc);
+        if (!(i == 4 || i == 2)) fe_mul(&acc, &acc, a);
+    }
+    *r = acc;
+}
+
+/* The four addends of a validator slot as the ED_ADD cells hold them: (y + x, y - x, 2 d x y) of O, B, -A, B - A, each
+ * component a limb vector.  O and B are canonical constants; for -A and B - A the sums / differences are taken LIMB-WISE
+ * (plus 2p where a difference could go negative), because that is the linear expression of committed cells the logic
+ * table provides on the bus.  A must be affine (Z = 1).  xD, yD: affine coordinates of D = B - A. */
+void ge_straus_table(const ge_t *A, ge_cached_t T[4], fe_t *xD, fe_t *yD) {
+    init_consts();
+    memset(T, 0, 4 * sizeof(ge_cached_t));
+    T[0].ypx[0] = 1;
+    T[0].ymx[0] = 1;
+    fe_t t;
+    ge_t B, nA, D, dummy;
+    fe_mul_witness_t wit[17];
+    ge_basepoint(&B);
+    fe_add(&t, &B.Y, &B.X); memcpy(T[1].ypx, t.l, sizeof t.l);
+    fe_sub(&t, &B.Y, &B.X); memcpy(T[1].ymx, t.l, sizeof t.l);
+    fe_mul(&t, &FE_2D, &B.T); memcpy(T[1].t2d, t.l, sizeof t.l);
+    fe_t tA;
+    fe_mul(&tA, &FE_2D, &A->T);
+    for (int i = 0; i < 16; i++) {
+        T[2].ypx[i] = A->Y.l[i] - A->X.l[i] + 2 * P_LIMBS[i];
+        T[2].ymx[i] = A->Y.l[i] + A->X.l[i];
+        T[2].t2d[i] = 2 * P_LIMBS[i] - tA.l[i];
+    }
+    fe_sub(&nA.X, &FE_ZERO, &A->X);
+    nA.Y = A->Y;
+    nA.Z = FE_ONE;
+    fe_sub(&nA.T, &FE_ZERO, &A->T);
+    ge_ladder_row(&B, &nA, &D, &dummy, wit); /* D = B + (-A), projective */
+    fe_t zi, tD;
+    fe_invert(&zi, &D.Z);
+    fe_mul(xD, &D.X, &zi);
+    fe_mul(yD, &D.Y, &zi);
+    fe_mul(&tD, xD, yD);
+    fe_mul(&tD, &FE_2D, &tD);
+    for (int i = 0; i < 16; i++) {
+        T[3].ypx[i] = yD->l[i] + xD->l[i];
+        T[3].ymx[i] = yD->l[i] - xD->l[i] + 2 * P_LIMBS[i];
+        T[3].t2d[i] = tD.l[i];
+    }
+}
+
+/* One row: out = 2 * acc + addend.  dbl-2008-hwcd (a = -1) then add-2008-hwcd-3 with Z2 = 1 and no T output:
+ *   m0 A = X^2  m1 B = Y^2  m2 Cz = Z^2  m3 S = (X+Y)^2
+ *   E = S-A-B+2p  G = B-A+p  F = B-A-2Cz+3p  H = 2p-A-B
+ *   m4 X3 = E*F  m5 Y3 = G*H  m6 T3 = E*H  m7 Z3 = F*G
+ *   m8 a = (Y3-X3+p)*(y-x)  m9 b = (Y3+X3)*(y+x)  m10 c = T3*2dxy
+ *   E' = b-a+p  F' = 2Z3-c+p  G' = 2Z3+c  H' = b+a
+ *   m11 X4 = E'*F'  m12 Y4 = G'*H'  m13 Z4 = F'*G' */
+void ge_straus_row(const fe_t acc[3], const ge_cached_t *add, fe_t out[3], fe_mul_witness_t wit[14]) {
+    init_consts();
+    int64_t u[16], E[16], F[16], G[16], H[16];
+    fe_t A2, B2, Cz, S, X3, Y3, T3, Z3, a, b, c;
+    fe_mul_gadget(acc[0].l, acc[0].l, &wit[0]); wit_out(&A2, &wit[0]);
+    fe_mul_gadget(acc[1].l, acc[1].l, &wit[1]); wit_out(&B2, &wit[1]);
+    fe_mul_gadget(acc[2].l, acc[2].l, &wit[2]); wit_out(&Cz, &wit[2]);
+    lin2(u, 1, &acc[0], 1, &acc[1], 0);
+    fe_mul_gadget(u, u, &wit[3]); wit_out(&S, &wit[3]);
+    lin3(E, 1, &S, -1, &A2, -1, &B2, 2);
+    lin2(G, 1, &B2, -1, &A2, 1);
+    lin3(F, 1, &B2, -1, &A2, -2, &Cz, 3);
+    lin2(H, -1, &A2, -1, &B2, 2);
+    fe_mul_gadget(E, F, &wit[4]); wit_out(&X3, &wit[4]);
+    fe_mul_gadget(G, H, &wit[5]); wit_out(&Y3, &wit[5]);
+    fe_mul_gadget(E, H, &wit[6]); wit_out(&T3, &wit[6]);
+    fe_mul_gadget(F, G, &wit[7]); wit_out(&Z3, &wit[7]);
+    lin2(u, 1, &Y3, -1, &X3, 1);
+    fe_mul_gadget(u, add->ymx, &wit[8]); wit_out(&a, &wit[8]);
+    lin2(u, 1, &Y3, 1, &X3, 0);
+    fe_mul_gadget(u, add->ypx, &wit[9]); wit_out(&b, &wit[9]);
+    fe_mul_gadget(T3.l, add->t2d, &wit[10]); wit_out(&c, &wit[10]);
+    lin2(E, 1, &b, -1, &a, 1);
+    lin2(F, 2, &Z3, -1, &c, 1);
+    lin2(G, 2, &Z3, 1, &c, 0);
+    lin2(H, 1, &b, 1, &a, 0);
+    fe_mul_gadget(E, F, &wit[11]); wit_out(&out[0], &wit[11]);
+    fe_mul_gadget(G, H, &wit[12]); wit_out(&out[1], &wit[12]);
+    fe_mul_gadget(F, G, &wit[13]); wit_out(&out[2], &wit[13]);
+}
+
+/* [s]B + [h](-A) by the row recurrence (most significant bits first); result projective (X : Y : Z) */
+void ge_straus(const uint8_t s[32], const uint8_t h[32], const ge_t *A, fe_t out[3]) {
+    ge_cached_t T[4];
+    fe_t xD, yD, acc[3], nxt[3];
+    fe_mul_witness_t wit[14];
+    ge_straus_table(A, T, &xD, &yD);
+    acc[0] = FE_ZERO; acc[1] = FE_ONE; acc[2] = FE_ONE;
+    for (int r = 0; r < 256; r++) {
+        int j = 255 - r;
+        int sel = ((s[j >> 3] >> (j & 7)) & 1) + 2 * ((h[j >> 3] >> (j & 7)) & 1);
+        ge_straus_row(acc, &T[sel], nxt, wit);
+        memcpy(acc, nxt, sizeof acc);
+    }
+    memcpy(out, acc, sizeof acc);
+}
+/* does the projective (X : Y : Z) equal the affine point R?  (X = xR Z, Y = yR Z) */
+int ge_projective_equals_affine(const fe_t q[3], const ge_t *R) {
+    fe_t l;
+    fe_mul(&l, &R->X, &q[2]);
+    if (!fe_eq(&l, &q[0])) return 0;
+    fe_mul(&l, &R->Y, &q[2]);
+    return fe_eq(&l, &q[1]);
+}
+
 void ge_scalarmult(ge_t *r, const uint8_t scalar[32], const ge_t *p) {
     ge_t res, temp = *p, sum, dbl;
     fe_mul_witness_t wit[17];

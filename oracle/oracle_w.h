@@ -61,6 +61,14 @@ void ge_basepoint(ge_t *r);
 /* one double-and-add row: sum = res + temp, dbl = 2*temp; witnesses for the 17 multiplications */
 void ge_ladder_row(const ge_t *res, const ge_t *temp, ge_t *sum, ge_t *dbl, fe_mul_witness_t wit[17]);
 void ge_scalarmult(ge_t *r, const uint8_t scalar[32], const ge_t *p); /* LSB-first double-and-add, 256 rows */
+/* joint evaluation of [s]B + [h](-A): the row structure of the Ed25519 table (include/tmx_trace.h) */
+typedef struct {
+    int64_t ypx[16], ymx[16], t2d[16];
+} ge_cached_t;
+void ge_straus_table(const ge_t *A, ge_cached_t T[4], fe_t *xD, fe_t *yD);
+void ge_straus_row(const fe_t acc[3], const ge_cached_t *add, fe_t out[3], fe_mul_witness_t wit[14]);
+void ge_straus(const uint8_t s[32], const uint8_t h[32], const ge_t *A, fe_t out[3]);
+int ge_projective_equals_affine(const fe_t q[3], const ge_t *R);
 int ge_equal_projective(const ge_t *a, const ge_t *b);
 void sc_reduce512(uint8_t out[32], const uint8_t in[64]); /* 512-bit LE mod l */
 int sc_is_canonical(const uint8_t s[32]);

@@ -1,21 +1,28 @@
 /*
- * oracle/stark.c -- deterministic CPU prover and verifier for the three-table STARK that witnesses one skip /
- * step proof: trace commitment (PolynomialBatch), constraint quotient, openings at zeta and g*zeta, FRI
- * (arity 16, final polynomial, 16-bit proof of work with the MINIMUM witness, 84 queries).
- * TEST INFRASTRUCTURE ONLY (see oracle/gl.h header); also the CPU baseline that bench.py times.
+ * oracle/stark.c -- deterministic CPU prover and verifier for the multi-table STARK with a shared bus that witnesses
+ * one skip / step proof.  TEST INFRASTRUCTURE ONLY (see oracle/gl.h header); also the CPU baseline that bench.py times.
  *
- * Restates the plonky2 0.2.0 / starky pipeline the reference reaches through `circuit.prove()` /
+ * Protocol (DESIGN.md "Proof format and protocol"): round 1 commits the witness tables (SHA-256, SHA-512, Ed25519,
+ * logic, range); the bus challenges (beta, gamma) are drawn; round 2 commits, per table, the helper columns of its
+ * bus interactions and a running sum; then per table: constraint challenges, quotient commitment, openings at zeta and
+ * g*zeta of the constant / first-round / second-round columns, FRI (arity 16, final polynomial, 16-bit proof of work
+ * with the MINIMUM witness, 84 queries).  The verifier also checks that the per-table bus totals and its own
+ * public-input terms sum to zero.
+ *
+ * Restates the plonky2 0.2.0 / starky / Curta pipeline the reference reaches through `circuit.prove()` /
  * `circuit.verify()` [REF circuits/skip.rs:214,244,247; circuits/step.rs:196,223,226] -- fri/oracle.rs
- * (prove_openings), fri/prover.rs (fri_committed_trees, fri_proof_of_work, query rounds), fri/verifier.rs,
- * starky prover.rs (quotient polynomials, opening set) -- with Curta's STARK configuration (rate_bits 1,
- * cap height 4, 84 queries).  The dependency sources are absent and the reference pins no proof bytes:
- * PARITY UNPINNED at the proof level; the primitives underneath are KAT-pinned.
- * The FRI commit phase deliberately works in COEFFICIENT space like plonky2 (fold coefficients, re-evaluate with
- * a coset FFT), while the CUDA product folds evaluations; agreement of the two is part of the parity test.
+ * (prove_openings), fri/prover.rs (fri_committed_trees, fri_proof_of_work, query rounds), fri/verifier.rs, starky
+ * prover.rs (quotient polynomials, opening set), Curta's lookup / bus accumulators -- with Curta's STARK
+ * configuration (rate_bits 1, cap height 4, 84 queries).  The dependency sources are absent and the reference pins no
+ * proof bytes: PARITY UNPINNED at the proof level; the primitives underneath are
+ * KAT-pinned.  The constraint systems are not typed in here: they are DATA, read from the build artefact
+ * (oracle/circuit.c) and evaluated by this file's own interpreter, bus logic and quotient code.  The FRI commit phase
+ * deliberately works in COEFFICIENT space like plonky2 (fold coefficients, re-evaluate with a coset FFT), while the
+ * CUDA product folds evaluations; agreement of the two is part of the parity test.
  */
 #include "oracle.h"
 #include "oracle_w.h"
-#include "../include/tmx_trace.h"
+#include "circuit.h"
 #include <stdlib.h>
 #include <string.h>
 #include <stdio.h>
@@ -30,7 +37,7 @@
 #define FINAL_POLY_BITS 5
 #define QDF 2 /* quotient degree factor */
 #define N_QUOT (NUM_CHALLENGES * QDF)
-#define PROOF_MAGIC 0x50584D54ULL /* "TMXP" */
+#define PROOF_MAGIC 0x32504D54ULL /* "TMP2" */
 
 typedef struct {
     size_t n_rows, n_cols;
@@ -38,106 +45,6 @@ typedef struct {
 } trace_t;
 int tm_build_traces(const uint8_t *blob, size_t blob_len, trace_t out[3]);
 void tm_free_traces(trace_t out[3]);
-void tm_trace_dims(uint32_t kind, uint32_t n_max, size_t dims[6]);
-
-/* ------------------------------------------------------------------ AIR instantiations */
-#define FT gl_t
-#define F_ADD gl_add
-#define F_SUB gl_sub
-#define F_MUL gl_mul
-#define F_C(x) ((gl_t)(x))
-#define SUF(name) name##_b
-#include "air.inc"
-#undef FT
-#undef F_ADD
-#undef F_SUB
-#undef F_MUL
-#undef F_C
-#undef SUF
-#define FT gl2_t
-#define F_ADD gl2_add
-#define F_SUB gl2_sub
-#define F_MUL gl2_mul
-#define F_C(x) gl2_from((gl_t)(x))
-#define SUF(name) name##_e
-#include "air.inc"
-#undef FT
-#undef F_ADD
-#undef F_SUB
-#undef F_MUL
-#undef F_C
-#undef SUF
-
-enum { T_SHA256 = 0, T_SHA512 = 1, T_ED = 2, N_TABLES = 3 };
-static const int TABLE_COLS[3] = {S256_COLS, S512_COLS, ED_COLS};
-static const int TABLE_NPER[3] = {6, 11, 3};
-/* The SHA-256 table's last two "periodic" columns are not periodic: which chunk starts a message (chaining value = IV)
- * and which chunk continues one (chaining value = previous digest) is fixed by the circuit shape (kind, n_max), see
- * sha256_chunk_continues().  They are public columns of full length: the prover evaluates them on the LDE coset, the
- * verifier evaluates their interpolant at zeta itself.  So the "period" of that table is its length. */
-static __thread uint32_t g_kind, g_n_max; /* shape of the circuit being proved / verified (set by the entry points) */
-static size_t table_period(int table, size_t n) {
-    return table == 0 ? n : (table == 1 ? S512_ROWS_PER_VALIDATOR : ED_ROWS_PER_VALIDATOR);
-}
-/* Does 64-row chunk c of the SHA-256 table continue the message of chunk c - 1?  Layout (oracle/trace.c build_sha256):
- * per validator set n_max one-chunk leaf hashes, then np - 1 two-chunk inner nodes; then the header proofs, each a leaf
- * (two chunks for the 72-byte last-block-id leaf of the step circuit, else one) and four two-chunk inner nodes; then
- * one-chunk padding messages. */
-static int sha256_chunk_continues(uint32_t kind, uint32_t n_max, size_t c) {
-    size_t np = 1;
-    while (np < n_max) np *= 2;
-    const size_t set_chunks = n_max + 2 * (np - 1), sets = kind == TMX_KIND_SKIP ? 2 : 1;
-    if (c < sets * set_chunks) {
-        const size_t local = c % set_chunks;
-        return local >= n_max && ((local - n_max) & 1);
-    }
-    size_t h = c - sets * set_chunks;
-    const int n_proofs = kind == TMX_KIND_SKIP ? 4 : 5;
-    for (int k = 0; k < n_proofs; k++) {
-        const size_t leaf = (kind == TMX_KIND_STEP && k == 3) ? 2 : 1, len = leaf + 8;
-        if (h < len) return h < leaf ? h == 1 : ((h - leaf) & 1);
-        h -= len;
-    }
-    return 0;
-}
-
-/* periodic pattern value of column pc at row r (r < period) */
-static gl_t periodic_pattern(int table, int pc, size_t row) {
-    const int r = (int)(row & 511);
-    if (table == T_SHA256) {
-        const int rr = (int)(row & 63);
-        const size_t chunk = row >> 6;
-        switch (pc) {
-            case 0: return SHA256_K[rr];
-            case 1: return rr == 63;
-            case 2: return rr != 63;
-            case 3: return rr >= 15 && rr <= 62;
-            case 4: return rr == 0 && !sha256_chunk_continues(g_kind, g_n_max, chunk);      /* FIRST: chaining value = IV */
-            default: return rr == 63 && sha256_chunk_continues(g_kind, g_n_max, chunk + 1); /* LINK: next chunk chains */
-        }
-    }
-    if (table == T_SHA512) {
-        const int rr = r % S512_ROWS_PER_CHUNK; /* row inside the chunk; r inside the validator's two-chunk slot */
-        switch (pc) {
-            case 0: return rr < 80 ? (uint32_t)SHA512_K[rr] : 0;
-            case 1: return rr < 80 ? SHA512_K[rr] >> 32 : 0;
-            case 2: return rr == 79;
-            case 3: return rr != 79;
-            case 4: return rr != S512_ROWS_PER_CHUNK - 1;
-            case 5: return rr >= 15 && rr <= S512_ROWS_PER_CHUNK - 2;
-            case 6: return r == 0;
-            case 7: return rr < 79;
-            case 8: return rr >= 79 && rr <= S512_ROWS_PER_CHUNK - 2;
-            case 9: return r == S512_ROWS_PER_CHUNK - 1;
-            default: return r != S512_ROWS_PER_VALIDATOR - 1;
-        }
-    }
-    switch (pc) { /* Ed25519 */
-        case 0: return (r & 255) != 255;
-        case 1: return r == 0;
-        default: return r == 256;
-    }
-}
 
 /* ------------------------------------------------------------------ small utilities */
 typedef struct {
@@ -200,22 +107,6 @@ static size_t fri_num_layers(unsigned degree_bits) {
     return l;
 }
 
-/* circuit digest: binds kind, sizes, chain id, skip_max and the protocol parameters */
-static void circuit_digest(uint32_t kind, uint32_t n_max, const uint8_t *chain_id, size_t chain_id_len, uint64_t skip_max,
-                           gl_t out[4]) {
-    gl_t in[96];
-    size_t k = 0;
-    in[k++] = PROOF_MAGIC; in[k++] = kind; in[k++] = n_max; in[k++] = skip_max;
-    in[k++] = RATE_BITS; in[k++] = CAP_HEIGHT; in[k++] = NUM_CHALLENGES; in[k++] = POW_BITS; in[k++] = NUM_QUERIES;
-    in[k++] = ARITY_BITS; in[k++] = FINAL_POLY_BITS;
-    size_t dims[6];
-    tm_trace_dims(kind, n_max, dims);
-    for (int i = 0; i < 6; i++) in[k++] = dims[i];
-    in[k++] = chain_id_len;
-    for (size_t i = 0; i < chain_id_len && i < 64; i++) in[k++] = chain_id[i];
-    poseidon_hash_no_pad(in, k, out);
-}
-
 static void ext_poly_fft(gl2_t *a, size_t n, gl_t shift) { /* coset evaluation, natural order, componentwise */
     gl_t *t = (gl_t *)malloc(n * sizeof(gl_t));
     for (int comp = 0; comp < 2; comp++) {
@@ -270,33 +161,6 @@ static gl2_t fri_fold_coset(gl_t x, unsigned idx_in_coset, const gl2_t evals[16]
     return interpolate16(xs, ys, beta);
 }
 
-typedef struct {
-    gl_t acc[NUM_CHALLENGES];
-    gl_t alpha[NUM_CHALLENGES];
-} acc_b_t;
-static void emit_b(void *ctx, gl_t c) {
-    acc_b_t *a = (acc_b_t *)ctx;
-    for (int i = 0; i < NUM_CHALLENGES; i++) a->acc[i] = gl_add(gl_mul(a->acc[i], a->alpha[i]), c);
-}
-typedef struct {
-    gl2_t acc[NUM_CHALLENGES];
-    gl2_t alpha[NUM_CHALLENGES];
-} acc_e_t;
-static void emit_e(void *ctx, gl2_t c) {
-    acc_e_t *a = (acc_e_t *)ctx;
-    for (int i = 0; i < NUM_CHALLENGES; i++) a->acc[i] = gl2_add(gl2_mul(a->acc[i], a->alpha[i]), c);
-}
-static void air_eval_b(int table, const gl_t *l, const gl_t *n, const gl_t *per, acc_b_t *a) {
-    if (table == T_SHA256) air_sha256_b(l, n, per, emit_b, a);
-    else if (table == T_SHA512) air_sha512_b(l, n, per, emit_b, a);
-    else air_ed25519_b(l, n, per, emit_b, a);
-}
-static void air_eval_e(int table, const gl2_t *l, const gl2_t *n, const gl2_t *per, acc_e_t *a) {
-    if (table == T_SHA256) air_sha256_e(l, n, per, emit_e, a);
-    else if (table == T_SHA512) air_sha512_e(l, n, per, emit_e, a);
-    else air_ed25519_e(l, n, per, emit_e, a);
-}
-
 /* ------------------------------------------------------------------ prover: one table */
 static void merkle_open(wbuf_t *w, const merkle_tree_t *t, size_t idx) {
     gl_t sib[4 * 40];
@@ -312,65 +176,334 @@ static void tick(const char *what) {
     t_last = t;
 }
 
-static void prove_table(int table, const trace_t *tr, challenger_t *ch, wbuf_t *w) {
-    t_last = omp_get_wtime();
-    const size_t n = tr->n_rows, C = tr->n_cols, m = n << RATE_BITS;
-    const unsigned k = tmx_log2(n), km = k + RATE_BITS;
-    /* 1. trace commitment */
-    gl_t *lde = (gl_t *)malloc(C * m * sizeof(gl_t));
-    gl_t *coeffs = (gl_t *)malloc(C * n * sizeof(gl_t));
-    ntt_lde_batch(tr->data, C, n, RATE_BITS, lde, coeffs);
-    tick("lde");
-    merkle_tree_t tree_t;
-    commit_columns(&tree_t, lde, C, m, CAP_HEIGHT);
-    const size_t cap_n = (size_t)1 << tree_t.cap_height;
-    wb_push_many(w, tree_t.cap, 4 * cap_n);
-    observe_cap(ch, tree_t.cap, cap_n);
-    tick("trace merkle");
-    /* 2. constraint challenges */
-    gl_t alpha[NUM_CHALLENGES];
-    for (int i = 0; i < NUM_CHALLENGES; i++) alpha[i] = challenger_get(ch);
-    /* 3. quotient on the LDE coset */
-    const int nper = TABLE_NPER[table];
-    const size_t P = table_period(table, n);
-    gl_t *pertab = NULL; /* [nper][2P] values at natural LDE index mod 2P */
-    if (nper) {
-        pertab = (gl_t *)malloc((size_t)nper * 2 * P * sizeof(gl_t));
-        gl_t shift = gl_pow(GL_GENERATOR, n / P);
-        for (int pc = 0; pc < nper; pc++) {
-            gl_t *t = pertab + (size_t)pc * 2 * P;
-            for (size_t r = 0; r < P; r++) t[r] = periodic_pattern(table, pc, r);
-            ntt_inverse(t, P);
-            memset(t + P, 0, P * sizeof(gl_t));
-            ntt_coset_forward(t, 2 * P, shift);
+/* ------------------------------------------------------------------ bus */
+/* fingerprint gamma + tag + beta v_0 + beta^2 v_1 + ... of one bus item part at prog[p] = {tag, m, len, v..} */
+static gl2_t bus_fingerprint_b(const uint64_t *part, const gl_t *v, gl2_t beta, gl2_t gamma) {
+    gl2_t acc = gl2_from(0);
+    const uint64_t len = part[2];
+    for (uint64_t i = len; i-- > 0;) {
+        acc.a0 = gl_add(acc.a0, v[part[3 + i]]);
+        acc = gl2_mul(acc, beta);
+    }
+    acc.a0 = gl_add(acc.a0, (gl_t)part[0]);
+    return gl2_add(acc, gamma);
+}
+
+/* the same over openings at zeta: every component is an extension element, the algebra is F[X]/(X^2 - 7) on top */
+typedef struct {
+    gl2_t a0, a1;
+} e2e_t;
+static e2e_t e2e_add(e2e_t a, e2e_t b) { return (e2e_t){gl2_add(a.a0, b.a0), gl2_add(a.a1, b.a1)}; }
+static e2e_t e2e_sub(e2e_t a, e2e_t b) { return (e2e_t){gl2_sub(a.a0, b.a0), gl2_sub(a.a1, b.a1)}; }
+static e2e_t e2e_mul(e2e_t a, e2e_t b) {
+    return (e2e_t){gl2_add(gl2_mul(a.a0, b.a0), gl2_scale(gl2_mul(a.a1, b.a1), 7)), gl2_add(gl2_mul(a.a0, b.a1), gl2_mul(a.a1, b.a0))};
+}
+static e2e_t e2e_scale(e2e_t a, gl2_t s) { return (e2e_t){gl2_mul(a.a0, s), gl2_mul(a.a1, s)}; }
+static e2e_t bus_fingerprint_e(const uint64_t *part, const gl2_t *v, gl2_t beta, gl2_t gamma) {
+    const e2e_t b = {gl2_from(beta.a0), gl2_from(beta.a1)};
+    e2e_t acc = {gl2_from(0), gl2_from(0)};
+    const uint64_t len = part[2];
+    for (uint64_t i = len; i-- > 0;) {
+        acc.a0 = gl2_add(acc.a0, v[part[3 + i]]);
+        acc = e2e_mul(acc, b);
+    }
+    acc.a0 = gl2_add(acc.a0, gl2_from((gl_t)part[0]));
+    return e2e_add(acc, (e2e_t){gl2_from(gamma.a0), gl2_from(gamma.a1)});
+}
+
+/* periodic values of the row (trace domain) */
+static void periodic_at_row(const table_def_t *d, size_t row, gl_t *per) {
+    for (uint32_t pc = 0; pc < d->n_per; pc++) per[pc] = d->periodic[(size_t)pc * d->period + row % d->period];
+}
+
+/* first-round trace of the range table: how often each value is looked up by the other tables */
+#define HIST_SIZE ((1u << 16) + (1u << 11) + (1u << 8))
+static int count_lookups(const circuit_def_t *c, trace_t tr[TMX_N_TABLES], uint64_t *hist) {
+    int bad = 0;
+    for (int ti = 0; ti < TMX_N_TABLES; ti++) {
+        const table_def_t *d = &c->t[ti];
+        if (!d->present || ti == TMX_T_RANGE) continue;
+        const size_t n = tr[ti].n_rows;
+#pragma omp parallel
+        {
+            gl_t *v = (gl_t *)malloc((d->n_nodes ? d->n_nodes : 1) * sizeof(gl_t));
+            gl_t *loc = (gl_t *)malloc(d->n_main * sizeof(gl_t)), *nxt = (gl_t *)malloc(d->n_main * sizeof(gl_t));
+            gl_t *k = (gl_t *)malloc((d->n_const ? d->n_const : 1) * sizeof(gl_t)), per[16];
+            uint64_t *local_hist = (uint64_t *)calloc(HIST_SIZE, sizeof(uint64_t));
+#pragma omp for schedule(static)
+            for (size_t r = 0; r < n; r++) {
+                for (size_t col = 0; col < d->n_main; col++) {
+                    loc[col] = tr[ti].data[col * n + r];
+                    nxt[col] = tr[ti].data[col * n + (r + 1) % n];
+                }
+                for (size_t col = 0; col < d->n_const; col++) k[col] = d->constants[col * n + r];
+                periodic_at_row(d, r, per);
+                circuit_eval_b(d, d->bus_mask, loc, nxt, k, per, v);
+                for (size_t p = 0; p < d->prog_len;) {
+                    const uint64_t kind = d->prog[p++];
+                    if (kind == 0) { p++; continue; }
+                    for (uint64_t part = 0; part < kind; part++) {
+                        const uint64_t *it = d->prog + p;
+                        p += 3 + it[2];
+                        if (v[it[1]] != GL_P - 1) continue;
+                        size_t base, lim;
+                        if (it[0] == BUS_R16) { base = 0; lim = 1u << 16; }
+                        else if (it[0] == BUS_R11) { base = 1u << 16; lim = 1u << 11; }
+                        else if (it[0] == BUS_R8) { base = (1u << 16) + (1u << 11); lim = 1u << 8; }
+                        else continue;
+                        const gl_t val = v[it[3]];
+                        if (val >= lim) {
+#pragma omp atomic write
+                            bad = 1;
+                        } else
+                            local_hist[base + val]++;
+                    }
+                }
+            }
+#pragma omp critical
+            for (size_t i = 0; i < HIST_SIZE; i++) hist[i] += local_hist[i];
+            free(v); free(loc); free(nxt); free(k); free(local_hist);
         }
     }
-    gl_t *qv = (gl_t *)malloc((size_t)NUM_CHALLENGES * m * sizeof(gl_t)); /* natural order */
-    const gl_t gn = gl_pow(GL_GENERATOR, n);
-    const gl_t zh_inv[2] = {gl_inv(gl_sub(gn, 1)), gl_inv(gl_sub(gl_neg(gn), 1))};
+    return bad;
+}
+
+/* second-round trace of one table: helper columns of its bus items and the running sum; returns the table's total */
+static gl2_t build_aux(const table_def_t *d, const trace_t *tr, gl2_t beta, gl2_t gamma, gl_t *aux /* [2 (H + 1)][n] */) {
+    const size_t n = tr->n_rows, H = d->n_helpers;
+    gl2_t *rowsum = (gl2_t *)malloc(n * sizeof(gl2_t));
 #pragma omp parallel
     {
-        gl_t *loc = (gl_t *)malloc(C * sizeof(gl_t)), *nxt = (gl_t *)malloc(C * sizeof(gl_t));
-        gl_t per[16];
+        gl_t *v = (gl_t *)malloc((d->n_nodes ? d->n_nodes : 1) * sizeof(gl_t));
+        gl_t *loc = (gl_t *)malloc(d->n_main * sizeof(gl_t)), *nxt = (gl_t *)malloc(d->n_main * sizeof(gl_t));
+        gl_t *k = (gl_t *)malloc((d->n_const ? d->n_const : 1) * sizeof(gl_t)), per[16];
+#pragma omp for schedule(static)
+        for (size_t r = 0; r < n; r++) {
+            for (size_t col = 0; col < d->n_main; col++) {
+                loc[col] = tr->data[col * n + r];
+                nxt[col] = tr->data[col * n + (r + 1) % n];
+            }
+            for (size_t col = 0; col < d->n_const; col++) k[col] = d->constants[col * n + r];
+            periodic_at_row(d, r, per);
+            circuit_eval_b(d, d->bus_mask, loc, nxt, k, per, v);
+            gl2_t sum = gl2_from(0);
+            size_t h = 0;
+            for (size_t p = 0; p < d->prog_len;) {
+                const uint64_t kind = d->prog[p++];
+                if (kind == 0) { p++; continue; }
+                gl2_t val;
+                if (kind == 1) {
+                    const uint64_t *a = d->prog + p;
+                    p += 3 + a[2];
+                    const gl_t m = v[a[1]];
+                    val = m ? gl2_scale(gl2_inv(bus_fingerprint_b(a, v, beta, gamma)), m) : gl2_from(0);
+                } else {
+                    const uint64_t *a = d->prog + p;
+                    p += 3 + a[2];
+                    const uint64_t *b = d->prog + p;
+                    p += 3 + b[2];
+                    const gl_t ma = v[a[1]], mb = v[b[1]];
+                    if (!ma && !mb)
+                        val = gl2_from(0);
+                    else {
+                        const gl2_t fa = bus_fingerprint_b(a, v, beta, gamma), fb = bus_fingerprint_b(b, v, beta, gamma);
+                        val = gl2_mul(gl2_add(gl2_scale(fb, ma), gl2_scale(fa, mb)), gl2_inv(gl2_mul(fa, fb)));
+                    }
+                }
+                aux[(2 * h) * n + r] = val.a0;
+                aux[(2 * h + 1) * n + r] = val.a1;
+                sum = gl2_add(sum, val);
+                h++;
+            }
+            rowsum[r] = sum;
+        }
+        free(v); free(loc); free(nxt); free(k);
+    }
+    gl2_t total = gl2_from(0);
+    for (size_t r = 0; r < n; r++) total = gl2_add(total, rowsum[r]);
+    /* Z(0) = 0, Z(r + 1) = Z(r) + rowsum(r) - total / n: closes up cyclically */
+    const gl2_t step = gl2_scale(total, gl_inv((gl_t)n));
+    gl2_t z = gl2_from(0);
+    for (size_t r = 0; r < n; r++) {
+        aux[(2 * H) * n + r] = z.a0;
+        aux[(2 * H + 1) * n + r] = z.a1;
+        z = gl2_sub(gl2_add(z, rowsum[r]), step);
+    }
+    free(rowsum);
+    return total;
+}
+
+/* folds the constraints of one evaluation point (base field): table constraints, helper constraints, running sum */
+static void fold_constraints_b(const table_def_t *d, const gl_t *v, const gl_t *aux_l, const gl_t *aux_n, gl2_t beta, gl2_t gamma,
+                               gl2_t s_over_n, const gl_t alpha[NUM_CHALLENGES], gl_t acc[NUM_CHALLENGES]) {
+#define EMIT(x)                                                                              \
+    do {                                                                                     \
+        const gl_t _c = (x);                                                                 \
+        for (int _i = 0; _i < NUM_CHALLENGES; _i++) acc[_i] = gl_add(gl_mul(acc[_i], alpha[_i]), _c); \
+    } while (0)
+    for (int i = 0; i < NUM_CHALLENGES; i++) acc[i] = 0;
+    gl2_t sum = gl2_from(0);
+    size_t h = 0;
+    for (size_t p = 0; p < d->prog_len;) {
+        const uint64_t kind = d->prog[p++];
+        if (kind == 0) {
+            EMIT(v[d->prog[p++]]);
+            continue;
+        }
+        const gl2_t H = gl2_make(aux_l[2 * h], aux_l[2 * h + 1]);
+        h++;
+        sum = gl2_add(sum, H);
+        gl2_t c;
+        if (kind == 1) {
+            const uint64_t *a = d->prog + p;
+            p += 3 + a[2];
+            c = gl2_mul(H, bus_fingerprint_b(a, v, beta, gamma));
+            c.a0 = gl_sub(c.a0, v[a[1]]);
+        } else {
+            const uint64_t *a = d->prog + p;
+            p += 3 + a[2];
+            const uint64_t *b = d->prog + p;
+            p += 3 + b[2];
+            const gl2_t fa = bus_fingerprint_b(a, v, beta, gamma), fb = bus_fingerprint_b(b, v, beta, gamma);
+            c = gl2_sub(gl2_mul(H, gl2_mul(fa, fb)), gl2_add(gl2_scale(fb, v[a[1]]), gl2_scale(fa, v[b[1]])));
+        }
+        EMIT(c.a0);
+        EMIT(c.a1);
+    }
+    const gl2_t z = gl2_make(aux_l[2 * h], aux_l[2 * h + 1]), zn = gl2_make(aux_n[2 * h], aux_n[2 * h + 1]);
+    const gl2_t c = gl2_add(gl2_sub(gl2_sub(zn, z), sum), s_over_n);
+    EMIT(c.a0);
+    EMIT(c.a1);
+#undef EMIT
+}
+
+static void fold_constraints_e(const table_def_t *d, const gl2_t *v, const gl2_t *aux_l, const gl2_t *aux_n, gl2_t beta, gl2_t gamma,
+                               gl2_t s_over_n, const gl_t alpha[NUM_CHALLENGES], gl2_t acc[NUM_CHALLENGES]) {
+#define EMIT(x)                                                                                              \
+    do {                                                                                                     \
+        const gl2_t _c = (x);                                                                                \
+        for (int _i = 0; _i < NUM_CHALLENGES; _i++) acc[_i] = gl2_add(gl2_scale(acc[_i], alpha[_i]), _c);    \
+    } while (0)
+    for (int i = 0; i < NUM_CHALLENGES; i++) acc[i] = gl2_from(0);
+    e2e_t sum = {gl2_from(0), gl2_from(0)};
+    size_t h = 0;
+    for (size_t p = 0; p < d->prog_len;) {
+        const uint64_t kind = d->prog[p++];
+        if (kind == 0) {
+            EMIT(v[d->prog[p++]]);
+            continue;
+        }
+        const e2e_t H = {aux_l[2 * h], aux_l[2 * h + 1]};
+        h++;
+        sum = e2e_add(sum, H);
+        e2e_t c;
+        if (kind == 1) {
+            const uint64_t *a = d->prog + p;
+            p += 3 + a[2];
+            c = e2e_mul(H, bus_fingerprint_e(a, v, beta, gamma));
+            c.a0 = gl2_sub(c.a0, v[a[1]]);
+        } else {
+            const uint64_t *a = d->prog + p;
+            p += 3 + a[2];
+            const uint64_t *b = d->prog + p;
+            p += 3 + b[2];
+            const e2e_t fa = bus_fingerprint_e(a, v, beta, gamma), fb = bus_fingerprint_e(b, v, beta, gamma);
+            c = e2e_sub(e2e_mul(H, e2e_mul(fa, fb)), e2e_add(e2e_scale(fb, v[a[1]]), e2e_scale(fa, v[b[1]])));
+        }
+        EMIT(c.a0);
+        EMIT(c.a1);
+    }
+    const e2e_t z = {aux_l[2 * h], aux_l[2 * h + 1]}, zn = {aux_n[2 * h], aux_n[2 * h + 1]};
+    e2e_t c = e2e_sub(e2e_sub(zn, z), sum);
+    c.a0 = gl2_add(c.a0, gl2_from(s_over_n.a0));
+    c.a1 = gl2_add(c.a1, gl2_from(s_over_n.a1));
+    EMIT(c.a0);
+    EMIT(c.a1);
+#undef EMIT
+}
+
+/* ------------------------------------------------------------------ prover */
+typedef struct {
+    const table_def_t *d;
+    size_t n, m;
+    unsigned k, km;
+    size_t Kc, C, A;
+    gl_t *lde_k, *coef_k, *lde_m, *coef_m, *lde_a, *coef_a;
+    merkle_tree_t tree_k, tree_m, tree_a;
+    gl2_t total;
+} ptable_t;
+
+static void commit_batch(const gl_t *values, size_t cols, size_t n, gl_t **lde, gl_t **coef, merkle_tree_t *tree) {
+    const size_t m = n << RATE_BITS;
+    *lde = (gl_t *)malloc((cols ? cols : 1) * m * sizeof(gl_t));
+    *coef = (gl_t *)malloc((cols ? cols : 1) * n * sizeof(gl_t));
+    memset(tree, 0, sizeof *tree);
+    if (!cols) return;
+    ntt_lde_batch(values, cols, n, RATE_BITS, *lde, *coef);
+    commit_columns(tree, *lde, cols, m, CAP_HEIGHT);
+}
+
+/* values on the LDE coset (natural index mod 2P) of the periodic columns, [n_per][2P] */
+static gl_t *periodic_lde(const table_def_t *d, size_t n) {
+    const size_t P = d->period;
+    gl_t *pertab = (gl_t *)calloc((size_t)(d->n_per ? d->n_per : 1) * 2 * P, sizeof(gl_t));
+    const gl_t shift = gl_pow(GL_GENERATOR, n / P);
+    for (uint32_t pc = 0; pc < d->n_per; pc++) {
+        gl_t *t = pertab + (size_t)pc * 2 * P;
+        memcpy(t, d->periodic + (size_t)pc * P, P * sizeof(gl_t));
+        ntt_inverse(t, P);
+        memset(t + P, 0, P * sizeof(gl_t));
+        ntt_coset_forward(t, 2 * P, shift);
+    }
+    return pertab;
+}
+
+/* quotient values on the LDE coset, natural order, [NUM_CHALLENGES][m] */
+static void quotient_values(const ptable_t *pt, gl2_t beta, gl2_t gamma, const gl_t alpha[NUM_CHALLENGES], gl_t *qv) {
+    const table_def_t *d = pt->d;
+    const size_t n = pt->n, m = pt->m, P = d->period;
+    gl_t *pertab = periodic_lde(d, n);
+    const gl_t gn = gl_pow(GL_GENERATOR, n);
+    const gl_t zh_inv[2] = {gl_inv(gl_sub(gn, 1)), gl_inv(gl_sub(gl_neg(gn), 1))};
+    const gl2_t s_over_n = gl2_scale(pt->total, gl_inv((gl_t)n));
+#pragma omp parallel
+    {
+        gl_t *v = (gl_t *)malloc((d->n_nodes ? d->n_nodes : 1) * sizeof(gl_t));
+        gl_t *loc = (gl_t *)malloc(pt->C * sizeof(gl_t)), *nxt = (gl_t *)malloc(pt->C * sizeof(gl_t));
+        gl_t *k = (gl_t *)malloc((pt->Kc ? pt->Kc : 1) * sizeof(gl_t)), per[16];
+        gl_t *al = (gl_t *)malloc(pt->A * sizeof(gl_t)), *an = (gl_t *)malloc(pt->A * sizeof(gl_t));
 #pragma omp for schedule(static)
         for (size_t j = 0; j < m; j++) {
-            size_t p = tmx_bitrev(j, km), p2 = tmx_bitrev((j + (1u << RATE_BITS)) & (m - 1), km);
-            for (size_t c = 0; c < C; c++) {
-                loc[c] = lde[c * m + p];
-                nxt[c] = lde[c * m + p2];
+            const size_t p = tmx_bitrev(j, pt->km), p2 = tmx_bitrev((j + (1u << RATE_BITS)) & (m - 1), pt->km);
+            for (size_t c = 0; c < pt->C; c++) {
+                loc[c] = pt->lde_m[c * m + p];
+                nxt[c] = pt->lde_m[c * m + p2];
             }
-            for (int pc = 0; pc < nper; pc++) per[pc] = pertab[(size_t)pc * 2 * P + (j & (2 * P - 1))];
-            acc_b_t a;
-            for (int i = 0; i < NUM_CHALLENGES; i++) {
-                a.acc[i] = 0;
-                a.alpha[i] = alpha[i];
+            for (size_t c = 0; c < pt->Kc; c++) k[c] = pt->lde_k[c * m + p];
+            for (size_t c = 0; c < pt->A; c++) {
+                al[c] = pt->lde_a[c * m + p];
+                an[c] = pt->lde_a[c * m + p2];
             }
-            air_eval_b(table, loc, nxt, per, &a);
-            for (int i = 0; i < NUM_CHALLENGES; i++) qv[(size_t)i * m + j] = gl_mul(a.acc[i], zh_inv[j & 1]);
+            for (uint32_t pc = 0; pc < d->n_per; pc++) per[pc] = pertab[(size_t)pc * 2 * P + (j & (2 * P - 1))];
+            circuit_eval_b(d, NULL, loc, nxt, k, per, v);
+            gl_t acc[NUM_CHALLENGES];
+            fold_constraints_b(d, v, al, an, beta, gamma, s_over_n, alpha, acc);
+            for (int i = 0; i < NUM_CHALLENGES; i++) qv[(size_t)i * m + j] = gl_mul(acc[i], zh_inv[j & 1]);
         }
-        free(loc);
-        free(nxt);
+        free(v); free(loc); free(nxt); free(k); free(al); free(an);
     }
+    free(pertab);
+}
+
+/* everything of one table after both commitment rounds */
+static void prove_table_tail(ptable_t *pt, gl2_t beta, gl2_t gamma, challenger_t *ch, wbuf_t *w) {
+    t_last = omp_get_wtime();
+    const size_t n = pt->n, m = pt->m, CT = pt->Kc + pt->C + pt->A;
+    const unsigned k = pt->k, km = pt->km;
+    gl_t alpha[NUM_CHALLENGES];
+    for (int i = 0; i < NUM_CHALLENGES; i++) alpha[i] = challenger_get(ch);
+    gl_t *qv = (gl_t *)malloc((size_t)NUM_CHALLENGES * m * sizeof(gl_t)); /* natural order */
+    quotient_values(pt, beta, gamma, alpha, qv);
     tick("quotient eval");
     /* quotient chunks: coefficients of degree < 2n split in two */
     gl_t *qcoef = (gl_t *)malloc((size_t)N_QUOT * n * sizeof(gl_t));
@@ -388,43 +521,48 @@ static void prove_table(int table, const trace_t *tr, challenger_t *ch, wbuf_t *
     }
     merkle_tree_t tree_q;
     commit_columns(&tree_q, qlde, N_QUOT, m, CAP_HEIGHT);
+    const size_t cap_n = (size_t)1 << tree_q.cap_height;
     wb_push_many(w, tree_q.cap, 4 * cap_n);
     observe_cap(ch, tree_q.cap, cap_n);
     tick("quotient commit");
-    /* 4. openings */
+    /* polynomials in opening order: constant, first-round, second-round columns, then the quotient chunks */
+    const gl_t **poly = (const gl_t **)malloc((CT + N_QUOT) * sizeof(gl_t *));
+    {
+        size_t o = 0;
+        for (size_t c = 0; c < pt->Kc; c++) poly[o++] = pt->coef_k + c * n;
+        for (size_t c = 0; c < pt->C; c++) poly[o++] = pt->coef_m + c * n;
+        for (size_t c = 0; c < pt->A; c++) poly[o++] = pt->coef_a + c * n;
+        for (int q = 0; q < N_QUOT; q++) poly[o++] = qcoef + (size_t)q * n;
+    }
+    /* openings */
     const gl2_t zeta = challenger_get_ext(ch);
     const gl2_t zeta_next = gl2_scale(zeta, gl_root_of_unity(k));
-    gl2_t *op_local = (gl2_t *)malloc(C * sizeof(gl2_t)), *op_next = (gl2_t *)malloc(C * sizeof(gl2_t));
-    gl2_t op_quot[N_QUOT];
+    gl2_t *op_local = (gl2_t *)malloc((CT + N_QUOT) * sizeof(gl2_t)), *op_next = (gl2_t *)malloc(CT * sizeof(gl2_t));
 #pragma omp parallel for schedule(dynamic, 8)
-    for (size_t c = 0; c < C; c++) {
-        op_local[c] = base_poly_eval(coeffs + c * n, n, zeta);
-        op_next[c] = base_poly_eval(coeffs + c * n, n, zeta_next);
+    for (size_t c = 0; c < CT + N_QUOT; c++) {
+        op_local[c] = base_poly_eval(poly[c], n, zeta);
+        if (c < CT) op_next[c] = base_poly_eval(poly[c], n, zeta_next);
     }
-    for (int q = 0; q < N_QUOT; q++) op_quot[q] = base_poly_eval(qcoef + (size_t)q * n, n, zeta);
-    for (size_t c = 0; c < C; c++) wb_push_ext(w, op_local[c]);
-    for (size_t c = 0; c < C; c++) wb_push_ext(w, op_next[c]);
-    for (int q = 0; q < N_QUOT; q++) wb_push_ext(w, op_quot[q]);
-    for (size_t c = 0; c < C; c++) observe_ext(ch, op_local[c]);
-    for (int q = 0; q < N_QUOT; q++) observe_ext(ch, op_quot[q]);
-    for (size_t c = 0; c < C; c++) observe_ext(ch, op_next[c]);
+    for (size_t c = 0; c < CT; c++) wb_push_ext(w, op_local[c]);
+    for (size_t c = 0; c < CT; c++) wb_push_ext(w, op_next[c]);
+    for (int q = 0; q < N_QUOT; q++) wb_push_ext(w, op_local[CT + q]);
+    for (size_t c = 0; c < CT; c++) observe_ext(ch, op_local[c]);
+    for (int q = 0; q < N_QUOT; q++) observe_ext(ch, op_local[CT + q]);
+    for (size_t c = 0; c < CT; c++) observe_ext(ch, op_next[c]);
     tick("openings");
-    /* 5. FRI batch polynomial, coefficient space (plonky2 fri/oracle.rs prove_openings) */
+    /* FRI batch polynomial, coefficient space (plonky2 fri/oracle.rs prove_openings) */
     const gl2_t fa = challenger_get_ext(ch);
     gl2_t *final_poly = (gl2_t *)calloc(m, sizeof(gl2_t));
     {
         gl2_t *comp = (gl2_t *)malloc(n * sizeof(gl2_t));
         for (int batch = 0; batch < 2; batch++) {
-            const size_t npoly = batch == 0 ? C + N_QUOT : C;
+            const size_t npoly = batch == 0 ? CT + N_QUOT : CT;
             const gl2_t z = batch == 0 ? zeta : zeta_next;
             /* composition = sum_j alpha^j f_j (Horner from the last polynomial) */
 #pragma omp parallel for schedule(static)
             for (size_t i = 0; i < n; i++) {
                 gl2_t acc = gl2_from(0);
-                for (size_t j = npoly; j-- > 0;) {
-                    gl_t v = j < C ? coeffs[j * n + i] : qcoef[(j - C) * n + i];
-                    acc = gl2_add(gl2_mul(acc, fa), gl2_from(v));
-                }
+                for (size_t j = npoly; j-- > 0;) acc = gl2_add(gl2_mul(acc, fa), gl2_from(poly[j][i]));
                 comp[i] = acc;
             }
             /* divide by (X - z), drop the remainder: b_{i-1} = a_i + z * b_i */
@@ -441,7 +579,7 @@ static void prove_table(int table, const trace_t *tr, challenger_t *ch, wbuf_t *
         free(comp);
     }
     tick("fri batch poly");
-    /* 6. FRI commit phase (fri_committed_trees) */
+    /* FRI commit phase (fri_committed_trees) */
     const size_t n_layers = fri_num_layers(k);
     merkle_tree_t *layer_trees = (merkle_tree_t *)calloc(n_layers ? n_layers : 1, sizeof(merkle_tree_t));
     gl_t **layer_leaves = (gl_t **)calloc(n_layers ? n_layers : 1, sizeof(gl_t *));
@@ -464,11 +602,11 @@ static void prove_table(int table, const trace_t *tr, challenger_t *ch, wbuf_t *
         const size_t lcap = (size_t)1 << layer_trees[l].cap_height;
         wb_push_many(w, layer_trees[l].cap, 4 * lcap);
         observe_cap(ch, layer_trees[l].cap, lcap);
-        const gl2_t beta = challenger_get_ext(ch);
+        const gl2_t fbeta = challenger_get_ext(ch);
         size_t new_len = cur_len >> ARITY_BITS;
         for (size_t i = 0; i < new_len; i++) {
             gl2_t acc = gl2_from(0);
-            for (int j = 15; j >= 0; j--) acc = gl2_add(gl2_mul(acc, beta), cf[16 * i + j]);
+            for (int j = 15; j >= 0; j--) acc = gl2_add(gl2_mul(acc, fbeta), cf[16 * i + j]);
             cf[i] = acc;
         }
         cur_len = new_len;
@@ -483,17 +621,23 @@ static void prove_table(int table, const trace_t *tr, challenger_t *ch, wbuf_t *
         observe_ext(ch, cf[i]);
     }
     tick("fri commit phase");
-    /* 7. proof of work: minimum witness */
+    /* proof of work: minimum witness */
     gl_t pow_witness = challenger_pow_grind(ch, POW_BITS);
     challenger_observe(ch, pow_witness);
     (void)challenger_get(ch);
     wb_push(w, pow_witness);
     tick("pow");
-    /* 8. queries */
+    /* queries */
     for (int qi = 0; qi < NUM_QUERIES; qi++) {
         size_t x = (size_t)(challenger_get(ch) % m);
-        for (size_t c = 0; c < C; c++) wb_push(w, lde[c * m + x]);
-        merkle_open(w, &tree_t, x);
+        if (pt->Kc) {
+            for (size_t c = 0; c < pt->Kc; c++) wb_push(w, pt->lde_k[c * m + x]);
+            merkle_open(w, &pt->tree_k, x);
+        }
+        for (size_t c = 0; c < pt->C; c++) wb_push(w, pt->lde_m[c * m + x]);
+        merkle_open(w, &pt->tree_m, x);
+        for (size_t c = 0; c < pt->A; c++) wb_push(w, pt->lde_a[c * m + x]);
+        merkle_open(w, &pt->tree_a, x);
         for (int q = 0; q < N_QUOT; q++) wb_push(w, qlde[(size_t)q * m + x]);
         merkle_open(w, &tree_q, x);
         for (size_t l = 0; l < n_layers; l++) {
@@ -508,22 +652,25 @@ static void prove_table(int table, const trace_t *tr, challenger_t *ch, wbuf_t *
         free(layer_leaves[l]);
     }
     free(layer_trees); free(layer_leaves); free(vals); free(final_poly);
-    free(op_local); free(op_next); free(qlde); free(qcoef); free(qv); free(pertab);
-    merkle_free(&tree_t); merkle_free(&tree_q);
-    free(lde); free(coeffs);
+    free(op_local); free(op_next); free(qlde); free(qcoef); free(qv); free(poly);
+    merkle_free(&tree_q);
 }
 
-static void transcript_init(challenger_t *ch, uint32_t kind, uint32_t n_max, const uint8_t *chain_id, size_t chain_id_len,
-                            uint64_t skip_max, const uint8_t *input, size_t input_len, const uint8_t out32[32]) {
-    gl_t dg[4], pub[128], ph[4];
-    circuit_digest(kind, n_max, chain_id, chain_id_len, skip_max, dg);
+static void transcript_init(challenger_t *ch, const circuit_def_t *c, const uint8_t *input, size_t input_len, const uint8_t out32[32]) {
+    gl_t pub[128], ph[4];
     challenger_init(ch);
-    challenger_observe_many(ch, dg, 4);
+    challenger_observe_many(ch, c->digest, 4);
     size_t k = 0;
-    for (size_t i = 0; i < input_len; i++) pub[k++] = input[i];
+    for (size_t i = 0; i < input_len && k < 96; i++) pub[k++] = input[i];
     for (size_t i = 0; i < 32; i++) pub[k++] = out32[i];
     poseidon_hash_no_pad(pub, k, ph);
     challenger_observe_many(ch, ph, 4);
+}
+
+/* the verifier's own bus terms (public input / output bindings); none until the logic table carries the links */
+static gl2_t public_terms(const circuit_def_t *c, const uint8_t *input, const uint8_t out32[32], gl2_t beta, gl2_t gamma) {
+    (void)c; (void)input; (void)out32; (void)beta; (void)gamma;
+    return gl2_from(0);
 }
 
 /* debug / test hook: the NEXT tm_prove() on this thread adds one to cell (col, row) of `table` after witness generation,
@@ -535,38 +682,157 @@ void tm_debug_corrupt_next_proof(int table, size_t col, size_t row) {
     g_corrupt.col = col;
     g_corrupt.row = row;
 }
+/* debug / test hook: the NEXT tm_prove() on this thread skips the statement pre-check (verify_skip / verify_step on the
+ * inputs), i.e. it plays a prover that tries to prove a false statement with otherwise honest tables */
+static _Thread_local int g_skip_precheck;
+void tm_debug_skip_precheck_next_proof(void) { g_skip_precheck = 1; }
 
-/* proof = header (8 u64), then the three table proofs.  Returns a TMX_CHECK id (0 = ok). */
-int tm_prove(const uint8_t *input, size_t input_len, const uint8_t *blob, size_t blob_len, const uint8_t *chain_id,
-             size_t chain_id_len, uint64_t skip_max, uint64_t **proof_out, size_t *proof_len, uint8_t out32[32]) {
-    int rc = tm_verify_circuit(input, input_len, blob, blob_len, chain_id, chain_id_len, skip_max, out32);
+void *tm_circuit_load(const uint64_t *words, size_t n_words, int *rc) {
+    circuit_def_t *c = (circuit_def_t *)malloc(sizeof *c);
+    *rc = circuit_parse(words, n_words, c);
+    if (*rc) {
+        free(c);
+        return NULL;
+    }
+    return c;
+}
+void tm_circuit_unload(void *c) {
+    if (!c) return;
+    circuit_free((circuit_def_t *)c);
+    free(c);
+}
+void tm_circuit_digest(const void *c, uint64_t out[4]) { memcpy(out, ((const circuit_def_t *)c)->digest, 32); }
+
+/* all first-round traces of one proof: the three witness tables, the logic table (given by the caller) and the range
+ * table (counted here).  Returns a TMX_CHECK id. */
+static int build_all_traces(const circuit_def_t *c, const uint8_t *blob, size_t blob_len, const uint64_t *logic_trace,
+                            trace_t tr[TMX_N_TABLES]) {
+    memset(tr, 0, TMX_N_TABLES * sizeof(trace_t));
+    int rc = tm_build_traces(blob, blob_len, tr);
     if (rc) return rc;
+    for (int t = 0; t < 3; t++)
+        if (!c->t[t].present || tr[t].n_rows != ((size_t)1 << c->t[t].log_n) || tr[t].n_cols != c->t[t].n_main) return TMX_CHECK_INPUT;
+    if (c->t[TMX_T_LOGIC].present) {
+        const table_def_t *d = &c->t[TMX_T_LOGIC];
+        if (!logic_trace) return TMX_CHECK_INPUT;
+        tr[TMX_T_LOGIC].n_rows = (size_t)1 << d->log_n;
+        tr[TMX_T_LOGIC].n_cols = d->n_main;
+        const size_t cells = tr[TMX_T_LOGIC].n_rows * d->n_main;
+        tr[TMX_T_LOGIC].data = (uint64_t *)malloc(cells * sizeof(uint64_t));
+        memcpy(tr[TMX_T_LOGIC].data, logic_trace, cells * sizeof(uint64_t));
+    }
+    return 0;
+}
+static int build_range_trace(const circuit_def_t *c, trace_t tr[TMX_N_TABLES]) {
+    const table_def_t *d = &c->t[TMX_T_RANGE];
+    if (!d->present) return 0;
+    const size_t n = (size_t)1 << d->log_n;
+    uint64_t *hist = (uint64_t *)calloc(HIST_SIZE, sizeof(uint64_t));
+    const int bad = count_lookups(c, tr, hist);
+    tr[TMX_T_RANGE].n_rows = n;
+    tr[TMX_T_RANGE].n_cols = RG_COLS;
+    tr[TMX_T_RANGE].data = (uint64_t *)calloc(n * RG_COLS, sizeof(uint64_t));
+    for (size_t i = 0; i < (1u << 16) && i < n; i++) tr[TMX_T_RANGE].data[RG_M16 * n + i] = hist[i];
+    for (size_t i = 0; i < (1u << 11); i++) tr[TMX_T_RANGE].data[RG_M11 * n + i] = hist[(1u << 16) + i];
+    for (size_t i = 0; i < (1u << 8); i++) tr[TMX_T_RANGE].data[RG_M8 * n + i] = hist[(1u << 16) + (1u << 11) + i];
+    free(hist);
+    return bad;
+}
+static void free_all_traces(trace_t tr[TMX_N_TABLES]) {
+    for (int t = 0; t < TMX_N_TABLES; t++) {
+        free(tr[t].data);
+        tr[t].data = NULL;
+    }
+}
+
+/* proof = header (8 u64), round-1 caps, round-2 caps and totals, then the per-table tails.  Returns a TMX_CHECK id (0 = ok). */
+int tm_prove(const void *circuit, const uint8_t *input, size_t input_len, const uint8_t *blob, size_t blob_len,
+             const uint64_t *logic_trace, uint64_t **proof_out, size_t *proof_len, uint8_t out32[32]) {
+    const circuit_def_t *c = (const circuit_def_t *)circuit;
     const tmx_offchain_head *h = (const tmx_offchain_head *)blob;
-    trace_t tr[3];
-    rc = tm_build_traces(blob, blob_len, tr);
+    if (blob_len < sizeof *h || h->kind != c->kind || h->n_max != c->n_max) return TMX_CHECK_INPUT;
+    int rc = tm_verify_circuit(input, input_len, blob, blob_len, c->chain_id, c->chain_len, c->skip_max, out32);
+    if (g_skip_precheck) {
+        g_skip_precheck = 0;
+        if (rc) memcpy(out32, h->header, 32);
+        rc = 0;
+    }
     if (rc) return rc;
+    trace_t tr[TMX_N_TABLES];
+    rc = build_all_traces(c, blob, blob_len, logic_trace, tr);
+    if (rc) {
+        free_all_traces(tr);
+        return rc;
+    }
+    /* a value outside its range table cannot be proved: the honest prover stops, a cheating one would go on with wrong
+     * multiplicities and be rejected by the bus balance (tm_debug hooks exercise that path) */
+    const int range_bad = build_range_trace(c, tr);
+    (void)range_bad;
     if (g_corrupt.active) {
         trace_t *t = &tr[g_corrupt.table];
-        uint64_t *cell = &t->data[(g_corrupt.col % t->n_cols) * t->n_rows + g_corrupt.row % t->n_rows];
-        *cell = gl_add(*cell, 1);
+        if (t->data) {
+            uint64_t *cell = &t->data[(g_corrupt.col % t->n_cols) * t->n_rows + g_corrupt.row % t->n_rows];
+            *cell = gl_add(*cell, 1);
+        }
         g_corrupt.active = 0;
     }
     challenger_t ch;
-    transcript_init(&ch, h->kind, h->n_max, chain_id, chain_id_len, skip_max, input, input_len, out32);
-    g_kind = h->kind;
-    g_n_max = h->n_max;
+    transcript_init(&ch, c, input, input_len, out32);
     wbuf_t w = {0};
     wb_push(&w, PROOF_MAGIC);
     wb_push(&w, h->kind);
     wb_push(&w, h->n_max);
-    wb_push(&w, N_TABLES);
+    wb_push(&w, TMX_N_TABLES);
     for (int i = 0; i < 4; i++) {
         gl_t x = 0;
         for (int j = 0; j < 8; j++) x |= (gl_t)out32[8 * i + j] << (8 * j);
         wb_push(&w, x);
     }
-    for (int t = 0; t < N_TABLES; t++) prove_table(t, &tr[t], &ch, &w);
-    tm_free_traces(tr);
+    ptable_t pt[TMX_N_TABLES];
+    memset(pt, 0, sizeof pt);
+    t_last = omp_get_wtime();
+    /* round 1 */
+    for (int t = 0; t < TMX_N_TABLES; t++) {
+        const table_def_t *d = &c->t[t];
+        if (!d->present) continue;
+        ptable_t *p = &pt[t];
+        p->d = d;
+        p->n = (size_t)1 << d->log_n;
+        p->m = p->n << RATE_BITS;
+        p->k = d->log_n;
+        p->km = p->k + RATE_BITS;
+        p->Kc = d->n_const; p->C = d->n_main; p->A = 2 * ((size_t)d->n_helpers + 1);
+        commit_batch(d->constants, p->Kc, p->n, &p->lde_k, &p->coef_k, &p->tree_k);
+        commit_batch(tr[t].data, p->C, p->n, &p->lde_m, &p->coef_m, &p->tree_m);
+        const size_t cap_n = (size_t)1 << p->tree_m.cap_height;
+        wb_push_many(&w, p->tree_m.cap, 4 * cap_n);
+        observe_cap(&ch, p->tree_m.cap, cap_n);
+    }
+    tick("round 1 commitments");
+    const gl2_t beta = challenger_get_ext(&ch), gamma = challenger_get_ext(&ch);
+    /* round 2 */
+    for (int t = 0; t < TMX_N_TABLES; t++) {
+        if (!c->t[t].present) continue;
+        ptable_t *p = &pt[t];
+        gl_t *aux = (gl_t *)malloc(p->A * p->n * sizeof(gl_t));
+        p->total = build_aux(p->d, &tr[t], beta, gamma, aux);
+        commit_batch(aux, p->A, p->n, &p->lde_a, &p->coef_a, &p->tree_a);
+        free(aux);
+        const size_t cap_n = (size_t)1 << p->tree_a.cap_height;
+        wb_push_many(&w, p->tree_a.cap, 4 * cap_n);
+        wb_push_ext(&w, p->total);
+        observe_cap(&ch, p->tree_a.cap, cap_n);
+        observe_ext(&ch, p->total);
+    }
+    tick("round 2 commitments");
+    free_all_traces(tr);
+    for (int t = 0; t < TMX_N_TABLES; t++) {
+        if (!c->t[t].present) continue;
+        ptable_t *p = &pt[t];
+        prove_table_tail(p, beta, gamma, &ch, &w);
+        free(p->lde_k); free(p->coef_k); free(p->lde_m); free(p->coef_m); free(p->lde_a); free(p->coef_a);
+        merkle_free(&p->tree_k); merkle_free(&p->tree_m); merkle_free(&p->tree_a);
+    }
     *proof_out = w.v;
     *proof_len = w.n;
     return 0;
@@ -575,14 +841,14 @@ int tm_prove(const uint8_t *input, size_t input_len, const uint8_t *blob, size_t
 void tm_proof_free(uint64_t *p) { free(p); }
 
 /* ------------------------------------------------------------------ verifier */
-static int verify_table(int table, size_t n, rbuf_t *r, challenger_t *ch) {
-    const size_t C = TABLE_COLS[table], m = n << RATE_BITS;
-    const unsigned k = tmx_log2(n), km = k + RATE_BITS;
+static int verify_table_tail(const circuit_def_t *c, int table, const gl_t *cap_m, const gl_t *cap_a, gl2_t beta, gl2_t gamma,
+                             gl2_t total, rbuf_t *r, challenger_t *ch) {
+    const table_def_t *d = &c->t[table];
+    const size_t n = (size_t)1 << d->log_n, m = n << RATE_BITS;
+    const size_t Kc = d->n_const, C = d->n_main, A = 2 * ((size_t)d->n_helpers + 1), CT = Kc + C + A;
+    const unsigned k = d->log_n, km = k + RATE_BITS;
     const unsigned cap_h = km < CAP_HEIGHT ? km : CAP_HEIGHT;
     const size_t cap_n = (size_t)1 << cap_h;
-    const gl_t *cap_t = rb_take(r, 4 * cap_n);
-    if (r->err) return 1;
-    observe_cap(ch, cap_t, cap_n);
     gl_t alpha[NUM_CHALLENGES];
     for (int i = 0; i < NUM_CHALLENGES; i++) alpha[i] = challenger_get(ch);
     const gl_t *cap_q = rb_take(r, 4 * cap_n);
@@ -590,54 +856,43 @@ static int verify_table(int table, size_t n, rbuf_t *r, challenger_t *ch) {
     observe_cap(ch, cap_q, cap_n);
     const gl2_t zeta = challenger_get_ext(ch);
     const gl2_t zeta_next = gl2_scale(zeta, gl_root_of_unity(k));
-    gl2_t *op_local = (gl2_t *)malloc(C * sizeof(gl2_t)), *op_next = (gl2_t *)malloc(C * sizeof(gl2_t));
-    gl2_t op_quot[N_QUOT];
-    for (size_t c = 0; c < C; c++) op_local[c] = rb_get_ext(r);
-    for (size_t c = 0; c < C; c++) op_next[c] = rb_get_ext(r);
-    for (int q = 0; q < N_QUOT; q++) op_quot[q] = rb_get_ext(r);
+    gl2_t *op_local = (gl2_t *)malloc((CT + N_QUOT) * sizeof(gl2_t)), *op_next = (gl2_t *)malloc(CT * sizeof(gl2_t));
+    for (size_t i = 0; i < CT; i++) op_local[i] = rb_get_ext(r);
+    for (size_t i = 0; i < CT; i++) op_next[i] = rb_get_ext(r);
+    for (int q = 0; q < N_QUOT; q++) op_local[CT + q] = rb_get_ext(r);
     int bad = r->err;
-    for (size_t c = 0; c < C && !bad; c++) observe_ext(ch, op_local[c]);
-    for (int q = 0; q < N_QUOT && !bad; q++) observe_ext(ch, op_quot[q]);
-    for (size_t c = 0; c < C && !bad; c++) observe_ext(ch, op_next[c]);
+    for (size_t i = 0; i < CT && !bad; i++) observe_ext(ch, op_local[i]);
+    for (int q = 0; q < N_QUOT && !bad; q++) observe_ext(ch, op_local[CT + q]);
+    for (size_t i = 0; i < CT && !bad; i++) observe_ext(ch, op_next[i]);
     /* constraint identity at zeta */
     if (!bad) {
-        const int nper = TABLE_NPER[table];
-        const size_t P = table_period(table, n);
+        const size_t P = d->period;
         gl2_t per[16];
-        gl2_t y = gl2_pow(zeta, n / P);
+        const gl2_t y = gl2_pow(zeta, n / P);
         gl_t *pat = (gl_t *)malloc(P * sizeof(gl_t));
-        for (int pc = 0; pc < nper; pc++) {
-            for (size_t rr = 0; rr < P; rr++) pat[rr] = periodic_pattern(table, pc, rr);
+        for (uint32_t pc = 0; pc < d->n_per; pc++) {
+            memcpy(pat, d->periodic + (size_t)pc * P, P * sizeof(gl_t));
             ntt_inverse(pat, P);
             per[pc] = base_poly_eval(pat, P, y);
         }
         free(pat);
-        acc_e_t a;
+        gl2_t *v = (gl2_t *)malloc((d->n_nodes ? d->n_nodes : 1) * sizeof(gl2_t));
+        circuit_eval_e(d, op_local + Kc, op_next + Kc, op_local, per, v);
+        gl2_t acc[NUM_CHALLENGES];
+        fold_constraints_e(d, v, op_local + Kc + C, op_next + Kc + C, beta, gamma, gl2_scale(total, gl_inv((gl_t)n)), alpha, acc);
+        free(v);
+        const gl2_t zn = gl2_pow(zeta, n), zh = gl2_sub(zn, gl2_from(1));
         for (int i = 0; i < NUM_CHALLENGES; i++) {
-            a.acc[i] = gl2_from(0);
-            a.alpha[i] = gl2_from(alpha[i]);
-        }
-        air_eval_e(table, op_local, op_next, per, &a);
-        gl2_t zh = gl2_sub(gl2_pow(zeta, n), gl2_from(1));
-        gl2_t zn = gl2_pow(zeta, n);
-        for (int i = 0; i < NUM_CHALLENGES; i++) {
-            gl2_t q = gl2_add(op_quot[QDF * i], gl2_mul(zn, op_quot[QDF * i + 1]));
-            if (!gl2_eq(gl2_mul(q, zh), a.acc[i])) bad = 2;
+            gl2_t q = gl2_add(op_local[CT + QDF * i], gl2_mul(zn, op_local[CT + QDF * i + 1]));
+            if (!gl2_eq(gl2_mul(q, zh), acc[i])) bad = 2;
         }
     }
     /* FRI */
     const gl2_t fa = challenger_get_ext(ch);
-    gl2_t red[2];
+    gl2_t red[2] = {gl2_from(0), gl2_from(0)};
     if (!bad) {
-        for (int batch = 0; batch < 2; batch++) {
-            const size_t npoly = batch == 0 ? C + N_QUOT : C;
-            gl2_t acc = gl2_from(0);
-            for (size_t j = npoly; j-- > 0;) {
-                gl2_t v = batch == 0 ? (j < C ? op_local[j] : op_quot[j - C]) : op_next[j];
-                acc = gl2_add(gl2_mul(acc, fa), v);
-            }
-            red[batch] = acc;
-        }
+        for (size_t j = CT + N_QUOT; j-- > 0;) red[0] = gl2_add(gl2_mul(red[0], fa), op_local[j]);
+        for (size_t j = CT; j-- > 0;) red[1] = gl2_add(gl2_mul(red[1], fa), op_next[j]);
     }
     const size_t n_layers = fri_num_layers(k);
     const gl_t *layer_caps[16];
@@ -653,7 +908,7 @@ static int verify_table(int table, size_t n, rbuf_t *r, challenger_t *ch) {
         betas[l] = challenger_get_ext(ch);
     }
     size_t final_len = (size_t)rb_get(r);
-    if (final_len != ((m >> (ARITY_BITS * n_layers)) >> RATE_BITS)) bad = bad ? bad : 3;
+    if (final_len != ((m >> (ARITY_BITS * n_layers)) >> RATE_BITS) || final_len > 64) bad = bad ? bad : 3;
     gl2_t final_coeffs[64];
     for (size_t i = 0; i < final_len && i < 64 && !bad; i++) {
         final_coeffs[i] = rb_get_ext(r);
@@ -665,29 +920,38 @@ static int verify_table(int table, size_t n, rbuf_t *r, challenger_t *ch) {
         gl_t resp = challenger_get(ch);
         if (POW_BITS && (resp >> (64 - POW_BITS)) != 0) bad = 4;
     }
-    const gl2_t alpha_c = gl2_pow(fa, C);
+    const gl2_t alpha_c = gl2_pow(fa, CT);
+    gl_t *row = (gl_t *)malloc((CT + N_QUOT) * sizeof(gl_t));
     for (int qi = 0; qi < NUM_QUERIES && !bad; qi++) {
         size_t x = (size_t)(challenger_get(ch) % m);
-        const gl_t *row_t = rb_take(r, C);
-        const gl_t *path_t = rb_take(r, 4 * (km - cap_h));
+        const unsigned ns = km - cap_h;
+        const gl_t *row_k = Kc ? rb_take(r, Kc) : NULL;
+        const gl_t *path_k = Kc ? rb_take(r, 4 * ns) : NULL;
+        const gl_t *row_m = rb_take(r, C);
+        const gl_t *path_m = rb_take(r, 4 * ns);
+        const gl_t *row_a = rb_take(r, A);
+        const gl_t *path_a = rb_take(r, 4 * ns);
         const gl_t *row_q = rb_take(r, N_QUOT);
-        const gl_t *path_q = rb_take(r, 4 * (km - cap_h));
+        const gl_t *path_q = rb_take(r, 4 * ns);
         if (r->err) { bad = 1; break; }
-        if (!merkle_verify(row_t, C, x, path_t, km - cap_h, cap_t, cap_h)) { bad = 5; break; }
-        if (!merkle_verify(row_q, N_QUOT, x, path_q, km - cap_h, cap_q, cap_h)) { bad = 5; break; }
+        if (Kc && !merkle_verify(row_k, Kc, x, path_k, ns, d->const_cap, cap_h)) { bad = 5; break; }
+        if (!merkle_verify(row_m, C, x, path_m, ns, cap_m, cap_h)) { bad = 5; break; }
+        if (!merkle_verify(row_a, A, x, path_a, ns, cap_a, cap_h)) { bad = 5; break; }
+        if (!merkle_verify(row_q, N_QUOT, x, path_q, ns, cap_q, cap_h)) { bad = 5; break; }
+        if (Kc) memcpy(row, row_k, Kc * sizeof(gl_t));
+        memcpy(row + Kc, row_m, C * sizeof(gl_t));
+        memcpy(row + Kc + C, row_a, A * sizeof(gl_t));
+        memcpy(row + CT, row_q, N_QUOT * sizeof(gl_t));
         gl_t sx = gl_mul(GL_GENERATOR, gl_pow(gl_root_of_unity(km), tmx_bitrev(x, km)));
         /* fri_combine_initial */
         gl2_t sum = gl2_from(0);
         for (int batch = 0; batch < 2; batch++) {
-            const size_t npoly = batch == 0 ? C + N_QUOT : C;
+            const size_t npoly = batch == 0 ? CT + N_QUOT : CT;
             gl2_t acc = gl2_from(0);
-            for (size_t j = npoly; j-- > 0;) {
-                gl_t v = j < C ? row_t[j] : row_q[j - C];
-                acc = gl2_add(gl2_mul(acc, fa), gl2_from(v));
-            }
+            for (size_t j = npoly; j-- > 0;) acc = gl2_add(gl2_mul(acc, fa), gl2_from(row[j]));
             gl2_t num = gl2_sub(acc, red[batch]);
             gl2_t den = gl2_sub(gl2_from(sx), batch == 0 ? zeta : zeta_next);
-            gl2_t sh = batch == 0 ? gl2_pow(fa, C + N_QUOT) : alpha_c;
+            gl2_t sh = batch == 0 ? gl2_pow(fa, CT + N_QUOT) : alpha_c;
             sum = gl2_add(gl2_mul(sum, sh), gl2_mul(num, gl2_inv(den)));
         }
         gl2_t old = sum;
@@ -712,100 +976,138 @@ static int verify_table(int table, size_t n, rbuf_t *r, challenger_t *ch) {
         if (bad) break;
         if (!gl2_eq(ext_poly_eval(final_coeffs, final_len, gl2_from(sx)), old)) bad = 7;
     }
+    free(row);
     free(op_local);
     free(op_next);
     return bad;
 }
 
-/* Returns 0 if the proof verifies for (input, output) under the circuit (kind, n_max, chain id, skip_max). */
-int tm_verify_proof(const uint64_t *proof, size_t proof_len, const uint8_t *input, size_t input_len, const uint8_t *chain_id,
-                    size_t chain_id_len, uint64_t skip_max, uint32_t kind, uint32_t n_max, const uint8_t out32[32]) {
+/* Returns 0 if the proof verifies for (input, output) under the circuit. */
+int tm_verify_proof(const void *circuit, const uint64_t *proof, size_t proof_len, const uint8_t *input, size_t input_len,
+                    const uint8_t out32[32]) {
+    const circuit_def_t *c = (const circuit_def_t *)circuit;
     rbuf_t r = {proof, proof_len, 0, 0};
-    if (rb_get(&r) != PROOF_MAGIC || rb_get(&r) != kind || rb_get(&r) != n_max || rb_get(&r) != N_TABLES) return 100;
+    if (rb_get(&r) != PROOF_MAGIC || rb_get(&r) != c->kind || rb_get(&r) != c->n_max || rb_get(&r) != TMX_N_TABLES) return 100;
     for (int i = 0; i < 4; i++) {
         gl_t x = 0;
         for (int j = 0; j < 8; j++) x |= (gl_t)out32[8 * i + j] << (8 * j);
         if (rb_get(&r) != x) return 101;
     }
-    if (input_len != (kind == TMX_KIND_SKIP ? 48u : 40u)) return 102;
+    if (input_len != (c->kind == TMX_KIND_SKIP ? 48u : 40u)) return 102;
+    for (size_t i = 0; i < proof_len; i++)
+        if (proof[i] >= GL_P) return 104; /* non-canonical field element */
     challenger_t ch;
-    transcript_init(&ch, kind, n_max, chain_id, chain_id_len, skip_max, input, input_len, out32);
-    size_t dims[6];
-    tm_trace_dims(kind, n_max, dims);
-    g_kind = kind;
-    g_n_max = n_max;
-    for (int t = 0; t < N_TABLES; t++) {
-        int rc = verify_table(t, dims[2 * t], &r, &ch);
+    transcript_init(&ch, c, input, input_len, out32);
+    const gl_t *cap_m[TMX_N_TABLES], *cap_a[TMX_N_TABLES];
+    gl2_t total[TMX_N_TABLES];
+    size_t cap_words[TMX_N_TABLES];
+    for (int t = 0; t < TMX_N_TABLES; t++) {
+        if (!c->t[t].present) continue;
+        const unsigned km = c->t[t].log_n + RATE_BITS;
+        cap_words[t] = 4 * ((size_t)1 << (km < CAP_HEIGHT ? km : CAP_HEIGHT));
+        cap_m[t] = rb_take(&r, cap_words[t]);
+        if (r.err) return 100;
+        challenger_observe_many(&ch, cap_m[t], cap_words[t]);
+    }
+    const gl2_t beta = challenger_get_ext(&ch), gamma = challenger_get_ext(&ch);
+    gl2_t balance = public_terms(c, input, out32, beta, gamma);
+    for (int t = 0; t < TMX_N_TABLES; t++) {
+        if (!c->t[t].present) continue;
+        cap_a[t] = rb_take(&r, cap_words[t]);
+        total[t] = rb_get_ext(&r);
+        if (r.err) return 100;
+        challenger_observe_many(&ch, cap_a[t], cap_words[t]);
+        observe_ext(&ch, total[t]);
+        balance = gl2_add(balance, total[t]);
+    }
+    if (balance.a0 || balance.a1) return 200;
+    for (int t = 0; t < TMX_N_TABLES; t++) {
+        if (!c->t[t].present) continue;
+        int rc = verify_table_tail(c, t, cap_m[t], cap_a[t], beta, gamma, total[t], &r, &ch);
         if (rc) return 10 * (t + 1) + rc;
     }
     if (r.err || r.pos != r.n) return 103;
     return 0;
 }
 
-void tm_debug_set_shape(uint32_t kind, uint32_t n_max) {
-    g_kind = kind;
-    g_n_max = n_max;
+/* ------------------------------------------------------------------ debug / test hooks */
+/* all first-round traces of a blob (tables in TMX_T_* order); out[t] must hold rows * cols words (NULL = skip) */
+int tm_debug_traces(const void *circuit, const uint8_t *blob, size_t blob_len, const uint64_t *logic_trace, uint64_t *out[TMX_N_TABLES]) {
+    const circuit_def_t *c = (const circuit_def_t *)circuit;
+    trace_t tr[TMX_N_TABLES];
+    int rc = build_all_traces(c, blob, blob_len, logic_trace, tr);
+    if (!rc) rc = build_range_trace(c, tr) ? TMX_CHECK_INPUT : 0;
+    for (int t = 0; t < TMX_N_TABLES && !rc; t++)
+        if (out[t] && tr[t].data) memcpy(out[t], tr[t].data, tr[t].n_rows * tr[t].n_cols * sizeof(uint64_t));
+    free_all_traces(tr);
+    return rc;
 }
 
-/* debug / test hook (shape from tm_debug_set_shape): LDE of a trace and the quotient values on the LDE coset in natural order, [2][m] */
-void tm_debug_quotient(int table, const uint64_t *trace, size_t n, size_t C, const uint64_t alpha[2], uint64_t *lde_out,
-                       uint64_t *qv_out) {
-    const size_t m = n << RATE_BITS;
-    const unsigned km = tmx_log2(m);
-    gl_t *coeffs = (gl_t *)malloc(C * n * sizeof(gl_t));
-    ntt_lde_batch(trace, C, n, RATE_BITS, lde_out, coeffs);
-    free(coeffs);
-    const int nper = TABLE_NPER[table];
-    const size_t P = table_period(table, n);
-    gl_t *pertab = (gl_t *)calloc((size_t)(nper ? nper : 1) * 2 * P, sizeof(gl_t));
-    gl_t shift = gl_pow(GL_GENERATOR, n / P);
-    for (int pc = 0; pc < nper; pc++) {
-        gl_t *t = pertab + (size_t)pc * 2 * P;
-        for (size_t r = 0; r < P; r++) t[r] = periodic_pattern(table, pc, r);
-        ntt_inverse(t, P);
-        memset(t + P, 0, P * sizeof(gl_t));
-        ntt_coset_forward(t, 2 * P, shift);
-    }
-    const gl_t gn = gl_pow(GL_GENERATOR, n);
-    const gl_t zh_inv[2] = {gl_inv(gl_sub(gn, 1)), gl_inv(gl_sub(gl_neg(gn), 1))};
-    gl_t *loc = (gl_t *)malloc(C * sizeof(gl_t)), *nxt = (gl_t *)malloc(C * sizeof(gl_t));
-    for (size_t j = 0; j < m; j++) {
-        size_t p = tmx_bitrev(j, km), p2 = tmx_bitrev((j + 2) & (m - 1), km);
-        for (size_t c = 0; c < C; c++) {
-            loc[c] = lde_out[c * m + p];
-            nxt[c] = lde_out[c * m + p2];
-        }
-        gl_t per[16];
-        for (int pc = 0; pc < nper; pc++) per[pc] = pertab[(size_t)pc * 2 * P + (j & (2 * P - 1))];
-        acc_b_t a;
-        for (int i = 0; i < 2; i++) { a.acc[i] = 0; a.alpha[i] = alpha[i]; }
-        air_eval_b(table, loc, nxt, per, &a);
-        for (int i = 0; i < 2; i++) qv_out[(size_t)i * m + j] = gl_mul(a.acc[i], zh_inv[j & 1]);
-    }
-    free(loc); free(nxt); free(pertab);
+/* second-round trace of one table for given first-round trace and bus challenges: aux [2 (H + 1)][n], total[2] */
+void tm_debug_aux(const void *circuit, int table, const uint64_t *trace, const uint64_t beta[2], const uint64_t gamma[2], uint64_t *aux,
+                  uint64_t total[2]) {
+    const circuit_def_t *c = (const circuit_def_t *)circuit;
+    const table_def_t *d = &c->t[table];
+    trace_t tr = {(size_t)1 << d->log_n, d->n_main, (uint64_t *)trace};
+    const gl2_t t = build_aux(d, &tr, gl2_make(beta[0], beta[1]), gl2_make(gamma[0], gamma[1]), aux);
+    total[0] = t.a0;
+    total[1] = t.a1;
 }
 
-/* debug / test hook (shape from tm_debug_set_shape): the folded constraint values (two challenges) of the transitions
- * rows[i] -> rows[i] + 1 (cyclic) evaluated on the TRACE domain itself; all zero for a satisfying trace.  trace is
- * column-major [C][n]; out is [n_rows][2]. */
-void tm_debug_constraints_at_rows(int table, const uint64_t *trace, size_t n, size_t C, const uint64_t alpha[2], const uint64_t *rows,
+/* LDE of the first- and second-round traces and the quotient values on the LDE coset in natural order, [2][m] */
+void tm_debug_quotient(const void *circuit, int table, const uint64_t *trace, const uint64_t *aux, const uint64_t total[2],
+                       const uint64_t beta[2], const uint64_t gamma[2], const uint64_t alpha[2], uint64_t *lde_main_out,
+                       uint64_t *lde_aux_out, uint64_t *qv_out) {
+    const circuit_def_t *c = (const circuit_def_t *)circuit;
+    const table_def_t *d = &c->t[table];
+    ptable_t p;
+    memset(&p, 0, sizeof p);
+    p.d = d;
+    p.n = (size_t)1 << d->log_n;
+    p.m = p.n << RATE_BITS;
+    p.k = d->log_n;
+    p.km = p.k + RATE_BITS;
+    p.Kc = d->n_const; p.C = d->n_main; p.A = 2 * ((size_t)d->n_helpers + 1);
+    p.total = gl2_make(total[0], total[1]);
+    p.lde_k = (gl_t *)malloc((p.Kc ? p.Kc : 1) * p.m * sizeof(gl_t));
+    if (p.Kc) ntt_lde_batch(d->constants, p.Kc, p.n, RATE_BITS, p.lde_k, NULL);
+    p.lde_m = lde_main_out;
+    p.lde_a = lde_aux_out;
+    ntt_lde_batch(trace, p.C, p.n, RATE_BITS, p.lde_m, NULL);
+    ntt_lde_batch(aux, p.A, p.n, RATE_BITS, p.lde_a, NULL);
+    quotient_values(&p, gl2_make(beta[0], beta[1]), gl2_make(gamma[0], gamma[1]), alpha, qv_out);
+    free(p.lde_k);
+}
+
+/* The folded constraint values (two challenges) of the transitions rows[i] -> rows[i] + 1 (cyclic) evaluated on the TRACE
+ * domain itself, second-round columns included; all zero for a satisfying pair of traces.  out is [n_rows][2]. */
+void tm_debug_constraints_at_rows(const void *circuit, int table, const uint64_t *trace, const uint64_t *aux, const uint64_t total[2],
+                                  const uint64_t beta[2], const uint64_t gamma[2], const uint64_t alpha[2], const uint64_t *rows,
                                   size_t n_rows, uint64_t *out) {
-    const int nper = TABLE_NPER[table];
-    const size_t P = table_period(table, n);
-    gl_t *loc = (gl_t *)malloc(C * sizeof(gl_t)), *nxt = (gl_t *)malloc(C * sizeof(gl_t));
+    const circuit_def_t *c = (const circuit_def_t *)circuit;
+    const table_def_t *d = &c->t[table];
+    const size_t n = (size_t)1 << d->log_n, C = d->n_main, Kc = d->n_const, A = 2 * ((size_t)d->n_helpers + 1);
+    const gl2_t s_over_n = gl2_scale(gl2_make(total[0], total[1]), gl_inv((gl_t)n));
+    gl_t *v = (gl_t *)malloc((d->n_nodes ? d->n_nodes : 1) * sizeof(gl_t));
+    gl_t *loc = (gl_t *)malloc(C * sizeof(gl_t)), *nxt = (gl_t *)malloc(C * sizeof(gl_t)), *k = (gl_t *)malloc((Kc ? Kc : 1) * sizeof(gl_t));
+    gl_t *al = (gl_t *)malloc(A * sizeof(gl_t)), *an = (gl_t *)malloc(A * sizeof(gl_t)), per[16];
     for (size_t i = 0; i < n_rows; i++) {
         const size_t r = rows[i] % n, r2 = (r + 1) % n;
-        for (size_t c = 0; c < C; c++) {
-            loc[c] = trace[c * n + r];
-            nxt[c] = trace[c * n + r2];
+        for (size_t col = 0; col < C; col++) {
+            loc[col] = trace[col * n + r];
+            nxt[col] = trace[col * n + r2];
         }
-        gl_t per[16];
-        for (int pc = 0; pc < nper; pc++) per[pc] = periodic_pattern(table, pc, r % P);
-        acc_b_t a;
-        for (int k = 0; k < 2; k++) { a.acc[k] = 0; a.alpha[k] = alpha[k]; }
-        air_eval_b(table, loc, nxt, per, &a);
-        out[2 * i] = a.acc[0];
-        out[2 * i + 1] = a.acc[1];
+        for (size_t col = 0; col < Kc; col++) k[col] = d->constants[col * n + r];
+        for (size_t col = 0; col < A; col++) {
+            al[col] = aux[col * n + r];
+            an[col] = aux[col * n + r2];
+        }
+        periodic_at_row(d, r, per);
+        circuit_eval_b(d, NULL, loc, nxt, k, per, v);
+        gl_t acc[NUM_CHALLENGES];
+        fold_constraints_b(d, v, al, an, gl2_make(beta[0], beta[1]), gl2_make(gamma[0], gamma[1]), s_over_n, alpha, acc);
+        out[2 * i] = acc[0];
+        out[2 * i + 1] = acc[1];
     }
-    free(loc); free(nxt);
+    free(v); free(loc); free(nxt); free(k); free(al); free(an);
 }

@@ -13,6 +13,7 @@
  */
 #include "oracle_w.h"
 #include "../include/tmx_trace.h"
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -401,34 +402,54 @@ static void put_fe(trace_t *t, int col, size_t row, const fe_t *a) {
     for (int i = 0; i < 16; i++) CELL(t, col + i, row) = (uint64_t)a->l[i];
 }
 
-static void ed_ladder_rows(trace_t *t, size_t row0, const uint8_t scalar[32], const ge_t *point) {
-    ge_t res, temp = *point, sum, dbl;
-    fe_mul_witness_t wit[17];
-    ge_identity(&res);
-    for (int i = 0; i < 256; i++) {
-        size_t row = row0 + i;
-        int bit = (scalar[i >> 3] >> (i & 7)) & 1;
-        ge_ladder_row(&res, &temp, &sum, &dbl, wit);
-        CELL(t, ED_BIT, row) = bit;
-        put_fe(t, ED_RES, row, &res.X); put_fe(t, ED_RES + 16, row, &res.Y);
-        put_fe(t, ED_RES + 32, row, &res.Z); put_fe(t, ED_RES + 48, row, &res.T);
-        put_fe(t, ED_TMP, row, &temp.X); put_fe(t, ED_TMP + 16, row, &temp.Y);
-        put_fe(t, ED_TMP + 32, row, &temp.Z); put_fe(t, ED_TMP + 48, row, &temp.T);
+/* rows of one validator slot: acc' = 2 acc + T[bs + 2 bh], most significant scalar bits first (include/tmx_trace.h) */
+static void ed_slot_rows(trace_t *t, size_t row0, const uint8_t s[32], const uint8_t h[32], const ge_cached_t T[4]) {
+    fe_t acc[3], nxt[3];
+    fe_mul_witness_t wit[ED_N_MUL];
+    memset(acc, 0, sizeof acc);
+    acc[1].l[0] = 1;
+    acc[2].l[0] = 1;
+    uint64_t sacc_s = 0, sacc_h = 0;
+    for (int r = 0; r < ED_ROWS_PER_VALIDATOR; r++) {
+        const size_t row = row0 + r;
+        const int j = 255 - r;
+        const int bs = (s[j >> 3] >> (j & 7)) & 1, bh = (h[j >> 3] >> (j & 7)) & 1;
+        const ge_cached_t *add = &T[bs + 2 * bh];
+        if ((r & 15) == 0) sacc_s = sacc_h = 0;
+        CELL(t, ED_BS, row) = bs;
+        CELL(t, ED_BH, row) = bh;
+        CELL(t, ED_SACC_S, row) = sacc_s;
+        CELL(t, ED_SACC_H, row) = sacc_h;
+        sacc_s = 2 * sacc_s + bs;
+        sacc_h = 2 * sacc_h + bh;
+        for (int co = 0; co < 3; co++) put_fe(t, ED_ACC + 16 * co, row, &acc[co]);
+        for (int i = 0; i < 16; i++) {
+            CELL(t, ED_ADD + i, row) = (uint64_t)add->ypx[i];
+            CELL(t, ED_ADD + 16 + i, row) = (uint64_t)add->ymx[i];
+            CELL(t, ED_ADD + 32 + i, row) = (uint64_t)add->t2d[i];
+        }
+        ge_straus_row(acc, add, nxt, wit);
         for (int m = 0; m < ED_N_MUL; m++) {
-            int base = ED_MUL + m * ED_MUL_STRIDE;
+            const int base = ED_MUL + m * ED_MUL_STRIDE;
             for (int k = 0; k < 16; k++) CELL(t, base + k, row) = (uint64_t)wit[m].c[k];
             for (int k = 0; k < 17; k++) CELL(t, base + ED_MUL_Q + k, row) = (uint64_t)wit[m].q[k];
-            /* the limb equations are checked in pairs (air.inc), so only the carries out of the odd limbs are committed */
-            for (int k = 0; k < ED_MUL_NW; k++) CELL(t, base + ED_MUL_W + k, row) = (uint64_t)(wit[m].w[2 * k + 1] + ED_W_OFFSET);
+            /* the limb equations are checked in pairs, so only the carries out of the odd limbs are committed, split into a
+             * 16-bit and an 11-bit part (both range checked on the bus) */
+            for (int k = 0; k < ED_MUL_NW; k++) {
+                const int64_t w = wit[m].w[2 * k + 1] + ED_W_OFFSET;
+                if (w < 0 || w >= ((int64_t)1 << 27)) {
+                    fprintf(stderr, "oracle: Ed25519 carry out of range\n");
+                    abort();
+                }
+                CELL(t, base + ED_MUL_WLO + k, row) = (uint64_t)(w & 0xFFFF);
+                CELL(t, base + ED_MUL_WHI + k, row) = (uint64_t)(w >> 16);
+            }
         }
-        if (bit) res = sum;
-        temp = dbl;
+        memcpy(acc, nxt, sizeof acc);
     }
 }
 
 static int build_ed25519(trace_t *t, const tmx_offchain_head *h, const tmx_validator *vals, uint8_t (*hdigest)[64]) {
-    ge_t B;
-    ge_basepoint(&B);
     int bad = 0;
 #pragma omp parallel for schedule(dynamic, 1) reduction(| : bad)
     for (size_t i = 0; i < h->n_max; i++) {
@@ -441,18 +462,24 @@ static int build_ed25519(trace_t *t, const tmx_offchain_head *h, const tmx_valid
             continue;
         }
         sc_reduce512(hs, hdigest[i]);
-        size_t row = i * ED_ROWS_PER_VALIDATOR;
-        ed_ladder_rows(t, row, sig + 32, &B);
-        ed_ladder_rows(t, row + 256, hs, &A);
+        ge_cached_t T[4];
+        fe_t xD, yD;
+        ge_straus_table(&A, T, &xD, &yD);
+        ed_slot_rows(t, i * ED_ROWS_PER_VALIDATOR, sig + 32, hs, T);
     }
-    uint8_t zero[32] = {0};
-    size_t first = (size_t)h->n_max * ED_ROWS_PER_VALIDATOR;
+    const size_t first = (size_t)h->n_max * ED_ROWS_PER_VALIDATOR;
     if (first < t->n_rows) {
-        /* padding blocks: [0]B ladders; compute one and copy */
-        ed_ladder_rows(t, first, zero, &B);
-        for (size_t row = first + 256; row < t->n_rows; row += 256)
+        /* padding slots: all scalar bits zero, addend O in every row (valid rows; nothing of them reaches the bus); compute
+         * one slot and copy */
+        uint8_t zero[32] = {0};
+        ge_cached_t T[4];
+        memset(T, 0, sizeof T);
+        T[0].ypx[0] = 1;
+        T[0].ymx[0] = 1;
+        ed_slot_rows(t, first, zero, zero, T);
+        for (size_t row = first + ED_ROWS_PER_VALIDATOR; row < t->n_rows; row += ED_ROWS_PER_VALIDATOR)
             for (size_t c = 0; c < t->n_cols; c++)
-                memcpy(&CELL(t, c, row), &CELL(t, c, first), 256 * sizeof(uint64_t));
+                memcpy(&CELL(t, c, row), &CELL(t, c, first), ED_ROWS_PER_VALIDATOR * sizeof(uint64_t));
     }
     return bad;
 }

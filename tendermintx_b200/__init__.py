@@ -127,7 +127,31 @@ class Context:
         return tabs, aux
 
 
+    def sha512_trace(self, blob, kind, n_max):
+        """K7 alone: the SHA-512 table as a [cols, rows] int64 CUDA tensor."""
+        import torch
+
+        dev = f"cuda:{self.device}"
+        d_blob = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
+        r, c = self.trace_dims(kind, n_max)[1]
+        tab = torch.empty((c, r), dtype=torch.int64, device=dev)
+        _check(lib().tmx_sha512_trace(self._h, _ptr(d_blob), kind, n_max, _ptr(tab), self._stream()))
+        return tab
+
+    # ---- K3 (fold) ----
+    def fri_fold(self, values, log_cosets, shift, beta):
+        """One arity-16 FRI fold: values [16 << log_cosets, 2] int64 CUDA tensor (extension elements, bit-reversed order) on
+        shift * <w> -> [1 << log_cosets, 2] on shift^16 * <w^16>."""
+        import torch
+
+        out = torch.empty((1 << log_cosets, 2), dtype=torch.int64, device=values.device)
+        b = (ctypes.c_uint64 * 2)(*[int(x) for x in beta])
+        _check(lib().tmx_fri_fold(self._h, _ptr(values), log_cosets, int(shift), b, _ptr(out), self._stream()))
+        return out
+
+
 KIND_STEP, KIND_SKIP = 0, 1
+T_SHA256, T_SHA512, T_ED, T_LOGIC, T_RANGE = range(5)
 SKIP_MAX = 100800  # REF circuits/config.rs:12
 CHECK_NAMES = ["OK", "SKIP_DISTANCE", "TRUSTED_HEADER_PROOF", "TRUSTED_VALHASH", "TRUSTED_THRESHOLD", "SIGNATURE",
                "VALHASH", "VALHASH_PROOF", "THRESHOLD", "SIGN_BYTES", "CHAIN_ID", "HEIGHT", "LAST_BLOCK_ID",
@@ -284,6 +308,46 @@ class Circuit:
     def verify(self, proof, public_input, output):
         proof, public_input, output = bytes(proof), bytes(public_input), bytes(output)
         _check(lib().tmx_verify(self._h, proof, len(proof), public_input, len(public_input), output))
+
+    # ---- kernel-level entry points that need the circuit's constant / periodic columns ----
+    def table_shape(self, table):
+        """(rows, first-round columns, constant columns, second-round columns); rows = 0 when the table is absent."""
+        out = (ctypes.c_size_t * 4)()
+        _check(lib().tmx_circuit_table_shape(self._h, table, out))
+        return tuple(out)
+
+    def bus_count(self, table, trace):
+        """Histogram (int32 CUDA tensor, 2^16 + 2^11 + 2^8 entries) of the range lookups of a first-round trace, and the
+        out-of-range flag."""
+        import torch
+
+        hist = torch.zeros((1 << 16) + (1 << 11) + (1 << 8), dtype=torch.int32, device=trace.device)
+        bad = ctypes.c_int(0)
+        _check(lib().tmx_bus_count(self._h, table, _ptr(trace), _ptr(hist), ctypes.byref(bad), self.ctx._stream()))
+        return hist, bool(bad.value)
+
+    def bus_aux(self, table, trace, beta, gamma):
+        """Second-round trace ([aux cols, rows] int64 CUDA tensor) and the table's bus total (two ints)."""
+        import torch
+
+        rows, _, _, a = self.table_shape(table)
+        aux = torch.empty((a, rows), dtype=torch.int64, device=trace.device)
+        b = (ctypes.c_uint64 * 2)(*[int(x) for x in beta])
+        g = (ctypes.c_uint64 * 2)(*[int(x) for x in gamma])
+        tot = (ctypes.c_uint64 * 2)()
+        _check(lib().tmx_bus_aux(self._h, table, _ptr(trace), b, g, _ptr(aux), tot, self.ctx._stream()))
+        return aux, (tot[0], tot[1])
+
+    def quotient(self, table, lde_main, lde_aux, total, beta, gamma, alpha):
+        """K5: quotient values on the LDE coset, [2, 2 rows] int64 CUDA tensor in natural order."""
+        import torch
+
+        rows = self.table_shape(table)[0]
+        out = torch.empty((2, 2 * rows), dtype=torch.int64, device=lde_main.device)
+        arr = lambda v: (ctypes.c_uint64 * 2)(*[int(x) for x in v])
+        _check(lib().tmx_quotient(self._h, table, _ptr(lde_main), _ptr(lde_aux), arr(total), arr(beta), arr(gamma), arr(alpha),
+                                  _ptr(out), self.ctx._stream()))
+        return out
 
 
 class ProverPool:

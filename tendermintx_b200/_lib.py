@@ -49,13 +49,18 @@ def load():
         "tmx_poseidon_merkle": (i32, [vp, u64p, sz, u32, u32, u64p, vp]),
         "tmx_poseidon_permute": (i32, [vp, u64p, sz, vp]),
         "tmx_host_poseidon_permute": (i32, [u64p, sz, i32]),
-        "tmx_host_air_ed25519": (i32, [u64p, u64p, u64p, u64p, u64p]),
         "tmx_trace_dims": (i32, [u32, u32, c.POINTER(sz)]),
         "tmx_witness_aux_bytes": (sz, [u32]),
         "tmx_sha256_trace": (i32, [vp, vp, u32, u32, u64p, vp, vp]),
         "tmx_ed25519_trace": (i32, [vp, vp, u32, u32, u64p, u64p, vp, vp]),
         "tmx_witness_generate": (i32, [vp, vp, u32, u32, u64p, u64p, u64p, vp, vp]),
-        "tmx_quotient": (i32, [vp, u32, u32, i32, u64p, u32, vp, u64p, vp]),
+        "tmx_sha512_trace": (i32, [vp, vp, u32, u32, u64p, vp]),
+        "tmx_quotient": (i32, [vp, i32, u64p, u64p, vp, vp, vp, vp, u64p, vp]),
+        "tmx_bus_aux": (i32, [vp, i32, u64p, vp, vp, u64p, vp, vp]),
+        "tmx_bus_count": (i32, [vp, i32, u64p, vp, c.POINTER(c.c_int), vp]),
+        "tmx_fri_fold": (i32, [vp, u64p, u32, c.c_uint64, vp, u64p, vp]),
+        "tmx_circuit_table_shape": (i32, [vp, i32, c.POINTER(sz)]),
+        "tmx_circuit_artefact": (sz, [u32, u32, c.c_char_p, sz, c.c_uint64, vp, sz]),
         "tmx_pow_grind": (i32, [vp, vp, i32, u32, c.POINTER(c.c_uint64), vp]),
         "tmx_circuit_build": (i32, [vp, u32, u32, c.c_char_p, sz, c.c_uint64, c.POINTER(vp)]),
         "tmx_circuit_free": (None, [vp]),
@@ -97,8 +102,8 @@ def load():
 EXPORTED_SYMBOLS = [
     "tmx_last_error", "tmx_version", "tmx_ctx_create", "tmx_ctx_destroy", "tmx_ctx_sync",
     "tmx_ctx_stream", "tmx_ctx_launch_count", "tmx_ntt", "tmx_lde", "tmx_merkle_digest_count", "tmx_poseidon_merkle",
-    "tmx_poseidon_permute", "tmx_host_poseidon_permute", "tmx_host_air_ed25519", "tmx_trace_dims", "tmx_witness_aux_bytes", "tmx_sha256_trace", "tmx_ed25519_trace",
-    "tmx_witness_generate", "tmx_quotient", "tmx_pow_grind", "tmx_circuit_build", "tmx_circuit_free", "tmx_circuit_digest",
+    "tmx_poseidon_permute", "tmx_host_poseidon_permute", "tmx_trace_dims", "tmx_witness_aux_bytes", "tmx_sha256_trace", "tmx_ed25519_trace",
+    "tmx_witness_generate", "tmx_sha512_trace", "tmx_quotient", "tmx_bus_aux", "tmx_bus_count", "tmx_fri_fold", "tmx_circuit_table_shape", "tmx_circuit_artefact", "tmx_pow_grind", "tmx_circuit_build", "tmx_circuit_free", "tmx_circuit_digest",
     "tmx_circuit_save", "tmx_circuit_load", "tmx_prove", "tmx_last_check", "tmx_circuit_last_phase_ms", "tmx_circuit_set_inputs", "tmx_header_hash_from_fixture", "tmx_skip_inputs_from_fixture",
     "tmx_step_inputs_from_fixture", "tmx_is_valid_skip_from_fixture", "tmx_find_block_to_request", "tmx_prove_fixture",
     "tmx_pool_create", "tmx_pool_create_from_artefact", "tmx_pool_destroy", "tmx_pool_set_inputs", "tmx_pool_submit", "tmx_pool_wait", "tmx_pool_in_flight",

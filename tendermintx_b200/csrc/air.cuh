@@ -1,11 +1,19 @@
-// Constraint systems (AIR) of the SHA-256, SHA-512 and Ed25519 tables, generic over the field: the quotient
-// kernel (K5) instantiates them on base-field LDE values, the verifier on extension-field openings at zeta.
+// Constraint systems (AIR) of the SHA-256, SHA-512, Ed25519, logic and range tables, generic over the field: the
+// quotient kernels (K5) instantiate them on base-field LDE values, the verifier on extension-field openings at zeta,
+// the circuit builder on symbolic nodes (circuit_def.cu: that is how the build artefact gets its constraint DAG).
 //
 // The arithmetisation is this repo's own -- upstream the equivalent lives in starkyx's SHA-256 / SHA-512 /
-// Ed25519 AIRs, reached by the reference through `curta_sha256_variable` and
-// `curta_eddsa_verify_sigs_conditional` [REF circuits/builder/verify.rs:202,248-259].  Rules: every constraint
-// has degree <= 3 in (trace, periodic) columns; a constraint that reads the next row carries a periodic
-// selector that is zero on the last row of the table; emission order is fixed (it defines the alpha powers).
+// Ed25519 AIRs and plonky2's gates, reached by the reference through `curta_sha256_variable`,
+// `curta_eddsa_verify_sigs_conditional` and the plain-gate gadgets of circuits/builder
+// [REF circuits/builder/verify.rs:202,248-259].  Rules: every constraint has degree <= 3 in (trace, constant,
+// periodic) columns; a constraint that reads the next row carries a selector that is zero on the last row of the
+// table; a table first emits its own constraints, then declares its bus interactions (bus.one / bus.two, in a
+// fixed order: it defines the helper columns of the second commitment round); emission order defines the alpha powers.
+//
+// Bus (logUp): a message is (tag, v_0 .. v_{k-1}) with fingerprint f = gamma + tag + beta v_0 + beta^2 v_1 + ...
+// in the quadratic extension; a table row contributes multiplicity / f for each of its interactions (positive: sends /
+// provides, negative: receives / looks up) and the sum over all rows of all tables plus the verifier's public
+// terms must vanish.
 #pragma once
 #include "gl.cuh"
 #include "../../include/tmx_trace.h"
@@ -60,19 +68,73 @@ TMX_HD F pack_bits(const Row& r, int col0, int nbits) {
     return acc;
 }
 
-constexpr int AIR_SHA256 = 0, AIR_SHA512 = 1, AIR_ED25519 = 2;
-TMX_HD int air_cols(int t) { return t == AIR_SHA256 ? S256_COLS : (t == AIR_SHA512 ? S512_COLS : ED_COLS); }
-// Circuit shape the SHA-256 table's public columns depend on.
+// two-component algebra F[X] / (X^2 - 7) over any of the field wrappers: with F = FB it is the quadratic extension, with
+// F = FE (openings at zeta of the two component polynomials of an extension-valued column) the same identities hold
+// component-wise, which is all the constraint check needs
+template <class F>
+struct Ext2 {
+    F a0, a1;
+};
+template <class F>
+TMX_HD Ext2<F> e2_mk(F a0, F a1) { Ext2<F> r; r.a0 = a0; r.a1 = a1; return r; }
+template <class F>
+TMX_HD Ext2<F> e2_add(Ext2<F> a, Ext2<F> b) { return e2_mk<F>(a.a0 + b.a0, a.a1 + b.a1); }
+template <class F>
+TMX_HD Ext2<F> e2_sub(Ext2<F> a, Ext2<F> b) { return e2_mk<F>(a.a0 - b.a0, a.a1 - b.a1); }
+template <class F>
+TMX_HD Ext2<F> e2_mul(Ext2<F> a, Ext2<F> b) {
+    return e2_mk<F>(a.a0 * b.a0 + F::c(7) * (a.a1 * b.a1), a.a0 * b.a1 + a.a1 * b.a0);
+}
+template <class F>
+TMX_HD Ext2<F> e2_scale(Ext2<F> a, F s) { return e2_mk<F>(a.a0 * s, a.a1 * s); }
+
+// fingerprint of (tag, tup(0) .. tup(len - 1)): gamma + tag + beta (v_0 + beta (v_1 + ...))
+template <class F, class Tup>
+TMX_HD Ext2<F> bus_fingerprint(Ext2<F> beta, Ext2<F> gamma, int tag, int len, const Tup& tup) {
+    Ext2<F> acc = e2_mk<F>(F::c(0), F::c(0));
+    for (int i = len - 1; i >= 0; i--) {
+        acc.a0 = acc.a0 + tup(i);
+        acc = e2_mul<F>(acc, beta);
+    }
+    acc.a0 = acc.a0 + F::c((uint64_t)tag);
+    return e2_add<F>(acc, gamma);
+}
+
+// single-value lookups (range checks) are declared through this pairing buffer: two per helper column
+template <class F, class Bus>
+struct LookupPairs {
+    Bus& bus;
+    bool have;
+    int tag0;
+    F v0;
+    TMX_HD LookupPairs(Bus& b) : bus(b), have(false), tag0(0) { v0 = F::c(0); }
+    TMX_HD void push(int tag, F v) {
+        const F minus1 = F::c(0xFFFFFFFF00000000ULL);  // p - 1
+        if (!have) {
+            have = true;
+            tag0 = tag;
+            v0 = v;
+            return;
+        }
+        have = false;
+        const F a = v0, b = v;
+        bus.two(tag0, minus1, 1, [&](int) { return a; }, tag, minus1, 1, [&](int) { return b; });
+    }
+    TMX_HD void flush() {
+        if (!have) return;
+        have = false;
+        const F a = v0;
+        bus.one(tag0, F::c(0xFFFFFFFF00000000ULL), 1, [&](int) { return a; });
+    }
+};
+
+constexpr int AIR_SHA256 = TMX_T_SHA256, AIR_SHA512 = TMX_T_SHA512, AIR_ED25519 = TMX_T_ED, AIR_LOGIC = TMX_T_LOGIC,
+              AIR_RANGE = TMX_T_RANGE;
+// Circuit shape the constant columns depend on.
 struct AirShape {
     uint32_t kind, n_max;
 };
-TMX_HD int air_n_periodic(int t) { return t == AIR_SHA256 ? 6 : (t == AIR_SHA512 ? 11 : 3); }
 constexpr int AIR_MAX_PERIODIC = 16;
-// The last two columns of the SHA-256 table are not periodic: which chunk starts a message and which continues one is
-// fixed by the circuit shape (sha256_chunk_continues).  They are public columns of full length -- the prover evaluates
-// them on the LDE coset once per circuit, the verifier evaluates their interpolant at zeta itself -- so that table's
-// "period" is its length n.
-TMX_HD size_t air_period(int t, size_t n) { return t == AIR_SHA256 ? n : (t == AIR_SHA512 ? S512_ROWS_PER_VALIDATOR : ED_ROWS_PER_VALIDATOR); }
 
 // Does 64-row chunk c of the SHA-256 table continue the message of chunk c - 1?  Layout (witness_jobs.cuh): per
 // validator set n_max one-chunk leaf hashes, then np - 1 two-chunk inner nodes; then the header proofs, each a leaf (two
@@ -97,11 +159,11 @@ TMX_HD bool sha256_chunk_continues(AirShape sh, size_t c) {
 }
 
 // ------------------------------------------------------------------------------------------ SHA-256
-// per = {K_t, is_last_round, not_last_round, schedule_active (rounds 15..62)} with period 64, then the two public
-// full-length columns {FIRST: row 0 of a chunk that starts a message, LINK: row 63 of a chunk whose successor continues it}
-template <class F, class Row, class Per, class Emit>
-TMX_HD void air_sha256(const Row& l, const Row& n, const Per& per, Emit& emit) {
-    const F K = per[0], LAST = per[1], NOTLAST = per[2], SCHED = per[3];
+// per = {K_t, is_last_round, not_last_round, schedule_active (rounds 15..62), first_round} with period 64; k = the
+// table's constant columns (S256K_*: message boundaries, chunk index, bus multiplicities -- fixed by the circuit shape)
+template <class F, class Row, class KRow, class Per, class Emit, class Bus>
+TMX_HD void air_sha256(const Row& l, const Row& n, const KRow& k, const Per& per, Emit& emit, Bus& bus) {
+    const F K = per[0], LAST = per[1], NOTLAST = per[2], SCHED = per[3], FIRSTROW = per[4];
     const F two32 = F::c(1ULL << 32);
     for (int i = S256_A; i < S256_D; i++) emit(is_bool<F>(l[i]));
     for (int i = S256_AN; i < S256_W; i++) emit(is_bool<F>(l[i]));
@@ -164,8 +226,18 @@ TMX_HD void air_sha256(const Row& l, const Row& n, const Per& per, Emit& emit) {
     }
     // message chaining: a message starts from the IV, a continuation chunk from the previous chunk's digest
     const uint32_t IV[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
-    for (int j = 0; j < 8; j++) emit(per[4] * (l[S256_CV + j] - F::c(IV[j])));
-    for (int j = 0; j < 8; j++) emit(per[5] * (n[S256_CV + j] - l[S256_DG + j]));
+    for (int j = 0; j < 8; j++) emit(k[S256K_FIRST] * (l[S256_CV + j] - F::c(IV[j])));
+    for (int j = 0; j < 8; j++) emit(k[S256K_LINK] * (n[S256_CV + j] - l[S256_DG + j]));
+    // the compression starts from the chunk's chaining value: working variables of round 0 = CV
+    {
+        const F st[8] = {fin[1], fin[2], fin[3], l[S256_D], fin[5], fin[6], fin[7], l[S256_H]};
+        for (int j = 0; j < 8; j++) emit(FIRSTROW * (st[j] - l[S256_CV + j]));
+    }
+    // bus: the chunk's 16 message words (all in the schedule window on row 15) are received, its digest is sent
+    const F minus_msg = F::c(0) - k[S256K_MSG];
+    bus.two(
+        BUS_MSG256, minus_msg, 17, [&](int i) { return i == 0 ? k[S256K_CID] : l[S256_W + i - 1]; },
+        BUS_DIG256, k[S256K_DIG], 9, [&](int i) { return i == 0 ? k[S256K_CID] : l[S256_DG + i - 1]; });
 }
 
 // ------------------------------------------------------------------------------------------ SHA-512
@@ -177,8 +249,9 @@ TMX_HD void air_sha256(const Row& l, const Row& n, const Per& per, Emit& emit) {
 // 64-bit words are (lo, hi) pairs of 32-bit field elements with an explicit carry from lo to hi.  Rows 80..127 of a chunk
 // continue the round function with round constant 0 (include/tmx_trace.h), so only what reads the next row, the digest
 // and the schedule hand-over need a selector.
-template <class F, class Row, class Per, class Emit>
-TMX_HD void air_sha512(const Row& l, const Row& n, const Per& per, Emit& emit) {
+// per[11] = first row of a chunk (the working variables of round 0 equal the chaining value); k = constant columns S512K_*
+template <class F, class Row, class KRow, class Per, class Emit, class Bus>
+TMX_HD void air_sha512(const Row& l, const Row& n, const KRow& kc, const Per& per, Emit& emit, Bus& bus) {
     const F KLO = per[0], KHI = per[1], LAST = per[2], NOTLAST = per[3], NOTEND = per[4], SCHED = per[5];
     const F two32 = F::c(1ULL << 32);
     for (int i = S512_A; i < S512_D; i++) emit(is_bool<F>(l[i]));
@@ -279,19 +352,36 @@ TMX_HD void air_sha512(const Row& l, const Row& n, const Per& per, Emit& emit) {
             emit(per[6] * (l[S512_CV + 2 * j + k] - iv));
             emit(per[9] * (n[S512_CV + 2 * j + k] - (iv + two * (l[S512_DG + 2 * j + k] - iv))));
         }
+    // the compression starts from the chunk's chaining value
+    {
+        const F st[8][2] = {{fin[1][0], fin[1][1]}, {fin[2][0], fin[2][1]}, {fin[3][0], fin[3][1]}, {l[S512_D], l[S512_D + 1]},
+                            {fin[5][0], fin[5][1]}, {fin[6][0], fin[6][1]}, {fin[7][0], fin[7][1]}, {l[S512_H], l[S512_H + 1]}};
+        for (int j = 0; j < 8; j++)
+            for (int h = 0; h < 2; h++) emit(per[11] * (st[j][h] - l[S512_CV + 2 * j + h]));
+    }
+    // bus: each chunk of an active slot receives its 16 message words (row 15); the digest of the slot's message leaves
+    // from row 79 of the second chunk when the message has two blocks, else of the first
+    const F minus_msg = F::c(0) - kc[S512K_MSG];
+    const F dig_mult = kc[S512K_DIG0] * (F::c(1) - two) + kc[S512K_DIG1] * two;
+    bus.two(
+        BUS_MSG512, minus_msg, 35,
+        [&](int i) { return i == 0 ? kc[S512K_VID] : (i == 1 ? kc[S512K_CHUNK] : (i == 2 ? two : l[S512_W + i - 3])); },
+        BUS_DIG512, dig_mult, 17, [&](int i) { return i == 0 ? kc[S512K_VID] : l[S512_DG + i - 1]; });
 }
 
 // ------------------------------------------------------------------------------------------ Ed25519
 TMX_HD uint64_t p25519_limb(int i) { return i == 0 ? 0xFFEDULL : (i == 15 ? 0x7FFFULL : 0xFFFFULL); }
 
-// U * V = c + q * p with carries: the 32 limb equations of one multiplication gadget (cells from column g0), in 16 pairs
+// U * V = c + q * p with carries: the 32 limb equations of one multiplication gadget (cells from column g0), in 16
+// pairs:  e_2K + 2^16 e_2K+1 + w_{K-1} = 2^32 w_K,  w_K = wlo_K + 2^16 whi_K - ED_W_OFFSET,  w_{-1} = w_15 = 0.
+// Operand limbs are below 2^19 in magnitude and every committed cell is range checked on the bus (c, q, wlo < 2^16,
+// whi < 2^11), so every term stays below 2^60: the equations hold over the integers, not just in F_p.
 template <class F, class Row, class Emit>
 TMX_HD void ed_mul_gadget(const F U[16], const F V[16], const Row& l, int g0, Emit& emit) {
     const F off = F::c(ED_W_OFFSET), two16 = F::c(1 << 16), two32 = F::c(1ULL << 32);
     F q[17];
     for (int i = 0; i < 17; i++) q[i] = l[g0 + ED_MUL_Q + i];
     F wprev = F::c(0);
-    // limb equations in pairs: e_2K + 2^16 e_2K+1 + w'_{K-1} = 2^32 w'_K  (|operand limbs| < 2^19, so every term is below 2^58: no wrap in F_p)
     for (int K = 0; K < 16; K++) {
         F s = F::c(0);
         for (int h = 0; h < 2; h++) {
@@ -310,117 +400,173 @@ TMX_HD void ed_mul_gadget(const F U[16], const F V[16], const Row& l, int g0, Em
         }
         if (K >= 1) s = s + wprev;
         if (K < ED_MUL_NW) {
-            wprev = l[g0 + ED_MUL_W + K] - off;
+            wprev = (l[g0 + ED_MUL_WLO + K] + two16 * l[g0 + ED_MUL_WHI + K]) - off;
             s = s - two32 * wprev;
         }
         emit(s);
     }
 }
 
-// per = {not_block_end (row % 256 != 255), first row of the [s]B ladder (row == 0), first row of the [h]A ladder (row == 256)},
-// period 512
-template <class F, class Row, class Per, class Emit>
-TMX_HD void air_ed25519(const Row& l, const Row& n, const Per& per, Emit& emit) {
-    const F NOTEND = per[0];
-    const F bit = l[ED_BIT];
-    emit(is_bool<F>(bit));
-    const uint64_t TWOD[16] = {0xF159, 0x26B2, 0x9B94, 0xEBD6, 0xB156, 0x8283, 0x149A, 0x00E0,
-                               0xD130, 0xEEF3, 0x80F2, 0x198E, 0xFCE7, 0x56DF, 0xD9DC, 0x2406};
-    const int X1 = ED_RES, Y1 = ED_RES + 16, Z1 = ED_RES + 32, T1 = ED_RES + 48;
-    const int X2 = ED_TMP, Y2 = ED_TMP + 16, Z2 = ED_TMP + 32, T2 = ED_TMP + 48;
+// per = {not_block_end (row % 256 != 255), first row of a slot (row % 256 == 0), not last row of a 16-row group, first row
+// of a 16-row group}, period 256; k = constant columns EDK_*
+template <class F, class Row, class KRow, class Per, class Emit, class Bus>
+TMX_HD void air_ed25519(const Row& l, const Row& n, const KRow& k, const Per& per, Emit& emit, Bus& bus) {
+    const F NOTEND = per[0], FIRST = per[1], NOT16END = per[2], FIRST16 = per[3];
+    const F bs = l[ED_BS], bh = l[ED_BH];
+    emit(is_bool<F>(bs));
+    emit(is_bool<F>(bh));
+    // scalar limbs: inside a 16-row group acc' = 2 acc + bit, starting from 0
+    emit(FIRST16 * l[ED_SACC_S]);
+    emit(FIRST16 * l[ED_SACC_H]);
+    const F limb_s = (l[ED_SACC_S] + l[ED_SACC_S]) + bs, limb_h = (l[ED_SACC_H] + l[ED_SACC_H]) + bh;
+    emit(NOT16END * (n[ED_SACC_S] - limb_s));
+    emit(NOT16END * (n[ED_SACC_H] - limb_h));
+    const int X1 = ED_ACC, Y1 = ED_ACC + 16, Z1 = ED_ACC + 32;
+    const int YPX = ED_ADD, YMX = ED_ADD + 16, T2D = ED_ADD + 32;
     auto G = [](int m) { return ED_MUL + m * ED_MUL_STRIDE; };
     F u[16], v[16], E[16], Fq[16], Gq[16], H[16];
-    for (int i = 0; i < 16; i++) {
-        const F pl = F::c(p25519_limb(i));
-        u[i] = (l[Y1 + i] - l[X1 + i]) + pl;
-        v[i] = (l[Y2 + i] - l[X2 + i]) + pl;
-    }
-    ed_mul_gadget<F>(u, v, l, G(0), emit);
-    for (int i = 0; i < 16; i++) { u[i] = l[Y1 + i] + l[X1 + i]; v[i] = l[Y2 + i] + l[X2 + i]; }
-    ed_mul_gadget<F>(u, v, l, G(1), emit);
-    for (int i = 0; i < 16; i++) { u[i] = l[T1 + i]; v[i] = l[T2 + i]; }
-    ed_mul_gadget<F>(u, v, l, G(2), emit);
-    for (int i = 0; i < 16; i++) { u[i] = l[G(2) + i]; v[i] = F::c(TWOD[i]); }
-    ed_mul_gadget<F>(u, v, l, G(3), emit);
-    for (int i = 0; i < 16; i++) { u[i] = l[Z1 + i]; v[i] = l[Z2 + i]; }
-    ed_mul_gadget<F>(u, v, l, G(4), emit);
-    for (int i = 0; i < 16; i++) {
-        const F pl = F::c(p25519_limb(i));
-        const F A = l[G(0) + i], B = l[G(1) + i], C = l[G(3) + i], Dh = l[G(4) + i];
-        const F d2 = Dh + Dh;
-        E[i] = (B - A) + pl;
-        Fq[i] = (d2 - C) + pl;
-        Gq[i] = d2 + C;
-        H[i] = B + A;
-    }
-    ed_mul_gadget<F>(E, Fq, l, G(5), emit);
-    ed_mul_gadget<F>(Gq, H, l, G(6), emit);
-    ed_mul_gadget<F>(E, H, l, G(7), emit);
-    ed_mul_gadget<F>(Fq, Gq, l, G(8), emit);
-    for (int i = 0; i < 16; i++) u[i] = l[X2 + i];
-    ed_mul_gadget<F>(u, u, l, G(9), emit);
-    for (int i = 0; i < 16; i++) u[i] = l[Y2 + i];
-    ed_mul_gadget<F>(u, u, l, G(10), emit);
-    for (int i = 0; i < 16; i++) u[i] = l[Z2 + i];
-    ed_mul_gadget<F>(u, u, l, G(11), emit);
-    for (int i = 0; i < 16; i++) u[i] = l[X2 + i] + l[Y2 + i];
-    ed_mul_gadget<F>(u, u, l, G(12), emit);
+    // ---- doubling (dbl-2008-hwcd, a = -1) ----
+    for (int i = 0; i < 16; i++) u[i] = l[X1 + i];
+    ed_mul_gadget<F>(u, u, l, G(ED_G_A), emit);
+    for (int i = 0; i < 16; i++) u[i] = l[Y1 + i];
+    ed_mul_gadget<F>(u, u, l, G(ED_G_B), emit);
+    for (int i = 0; i < 16; i++) u[i] = l[Z1 + i];
+    ed_mul_gadget<F>(u, u, l, G(ED_G_CZ), emit);
+    for (int i = 0; i < 16; i++) u[i] = l[X1 + i] + l[Y1 + i];
+    ed_mul_gadget<F>(u, u, l, G(ED_G_S), emit);
     for (int i = 0; i < 16; i++) {
         const F pl = F::c(p25519_limb(i)), p2 = pl + pl;
-        const F A2 = l[G(9) + i], B2 = l[G(10) + i], Cz = l[G(11) + i], S = l[G(12) + i];
+        const F A2 = l[G(ED_G_A) + i], B2 = l[G(ED_G_B) + i], Cz = l[G(ED_G_CZ) + i], S = l[G(ED_G_S) + i];
         const F ba = B2 - A2;
         E[i] = ((S - A2) - B2) + p2;
         Gq[i] = ba + pl;
         Fq[i] = (ba - (Cz + Cz)) + (p2 + pl);
         H[i] = (p2 - A2) - B2;
     }
-    ed_mul_gadget<F>(E, Fq, l, G(13), emit);
-    ed_mul_gadget<F>(Gq, H, l, G(14), emit);
-    ed_mul_gadget<F>(E, H, l, G(15), emit);
-    ed_mul_gadget<F>(Fq, Gq, l, G(16), emit);
-    const int sum_slot[4] = {5, 6, 8, 7}, dbl_slot[4] = {13, 14, 16, 15};  // X, Y, Z, T
-    for (int co = 0; co < 4; co++)
-        for (int i = 0; i < 16; i++) {
-            const F r = l[ED_RES + 16 * co + i], s = l[G(sum_slot[co]) + i];
-            emit(NOTEND * (n[ED_RES + 16 * co + i] - (r + bit * (s - r))));
-            emit(NOTEND * (n[ED_TMP + 16 * co + i] - l[G(dbl_slot[co]) + i]));
-        }
-    // block initialisation: res = O at the start of both ladders, temp = B at the start of [s]B, temp.Z = 1 at the start of [h]A
-    const uint64_t BXL[16] = ED_BASE_X_LIMBS, BYL[16] = ED_BASE_Y_LIMBS, BTL[16] = ED_BASE_T_LIMBS;
-    const F S0 = per[1], H0 = per[2];
-    for (int co = 0; co < 4; co++)
-        for (int i = 0; i < 16; i++) emit(S0 * (l[ED_RES + 16 * co + i] - F::c((co == 1 || co == 2) && i == 0 ? 1 : 0)));
-    for (int co = 0; co < 4; co++)
-        for (int i = 0; i < 16; i++) {
-            const uint64_t want = co == 0 ? BXL[i] : (co == 1 ? BYL[i] : (co == 2 ? (uint64_t)(i == 0) : BTL[i]));
-            emit(S0 * (l[ED_TMP + 16 * co + i] - F::c(want)));
-        }
-    for (int co = 0; co < 4; co++)
-        for (int i = 0; i < 16; i++) emit(H0 * (l[ED_RES + 16 * co + i] - F::c((co == 1 || co == 2) && i == 0 ? 1 : 0)));
-    for (int i = 0; i < 16; i++) emit(H0 * (l[ED_TMP + 32 + i] - F::c(i == 0 ? 1 : 0)));
+    ed_mul_gadget<F>(E, Fq, l, G(ED_G_X3), emit);
+    ed_mul_gadget<F>(Gq, H, l, G(ED_G_Y3), emit);
+    ed_mul_gadget<F>(E, H, l, G(ED_G_T3), emit);
+    ed_mul_gadget<F>(Fq, Gq, l, G(ED_G_Z3), emit);
+    // ---- mixed addition of the row's addend (add-2008-hwcd-3 with Z2 = 1; the T output is never used) ----
+    for (int i = 0; i < 16; i++) {
+        u[i] = (l[G(ED_G_Y3) + i] - l[G(ED_G_X3) + i]) + F::c(p25519_limb(i));
+        v[i] = l[YMX + i];
+    }
+    ed_mul_gadget<F>(u, v, l, G(ED_G_AA), emit);
+    for (int i = 0; i < 16; i++) {
+        u[i] = l[G(ED_G_Y3) + i] + l[G(ED_G_X3) + i];
+        v[i] = l[YPX + i];
+    }
+    ed_mul_gadget<F>(u, v, l, G(ED_G_BB), emit);
+    for (int i = 0; i < 16; i++) {
+        u[i] = l[G(ED_G_T3) + i];
+        v[i] = l[T2D + i];
+    }
+    ed_mul_gadget<F>(u, v, l, G(ED_G_CC), emit);
+    for (int i = 0; i < 16; i++) {
+        const F pl = F::c(p25519_limb(i));
+        const F A = l[G(ED_G_AA) + i], B = l[G(ED_G_BB) + i], C = l[G(ED_G_CC) + i], Z3 = l[G(ED_G_Z3) + i];
+        const F d2 = Z3 + Z3;
+        E[i] = (B - A) + pl;
+        Fq[i] = (d2 - C) + pl;
+        Gq[i] = d2 + C;
+        H[i] = B + A;
+    }
+    ed_mul_gadget<F>(E, Fq, l, G(ED_G_X4), emit);
+    ed_mul_gadget<F>(Gq, H, l, G(ED_G_Y4), emit);
+    ed_mul_gadget<F>(Fq, Gq, l, G(ED_G_Z4), emit);
+    // ---- transitions inside a slot, accumulator = O = (0 : 1 : 1) on its first row ----
+    const int out_slot[3] = {ED_G_X4, ED_G_Y4, ED_G_Z4};
+    for (int co = 0; co < 3; co++)
+        for (int i = 0; i < 16; i++) emit(NOTEND * (n[ED_ACC + 16 * co + i] - l[G(out_slot[co]) + i]));
+    for (int co = 0; co < 3; co++)
+        for (int i = 0; i < 16; i++) emit(FIRST * (l[ED_ACC + 16 * co + i] - F::c(co >= 1 && i == 0 ? 1 : 0)));
+    // ---- bus: range checks of every gadget cell, then the addend lookup, the scalar limbs and the result ----
+    LookupPairs<F, Bus> rc(bus);
+    for (int m = 0; m < ED_N_MUL; m++) {
+        for (int i = 0; i < ED_MUL_WHI; i++) rc.push(BUS_R16, l[G(m) + i]);
+        for (int i = 0; i < ED_MUL_NW; i++) rc.push(BUS_R11, l[G(m) + ED_MUL_WHI + i]);
+    }
+    rc.flush();
+    const F sel = bs + (bh + bh);
+    bus.two(
+        BUS_ADDEND, F::c(0) - k[EDK_ACTIVE], 50, [&](int i) { return i == 0 ? k[EDK_VID] : (i == 1 ? sel : l[ED_ADD + i - 2]); },
+        BUS_SCALAR, k[EDK_SEND16], 4, [&](int i) { return i == 0 ? k[EDK_VID] : (i == 1 ? F::c(0) : (i == 2 ? k[EDK_LIMB] : limb_s)); });
+    bus.two(
+        BUS_SCALAR, k[EDK_SEND16], 4, [&](int i) { return i == 0 ? k[EDK_VID] : (i == 1 ? F::c(1) : (i == 2 ? k[EDK_LIMB] : limb_h)); },
+        BUS_EDRES, k[EDK_LAST], 49, [&](int i) { return i == 0 ? k[EDK_VID] : l[G(out_slot[(i - 1) >> 4]) + ((i - 1) & 15)]; });
 }
 
-template <class F, class Row, class Per, class Emit>
-TMX_HD void air_eval(int table, const Row& l, const Row& n, const Per& per, Emit& emit) {
-    if (table == AIR_SHA256) air_sha256<F>(l, n, per, emit);
-    else if (table == AIR_SHA512) air_sha512<F>(l, n, per, emit);
-    else air_ed25519<F>(l, n, per, emit);
+// ------------------------------------------------------------------------------------------ range table
+// row t provides the value t (constant column RGK_T) to the 16-bit lookups with multiplicity M16, and on its first 2^11 /
+// 2^8 rows to the 11-bit / 8-bit lookups
+template <class F, class Row, class KRow, class Per, class Emit, class Bus>
+TMX_HD void air_range(const Row& l, const Row&, const KRow& k, const Per&, Emit& emit, Bus& bus) {
+    emit((F::c(1) - k[RGK_S11]) * l[RG_M11]);
+    emit((F::c(1) - k[RGK_S8]) * l[RG_M8]);
+    const F t = k[RGK_T];
+    bus.two(BUS_R16, l[RG_M16], 1, [&](int) { return t; }, BUS_R11, l[RG_M11], 1, [&](int) { return t; });
+    bus.one(BUS_R8, l[RG_M8], 1, [&](int) { return t; });
 }
+
+// ------------------------------------------------------------------------------------------ dispatch and table shapes
+template <class F, class Row, class KRow, class Per, class Emit, class Bus>
+TMX_HD void air_eval(int table, const Row& l, const Row& n, const KRow& k, const Per& per, Emit& emit, Bus& bus) {
+    if (table == AIR_SHA256) air_sha256<F>(l, n, k, per, emit, bus);
+    else if (table == AIR_SHA512) air_sha512<F>(l, n, k, per, emit, bus);
+    else if (table == AIR_ED25519) air_ed25519<F>(l, n, k, per, emit, bus);
+    else if (table == AIR_RANGE) air_range<F>(l, n, k, per, emit, bus);
+}
+
+// helper columns of the second commitment round = number of bus.one / bus.two declarations of the table's AIR
+constexpr int ED_HELPERS = ED_N_MUL * ED_MUL_STRIDE / 2 + 2;
+TMX_HD int air_cols(int t) {
+    return t == AIR_SHA256 ? S256_COLS : t == AIR_SHA512 ? S512_COLS : t == AIR_ED25519 ? ED_COLS : t == AIR_RANGE ? RG_COLS : 0;
+}
+TMX_HD int air_const_cols(int t) {
+    return t == AIR_SHA256 ? S256K_COLS : t == AIR_SHA512 ? S512K_COLS : t == AIR_ED25519 ? EDK_COLS : t == AIR_RANGE ? RGK_COLS : 0;
+}
+TMX_HD int air_helpers(int t) { return t == AIR_SHA256 ? 1 : t == AIR_SHA512 ? 1 : t == AIR_ED25519 ? ED_HELPERS : t == AIR_RANGE ? 2 : 0; }
+TMX_HD int air_aux_cols(int t) { return air_cols(t) ? 2 * (air_helpers(t) + 1) : 0; }  // helpers and the running sum, two components each
+TMX_HD int air_n_periodic(int t) { return t == AIR_SHA256 ? 5 : t == AIR_SHA512 ? 12 : t == AIR_ED25519 ? 4 : 0; }
+TMX_HD size_t air_period(int t) { return t == AIR_SHA256 ? 64 : t == AIR_SHA512 ? S512_ROWS_PER_VALIDATOR : t == AIR_ED25519 ? ED_ROWS_PER_VALIDATOR : 1; }
+
+TMX_HD size_t air_pow2_at_least(size_t x) {
+    size_t p = 1;
+    while (p < x) p *= 2;
+    return p;
+}
+TMX_HD size_t air_sha256_used_chunks(AirShape sh) {
+    const size_t np = air_pow2_at_least(sh.n_max), set = (size_t)sh.n_max + 2 * (np - 1);
+    return sh.kind == 1 ? 2 * set + 36 : set + 46;
+}
+// rows of table t for a circuit shape (0 = the table is absent)
+TMX_HD size_t air_rows(int t, AirShape sh) {
+    if (t == AIR_SHA256) return air_pow2_at_least(air_sha256_used_chunks(sh) * S256_ROUNDS);
+    if (t == AIR_SHA512) return air_pow2_at_least((size_t)sh.n_max * S512_ROWS_PER_VALIDATOR);
+    if (t == AIR_ED25519) return air_pow2_at_least((size_t)sh.n_max * ED_ROWS_PER_VALIDATOR);
+    if (t == AIR_RANGE) return (size_t)1 << RG_LOG_ROWS;
+    return 0;
+}
+
+// The cross-table messages (hash inputs / digests, scalar limbs, addends, results) have their counterparty in the logic
+// table; until that table carries them their multiplicity columns are zero and only the range-check bus is live.
+#ifndef TMX_BUS_LINKS
+#define TMX_BUS_LINKS 0
+#endif
 
 // periodic pattern of column pc at row r of its period
-TMX_HD uint64_t air_periodic_pattern(int table, int pc, size_t row, const uint32_t* k256_table, const uint64_t* k512_table,
-                                     AirShape shape) {
-    const int r = (int)(row & 511);
+TMX_HD uint64_t air_periodic_pattern(int table, int pc, size_t row, const uint32_t* k256_table, const uint64_t* k512_table) {
     if (table == AIR_SHA256) {
         const int r64 = (int)(row & 63);
         if (pc == 0) return k256_table[r64];
         if (pc == 1) return r64 == 63;
         if (pc == 2) return r64 != 63;
         if (pc == 3) return r64 >= 15 && r64 <= 62;
-        if (pc == 4) return r64 == 0 && !sha256_chunk_continues(shape, row >> 6);
-        return r64 == 63 && sha256_chunk_continues(shape, (row >> 6) + 1);
+        return r64 == 0;
     }
     if (table == AIR_SHA512) {
+        const int r = (int)(row & 255);
         const int rr = r % S512_ROWS_PER_CHUNK;  // row inside the chunk; r is the row inside the validator's two-chunk slot
         if (pc == 0) return rr < S512_ROUNDS ? (uint32_t)k512_table[rr] : 0;
         if (pc == 1) return rr < S512_ROUNDS ? k512_table[rr] >> 32 : 0;
@@ -432,11 +578,55 @@ TMX_HD uint64_t air_periodic_pattern(int table, int pc, size_t row, const uint32
         if (pc == 7) return rr < S512_ROUNDS - 1;
         if (pc == 8) return rr >= S512_ROUNDS - 1 && rr <= S512_ROWS_PER_CHUNK - 2;
         if (pc == 9) return r == S512_ROWS_PER_CHUNK - 1;
-        return r != S512_ROWS_PER_VALIDATOR - 1;
+        if (pc == 10) return r != S512_ROWS_PER_VALIDATOR - 1;
+        return rr == 0;
     }
-    if (pc == 0) return (r & 255) != 255;
+    const int r = (int)(row & 255);  // Ed25519
+    if (pc == 0) return r != 255;
     if (pc == 1) return r == 0;
-    return r == 256;
+    if (pc == 2) return (r & 15) != 15;
+    return (r & 15) == 0;
+}
+
+// value of constant column kc of table t at row `row` (fixed by the circuit shape; committed once per circuit, the cap of
+// that commitment is part of the circuit digest)
+TMX_HD uint64_t air_const_value(int table, int kc, size_t row, AirShape sh) {
+    if (table == AIR_SHA256) {
+        const int r64 = (int)(row & 63);
+        const size_t chunk = row >> 6;
+        const bool used = chunk < air_sha256_used_chunks(sh);
+        if (kc == S256K_FIRST) return r64 == 0 && !sha256_chunk_continues(sh, chunk);
+        if (kc == S256K_LINK) return r64 == 63 && sha256_chunk_continues(sh, chunk + 1);
+        if (kc == S256K_CID) return chunk;
+        if (kc == S256K_MSG) return TMX_BUS_LINKS && used && r64 == 15;
+        return TMX_BUS_LINKS && used && r64 == 63 && !sha256_chunk_continues(sh, chunk + 1);
+    }
+    if (table == AIR_SHA512) {
+        const int r = (int)(row & 255);
+        const size_t slot = row >> 8;
+        const bool active = slot < sh.n_max;
+        if (kc == S512K_VID) return slot;
+        if (kc == S512K_CHUNK) return r >> 7;
+        if (kc == S512K_MSG) return TMX_BUS_LINKS && active && (r & 127) == 15;
+        if (kc == S512K_DIG0) return TMX_BUS_LINKS && active && r == S512_ROUNDS - 1;
+        return TMX_BUS_LINKS && active && r == S512_ROWS_PER_CHUNK + S512_ROUNDS - 1;
+    }
+    if (table == AIR_ED25519) {
+        const int r = (int)(row & 255);
+        const size_t slot = row >> 8;
+        const bool active = TMX_BUS_LINKS && slot < sh.n_max;
+        if (kc == EDK_VID) return slot;
+        if (kc == EDK_ACTIVE) return active;
+        if (kc == EDK_SEND16) return active && (r & 15) == 15;
+        if (kc == EDK_LIMB) return 15 - (r >> 4);
+        return active && r == 255;
+    }
+    if (table == AIR_RANGE) {
+        if (kc == RGK_T) return row;
+        if (kc == RGK_S11) return row < 2048;
+        return row < 256;
+    }
+    return 0;
 }
 
 // Host NTT (in place, natural order in and out) for the public columns: iterative radix-2, O(n log n).
@@ -467,11 +657,11 @@ inline void air_host_ntt(std::vector<gl>& a, bool inverse) {
     }
 }
 
-// coefficients of the interpolant of periodic / public column pc over one period (P values)
-inline std::vector<gl> air_periodic_coeffs(int table, int pc, size_t P, const uint32_t* k256_table, const uint64_t* k512_table,
-                                           AirShape shape) {
+// coefficients of the interpolant of periodic column pc over one period (P values)
+inline std::vector<gl> air_periodic_coeffs(int table, int pc, const uint32_t* k256_table, const uint64_t* k512_table) {
+    const size_t P = air_period(table);
     std::vector<gl> c(P);
-    for (size_t r = 0; r < P; r++) c[r] = (gl)air_periodic_pattern(table, pc, r, k256_table, k512_table, shape);
+    for (size_t r = 0; r < P; r++) c[r] = (gl)air_periodic_pattern(table, pc, r, k256_table, k512_table);
     air_host_ntt(c, true);
     return c;
 }
@@ -479,14 +669,13 @@ inline std::vector<gl> air_periodic_coeffs(int table, int pc, size_t P, const ui
 // Host: values of the periodic columns on the LDE coset, [nper][2P], indexed by (natural LDE index mod 2P).
 // Column pc is the interpolant s of its one-period pattern composed with x -> x^(n/P); on the coset
 // x_j = 7 w_m^j this only depends on j mod 2P: s(7^(n/P) w_2P^j).
-inline std::vector<gl> air_periodic_lde_table(int table, unsigned log_n, const uint32_t* k256_table, const uint64_t* k512_table,
-                                              AirShape shape) {
-    const size_t n = (size_t)1 << log_n, P = air_period(table, n);
+inline std::vector<gl> air_periodic_lde_table(int table, unsigned log_n, const uint32_t* k256_table, const uint64_t* k512_table) {
+    const size_t n = (size_t)1 << log_n, P = air_period(table);
     const int nper = air_n_periodic(table);
     std::vector<gl> tab((size_t)nper * 2 * P);
     const gl sh = gl_pow(GL_GEN, n / P);
     for (int pc = 0; pc < nper; pc++) {
-        std::vector<gl> coef = air_periodic_coeffs(table, pc, P, k256_table, k512_table, shape);
+        std::vector<gl> coef = air_periodic_coeffs(table, pc, k256_table, k512_table);
         coef.resize(2 * P, 0);
         gl s = 1;
         for (size_t k = 0; k < P; k++) {  // s(sh * x): scale coefficient k by sh^k, then a plain NTT of size 2P

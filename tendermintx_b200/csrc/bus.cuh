@@ -1,0 +1,131 @@
+// Bus (logUp) callbacks plugged into the AIR templates of air.cuh.  A table's AIR declares its interactions through
+// bus.one / bus.two; what happens then depends on the pass:
+//   BusCheck<F>  constraint side (quotient kernels with F = FB on the LDE coset, verifier with F = FE at zeta): every
+//                declaration owns one helper column H (extension valued, two committed columns) with
+//                    one:  H f = m                       two:  H fa fb = ma fb + mb fa
+//                and the running sum Z of the second-round trace satisfies, on EVERY row (cyclically),
+//                    Z(g x) - Z(x) - sum_k H_k(x) + S / n = 0,
+//                so S is the table's total bus contribution without any first / last row selector.
+//   BusGen       trace-domain pass of the prover: computes the helper values of one row.
+//   BusCount     trace-domain pass of the prover: histogram of the range-checked values (multiplicity columns of the
+//                range table).
+// Upstream the same role is played by Curta's lookup / bus arguments behind `curta_eddsa_verify_sigs_conditional` and
+// `curta_sha256_variable` [REF circuits/builder/verify.rs:202,248-259] and by plonky2's copy constraints.
+#pragma once
+#include "air.cuh"
+
+namespace tmx {
+
+struct NullEmit {
+    template <class F>
+    TMX_HD void operator()(F) const {}
+};
+
+template <class F, class AuxRow, class Emit>
+struct BusCheck {
+    Ext2<F> beta, gamma;
+    const AuxRow& al;
+    Emit& emit;
+    int h;
+    Ext2<F> sum;
+    TMX_HD BusCheck(Ext2<F> b, Ext2<F> g, const AuxRow& a, Emit& e) : beta(b), gamma(g), al(a), emit(e), h(0) {
+        sum = e2_mk<F>(F::c(0), F::c(0));
+    }
+    TMX_HD Ext2<F> helper() {
+        const Ext2<F> H = e2_mk<F>(al[2 * h], al[2 * h + 1]);
+        h++;
+        sum = e2_add<F>(sum, H);
+        return H;
+    }
+    template <class Tup>
+    TMX_HD void one(int tag, F m, int len, const Tup& tup) {
+        const Ext2<F> f = bus_fingerprint<F>(beta, gamma, tag, len, tup);
+        Ext2<F> c = e2_mul<F>(helper(), f);
+        c.a0 = c.a0 - m;
+        emit(c.a0);
+        emit(c.a1);
+    }
+    template <class TA, class TB>
+    TMX_HD void two(int tag_a, F ma, int len_a, const TA& ta, int tag_b, F mb, int len_b, const TB& tb) {
+        const Ext2<F> fa = bus_fingerprint<F>(beta, gamma, tag_a, len_a, ta);
+        const Ext2<F> fb = bus_fingerprint<F>(beta, gamma, tag_b, len_b, tb);
+        const Ext2<F> c = e2_sub<F>(e2_mul<F>(helper(), e2_mul<F>(fa, fb)), e2_add<F>(e2_scale<F>(fb, ma), e2_scale<F>(fa, mb)));
+        emit(c.a0);
+        emit(c.a1);
+    }
+    // an: the next row of the second-round trace; s_over_n: the table's claimed total divided by its length
+    TMX_HD void finish(const AuxRow& an, Ext2<F> s_over_n) {
+        const Ext2<F> z = e2_mk<F>(al[2 * h], al[2 * h + 1]), zn = e2_mk<F>(an[2 * h], an[2 * h + 1]);
+        const Ext2<F> c = e2_add<F>(e2_sub<F>(e2_sub<F>(zn, z), sum), s_over_n);
+        emit(c.a0);
+        emit(c.a1);
+    }
+};
+
+// helper values of one trace row, written to out[2 * h], out[2 * h + 1] with stride `stride`; the row's sum is kept
+struct BusGen {
+    gl2 beta, gamma;
+    gl* out;
+    size_t stride;
+    int h;
+    gl2 sum;
+    TMX_HD BusGen(gl2 b, gl2 g, gl* o, size_t s) : beta(b), gamma(g), out(o), stride(s), h(0) { sum = gl2_from(0); }
+    TMX_HD void put(gl2 H) {
+        out[(size_t)(2 * h) * stride] = H.a0;
+        out[(size_t)(2 * h + 1) * stride] = H.a1;
+        h++;
+        sum = gl2_add(sum, H);
+    }
+    template <class Tup>
+    TMX_HD gl2 fp(int tag, int len, const Tup& tup) const {
+        gl2 acc = gl2_from(0);
+        for (int i = len - 1; i >= 0; i--) {
+            acc.a0 = gl_add(acc.a0, tup(i).v);
+            acc = gl2_mul(acc, beta);
+        }
+        acc.a0 = gl_add(acc.a0, (gl)tag);
+        return gl2_add(acc, gamma);
+    }
+    template <class Tup>
+    TMX_HD void one(int tag, FB m, int len, const Tup& tup) {
+        if (m.v == 0) { put(gl2_from(0)); return; }
+        put(gl2_scale(gl2_inv(fp(tag, len, tup)), m.v));
+    }
+    template <class TA, class TB>
+    TMX_HD void two(int tag_a, FB ma, int len_a, const TA& ta, int tag_b, FB mb, int len_b, const TB& tb) {
+        if (ma.v == 0 && mb.v == 0) { put(gl2_from(0)); return; }
+        const gl2 fa = fp(tag_a, len_a, ta), fb = fp(tag_b, len_b, tb);
+        const gl2 num = gl2_add(gl2_scale(fb, ma.v), gl2_scale(fa, mb.v));
+        put(gl2_mul(num, gl2_inv(gl2_mul(fa, fb))));
+    }
+};
+
+// histogram of the range lookups (multiplicity p - 1 = -1) of one trace row: hist[0 .. 2^16) 16-bit, then 2^11, then 2^8
+struct BusCount {
+    unsigned int* hist;
+    int* bad;  // set when a looked-up value is outside its table (the witness cannot be proved)
+    TMX_HD void add(int tag, FB m, gl v) {
+        if (m.v != GL_P - 1) return;
+        size_t base, lim;
+        if (tag == BUS_R16) { base = 0; lim = 1u << 16; }
+        else if (tag == BUS_R11) { base = 1u << 16; lim = 1u << 11; }
+        else if (tag == BUS_R8) { base = (1u << 16) + (1u << 11); lim = 1u << 8; }
+        else return;
+        if (v >= lim) { *bad = 1; return; }
+#if defined(__CUDA_ARCH__)
+        atomicAdd(hist + base + v, 1u);
+#else
+        hist[base + v]++;
+#endif
+    }
+    template <class Tup>
+    TMX_HD void one(int tag, FB m, int, const Tup& tup) { add(tag, m, tup(0).v); }
+    template <class TA, class TB>
+    TMX_HD void two(int tag_a, FB ma, int, const TA& ta, int tag_b, FB mb, int, const TB& tb) {
+        add(tag_a, ma, ta(0).v);
+        add(tag_b, mb, tb(0).v);
+    }
+};
+constexpr size_t BUS_HIST_SIZE = (1u << 16) + (1u << 11) + (1u << 8);
+
+}  // namespace tmx

@@ -8,6 +8,7 @@
 // from the input blob and the digests the witness kernels produced, and abort the proof with TMX_E_UNSAT exactly
 // where the reference's witness generation would panic.
 #include "stark.cuh"
+#include "bus.cuh"
 #include "witness_jobs.cuh"
 #include <cstring>
 #include <cstdio>
@@ -22,18 +23,18 @@ struct tmx_circuit {
     std::string chain_id;
     uint64_t skip_max = 0;
     size_t dims[6] = {0, 0, 0, 0, 0, 0};
-    gl digest[4] = {0, 0, 0, 0};
+    std::shared_ptr<const CircuitDef> def;  // table shapes, constant columns, constraint DAG, digest
     // device state reused across proofs
     gl* d_trace[3] = {nullptr, nullptr, nullptr};
     uint8_t* d_blob = nullptr;
     uint8_t* d_aux = nullptr;
-    void* d_points = nullptr;           // Ed25519 ladder states (phase 1 -> phase 2)
-    cudaStream_t side = nullptr;        // second stream: the latency-bound ladders overlap with table 0's proving
+    void* d_points = nullptr;           // Ed25519 slot info + accumulators (phase 1 -> phase 2)
+    cudaStream_t side = nullptr;        // second stream: the latency-bound sequential Ed25519 rows
     cudaEvent_t ev_inputs = nullptr, ev_ladder = nullptr;
     std::vector<uint8_t> h_blob;  // host copy of the resident inputs (tmx_circuit_set_inputs)
     bool resident = false;
-    TableProver prover;
-    float phase_ms[6] = {0, 0, 0, 0, 0, 0};  // per table of the last proof: LDE (K1), trace Merkle tree (K2), device time
+    Prover prover;
+    float phase_ms[6] = {0, 0, 0, 0, 0, 0};  // per witness table of the last proof: LDE (K1), trace Merkle tree (K2), device time
 };
 
 struct tmx_proof {
@@ -43,38 +44,6 @@ struct tmx_proof {
 namespace tmx {
 
 static thread_local int g_last_check = 0;
-
-static void hash_no_pad_host(const gl* in, size_t n, gl out[4]) {
-    gl s[12] = {0};
-    for (size_t off = 0; off < n; off += 8) {
-        const size_t k = std::min<size_t>(8, n - off);
-        for (size_t i = 0; i < k; i++) s[i] = in[off + i];
-        poseidon_permute(s);
-    }
-    for (int i = 0; i < 4; i++) out[i] = s[i];
-}
-
-static void circuit_digest(const tmx_circuit* c, gl out[4]) {
-    gl in[96];
-    size_t k = 0;
-    in[k++] = STARK_PROOF_MAGIC; in[k++] = c->kind; in[k++] = c->n_max; in[k++] = c->skip_max;
-    in[k++] = STARK_RATE_BITS; in[k++] = STARK_CAP_HEIGHT; in[k++] = 2; in[k++] = STARK_POW_BITS; in[k++] = STARK_NUM_QUERIES;
-    in[k++] = STARK_ARITY_BITS; in[k++] = STARK_FINAL_POLY_BITS;
-    for (int i = 0; i < 6; i++) in[k++] = c->dims[i];
-    in[k++] = c->chain_id.size();
-    for (size_t i = 0; i < c->chain_id.size() && i < 64; i++) in[k++] = (uint8_t)c->chain_id[i];
-    hash_no_pad_host(in, k, out);
-}
-
-static void transcript_init(const tmx_circuit* c, const uint8_t* input, size_t input_len, const uint8_t out32[32], Challenger& ch) {
-    ch.observe(c->digest, 4);
-    gl pub[128], ph[4];
-    size_t k = 0;
-    for (size_t i = 0; i < input_len; i++) pub[k++] = input[i];
-    for (size_t i = 0; i < 32; i++) pub[k++] = out32[i];
-    hash_no_pad_host(pub, k, ph);
-    ch.observe(ph, 4);
-}
 
 static uint64_t be64(const uint8_t* p) {
     uint64_t v = 0;
@@ -209,40 +178,34 @@ extern "C" int tmx_last_check(void) { return g_last_check; }
 namespace tmx {
 void set_last_check(int check) { g_last_check = check; }  // pool.cu hands a worker's verdict to the waiting thread
 }
-extern "C" int tmx_verify(const tmx_circuit* c, const uint8_t* proof, size_t proof_len, const uint8_t* input, size_t input_len,
-                          const uint8_t out32[32]);
-
 extern "C" int tmx_circuit_build(tmx_ctx* ctx, uint32_t kind, uint32_t n_max, const char* chain_id, size_t chain_id_len,
                                  uint64_t skip_max, tmx_circuit** out) {
     if (!ctx || !out || !chain_id || kind > 1 || n_max == 0 || n_max > 4096 || chain_id_len == 0 || chain_id_len > 50)
         return fail(TMX_E_INPUT, "tmx_circuit_build: bad arguments");
-    tmx_circuit* c = new tmx_circuit();
+    std::unique_ptr<tmx_circuit, void (*)(tmx_circuit*)> c(new tmx_circuit(), tmx_circuit_free);
     c->ctx = ctx;
     c->kind = kind;
     c->n_max = n_max;
     c->chain_id.assign(chain_id, chain_id_len);
     c->skip_max = skip_max;
     tmx_trace_dims(kind, n_max, c->dims);
-    poseidon_generate_constants();
-    circuit_digest(c, c->digest);
+    c->def = circuit_def_get(kind, n_max, c->chain_id, skip_max);
+    if (!c->def) return fail(TMX_E_INPUT, std::string("tmx_circuit_build: ") + tmx_last_error());
     cudaSetDevice(ctx->device);
     for (int t = 0; t < 3; t++) {
         cudaError_t e = cudaMalloc((void**)&c->d_trace[t], c->dims[2 * t] * c->dims[2 * t + 1] * sizeof(gl));
-        if (e != cudaSuccess) {
-            tmx_circuit_free(c);
-            return fail(TMX_E_CUDA, std::string("tmx_circuit_build: cudaMalloc: ") + cudaGetErrorString(e));
-        }
+        if (e != cudaSuccess) return fail(TMX_E_CUDA, std::string("tmx_circuit_build: cudaMalloc: ") + cudaGetErrorString(e));
     }
     if (cudaMalloc((void**)&c->d_blob, TMX_BLOB_SIZE(kind, n_max)) != cudaSuccess ||
         cudaMalloc((void**)&c->d_aux, aux_bytes(n_max)) != cudaSuccess ||
         cudaMalloc(&c->d_points, witness_points_bytes(n_max)) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_inputs, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->ev_ladder, cudaEventDisableTiming) != cudaSuccess) {
-        tmx_circuit_free(c);
+        cudaEventCreateWithFlags(&c->ev_ladder, cudaEventDisableTiming) != cudaSuccess)
         return fail(TMX_E_CUDA, "tmx_circuit_build: cudaMalloc failed");
-    }
-    *out = c;
+    const int rc = c->prover.setup(ctx, c->def);
+    if (rc) return rc;
+    *out = c.release();
     return TMX_OK;
 }
 
@@ -262,21 +225,19 @@ extern "C" void tmx_circuit_free(tmx_circuit* c) {
 }
 
 extern "C" int tmx_circuit_digest(const tmx_circuit* c, uint64_t out[4]) {
-    if (!c || !out) return fail(TMX_E_INPUT, "tmx_circuit_digest: NULL argument");
-    for (int i = 0; i < 4; i++) out[i] = c->digest[i];
+    if (!c || !out || !c->def) return fail(TMX_E_INPUT, "tmx_circuit_digest: NULL argument");
+    for (int i = 0; i < 4; i++) out[i] = c->def->digest[i];
     return TMX_OK;
 }
 
-// build artefact: the parameters that define the circuit plus its digest (the preprocessed data is recomputed
-// from them on load; see DESIGN.md "Preprocessed data")
+// build artefact (./build/main.circuit [REF succinct.json:8,15]): the circuit definition as data -- table shapes,
+// constant columns and the caps of their commitments, periodic columns, constraint DAG and bus program, digest
 extern "C" int tmx_circuit_save(const tmx_circuit* c, const char* path) {
-    if (!c || !path) return fail(TMX_E_INPUT, "tmx_circuit_save: NULL argument");
+    if (!c || !path || !c->def) return fail(TMX_E_INPUT, "tmx_circuit_save: NULL argument");
     FILE* f = fopen(path, "wb");
     if (!f) return fail(TMX_E_IO, std::string("tmx_circuit_save: cannot open ") + path);
-    uint64_t hdr[4] = {STARK_PROOF_MAGIC ^ 0x43ULL, c->kind, c->n_max, c->skip_max};
-    uint64_t len = c->chain_id.size();
-    bool ok = fwrite(hdr, sizeof hdr, 1, f) == 1 && fwrite(&len, 8, 1, f) == 1 && fwrite(c->chain_id.data(), 1, len, f) == len &&
-              fwrite(c->digest, sizeof c->digest, 1, f) == 1;
+    const std::vector<uint64_t> w = c->def->serialize();
+    const bool ok = fwrite(w.data(), sizeof(uint64_t), w.size(), f) == w.size();
     fclose(f);
     return ok ? TMX_OK : fail(TMX_E_IO, "tmx_circuit_save: short write");
 }
@@ -285,16 +246,18 @@ extern "C" int tmx_circuit_load(tmx_ctx* ctx, const char* path, tmx_circuit** ou
     if (!ctx || !path || !out) return fail(TMX_E_INPUT, "tmx_circuit_load: NULL argument");
     FILE* f = fopen(path, "rb");
     if (!f) return fail(TMX_E_IO, std::string("tmx_circuit_load: cannot open ") + path);
-    uint64_t hdr[4], len = 0;
-    char cid[64];
-    gl dg[4];
-    bool ok = fread(hdr, sizeof hdr, 1, f) == 1 && fread(&len, 8, 1, f) == 1 && len <= 50 && fread(cid, 1, len, f) == len &&
-              fread(dg, sizeof dg, 1, f) == 1;
+    std::vector<uint64_t> w;
+    uint64_t buf[4096];
+    size_t got;
+    while ((got = fread(buf, sizeof(uint64_t), 4096, f)) > 0) w.insert(w.end(), buf, buf + got);
     fclose(f);
-    if (!ok || hdr[0] != (STARK_PROOF_MAGIC ^ 0x43ULL)) return fail(TMX_E_INPUT, "tmx_circuit_load: not a circuit file");
-    int rc = tmx_circuit_build(ctx, (uint32_t)hdr[1], (uint32_t)hdr[2], cid, len, hdr[3], out);
+    // the artefact authenticates itself (its digest covers shapes, caps and constraints); this build then re-derives the
+    // definition from the parameters and requires the same digest, i.e. the file was produced by a compatible version
+    auto parsed = circuit_def_parse(w.data(), w.size());
+    if (!parsed) return fail(TMX_E_INPUT, std::string("tmx_circuit_load: ") + tmx_last_error());
+    int rc = tmx_circuit_build(ctx, parsed->kind, parsed->n_max, parsed->chain_id.data(), parsed->chain_id.size(), parsed->skip_max, out);
     if (rc) return rc;
-    if (memcmp(dg, (*out)->digest, sizeof dg)) {
+    if (memcmp(parsed->digest, (*out)->def->digest, sizeof parsed->digest)) {
         tmx_circuit_free(*out);
         *out = nullptr;
         return fail(TMX_E_INPUT, "tmx_circuit_load: digest mismatch (built by a different version?)");
@@ -315,6 +278,25 @@ extern "C" int tmx_circuit_set_inputs(tmx_circuit* c, const uint8_t* blob, size_
     return TMX_OK;
 }
 
+// The length fields of the blob index fixed-size buffers inside the witness kernels: reject anything out of range before a
+// kernel sees it [REF circuits/consts.rs:4-37 for the bounds; the reference's fixed-size array types cannot hold more].
+static bool blob_lengths_ok(const tmx_circuit* c, const uint8_t* blob) {
+    const tmx_offchain_head* h = blob_head(blob);
+    if (h->nb_validators > c->n_max || (c->kind == TMX_KIND_SKIP && h->nb_trusted > c->n_max)) return false;
+    if (h->chain_id_proof.enc_chain_id_byte_length > TMX_PROTOBUF_CHAIN_ID_SIZE_BYTES) return false;
+    if (h->height_proof.enc_height_byte_length > 1 + TMX_VARINT_BYTES_LENGTH_MAX) return false;
+    const tmx_validator* v = blob_validators(blob);
+    for (uint32_t i = 0; i < c->n_max; i++)
+        if (v[i].validator_byte_length > TMX_VALIDATOR_BYTE_LENGTH_MAX || v[i].message_byte_length > TMX_VALIDATOR_MESSAGE_BYTES_LENGTH_MAX)
+            return false;
+    if (c->kind == TMX_KIND_SKIP) {
+        const tmx_hash_field* f = blob_hash_fields(blob, c->n_max);
+        for (uint32_t i = 0; i < c->n_max; i++)
+            if (f[i].validator_byte_length > TMX_VALIDATOR_BYTE_LENGTH_MAX) return false;
+    }
+    return true;
+}
+
 extern "C" int tmx_prove(tmx_circuit* c, const uint8_t* input, size_t input_len, const uint8_t* blob, size_t blob_len,
                          tmx_proof** proof_out, uint8_t out32[32]) {
     if (!c || !input || !proof_out || !out32) return fail(TMX_E_INPUT, "tmx_prove: NULL argument");
@@ -328,44 +310,37 @@ extern "C" int tmx_prove(tmx_circuit* c, const uint8_t* input, size_t input_len,
     *proof_out = nullptr;
     const tmx_offchain_head* h = blob_head(blob);
     if (blob_len < sizeof(tmx_offchain_head) || h->magic != TMX_BLOB_MAGIC || h->kind != c->kind || h->n_max != c->n_max ||
-        blob_len != TMX_BLOB_SIZE(c->kind, c->n_max) || input_len != (c->kind == TMX_KIND_SKIP ? 48u : 40u)) {
+        blob_len != TMX_BLOB_SIZE(c->kind, c->n_max) || input_len != (c->kind == TMX_KIND_SKIP ? 48u : 40u) ||
+        !blob_lengths_ok(c, blob)) {
         g_last_check = CHECK_INPUT;
         return fail(TMX_E_INPUT, "tmx_prove: input / blob does not match the circuit shape");
     }
     tmx_ctx* ctx = c->ctx;
     TMX_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    const bool timing = getenv("TMX_TIMING") != nullptr;
-    timespec ts0;
-    clock_gettime(CLOCK_MONOTONIC, &ts0);
-    // witness generation on the GPU
+    Prover& pr = c->prover;
+    // ---- witness generation on the GPU ----
     if (!use_resident) {
         TMX_CUDA(cudaMemcpyAsync(c->d_blob, blob, blob_len, cudaMemcpyHostToDevice, st));
         c->resident = false;
     }
     TMX_CUDA(cudaMemsetAsync(c->d_aux, 0, aux_bytes(c->n_max), st));
+    TMX_CUDA(cudaMemsetAsync(pr.d_hist, 0, (BUS_HIST_SIZE + 4) * sizeof(unsigned int), st));
     WitnessArgs wa;
     int rc = witness_make_args(ctx, c->d_blob, c->kind, c->n_max, c->d_trace[0], c->d_trace[1], c->d_trace[2], c->d_aux, &wa);
     if (rc) return rc;
-    // side stream: Ed25519 phase 1 (sequential ladders, ~6 ms of latency, two warps per validator) overlaps with the
-    // latency-bound part of the SHA-256 table's proof (quotient, openings, FRI: small kernels and host round trips).  It is
-    // started only after that table's commitment: run next to the LDE it kept the NTT tiles off its 128 SMs (the LDE
-    // took 6.8 ms instead of 1.5), and next to the leaf hashing its 11 k registers per SM push one hashing CTA per SM
-    // into a second wave.
+    // side stream: the sequential Ed25519 rows (one thread per validator slot, milliseconds of latency) run next to the
+    // SHA-256 table's witness generation and commitment
     TMX_CUDA(cudaEventRecord(c->ev_inputs, st));
-    auto start_ladders = [&](cudaEvent_t committed) -> int {
-        TMX_CUDA(cudaStreamWaitEvent(c->side, c->ev_inputs, 0));
-        TMX_CUDA(cudaStreamWaitEvent(c->side, committed, 0));
-        int r = run_ed25519_ladder(ctx, wa, c->d_points, c->side);
-        if (r) return r;
-        TMX_CUDA(cudaEventRecord(c->ev_ladder, c->side));
-        return TMX_OK;
-    };
+    TMX_CUDA(cudaStreamWaitEvent(c->side, c->ev_inputs, 0));
+    rc = run_ed25519_ladder(ctx, wa, c->d_points, c->side);
+    if (rc) return rc;
+    TMX_CUDA(cudaEventRecord(c->ev_ladder, c->side));
     rc = witness_run_sha256(ctx, wa, st);
     if (rc) return rc;
     memcpy(out32, h->header, 32);
-    // proof: header, then one STARK per table on a shared transcript
-    tmx_proof* p = new tmx_proof();
+    // ---- proof: header, round 1, round 2, one tail per table on a shared transcript ----
+    std::unique_ptr<tmx_proof> p(new tmx_proof());
     std::vector<gl>& w = p->words;
     w.push_back(STARK_PROOF_MAGIC);
     w.push_back(c->kind);
@@ -377,46 +352,42 @@ extern "C" int tmx_prove(tmx_circuit* c, const uint8_t* input, size_t input_len,
         w.push_back(x);
     }
     Challenger ch;
-    transcript_init(c, input, input_len, out32, ch);
-    c->prover.shape = AirShape{c->kind, c->n_max};
-    rc = c->prover.prove(ctx, 0, c->d_trace[0], ilog2(c->dims[0]), ch, w, st, start_ladders);
-    if (rc) {
-        delete p;
-        return rc;
-    }
-    c->phase_ms[0] = c->prover.last_lde_ms;
-    c->phase_ms[1] = c->prover.last_merkle_ms;
-    // join: phase 2 of the Ed25519 / SHA-512 tables, then the gadget checks that need the kernels' digests
+    transcript_init(c->def->digest, input, input_len, out32, ch);
+    // round 1
+    if ((rc = pr.count_lookups(ctx, AIR_SHA256, c->d_trace[0], st))) return rc;
+    if ((rc = pr.commit_main(ctx, AIR_SHA256, c->d_trace[0], st))) return rc;
     TMX_CUDA(cudaStreamWaitEvent(st, c->ev_ladder, 0));
-    rc = run_ed25519_expand(ctx, wa, c->d_points, st);
-    if (rc) {
-        delete p;
-        return rc;
-    }
+    if ((rc = run_ed25519_expand(ctx, wa, c->d_points, st))) return rc;
+    if ((rc = pr.count_lookups(ctx, AIR_SHA512, c->d_trace[1], st))) return rc;
+    if ((rc = pr.count_lookups(ctx, AIR_ED25519, c->d_trace[2], st))) return rc;
+    if ((rc = pr.commit_main(ctx, AIR_SHA512, c->d_trace[1], st))) return rc;
+    if ((rc = pr.commit_main(ctx, AIR_ED25519, c->d_trace[2], st))) return rc;
+    if ((rc = pr.fill_range_trace(ctx, st))) return rc;
+    if ((rc = pr.commit_main(ctx, AIR_RANGE, pr.d_range_trace, st))) return rc;
     std::vector<uint8_t> aux(aux_bytes(c->n_max));
     TMX_CUDA(cudaMemcpyAsync(aux.data(), c->d_aux, aux.size(), cudaMemcpyDeviceToHost, st));
-    TMX_CUDA(cudaStreamSynchronize(st));
-    if (timing) {
-        timespec ts1;
-        clock_gettime(CLOCK_MONOTONIC, &ts1);
-        fprintf(stderr, "  [tmx] witness + table 0     %8.3f ms\n", (ts1.tv_sec - ts0.tv_sec) * 1e3 + (ts1.tv_nsec - ts0.tv_nsec) / 1e6);
+    bool range_ok = true;
+    if ((rc = pr.finish_round1(ctx, ch, w, st, &range_ok))) return rc;
+    for (int t = 0; t < 3; t++) {
+        c->phase_ms[2 * t] = pr.lde_ms[t];
+        c->phase_ms[2 * t + 1] = pr.merkle_ms[t];
     }
+    // the gadget checks that need the kernels' digests: where the reference's witness generation would panic
     const int chk = check_statement(c, input, blob, aux.data());
     if (chk) {
-        delete p;
         g_last_check = chk;
         return fail(TMX_E_UNSAT, "tmx_prove: witness does not satisfy the circuit (check id " + std::to_string(chk) + ")");
     }
-    for (int t = 1; t < STARK_N_TABLES; t++) {
-        rc = c->prover.prove(ctx, t, c->d_trace[t], ilog2(c->dims[2 * t]), ch, w, st);
-        if (rc) {
-            delete p;
-            return rc;
-        }
-        c->phase_ms[2 * t] = c->prover.last_lde_ms;
-        c->phase_ms[2 * t + 1] = c->prover.last_merkle_ms;
-    }
-    *proof_out = p;
+    if (!range_ok) return fail(TMX_E_UNSAT, "tmx_prove: a witness cell is outside its range table");
+    const gl2 beta = ch.get_ext(), gamma = ch.get_ext();
+    // round 2
+    const gl* traces[STARK_N_TABLES] = {c->d_trace[0], c->d_trace[1], c->d_trace[2], nullptr, pr.d_range_trace};
+    for (int t = 0; t < STARK_N_TABLES; t++)
+        if ((rc = pr.commit_aux(ctx, t, traces[t], beta, gamma, st))) return rc;
+    if ((rc = pr.finish_round2(ctx, ch, w, st))) return rc;
+    for (int t = 0; t < STARK_N_TABLES; t++)
+        if ((rc = pr.prove_tail(ctx, t, beta, gamma, ch, w, st))) return rc;
+    *proof_out = p.release();
     return TMX_OK;
 }
 
@@ -455,44 +426,96 @@ extern "C" int tmx_proof_bytes(const tmx_proof* p, uint8_t* buf, size_t cap) {
 
 extern "C" void tmx_proof_free(tmx_proof* p) { delete p; }
 
+static int verify_with(const CircuitDef& def, const uint8_t* proof, size_t proof_len, const uint8_t* input, size_t input_len,
+                       const uint8_t out32[32]) {
+    if (proof_len % 8) return fail(TMX_E_VERIFY, "tmx_verify: malformed proof length");
+    std::vector<gl> w(proof_len / 8);
+    memcpy(w.data(), proof, proof_len);
+    // checks that depend on public data only are the verifier's own [REF verify.rs:508-526 verify_skip_distance]
+    if (def.kind == TMX_KIND_SKIP && input_len == 48) {
+        const uint64_t trusted = be64(input), target = be64(input + 40);
+        if (!(target > trusted + 1 && target <= trusted + def.skip_max)) return fail(TMX_E_VERIFY, "tmx_verify: skip distance out of range");
+    }
+    const int rc = verify_proof(def, w.data(), w.size(), input, input_len, out32);
+    if (rc) return fail(TMX_E_VERIFY, "tmx_verify: proof rejected (code " + std::to_string(rc) + ")");
+    return TMX_OK;
+}
+
 // Verification needs no GPU: the same check from the bare circuit parameters (what a light client would hold).
 extern "C" int tmx_verify_params(uint32_t kind, uint32_t n_max, const char* chain_id, size_t chain_id_len, uint64_t skip_max,
                                  const uint8_t* proof, size_t proof_len, const uint8_t* input, size_t input_len,
                                  const uint8_t out32[32]) {
-    if (!chain_id || kind > 1 || n_max == 0 || n_max > 4096 || chain_id_len == 0 || chain_id_len > 50)
+    if (!chain_id || !proof || !input || !out32 || kind > 1 || n_max == 0 || n_max > 4096 || chain_id_len == 0 || chain_id_len > 50)
         return fail(TMX_E_INPUT, "tmx_verify_params: bad arguments");
-    tmx_circuit c;
-    c.kind = kind;
-    c.n_max = n_max;
-    c.chain_id.assign(chain_id, chain_id_len);
-    c.skip_max = skip_max;
-    tmx_trace_dims(kind, n_max, c.dims);
-    poseidon_generate_constants();
-    circuit_digest(&c, c.digest);
-    return tmx_verify(&c, proof, proof_len, input, input_len, out32);
+    auto def = circuit_def_get(kind, n_max, std::string(chain_id, chain_id_len), skip_max);
+    if (!def) return fail(TMX_E_INPUT, std::string("tmx_verify_params: ") + tmx_last_error());
+    return verify_with(*def, proof, proof_len, input, input_len, out32);
 }
 
 extern "C" int tmx_verify(const tmx_circuit* c, const uint8_t* proof, size_t proof_len, const uint8_t* input, size_t input_len,
                           const uint8_t out32[32]) {
-    if (!c || !proof || !input || !out32) return fail(TMX_E_INPUT, "tmx_verify: NULL argument");
-    if (proof_len % 8 || input_len != (c->kind == TMX_KIND_SKIP ? 48u : 40u)) return fail(TMX_E_VERIFY, "tmx_verify: malformed proof / input length");
-    std::vector<gl> w(proof_len / 8);
-    memcpy(w.data(), proof, proof_len);
-    if (w.size() < 8 || w[0] != STARK_PROOF_MAGIC || w[1] != c->kind || w[2] != c->n_max || w[3] != STARK_N_TABLES)
-        return fail(TMX_E_VERIFY, "tmx_verify: proof header does not match the circuit");
-    for (int i = 0; i < 4; i++) {
-        gl x = 0;
-        for (int j = 0; j < 8; j++) x |= (gl)out32[8 * i + j] << (8 * j);
-        if (w[4 + i] != x) return fail(TMX_E_VERIFY, "tmx_verify: output does not match the proof");
-    }
-    poseidon_generate_constants();
-    Challenger ch;
-    transcript_init(c, input, input_len, out32, ch);
-    size_t pos = 8;
-    for (int t = 0; t < STARK_N_TABLES; t++) {
-        const int rc = verify_table(t, c->dims[2 * t], AirShape{c->kind, c->n_max}, w.data(), w.size(), &pos, ch);
-        if (rc) return fail(TMX_E_VERIFY, "tmx_verify: table " + std::to_string(t) + " rejected (code " + std::to_string(rc) + ")");
-    }
-    if (pos != w.size()) return fail(TMX_E_VERIFY, "tmx_verify: trailing data");
+    if (!c || !proof || !input || !out32 || !c->def) return fail(TMX_E_INPUT, "tmx_verify: NULL argument");
+    return verify_with(*c->def, proof, proof_len, input, input_len, out32);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel-level entry points that need a circuit's constant / periodic columns (parity tests, ncu).
+// ------------------------------------------------------------------------------------------------
+static bool table_ok(const tmx_circuit* c, int table) {
+    return c && c->def && table >= 0 && table < STARK_N_TABLES && c->def->tables[table].n_main != 0;
+}
+
+// rows / first-round / constant / second-round column counts of table t (0 rows: the table is absent)
+extern "C" int tmx_circuit_table_shape(const tmx_circuit* c, int table, size_t out[4]) {
+    if (!c || !c->def || !out || table < 0 || table >= STARK_N_TABLES) return fail(TMX_E_INPUT, "tmx_circuit_table_shape: bad arguments");
+    const TableDef& td = c->def->tables[table];
+    out[0] = td.n_main ? td.rows() : 0;
+    out[1] = td.n_main;
+    out[2] = td.n_const;
+    out[3] = (size_t)td.n_aux();
     return TMX_OK;
+}
+
+// Second commitment round of one table: helper columns of its bus interactions and the running sum, for given first-round
+// trace (device, [cols][n]) and bus challenges.  d_aux: [aux cols][n]; total: the table's bus contribution (extension element).
+extern "C" int tmx_bus_aux(tmx_circuit* c, int table, const uint64_t* d_trace, const uint64_t beta[2], const uint64_t gamma[2],
+                           uint64_t* d_aux, uint64_t total[2], void* stream) {
+    if (!table_ok(c, table) || !d_trace || !beta || !gamma || !d_aux || !total) return fail(TMX_E_INPUT, "tmx_bus_aux: bad arguments");
+    TMX_CUDA(cudaSetDevice(c->ctx->device));
+    cudaStream_t st = pick_stream(c->ctx, stream);
+    Prover& pr = c->prover;
+    const TableDef& td = c->def->tables[table];
+    int rc = pr.commit_aux(c->ctx, table, d_trace, gl2_make(beta[0], beta[1]), gl2_make(gamma[0], gamma[1]), st);
+    if (rc) return rc;
+    TMX_CUDA(cudaMemcpyAsync(d_aux, pr.tab[table].d_aux, (size_t)td.n_aux() * td.rows() * sizeof(gl), cudaMemcpyDeviceToDevice, st));
+    TMX_CUDA(cudaMemcpyAsync(total, pr.d_small + 66 * table + 64, 2 * sizeof(gl), cudaMemcpyDeviceToHost, st));
+    TMX_CUDA(cudaStreamSynchronize(st));
+    return TMX_OK;
+}
+
+// Histogram of the range lookups of one table's first-round trace: d_hist[2^16 + 2^11 + 2^8] (u32; 16-, 11-, 8-bit tables);
+// accumulates, so the caller zeroes it.  *bad is set when a value is outside its table.
+extern "C" int tmx_bus_count(tmx_circuit* c, int table, const uint64_t* d_trace, uint32_t* d_hist, int* bad, void* stream) {
+    if (!table_ok(c, table) || !d_trace || !d_hist || !bad) return fail(TMX_E_INPUT, "tmx_bus_count: bad arguments");
+    TMX_CUDA(cudaSetDevice(c->ctx->device));
+    cudaStream_t st = pick_stream(c->ctx, stream);
+    Prover& pr = c->prover;
+    TMX_CUDA(cudaMemsetAsync(pr.d_hist, 0, (BUS_HIST_SIZE + 4) * sizeof(unsigned int), st));
+    int rc = pr.count_lookups(c->ctx, table, d_trace, st);
+    if (rc) return rc;
+    unsigned int flag = 0;
+    TMX_CUDA(cudaMemcpyAsync(d_hist, pr.d_hist, BUS_HIST_SIZE * sizeof(unsigned int), cudaMemcpyDeviceToDevice, st));
+    TMX_CUDA(cudaMemcpyAsync(&flag, pr.d_hist + BUS_HIST_SIZE, sizeof flag, cudaMemcpyDeviceToHost, st));
+    TMX_CUDA(cudaStreamSynchronize(st));
+    *bad = flag != 0;
+    return TMX_OK;
+}
+
+extern "C" int tmx_quotient(tmx_circuit* c, int table, const uint64_t* d_lde_main, const uint64_t* d_lde_aux, const uint64_t total[2],
+                            const uint64_t beta[2], const uint64_t gamma[2], const uint64_t alpha[2], uint64_t* d_out, void* stream) {
+    if (!table_ok(c, table) || !d_lde_main || !d_lde_aux || !total || !beta || !gamma || !alpha || !d_out)
+        return fail(TMX_E_INPUT, "tmx_quotient: bad arguments");
+    TMX_CUDA(cudaSetDevice(c->ctx->device));
+    return stark_quotient(c->ctx, c->prover, table, d_lde_main, d_lde_aux, gl2_make(total[0], total[1]), gl2_make(beta[0], beta[1]),
+                          gl2_make(gamma[0], gamma[1]), alpha, d_out, pick_stream(c->ctx, stream));
 }

@@ -159,6 +159,17 @@ TMX_HD fe51 fe_pow22523(const fe51& a) {
     return acc;
 }
 
+// a^(p - 2), p - 2 = 2^255 - 21: all exponent bits set except bits 2 and 4
+TMX_HD fe51 fe_invert(const fe51& a) {
+    fe51 acc = fe_one();
+#pragma unroll 1
+    for (int i = 254; i >= 0; i--) {
+        acc = fe_sq(acc);
+        if (i != 2 && i != 4) acc = fe_mul(acc, a);
+    }
+    return acc;
+}
+
 struct ge51 {
     fe51 X, Y, Z, T;
 };
@@ -276,8 +287,9 @@ TMX_HD void sc_reduce512(const uint8_t in[64], uint64_t out[4]) {
 }
 
 // ---- multiplication gadget witness on 16-bit limbs ----
-// U, V: signed limb vectors (|limb| < 2^19); writes the 48 cells (c[16], q[17], the 15 odd carries + offset) of one gadget with
-// stride `stride` starting at `cells`; returns c limbs in c_out.
+// U, V: signed limb vectors (|limb| < 2^19); writes the 63 cells of one gadget (c[16], q[17], and the 15 carries out of the
+// odd limbs, offset by ED_W_OFFSET and split into a 16-bit and an 11-bit part) with stride `stride` starting at `cells`;
+// returns c limbs in c_out.
 TMX_HD void mul_gadget_cells(const int32_t U[16], const int32_t V[16], gl* cells, size_t stride, int32_t c_out[16]) {
     int64_t t[31];
 #pragma unroll
@@ -350,7 +362,11 @@ TMX_HD void mul_gadget_cells(const int32_t U[16], const int32_t V[16], gl* cells
             cells[(size_t)(ED_MUL_Q + k) * stride] = (gl)qk;
         }
         carry = s >> 16;
-        if ((k & 1) && k < 31) cells[(size_t)(ED_MUL_W + (k >> 1)) * stride] = (gl)(carry + ED_W_OFFSET);
+        if ((k & 1) && k < 31) {
+            const int64_t w = carry + ED_W_OFFSET;
+            cells[(size_t)(ED_MUL_WLO + (k >> 1)) * stride] = (gl)(w & 0xFFFF);
+            cells[(size_t)(ED_MUL_WHI + (k >> 1)) * stride] = (gl)(w >> 16);
+        }
     }
 }
 

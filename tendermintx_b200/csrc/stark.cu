@@ -1,15 +1,17 @@
-// GPU STARK prover for one witness table: K5 (constraint quotient over the LDE), openings at zeta / g*zeta,
-// K3 (FRI batch combination and arity-16 folding in EVALUATION space), K4 (query / opening gather), driven by
-// a host-side duplex challenger.  Commitment uses K1 (tmx_lde) and K2 (Poseidon Merkle).
+// GPU STARK prover for the witness tables on a shared bus: round 1 (first-round traces, range-lookup histogram), round 2
+// (helper columns and running sums of the bus interactions), then per table K5 (constraint quotient over the LDE),
+// openings at zeta / g*zeta, K3 (FRI batch combination and arity-16 folding in EVALUATION space), K4 (query / opening
+// gather), driven by a host-side duplex challenger.  Commitments use K1 (tmx_lde) and K2 (Poseidon Merkle).
 //
-// Replaces, on the GPU, the plonky2 / starky proving loops behind `circuit.prove()`
-// [REF circuits/skip.rs:214,244; circuits/step.rs:196,223]: PolynomialBatch::from_values, the quotient
-// computation, fri/oracle.rs prove_openings, fri/prover.rs fri_committed_trees / fri_proof_of_work / query rounds.
-// Same functions of the same field elements as the CPU oracle (oracle/stark.c), different algorithms: the batch
-// polynomial is formed pointwise on the LDE instead of dividing coefficient vectors, and FRI layers are folded by
-// a 16-point inverse NTT per coset instead of folding coefficients and re-running a coset FFT.
+// Replaces, on the GPU, the plonky2 / starky / Curta proving loops behind `circuit.prove()`
+// [REF circuits/skip.rs:214,244; circuits/step.rs:196,223]: PolynomialBatch::from_values, the lookup / bus accumulators,
+// the quotient computation, fri/oracle.rs prove_openings, fri/prover.rs fri_committed_trees / fri_proof_of_work / query
+// rounds.  Same functions of the same field elements as the CPU oracle (oracle/stark.c), different algorithms: the
+// constraints are compiled templates here and interpreted data there, the batch polynomial is formed pointwise on the LDE
+// instead of dividing coefficient vectors, and FRI layers are folded by a 16-point inverse NTT per coset instead of
+// folding coefficients and re-running a coset FFT.
 #include "stark.cuh"
-#include "air_ed_fast.cuh"
+#include "stark_rows.cuh"
 #include <cstring>
 #include <cstdio>
 #include <cstdlib>
@@ -20,86 +22,63 @@
 
 namespace tmx {
 
-// ------------------------------------------------------------------------------------------ K5: quotient
-struct LdeRow {
-    const gl* base;  // lde + position
-    size_t stride;   // m
-    TMX_D FB operator[](int c) const { return FB::mk(base[(size_t)c * stride]); }
-};
-// periodic column values at one LDE position, read straight from the device table
-struct LdePeriodic {
-    const gl* base;  // pertab + (j mod 2P)
-    size_t stride;   // 2P
-    TMX_D FB operator[](int pc) const { return FB::mk(base[(size_t)pc * stride]); }
-};
-
-// Position (bit-reversed order) of the row that follows position p on the trace domain: natural index j + 2^r.
-// The low log_n bits of p hold the bit-reversed row counter, so "+1" is a reverse-carry increment (flip ones from
-// the top bit down, set the first zero); the top r bits (the coset id) are unchanged.
-TMX_D size_t next_row_position(size_t p, unsigned log_n) {
-    const size_t low_mask = ((size_t)1 << log_n) - 1;
-    size_t q = p & low_mask;
-    size_t bit = (size_t)1 << (log_n - 1);
-    while (bit && (q & bit)) {
-        q ^= bit;
-        bit >>= 1;
-    }
-    q |= bit;
-    return (p & ~low_mask) | q;
-}
-
-struct QuotientArgs {
-    const gl* lde;
-    size_t m;
-    unsigned log_m;
-    unsigned rate_bits;
-    const gl* pertab;  // [nper][2P]
-    int nper, P;
-    gl alpha[2];
-    gl zh_inv[1 << 3];  // indexed by natural index mod 2^rate_bits
-    gl* out;            // [2][m] natural order
-};
-
 template <int TABLE>
 __global__ void __launch_bounds__(128) quotient_kernel(QuotientArgs a) {
     const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= a.m) return;
-    const uint32_t j = bitrev32((uint32_t)p, a.log_m);
-    const size_t pn = next_row_position(p, a.log_m - a.rate_bits);
-    LdeRow l{a.lde + p, a.m}, n{a.lde + pn, a.m};
-    LdePeriodic per{a.pertab + (j & (2 * a.P - 1)), (size_t)2 * a.P};
-    ConstraintAcc<FB> acc;
-    acc.acc0 = FB::c(0); acc.acc1 = FB::c(0);
-    acc.alpha0 = FB::mk(a.alpha[0]); acc.alpha1 = FB::mk(a.alpha[1]);
-    air_eval<FB>(TABLE, l, n, per, acc);
-    const gl zi = a.zh_inv[j & ((1u << a.rate_bits) - 1)];
-    a.out[j] = gl_mul(acc.acc0.v, zi);
-    a.out[a.m + j] = gl_mul(acc.acc1.v, zi);
+    if (p < a.m) quotient_point<TABLE>(a, p);
 }
-
-// Ed25519 table: factored evaluation (air_ed_fast.cuh), one thread per (LDE point, challenge); the two challenge
-// halves of a CTA read the same cells, so the second read is an L1 hit.
-struct QuotientEdArgs {
-    const gl* lde;
-    size_t m;
-    unsigned log_m, rate_bits;
-    const gl* pertab;  // [3][2P]: not_block_end, first row of [s]B, first row of [h]A
-    int P;
-    EdFastConsts k[2];
-    gl zh_inv[1 << 3];
-    gl* out;
-};
-__global__ void __launch_bounds__(128) quotient_ed25519_kernel(QuotientEdArgs a) {
-    const int which = threadIdx.x >> 6;
-    const size_t p = (size_t)blockIdx.x * 64 + (threadIdx.x & 63);
-    if (p >= a.m) return;
-    const uint32_t j = bitrev32((uint32_t)p, a.log_m);
-    const size_t pn = next_row_position(p, a.log_m - a.rate_bits);
-    LdeRow l{a.lde + p, a.m}, n{a.lde + pn, a.m};
-    const uint32_t jp = j & (2 * a.P - 1);
-    const gl per[3] = {a.pertab[jp], a.pertab[2 * a.P + jp], a.pertab[4 * a.P + jp]};
-    const gl v = ed25519_constraints_fast(l, n, per, a.k[which]);
-    a.out[(size_t)which * a.m + j] = gl_mul(v, a.zh_inv[j & ((1u << a.rate_bits) - 1)]);
+// helper columns of the table's bus interactions, one thread per trace row
+template <int TABLE>
+__global__ void __launch_bounds__(128) bus_gen_kernel(BusPassArgs a) {
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < a.n) bus_gen_row<TABLE>(a, r);
+}
+// histogram of the table's range lookups
+template <int TABLE>
+__global__ void __launch_bounds__(128) bus_count_kernel(BusPassArgs a) {
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < a.n) bus_count_row<TABLE>(a, r);
+}
+// running sum: Z(0) = 0, Z(r + 1) = Z(r) + rowsum(r) - total / n (closes up cyclically); one CTA
+__global__ void __launch_bounds__(1024) bus_scan_kernel(const gl2* __restrict__ rowsum, size_t n, gl* __restrict__ z0, gl* __restrict__ z1,
+                                                         gl* __restrict__ total_out) {
+    __shared__ gl2 s[1024];
+    __shared__ gl2 step;
+    const size_t chunk = (n + 1023) / 1024;
+    const size_t lo = std::min(n, (size_t)threadIdx.x * chunk), hi = std::min(n, lo + chunk);
+    gl2 acc = gl2_from(0);
+    for (size_t r = lo; r < hi; r++) acc = gl2_add(acc, rowsum[r]);
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {  // inclusive scan
+        gl2 v = gl2_from(0);
+        if ((int)threadIdx.x >= d) v = s[threadIdx.x - d];
+        __syncthreads();
+        s[threadIdx.x] = gl2_add(s[threadIdx.x], v);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const gl2 total = s[1023];
+        step = gl2_scale(total, gl_inv((gl)n));
+        total_out[0] = total.a0;
+        total_out[1] = total.a1;
+    }
+    __syncthreads();
+    gl2 z = threadIdx.x ? s[threadIdx.x - 1] : gl2_from(0);
+    z = gl2_sub(z, gl2_scale(step, (gl)lo));
+    for (size_t r = lo; r < hi; r++) {
+        z0[r] = z.a0;
+        z1[r] = z.a1;
+        z = gl2_sub(gl2_add(z, rowsum[r]), step);
+    }
+}
+// first-round trace of the range table from the histogram
+__global__ void range_fill_kernel(const unsigned int* __restrict__ hist, gl* __restrict__ trace, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    trace[(size_t)RG_M16 * n + i] = hist[i];
+    trace[(size_t)RG_M11 * n + i] = i < (1u << 11) ? hist[(1u << 16) + i] : 0;
+    trace[(size_t)RG_M8 * n + i] = i < (1u << 8) ? hist[(1u << 16) + (1u << 11) + i] : 0;
 }
 
 // after the inverse NTT of size m = 2n the buffer holds q_i * 7^i; chunk k of challenge c is coefficients
@@ -158,14 +137,15 @@ __global__ void __launch_bounds__(256) eval_columns_kernel(const gl* __restrict_
 
 // ------------------------------------------------------------------------------------------ K3: FRI
 struct FriBatchArgs {
-    const gl* lde_t;  // [C][m]
-    const gl* lde_q;  // [4][m]
-    size_t C, m;
+    const gl* seg[3];  // constant, first-round, second-round LDE columns, [count][m] each
+    size_t segc[3];
+    const gl* lde_q;   // [4][m]
+    size_t C, m;       // C = total number of columns opened at both points
     unsigned log_m;
-    const gl2* apow;  // alpha^j, j < C + 4
+    const gl2* apow;   // alpha^j, j < C + 4
     gl2 red0, red1, zeta, zeta_next, alpha_c;
-    gl w_m;           // primitive m-th root
-    gl2* out;         // [m] bit-reversed
+    gl w_m;            // primitive m-th root
+    gl2* out;          // [m] bit-reversed
 };
 
 // V(x) = alpha^C (S0(x) - S0(zeta)) / (x - zeta) + (S1(x) - S1(g zeta)) / (x - g zeta), S = alpha-combinations of
@@ -175,12 +155,16 @@ __global__ void __launch_bounds__(128) fri_batch_kernel(FriBatchArgs a) {
     if (p >= a.m) return;
     // S1 = sum_j alpha^j col_j (extension times base, component-wise): 192-bit accumulators, reduced once
     gl_acc192 u0 = gl_acc_zero(), u1 = gl_acc_zero();
-    const gl* col = a.lde_t + p;
-    for (size_t j = 0; j < a.C; j++) {
-        const gl v = col[j * a.m];
-        const gl2 w = a.apow[j];
-        gl_acc_mac(u0, w.a0, v);
-        gl_acc_mac(u1, w.a1, v);
+    size_t j0 = 0;
+    for (int s = 0; s < 3; s++) {
+        const gl* col = a.seg[s] + p;
+        for (size_t j = 0; j < a.segc[s]; j++) {
+            const gl v = col[j * a.m];
+            const gl2 w = a.apow[j0 + j];
+            gl_acc_mac(u0, w.a0, v);
+            gl_acc_mac(u1, w.a1, v);
+        }
+        j0 += a.segc[s];
     }
     const gl2 s1 = gl2_make(gl_acc_reduce(u0), gl_acc_reduce(u1));
     gl2 s0 = s1;
@@ -249,20 +233,41 @@ __global__ void gather_paths_kernel(const gl* __restrict__ digests, unsigned log
     }
 }
 
+// ------------------------------------------------------------------------------------------ host driver
 static int launch_quotient(tmx_ctx* ctx, int table, const QuotientArgs& qa, cudaStream_t st) {
     const unsigned qblocks = (unsigned)((qa.m + 127) / 128);
-    if (table == AIR_SHA256) quotient_kernel<AIR_SHA256><<<qblocks, 128, 0, st>>>(qa);
-    else if (table == AIR_SHA512) quotient_kernel<AIR_SHA512><<<qblocks, 128, 0, st>>>(qa);
-    else if (getenv("TMX_QUOTIENT_LITERAL")) quotient_kernel<AIR_ED25519><<<qblocks, 128, 0, st>>>(qa);  // debugging aid
-    else {
-        QuotientEdArgs ea;
-        memset(&ea, 0, sizeof ea);
-        ea.lde = qa.lde; ea.m = qa.m; ea.log_m = qa.log_m; ea.rate_bits = qa.rate_bits; ea.pertab = qa.pertab; ea.P = qa.P;
-        ea.k[0] = ed_fast_consts(qa.alpha[0]);
-        ea.k[1] = ed_fast_consts(qa.alpha[1]);
-        memcpy(ea.zh_inv, qa.zh_inv, sizeof ea.zh_inv);
-        ea.out = qa.out;
-        quotient_ed25519_kernel<<<(unsigned)((qa.m + 63) / 64), 128, 0, st>>>(ea);
+    switch (table) {
+        case AIR_SHA256: quotient_kernel<AIR_SHA256><<<qblocks, 128, 0, st>>>(qa); break;
+        case AIR_SHA512: quotient_kernel<AIR_SHA512><<<qblocks, 128, 0, st>>>(qa); break;
+        case AIR_ED25519: quotient_kernel<AIR_ED25519><<<qblocks, 128, 0, st>>>(qa); break;
+        case AIR_LOGIC: quotient_kernel<AIR_LOGIC><<<qblocks, 128, 0, st>>>(qa); break;
+        default: quotient_kernel<AIR_RANGE><<<qblocks, 128, 0, st>>>(qa); break;
+    }
+    ctx->launches++;
+    TMX_CUDA(cudaGetLastError());
+    return TMX_OK;
+}
+static int launch_bus_gen(tmx_ctx* ctx, int table, const BusPassArgs& a, cudaStream_t st) {
+    const unsigned blocks = (unsigned)((a.n + 127) / 128);
+    switch (table) {
+        case AIR_SHA256: bus_gen_kernel<AIR_SHA256><<<blocks, 128, 0, st>>>(a); break;
+        case AIR_SHA512: bus_gen_kernel<AIR_SHA512><<<blocks, 128, 0, st>>>(a); break;
+        case AIR_ED25519: bus_gen_kernel<AIR_ED25519><<<blocks, 128, 0, st>>>(a); break;
+        case AIR_LOGIC: bus_gen_kernel<AIR_LOGIC><<<blocks, 128, 0, st>>>(a); break;
+        default: bus_gen_kernel<AIR_RANGE><<<blocks, 128, 0, st>>>(a); break;
+    }
+    ctx->launches++;
+    TMX_CUDA(cudaGetLastError());
+    return TMX_OK;
+}
+static int launch_bus_count(tmx_ctx* ctx, int table, const BusPassArgs& a, cudaStream_t st) {
+    const unsigned blocks = (unsigned)((a.n + 127) / 128);
+    switch (table) {
+        case AIR_SHA256: bus_count_kernel<AIR_SHA256><<<blocks, 128, 0, st>>>(a); break;
+        case AIR_SHA512: bus_count_kernel<AIR_SHA512><<<blocks, 128, 0, st>>>(a); break;
+        case AIR_ED25519: bus_count_kernel<AIR_ED25519><<<blocks, 128, 0, st>>>(a); break;
+        case AIR_LOGIC: bus_count_kernel<AIR_LOGIC><<<blocks, 128, 0, st>>>(a); break;
+        default: return TMX_OK;  // the range table provides, it does not look up
     }
     ctx->launches++;
     TMX_CUDA(cudaGetLastError());
@@ -279,13 +284,6 @@ static void fill_zh_inv(QuotientArgs& qa, size_t n) {
     }
 }
 
-// ------------------------------------------------------------------------------------------ host driver
-static gl2 host_poly_eval_ext(const std::vector<gl2>& c, gl2 x) {
-    gl2 acc = gl2_from(0);
-    for (size_t i = c.size(); i-- > 0;) acc = gl2_add(gl2_mul(acc, x), c[i]);
-    return acc;
-}
-
 unsigned fri_num_layers(unsigned degree_bits) {
     unsigned l = 0;
     while (degree_bits > STARK_FINAL_POLY_BITS && degree_bits + STARK_RATE_BITS - STARK_ARITY_BITS >= STARK_CAP_HEIGHT) {
@@ -294,25 +292,6 @@ unsigned fri_num_layers(unsigned degree_bits) {
     }
     return l;
 }
-
-// device -> host through a pinned staging buffer owned by the prover (pageable destinations make every one of the
-// ~12 transcript round trips per table a staged, driver-synchronised copy)
-int TableProver::d2h(std::vector<gl>& dst, const gl* src, size_t n, cudaStream_t st) {
-    if (sz_pinned < n) {
-        if (h_pinned) cudaFreeHost(h_pinned);
-        h_pinned = nullptr;
-        sz_pinned = 0;
-        const size_t want = std::max<size_t>(n + n / 4, 1 << 16);
-        TMX_CUDA(cudaMallocHost((void**)&h_pinned, want * sizeof(gl)));
-        sz_pinned = want;
-    }
-    TMX_CUDA(cudaMemcpyAsync(h_pinned, src, n * sizeof(gl), cudaMemcpyDeviceToHost, st));
-    TMX_CUDA(cudaStreamSynchronize(st));
-    dst.assign(h_pinned, h_pinned + n);
-    return TMX_OK;
-}
-
-static void observe_ext(Challenger& ch, gl2 x) { ch.observe_ext(x); }
 
 // TMX_TIMING=1: host wall-clock per phase (with a stream sync at each boundary) on stderr
 struct PhaseTimer {
@@ -336,53 +315,276 @@ struct PhaseTimer {
     }
 };
 
-int TableProver::prove(tmx_ctx* ctx, int table, const gl* d_trace, unsigned log_n, Challenger& ch, std::vector<gl>& proof,
-                       cudaStream_t st, const std::function<int(cudaEvent_t)>& on_trace_committed) {
-    const size_t n = (size_t)1 << log_n, m = n << STARK_RATE_BITS;
-    const unsigned km = log_n + STARK_RATE_BITS;
-    const size_t C = (size_t)air_cols(table);
-    const unsigned cap_h = std::min<unsigned>(km, STARK_CAP_HEIGHT);
-    const size_t cap_n = (size_t)1 << cap_h;
-    int rc;
-    // ---- buffers (grow-only, owned by this prover) ----
-    const size_t dig_t = tmx_merkle_digest_count(km, cap_h);
-    rc = reserve(ctx, C, n, m, dig_t);
-    if (rc) return rc;
-    PhaseTimer pt(st);
-    for (int i = 0; i < 3; i++)
-        if (!ev_phase[i]) TMX_CUDA(cudaEventCreate(&ev_phase[i]));
-    // ---- 1. trace commitment ----
-    TMX_CUDA(cudaEventRecord(ev_phase[0], st));
-    rc = tmx_lde(ctx, d_trace, d_lde, d_coeffs, C, log_n, STARK_RATE_BITS, st);
-    if (rc) return rc;
-    TMX_CUDA(cudaEventRecord(ev_phase[1], st));
-    pt.tick("lde");
-    rc = merkle_generic(ctx, d_lde, C, 1, m, km, cap_h, d_dig_t, st);
-    if (rc) return rc;
-    TMX_CUDA(cudaEventRecord(ev_phase[2], st));
-    if (on_trace_committed) {
-        rc = on_trace_committed(ev_phase[2]);
-        if (rc) return rc;
+// device -> host through a pinned staging buffer owned by the prover (pageable destinations make every one of the
+// transcript round trips a staged, driver-synchronised copy)
+int Prover::d2h(std::vector<gl>& dst, const gl* src, size_t n, cudaStream_t st) {
+    if (sz_pinned < n) {
+        if (h_pinned) cudaFreeHost(h_pinned);
+        h_pinned = nullptr;
+        sz_pinned = 0;
+        const size_t want = std::max<size_t>(n + n / 4, 1 << 16);
+        TMX_CUDA(cudaMallocHost((void**)&h_pinned, want * sizeof(gl)));
+        sz_pinned = want;
     }
-    pt.tick("trace merkle");
-    std::vector<gl> cap;
-    rc = d2h(cap, d_dig_t + 4 * (dig_t - cap_n), 4 * cap_n, st);
+    TMX_CUDA(cudaMemcpyAsync(h_pinned, src, n * sizeof(gl), cudaMemcpyDeviceToHost, st));
+    TMX_CUDA(cudaStreamSynchronize(st));
+    dst.assign(h_pinned, h_pinned + n);
+    return TMX_OK;
+}
+
+int Prover::alloc(void** p, size_t bytes) {
+    *p = nullptr;
+    if (!bytes) bytes = 8;
+    TMX_CUDA(cudaMalloc(p, bytes));
+    owned.push_back(*p);
+    return TMX_OK;
+}
+
+static unsigned cap_height_of(unsigned km) { return std::min<unsigned>(km, STARK_CAP_HEIGHT); }
+
+int Prover::setup(tmx_ctx* ctx, std::shared_ptr<const CircuitDef> d) {
+    def = d;
+    shape = AirShape{d->kind, d->n_max};
+    cudaStream_t st = ctx->stream;
+    int rc;
+    size_t max_m = 0, max_ct = 0;
+    for (int t = 0; t < STARK_N_TABLES; t++) {
+        const TableDef& td = def->tables[t];
+        if (!td.n_main) continue;
+        TableDevice& tb = tab[t];
+        const size_t n = td.rows(), m = n << STARK_RATE_BITS, Kc = td.n_const, C = td.n_main, A = (size_t)td.n_aux();
+        const unsigned km = td.log_n + STARK_RATE_BITS;
+        const size_t dig = tmx_merkle_digest_count(km, cap_height_of(km));
+        max_m = std::max(max_m, m);
+        max_ct = std::max(max_ct, Kc + C + A);
+        if ((rc = alloc((void**)&tb.d_const, Kc * n * sizeof(gl)))) return rc;
+        if ((rc = alloc((void**)&tb.d_const_coef, Kc * n * sizeof(gl)))) return rc;
+        if ((rc = alloc((void**)&tb.d_const_lde, Kc * m * sizeof(gl)))) return rc;
+        if ((rc = alloc((void**)&tb.d_const_dig, 4 * dig * sizeof(gl)))) return rc;
+        if ((rc = alloc((void**)&tb.d_per_trace, (size_t)td.n_per * td.period * sizeof(gl)))) return rc;
+        if ((rc = alloc((void**)&tb.d_per_lde, (size_t)td.n_per * 2 * td.period * sizeof(gl)))) return rc;
+        if ((rc = alloc((void**)&tb.d_aux, A * n * sizeof(gl)))) return rc;
+        if ((rc = alloc((void**)&tb.d_lde_m, C * m * sizeof(gl)))) return rc;
+        if ((rc = alloc((void**)&tb.d_coef_m, C * n * sizeof(gl)))) return rc;
+        if ((rc = alloc((void**)&tb.d_dig_m, 4 * dig * sizeof(gl)))) return rc;
+        if ((rc = alloc((void**)&tb.d_lde_a, A * m * sizeof(gl)))) return rc;
+        if ((rc = alloc((void**)&tb.d_coef_a, A * n * sizeof(gl)))) return rc;
+        if ((rc = alloc((void**)&tb.d_dig_a, 4 * dig * sizeof(gl)))) return rc;
+        // constant columns: upload, commit, compare the cap with the definition's (computed on the host)
+        if (Kc) {
+            TMX_CUDA(cudaMemcpyAsync(tb.d_const, td.constants.data(), Kc * n * sizeof(gl), cudaMemcpyHostToDevice, st));
+            if ((rc = tmx_lde(ctx, tb.d_const, tb.d_const_lde, tb.d_const_coef, Kc, td.log_n, STARK_RATE_BITS, st))) return rc;
+            if ((rc = merkle_generic(ctx, tb.d_const_lde, Kc, 1, m, km, cap_height_of(km), tb.d_const_dig, st))) return rc;
+            const size_t cap_w = 4 * ((size_t)1 << cap_height_of(km));
+            std::vector<gl> cap;
+            if ((rc = d2h(cap, tb.d_const_dig + 4 * dig - cap_w, cap_w, st))) return rc;
+            if (cap != td.const_cap) return fail(TMX_E_CUDA, "constant-column commitment of table " + std::to_string(t) + " differs between the GPU and the host");
+        }
+        if (td.n_per) {
+            TMX_CUDA(cudaMemcpyAsync(tb.d_per_trace, td.periodic.data(), td.periodic.size() * sizeof(gl), cudaMemcpyHostToDevice, st));
+            // values of the periodic columns on the LDE coset: the interpolant of one period composed with x -> x^(n/P)
+            const size_t P = td.period;
+            std::vector<gl> lde((size_t)td.n_per * 2 * P);
+            const gl sh = gl_pow(GL_GEN, n / P);
+            for (uint32_t pc = 0; pc < td.n_per; pc++) {
+                std::vector<gl> coef(td.periodic.begin() + (size_t)pc * P, td.periodic.begin() + (size_t)(pc + 1) * P);
+                air_host_ntt(coef, true);
+                coef.resize(2 * P, 0);
+                gl s = 1;
+                for (size_t k = 0; k < P; k++) {
+                    coef[k] = gl_mul(coef[k], s);
+                    s = gl_mul(s, sh);
+                }
+                air_host_ntt(coef, false);
+                std::copy(coef.begin(), coef.end(), lde.begin() + (size_t)pc * 2 * P);
+            }
+            TMX_CUDA(cudaMemcpyAsync(tb.d_per_lde, lde.data(), lde.size() * sizeof(gl), cudaMemcpyHostToDevice, st));
+            TMX_CUDA(cudaStreamSynchronize(st));
+        }
+    }
+    const size_t max_n = max_m >> STARK_RATE_BITS;
+    const size_t dig_max = tmx_merkle_digest_count(ilog2(max_m), cap_height_of(ilog2(max_m)));
+    if ((rc = alloc((void**)&d_dig_q, 4 * dig_max * sizeof(gl)))) return rc;
+    if ((rc = alloc((void**)&d_dig_fri, 4 * (max_m / 4) * sizeof(gl)))) return rc;
+    if ((rc = alloc((void**)&d_qv, 2 * max_m * sizeof(gl)))) return rc;
+    if ((rc = alloc((void**)&d_qcoef, 4 * max_n * sizeof(gl)))) return rc;
+    if ((rc = alloc((void**)&d_qlde, 4 * max_m * sizeof(gl)))) return rc;
+    if ((rc = alloc((void**)&d_ypa, 2 * max_n * sizeof(gl2)))) return rc;
+    d_ypb = d_ypa + max_n;
+    if ((rc = alloc((void**)&d_open, (2 * max_ct + 4) * sizeof(gl2)))) return rc;
+    if ((rc = alloc((void**)&d_apow, (max_ct + 4) * sizeof(gl2)))) return rc;
+    if ((rc = alloc((void**)&d_idx, STARK_NUM_QUERIES * sizeof(uint32_t)))) return rc;
+    if ((rc = alloc((void**)&d_rowsum, max_n * sizeof(gl2)))) return rc;
+    if ((rc = alloc((void**)&d_small, (size_t)STARK_N_TABLES * 66 * sizeof(gl)))) return rc;
+    if ((rc = alloc((void**)&d_hist, (BUS_HIST_SIZE + 4) * sizeof(unsigned int)))) return rc;
+    if (def->tables[AIR_RANGE].n_main)
+        if ((rc = alloc((void**)&d_range_trace, def->tables[AIR_RANGE].rows() * RG_COLS * sizeof(gl)))) return rc;
+    // FRI layer arrays: m, m/16, m/256, ... ext values, carved from one allocation
+    size_t tot = 0, cur = max_m;
+    for (int l = 0; l < 9; l++) {
+        tot += cur;
+        cur = cur >> 4 ? cur >> 4 : 1;
+    }
+    if ((rc = alloc((void**)&d_fri_base, tot * sizeof(gl2)))) return rc;
+    for (auto& e : ev_phase) TMX_CUDA(cudaEventCreate(&e));
+    TMX_CUDA(cudaStreamSynchronize(st));
+    return TMX_OK;
+}
+
+void Prover::release() {
+    for (auto& e : ev_phase)
+        if (e) cudaEventDestroy(e);
+    if (h_pinned) cudaFreeHost(h_pinned);
+    if (d_query) cudaFree(d_query);
+    for (void* p : owned) cudaFree(p);
+    *this = Prover();
+}
+
+static BusPassArgs bus_pass_args(const Prover& pr, int t, const gl* d_trace) {
+    const TableDef& td = pr.def->tables[t];
+    BusPassArgs a;
+    memset(&a, 0, sizeof a);
+    a.trace = d_trace;
+    a.kconst = pr.tab[t].d_const;
+    a.per = pr.tab[t].d_per_trace;
+    a.n = td.rows();
+    a.P = (int)td.period;
+    a.shape = pr.shape;
+    return a;
+}
+
+int Prover::count_lookups(tmx_ctx* ctx, int t, const gl* d_trace, cudaStream_t st) {
+    if (!def->tables[t].n_main || t == AIR_RANGE) return TMX_OK;
+    BusPassArgs a = bus_pass_args(*this, t, d_trace);
+    a.hist = d_hist;
+    return launch_bus_count(ctx, t, a, st);
+}
+
+int Prover::fill_range_trace(tmx_ctx* ctx, cudaStream_t st) {
+    const size_t n = def->tables[AIR_RANGE].rows();
+    range_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_hist, d_range_trace, n);
+    ctx->launches++;
+    TMX_CUDA(cudaGetLastError());
+    return TMX_OK;
+}
+
+int Prover::commit_main(tmx_ctx* ctx, int t, const gl* d_trace, cudaStream_t st) {
+    const TableDef& td = def->tables[t];
+    if (!td.n_main) return TMX_OK;
+    TableDevice& tb = tab[t];
+    const size_t m = td.rows() << STARK_RATE_BITS;
+    const unsigned km = td.log_n + STARK_RATE_BITS;
+    const size_t dig = tmx_merkle_digest_count(km, cap_height_of(km)), cap_w = 4 * ((size_t)1 << cap_height_of(km));
+    int rc;
+    TMX_CUDA(cudaEventRecord(ev_phase[2 * t], st));
+    if ((rc = tmx_lde(ctx, d_trace, tb.d_lde_m, tb.d_coef_m, td.n_main, td.log_n, STARK_RATE_BITS, st))) return rc;
+    TMX_CUDA(cudaEventRecord(ev_phase[2 * t + 1], st));
+    if ((rc = merkle_generic(ctx, tb.d_lde_m, td.n_main, 1, m, km, cap_height_of(km), tb.d_dig_m, st))) return rc;
+    if (t + 1 < STARK_N_TABLES) TMX_CUDA(cudaEventRecord(ev_phase[2 * t + 2], st));
+    else TMX_CUDA(cudaEventRecord(ev_phase[2 * STARK_N_TABLES], st));
+    TMX_CUDA(cudaMemcpyAsync(d_small + 66 * t, tb.d_dig_m + 4 * dig - cap_w, cap_w * sizeof(gl), cudaMemcpyDeviceToDevice, st));
+    return TMX_OK;
+}
+
+// one device -> host copy for all first-round caps and the range-check verdict; the caps enter the proof and the transcript
+int Prover::finish_round1(tmx_ctx* ctx, Challenger& ch, std::vector<gl>& proof, cudaStream_t st, bool* range_ok) {
+    (void)ctx;
+    TMX_CUDA(cudaMemcpyAsync(d_small + 66 * (STARK_N_TABLES - 1) + 65, d_hist + BUS_HIST_SIZE, sizeof(unsigned int), cudaMemcpyDeviceToDevice, st));
+    std::vector<gl> all;
+    int rc = d2h(all, d_small, (size_t)STARK_N_TABLES * 66, st);
     if (rc) return rc;
-    proof.insert(proof.end(), cap.begin(), cap.end());
-    ch.observe(cap.data(), cap.size());
-    pt.tick("cap d2h + observe");
-    // ---- 2. constraint challenges, 3. quotient ----
+    *range_ok = (uint32_t)all[66 * (STARK_N_TABLES - 1) + 65] == 0;
+    for (int t = 0; t < STARK_N_TABLES; t++) {
+        const TableDef& td = def->tables[t];
+        if (!td.n_main) continue;
+        const size_t cap_w = 4 * ((size_t)1 << cap_height_of(td.log_n + STARK_RATE_BITS));
+        proof.insert(proof.end(), all.begin() + 66 * t, all.begin() + 66 * t + cap_w);
+        ch.observe(all.data() + 66 * t, cap_w);
+    }
+    // the commitment stamps are complete: LDE / Merkle device time per table
+    for (int t = 0; t < STARK_N_TABLES; t++) {
+        if (!def->tables[t].n_main) continue;
+        cudaEvent_t end = t + 1 < STARK_N_TABLES ? ev_phase[2 * t + 2] : ev_phase[2 * STARK_N_TABLES];
+        cudaEventElapsedTime(&lde_ms[t], ev_phase[2 * t], ev_phase[2 * t + 1]);
+        cudaEventElapsedTime(&merkle_ms[t], ev_phase[2 * t + 1], end);
+    }
+    return TMX_OK;
+}
+
+int Prover::commit_aux(tmx_ctx* ctx, int t, const gl* d_trace, gl2 beta, gl2 gamma, cudaStream_t st) {
+    const TableDef& td = def->tables[t];
+    if (!td.n_main) return TMX_OK;
+    TableDevice& tb = tab[t];
+    const size_t n = td.rows(), m = n << STARK_RATE_BITS, A = (size_t)td.n_aux(), H = td.n_helpers;
+    const unsigned km = td.log_n + STARK_RATE_BITS;
+    const size_t dig = tmx_merkle_digest_count(km, cap_height_of(km)), cap_w = 4 * ((size_t)1 << cap_height_of(km));
+    BusPassArgs a = bus_pass_args(*this, t, d_trace);
+    a.beta = beta;
+    a.gamma = gamma;
+    a.aux = tb.d_aux;
+    a.rowsum = d_rowsum;
+    int rc = launch_bus_gen(ctx, t, a, st);
+    if (rc) return rc;
+    bus_scan_kernel<<<1, 1024, 0, st>>>(d_rowsum, n, tb.d_aux + (2 * H) * n, tb.d_aux + (2 * H + 1) * n, d_small + 66 * t + 64);
+    ctx->launches++;
+    TMX_CUDA(cudaGetLastError());
+    if ((rc = tmx_lde(ctx, tb.d_aux, tb.d_lde_a, tb.d_coef_a, A, td.log_n, STARK_RATE_BITS, st))) return rc;
+    if ((rc = merkle_generic(ctx, tb.d_lde_a, A, 1, m, km, cap_height_of(km), tb.d_dig_a, st))) return rc;
+    TMX_CUDA(cudaMemcpyAsync(d_small + 66 * t, tb.d_dig_a + 4 * dig - cap_w, cap_w * sizeof(gl), cudaMemcpyDeviceToDevice, st));
+    return TMX_OK;
+}
+
+int Prover::finish_round2(tmx_ctx* ctx, Challenger& ch, std::vector<gl>& proof, cudaStream_t st) {
+    (void)ctx;
+    std::vector<gl> all;
+    int rc = d2h(all, d_small, (size_t)STARK_N_TABLES * 66, st);
+    if (rc) return rc;
+    for (int t = 0; t < STARK_N_TABLES; t++) {
+        const TableDef& td = def->tables[t];
+        if (!td.n_main) continue;
+        const size_t cap_w = 4 * ((size_t)1 << cap_height_of(td.log_n + STARK_RATE_BITS));
+        proof.insert(proof.end(), all.begin() + 66 * t, all.begin() + 66 * t + cap_w);
+        tab[t].total = gl2_make(all[66 * t + 64], all[66 * t + 65]);
+        proof.push_back(tab[t].total.a0);
+        proof.push_back(tab[t].total.a1);
+        ch.observe(all.data() + 66 * t, cap_w);
+        ch.observe_ext(tab[t].total);
+    }
+    return TMX_OK;
+}
+
+int Prover::prove_tail(tmx_ctx* ctx, int table, gl2 beta, gl2 gamma, Challenger& ch, std::vector<gl>& proof, cudaStream_t st) {
+    const TableDef& td = def->tables[table];
+    if (!td.n_main) return TMX_OK;
+    TableDevice& tb = tab[table];
+    const unsigned log_n = td.log_n, km = log_n + STARK_RATE_BITS;
+    const size_t n = td.rows(), m = n << STARK_RATE_BITS;
+    const size_t Kc = td.n_const, C = td.n_main, A = (size_t)td.n_aux(), CT = Kc + C + A;
+    const unsigned cap_h = cap_height_of(km);
+    const size_t cap_n = (size_t)1 << cap_h;
+    const size_t dig_t = tmx_merkle_digest_count(km, cap_h);
+    int rc;
+    PhaseTimer pt(st);
+    {   // FRI layer arrays of this table
+        size_t cur = m, o = 0;
+        for (int l = 0; l < 9; l++) {
+            d_fri[l] = d_fri_base + o;
+            o += cur;
+            cur = cur >> 4 ? cur >> 4 : 1;
+        }
+    }
+    // ---- constraint challenges, quotient ----
     QuotientArgs qa;
     memset(&qa, 0, sizeof qa);
-    qa.lde = d_lde; qa.m = m; qa.log_m = km; qa.rate_bits = STARK_RATE_BITS;
-    qa.nper = air_n_periodic(table); qa.P = (int)air_period(table, n);
+    qa.lde_m = tb.d_lde_m; qa.lde_k = tb.d_const_lde; qa.lde_a = tb.d_lde_a;
+    qa.m = m; qa.log_m = km; qa.rate_bits = STARK_RATE_BITS;
+    qa.pertab = tb.d_per_lde; qa.P = (int)td.period;
+    qa.shape = shape;
     qa.alpha[0] = ch.get();
     qa.alpha[1] = ch.get();
+    qa.beta = beta; qa.gamma = gamma;
+    qa.s_over_n = gl2_scale(tb.total, gl_inv((gl)n));
     fill_zh_inv(qa, n);
-    if (qa.nper) {
-        rc = periodic_tables(ctx, table, log_n, &qa.pertab);
-        if (rc) return rc;
-    }
     qa.out = d_qv;
     const unsigned qblocks = (unsigned)((m + 127) / 128);
     rc = launch_quotient(ctx, table, qa, st);
@@ -397,55 +599,70 @@ int TableProver::prove(tmx_ctx* ctx, int table, const gl* d_trace, unsigned log_
     if (rc) return rc;
     rc = merkle_generic(ctx, d_qlde, 4, 1, m, km, cap_h, d_dig_q, st);
     if (rc) return rc;
+    std::vector<gl> cap;
     rc = d2h(cap, d_dig_q + 4 * (dig_t - cap_n), 4 * cap_n, st);
     if (rc) return rc;
     proof.insert(proof.end(), cap.begin(), cap.end());
     ch.observe(cap.data(), cap.size());
     pt.tick("quotient commit");
-    // ---- 4. openings at zeta and g * zeta (coefficients are stored coset-scaled: evaluate at zeta / 7) ----
+    // ---- openings at zeta and g * zeta (coefficients are stored coset-scaled: evaluate at zeta / 7) ----
     const gl2 zeta = ch.get_ext();
     const gl2 zeta_next = gl2_scale(zeta, gl_root_of_unity(log_n));
     const gl ginv = gl_inv(GL_GEN);
     ext_powers_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(gl2_scale(zeta, ginv), n, d_ypa);
     ext_powers_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(gl2_scale(zeta_next, ginv), n, d_ypb);
-    eval_columns_kernel<<<(unsigned)C, 256, 0, st>>>(d_coeffs, n, d_ypa, d_ypb, d_open, d_open + C);
-    eval_columns_kernel<<<4, 256, 0, st>>>(d_qcoef, n, d_ypa, nullptr, d_open + 2 * C, nullptr);
-    ctx->launches += 4;
+    ctx->launches += 2;
+    {   // d_open: local[CT], next[CT], quotient[4]
+        const gl* seg[3] = {tb.d_const_coef, tb.d_coef_m, tb.d_coef_a};
+        const size_t segc[3] = {Kc, C, A};
+        size_t off = 0;
+        for (int s = 0; s < 3; s++) {
+            if (segc[s]) {
+                eval_columns_kernel<<<(unsigned)segc[s], 256, 0, st>>>(seg[s], n, d_ypa, d_ypb, d_open + off, d_open + CT + off);
+                ctx->launches++;
+            }
+            off += segc[s];
+        }
+        eval_columns_kernel<<<4, 256, 0, st>>>(d_qcoef, n, d_ypa, nullptr, d_open + 2 * CT, nullptr);
+        ctx->launches++;
+    }
     TMX_CUDA(cudaGetLastError());
     pt.tick("openings kernels");
     std::vector<gl> op;
-    rc = d2h(op, reinterpret_cast<const gl*>(d_open), 2 * (2 * C + 4), st);
+    rc = d2h(op, reinterpret_cast<const gl*>(d_open), 2 * (2 * CT + 4), st);
     if (rc) return rc;
-    proof.insert(proof.end(), op.begin(), op.end());  // local[C], next[C], quotient[4] as (a0, a1) pairs
+    proof.insert(proof.end(), op.begin(), op.end());  // local[CT], next[CT], quotient[4] as (a0, a1) pairs
     auto ext_at = [&](size_t i) { return gl2_make(op[2 * i], op[2 * i + 1]); };
-    for (size_t c = 0; c < C; c++) observe_ext(ch, ext_at(c));
-    for (size_t q = 0; q < 4; q++) observe_ext(ch, ext_at(2 * C + q));
-    for (size_t c = 0; c < C; c++) observe_ext(ch, ext_at(C + c));
+    for (size_t c = 0; c < CT; c++) ch.observe_ext(ext_at(c));
+    for (size_t q = 0; q < 4; q++) ch.observe_ext(ext_at(2 * CT + q));
+    for (size_t c = 0; c < CT; c++) ch.observe_ext(ext_at(CT + c));
     pt.tick("openings d2h+observe");
-    // ---- 5. FRI batch polynomial, pointwise ----
+    // ---- FRI batch polynomial, pointwise ----
     const gl2 fa = ch.get_ext();
-    std::vector<gl2> apow(C + 4);
+    std::vector<gl2> apow(CT + 4);
     apow[0] = gl2_from(1);
-    for (size_t j = 1; j < C + 4; j++) apow[j] = gl2_mul(apow[j - 1], fa);
+    for (size_t j = 1; j < CT + 4; j++) apow[j] = gl2_mul(apow[j - 1], fa);
     FriBatchArgs fb;
     memset(&fb, 0, sizeof fb);
     fb.red0 = gl2_from(0);
     fb.red1 = gl2_from(0);
-    for (size_t j = 0; j < C; j++) {
+    for (size_t j = 0; j < CT; j++) {
         fb.red0 = gl2_add(fb.red0, gl2_mul(apow[j], ext_at(j)));
-        fb.red1 = gl2_add(fb.red1, gl2_mul(apow[j], ext_at(C + j)));
+        fb.red1 = gl2_add(fb.red1, gl2_mul(apow[j], ext_at(CT + j)));
     }
-    for (size_t q = 0; q < 4; q++) fb.red0 = gl2_add(fb.red0, gl2_mul(apow[C + q], ext_at(2 * C + q)));
+    for (size_t q = 0; q < 4; q++) fb.red0 = gl2_add(fb.red0, gl2_mul(apow[CT + q], ext_at(2 * CT + q)));
     TMX_CUDA(cudaMemcpyAsync(d_apow, apow.data(), apow.size() * sizeof(gl2), cudaMemcpyHostToDevice, st));
-    fb.lde_t = d_lde; fb.lde_q = d_qlde; fb.C = C; fb.m = m; fb.log_m = km; fb.apow = d_apow;
-    fb.zeta = zeta; fb.zeta_next = zeta_next; fb.alpha_c = gl2_mul(apow[C - 1], fa);
+    fb.seg[0] = tb.d_const_lde; fb.seg[1] = tb.d_lde_m; fb.seg[2] = tb.d_lde_a;
+    fb.segc[0] = Kc; fb.segc[1] = C; fb.segc[2] = A;
+    fb.lde_q = d_qlde; fb.C = CT; fb.m = m; fb.log_m = km; fb.apow = d_apow;
+    fb.zeta = zeta; fb.zeta_next = zeta_next; fb.alpha_c = gl2_mul(apow[CT - 1], fa);
     fb.w_m = gl_root_of_unity(km);
     fb.out = d_fri[0];
     fri_batch_kernel<<<qblocks, 128, 0, st>>>(fb);
     ctx->launches++;
     TMX_CUDA(cudaGetLastError());
     pt.tick("fri batch");
-    // ---- 6. FRI commit phase: Merkle over cosets of 16, fold with beta ----
+    // ---- FRI commit phase: Merkle over cosets of 16, fold with beta ----
     const unsigned n_layers = fri_num_layers(log_n);
     size_t cur = m;
     gl shift = GL_GEN;
@@ -465,10 +682,10 @@ int TableProver::prove(tmx_ctx* ctx, int table, const gl* d_trace, unsigned log_
         if (rc) return rc;
         proof.insert(proof.end(), cap.begin(), cap.end());
         ch.observe(cap.data(), cap.size());
-        const gl2 beta = ch.get_ext();
+        const gl2 fbeta = ch.get_ext();
         const size_t cosets = cur >> STARK_ARITY_BITS;
         fri_fold_kernel<<<(unsigned)((cosets + 127) / 128), 128, 0, st>>>(d_fri[l], cosets, lg_rows, gl_inv(shift),
-                                                                         gl_inv(gl_root_of_unity(ilog2(cur))), beta, d_fri[l + 1]);
+                                                                         gl_inv(gl_root_of_unity(ilog2(cur))), fbeta, d_fri[l + 1]);
         ctx->launches++;
         TMX_CUDA(cudaGetLastError());
         cur = cosets;
@@ -493,16 +710,16 @@ int TableProver::prove(tmx_ctx* ctx, int table, const gl* d_trace, unsigned log_
         }
         const size_t final_len = cur >> STARK_RATE_BITS;
         for (size_t k = final_len; k < cur; k++)
-            if (coef[k].a0 || coef[k].a1) return fail(TMX_E_CUDA, "FRI: final polynomial exceeds its degree bound (internal error)");
+            if (coef[k].a0 || coef[k].a1) return fail(TMX_E_CUDA, "FRI: final polynomial exceeds its degree bound (the witness does not satisfy the constraints of table " + std::to_string(table) + ")");
         proof.push_back((gl)final_len);
         for (size_t k = 0; k < final_len; k++) {
             proof.push_back(coef[k].a0);
             proof.push_back(coef[k].a1);
-            observe_ext(ch, coef[k]);
+            ch.observe_ext(coef[k]);
         }
     }
     pt.tick("final poly");
-    // ---- 7. proof of work (K9) ----
+    // ---- proof of work (K9) ----
     {
         gl state[12];
         for (int i = 0; i < 12; i++) state[i] = ch.state[i];
@@ -515,27 +732,34 @@ int TableProver::prove(tmx_ctx* ctx, int table, const gl* d_trace, unsigned log_
         proof.push_back((gl)wit);
     }
     pt.tick("pow");
-    // ---- 8. queries (K4) ----
+    // ---- queries (K4) ----
     std::vector<uint32_t> idx(STARK_NUM_QUERIES);
     for (int q = 0; q < STARK_NUM_QUERIES; q++) idx[q] = (uint32_t)(ch.get() % m);
     TMX_CUDA(cudaMemcpyAsync(d_idx, idx.data(), idx.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     const unsigned n_sib = km - cap_h;
-    size_t qlen = C + 4 * n_sib + 4 + 4 * n_sib;
+    size_t qlen = (Kc ? Kc + 4 * n_sib : 0) + C + 4 * n_sib + A + 4 * n_sib + 4 + 4 * n_sib;
     for (unsigned l = 0; l < n_layers; l++)
         qlen += 32 + 4 * (layer_rows_log[l] - std::min<unsigned>((unsigned)layer_rows_log[l], STARK_CAP_HEIGHT));
-    rc = reserve_queries(ctx, qlen * STARK_NUM_QUERIES);
-    if (rc) return rc;
+    if (sz_query < qlen * STARK_NUM_QUERIES) {
+        if (d_query) TMX_CUDA(cudaFree(d_query));
+        d_query = nullptr;
+        sz_query = 0;
+        TMX_CUDA(cudaMalloc((void**)&d_query, qlen * STARK_NUM_QUERIES * sizeof(gl)));
+        sz_query = qlen * STARK_NUM_QUERIES;
+    }
     size_t off = 0;
     const unsigned NQ = STARK_NUM_QUERIES;
-    gather_rows_kernel<<<NQ, 256, 0, st>>>(d_lde, C, m, d_idx, 0, d_query, qlen, off);
-    off += C;
-    gather_paths_kernel<<<NQ, 32, 0, st>>>(d_dig_t, km, n_sib, d_idx, 0, d_query, qlen, off);
-    off += 4 * n_sib;
-    gather_rows_kernel<<<NQ, 32, 0, st>>>(d_qlde, 4, m, d_idx, 0, d_query, qlen, off);
-    off += 4;
-    gather_paths_kernel<<<NQ, 32, 0, st>>>(d_dig_q, km, n_sib, d_idx, 0, d_query, qlen, off);
-    off += 4 * n_sib;
-    ctx->launches += 4;
+    auto open_tree = [&](const gl* lde, size_t cols, const gl* dig) {
+        gather_rows_kernel<<<NQ, 256, 0, st>>>(lde, cols, m, d_idx, 0, d_query, qlen, off);
+        off += cols;
+        gather_paths_kernel<<<NQ, 32, 0, st>>>(dig, km, n_sib, d_idx, 0, d_query, qlen, off);
+        off += 4 * n_sib;
+        ctx->launches += 2;
+    };
+    if (Kc) open_tree(tb.d_const_lde, Kc, tb.d_const_dig);
+    open_tree(tb.d_lde_m, C, tb.d_dig_m);
+    open_tree(tb.d_lde_a, A, tb.d_dig_a);
+    open_tree(d_qlde, 4, d_dig_q);
     for (unsigned l = 0; l < n_layers; l++) {
         const unsigned lg_rows = (unsigned)layer_rows_log[l];
         const unsigned ns = lg_rows - std::min<unsigned>(lg_rows, STARK_CAP_HEIGHT);
@@ -552,147 +776,47 @@ int TableProver::prove(tmx_ctx* ctx, int table, const gl* d_trace, unsigned log_
     if (rc) return rc;
     proof.insert(proof.end(), qd.begin(), qd.end());
     pt.tick("queries");
-    // the stream has been synchronised by the copy above: the stamps of this table's commitment are complete
-    TMX_CUDA(cudaEventElapsedTime(&last_lde_ms, ev_phase[0], ev_phase[1]));
-    TMX_CUDA(cudaEventElapsedTime(&last_merkle_ms, ev_phase[1], ev_phase[2]));
-    (void)host_poly_eval_ext;
     return TMX_OK;
-}
-
-static int grow(void** p, size_t* have, size_t want) {
-    if (*have >= want) return TMX_OK;
-    if (*p) TMX_CUDA(cudaFree(*p));
-    *p = nullptr;
-    *have = 0;
-    TMX_CUDA(cudaMalloc(p, want));
-    *have = want;
-    return TMX_OK;
-}
-
-int TableProver::reserve(tmx_ctx* ctx, size_t C, size_t n, size_t m, size_t dig_t) {
-    (void)ctx;
-    int rc;
-    if ((rc = grow((void**)&d_lde, &sz_lde, C * m * sizeof(gl)))) return rc;
-    if ((rc = grow((void**)&d_coeffs, &sz_coeffs, C * n * sizeof(gl)))) return rc;
-    if ((rc = grow((void**)&d_dig_t, &sz_dig_t, 4 * dig_t * sizeof(gl)))) return rc;
-    if ((rc = grow((void**)&d_dig_q, &sz_dig_q, 4 * dig_t * sizeof(gl)))) return rc;
-    if ((rc = grow((void**)&d_dig_fri, &sz_dig_fri, 4 * (m / 4) * sizeof(gl)))) return rc;
-    if ((rc = grow((void**)&d_qv, &sz_qv, 2 * m * sizeof(gl)))) return rc;
-    if ((rc = grow((void**)&d_qcoef, &sz_qcoef, 4 * n * sizeof(gl)))) return rc;
-    if ((rc = grow((void**)&d_qlde, &sz_qlde, 4 * m * sizeof(gl)))) return rc;
-    if ((rc = grow((void**)&d_ypa, &sz_yp, 2 * n * sizeof(gl2)))) return rc;
-    d_ypb = d_ypa + n;
-    if ((rc = grow((void**)&d_open, &sz_open, (2 * C + 4) * sizeof(gl2)))) return rc;
-    if ((rc = grow((void**)&d_apow, &sz_apow, (C + 4) * sizeof(gl2)))) return rc;
-    if ((rc = grow((void**)&d_idx, &sz_idx, STARK_NUM_QUERIES * sizeof(uint32_t)))) return rc;
-    // FRI layer arrays: m, m/16, m/256, ... ext values, carved from one allocation
-    size_t tot = 0, cur = m;
-    for (int l = 0; l < 9; l++) {
-        tot += cur;
-        cur = cur >> 4 ? cur >> 4 : 1;
-    }
-    if ((rc = grow((void**)&d_fri_base, &sz_fri, tot * sizeof(gl2)))) return rc;
-    cur = m;
-    size_t o = 0;
-    for (int l = 0; l < 9; l++) {
-        d_fri[l] = d_fri_base + o;
-        o += cur;
-        cur = cur >> 4 ? cur >> 4 : 1;
-    }
-    return TMX_OK;
-}
-
-int TableProver::reserve_queries(tmx_ctx* ctx, size_t n) {
-    (void)ctx;
-    return grow((void**)&d_query, &sz_query, n * sizeof(gl));
-}
-
-int TableProver::periodic_tables(tmx_ctx* ctx, int table, unsigned log_n, const gl** out) {
-    const uint64_t key = ((uint64_t)shape.kind << 48) | ((uint64_t)shape.n_max << 16) | ((uint64_t)table << 8) | log_n;
-    auto it = pertabs.find(key);
-    if (it != pertabs.end()) {
-        *out = it->second;
-        return TMX_OK;
-    }
-    // the host-side values depend on (shape, table, log_n) only: computed once per process (the SHA-256 table's public
-    // columns cost six NTTs of the table length), shared by every prover / context
-    static std::mutex cache_mutex;
-    static std::map<uint64_t, std::shared_ptr<const std::vector<gl>>> cache;
-    std::shared_ptr<const std::vector<gl>> host;
-    {
-        std::lock_guard<std::mutex> lk(cache_mutex);
-        auto hit = cache.find(key);
-        if (hit == cache.end())
-            hit = cache.emplace(key, std::make_shared<const std::vector<gl>>(air_periodic_lde_table(table, log_n, h_K256, h_K512, shape))).first;
-        host = hit->second;
-    }
-    const std::vector<gl>& tab = *host;
-    void* d = nullptr;
-    TMX_CUDA(cudaMalloc(&d, tab.size() * sizeof(gl)));
-    TMX_CUDA(cudaMemcpy(d, tab.data(), tab.size() * sizeof(gl), cudaMemcpyHostToDevice));
-    TMX_CUDA(cudaStreamSynchronize(cudaStreamLegacy));  // staged copy: the DMA must land before kernels on other streams read it
-    pertabs[key] = (gl*)d;
-    *out = (gl*)d;
-    (void)ctx;
-    return TMX_OK;
-}
-
-void TableProver::release() {
-    for (int i = 0; i < 3; i++)
-        if (ev_phase[i]) cudaEventDestroy(ev_phase[i]);
-    if (h_pinned) cudaFreeHost(h_pinned);
-    void* ps[] = {d_lde, d_coeffs, d_dig_t, d_dig_q, d_dig_fri, d_qv, d_qcoef, d_qlde, d_ypa, d_open, d_apow, d_idx, d_fri_base, d_query};
-    for (void* p : ps)
-        if (p) cudaFree(p);
-    for (auto& kv : pertabs) cudaFree(kv.second);
-    pertabs.clear();
-    *this = TableProver();
 }
 
 }  // namespace tmx
 
 using namespace tmx;
 
-// Host-side self check (no GPU): the literal constraint fold of air_ed25519() and the factored evaluation used by the
-// quotient kernel on one (local row, next row) pair.  out = {literal(alpha0), literal(alpha1), fast(alpha0), fast(alpha1)}.
-struct HostRow {
-    const gl* p;
-    FB operator[](int c) const { return FB::mk(p[c]); }
-};
-extern "C" int tmx_host_air_ed25519(const uint64_t* row_l, const uint64_t* row_n, const uint64_t periodic[3], const uint64_t alpha[2],
-                                    uint64_t out[4]) {
-    if (!row_l || !row_n || !periodic || !alpha || !out) return fail(TMX_E_INPUT, "tmx_host_air_ed25519: NULL argument");
-    HostRow l{row_l}, n{row_n};
-    const FB per[3] = {FB::mk(periodic[0]), FB::mk(periodic[1]), FB::mk(periodic[2])};
-    ConstraintAcc<FB> acc;
-    acc.acc0 = FB::c(0); acc.acc1 = FB::c(0);
-    acc.alpha0 = FB::mk(alpha[0]); acc.alpha1 = FB::mk(alpha[1]);
-    air_ed25519<FB>(l, n, per, acc);
-    out[0] = acc.acc0.v;
-    out[1] = acc.acc1.v;
-    out[2] = ed25519_constraints_fast(l, n, periodic, ed_fast_consts(alpha[0]));
-    out[3] = ed25519_constraints_fast(l, n, periodic, ed_fast_consts(alpha[1]));
-    return TMX_OK;
-}
-
-// K5 as a kernel-level entry point (parity tests, ncu): constraint quotient of one table on its LDE coset.
-extern "C" int tmx_quotient(tmx_ctx* ctx, uint32_t kind, uint32_t n_max, int table, const uint64_t* d_lde, unsigned log_n,
-                            const uint64_t alpha[2], uint64_t* d_out, void* stream) {
-    if (!ctx || !d_lde || !alpha || !d_out || table < 0 || table > 2 || log_n < 8 || log_n > 28)
-        return fail(TMX_E_INPUT, "tmx_quotient: bad arguments");
-    static thread_local TableProver tp;  // only its periodic-table cache is used
-    tp.shape = AirShape{kind, n_max};
+// K5 as a kernel-level entry point (parity tests, ncu): constraint quotient of one table on its LDE coset.  d_lde_main /
+// d_lde_aux: LDEs ([cols][2n], bit-reversed rows, as tmx_lde produces them) of the first- and second-round traces; total:
+// the table's bus total; d_out: [2][2n] in NATURAL order, one row per constraint challenge alpha[i]:
+// sum_k alpha^(M-1-k) C_k(x) / (x^n - 1).  The constant and periodic columns are the circuit's.
+int tmx::stark_quotient(tmx_ctx* ctx, Prover& pr, int table, const gl* d_lde_main, const gl* d_lde_aux, gl2 total, gl2 beta, gl2 gamma,
+                        const gl alpha[2], gl* d_out, cudaStream_t st) {
+    const TableDef& td = pr.def->tables[table];
+    const size_t n = td.rows();
     QuotientArgs qa;
     memset(&qa, 0, sizeof qa);
-    const size_t n = (size_t)1 << log_n;
-    qa.lde = d_lde; qa.m = n << STARK_RATE_BITS; qa.log_m = log_n + STARK_RATE_BITS; qa.rate_bits = STARK_RATE_BITS;
-    qa.nper = air_n_periodic(table); qa.P = (int)air_period(table, n);
+    qa.lde_m = d_lde_main; qa.lde_k = pr.tab[table].d_const_lde; qa.lde_a = d_lde_aux;
+    qa.m = n << STARK_RATE_BITS; qa.log_m = td.log_n + STARK_RATE_BITS; qa.rate_bits = STARK_RATE_BITS;
+    qa.pertab = pr.tab[table].d_per_lde; qa.P = (int)td.period;
+    qa.shape = pr.shape;
     qa.alpha[0] = alpha[0]; qa.alpha[1] = alpha[1];
+    qa.beta = beta; qa.gamma = gamma;
+    qa.s_over_n = gl2_scale(total, gl_inv((gl)n));
     fill_zh_inv(qa, n);
-    if (qa.nper) {
-        int rc = tp.periodic_tables(ctx, table, log_n, &qa.pertab);
-        if (rc) return rc;
-    }
     qa.out = d_out;
-    return launch_quotient(ctx, table, qa, pick_stream(ctx, stream));
+    return launch_quotient(ctx, table, qa, st);
+}
+
+// K3 fold as a kernel-level entry point: one arity-16 FRI folding step in evaluation space.  d_in: 16 * n_cosets extension
+// elements (interleaved (a0, a1), bit-reversed order) on the coset shift * <w>, d_out: n_cosets folded values (bit-reversed)
+// on shift^16 * <w^16>.  [plonky2 fri/prover.rs fri_committed_trees, one layer]
+extern "C" int tmx_fri_fold(tmx_ctx* ctx, const uint64_t* d_in, unsigned log_cosets, uint64_t shift, const uint64_t beta[2],
+                            uint64_t* d_out, void* stream) {
+    if (!ctx || !d_in || !d_out || !beta || log_cosets > 26 || shift == 0) return fail(TMX_E_INPUT, "tmx_fri_fold: bad arguments");
+    const size_t cosets = (size_t)1 << log_cosets;
+    cudaStream_t st = pick_stream(ctx, stream);
+    fri_fold_kernel<<<(unsigned)((cosets + 127) / 128), 128, 0, st>>>(reinterpret_cast<const gl2*>(d_in), cosets, log_cosets, gl_inv(shift),
+                                                                     gl_inv(gl_root_of_unity(log_cosets + STARK_ARITY_BITS)),
+                                                                     gl2_make(beta[0], beta[1]), reinterpret_cast<gl2*>(d_out));
+    ctx->launches++;
+    TMX_CUDA(cudaGetLastError());
+    return TMX_OK;
 }

@@ -1,65 +1,77 @@
-// Shared declarations of the STARK layer: protocol parameters (Curta's STARK configuration as recalled in
-// rate_bits 1, cap height 4, 16-bit PoW, 84 queries, arity-16 FRI, final polynomial <= 2^5)
-// and the per-table GPU prover state.
+// Shared declarations of the STARK layer: the per-circuit GPU prover state (device buffers of every table, the constant
+// columns' commitment) and the phases of one proof.  Protocol parameters: params.cuh.
 #pragma once
 #include "ctx.cuh"
+#include "params.cuh"
 #include "poseidon.cuh"
 #include "air.cuh"
+#include "logic.cuh"
+#include "circuit_def.cuh"
 #include "witness.cuh"
 #include <vector>
 #include <map>
 #include <functional>
+#include <memory>
 
 namespace tmx {
 
-constexpr unsigned STARK_RATE_BITS = 1;
-constexpr unsigned STARK_CAP_HEIGHT = 4;
-constexpr unsigned STARK_POW_BITS = 16;
-constexpr int STARK_NUM_QUERIES = 84;
-constexpr unsigned STARK_ARITY_BITS = 4;
-constexpr unsigned STARK_FINAL_POLY_BITS = 5;
-constexpr uint64_t STARK_PROOF_MAGIC = 0x50584D54ULL;  // "TMXP"
-constexpr int STARK_N_TABLES = 3;
+constexpr int STARK_N_TABLES = TMX_N_TABLES;
 
 unsigned fri_num_layers(unsigned degree_bits);
 
-// Device buffers reused from proof to proof (grow-only) and the cached periodic-column tables.
-struct TableProver {
-    gl* d_lde = nullptr; size_t sz_lde = 0;
-    gl* d_coeffs = nullptr; size_t sz_coeffs = 0;
-    gl* d_dig_t = nullptr; size_t sz_dig_t = 0;
-    gl* d_dig_q = nullptr; size_t sz_dig_q = 0;
-    gl* d_dig_fri = nullptr; size_t sz_dig_fri = 0;
-    gl* d_qv = nullptr; size_t sz_qv = 0;
-    gl* d_qcoef = nullptr; size_t sz_qcoef = 0;
-    gl* d_qlde = nullptr; size_t sz_qlde = 0;
-    gl2* d_ypa = nullptr; gl2* d_ypb = nullptr; size_t sz_yp = 0;
-    gl2* d_open = nullptr; size_t sz_open = 0;
-    gl2* d_apow = nullptr; size_t sz_apow = 0;
-    uint32_t* d_idx = nullptr; size_t sz_idx = 0;
-    gl2* d_fri_base = nullptr; size_t sz_fri = 0;
-    gl2* d_fri[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    gl* d_query = nullptr; size_t sz_query = 0;
-    std::map<uint64_t, gl*> pertabs;
-    AirShape shape = {0, 0};  // circuit shape (kind, n_max): the SHA-256 table's public columns depend on it
-    // device-time stamps of the trace commitment of the last prove(): LDE start, LDE end = Merkle start, Merkle end
-    cudaEvent_t ev_phase[3] = {nullptr, nullptr, nullptr};
-    float last_lde_ms = 0.f, last_merkle_ms = 0.f;
-    gl* h_pinned = nullptr; size_t sz_pinned = 0;  // pinned staging buffer for the transcript's device -> host copies
-
-    // Appends this table's proof to `proof` and advances the transcript.  `on_trace_committed` (optional) is called once
-    // the trace commitment has been enqueued and its completion event recorded: the caller uses it to start
-    // work on another stream that should overlap with the latency-bound rest of this table's proof.
-    int prove(tmx_ctx* ctx, int table, const gl* d_trace, unsigned log_n, Challenger& ch, std::vector<gl>& proof, cudaStream_t st,
-              const std::function<int(cudaEvent_t)>& on_trace_committed = nullptr);
-    int d2h(std::vector<gl>& dst, const gl* src, size_t n, cudaStream_t st);
-    int reserve(tmx_ctx* ctx, size_t C, size_t n, size_t m, size_t dig_t);
-    int reserve_queries(tmx_ctx* ctx, size_t n);
-    int periodic_tables(tmx_ctx* ctx, int table, unsigned log_n, const gl** out);
-    void release();
+// device buffers of one table (grow-only, reused from proof to proof)
+struct TableDevice {
+    // per circuit: constant columns (trace values, coset-scaled coefficients, LDE, Merkle digests), periodic columns
+    gl* d_const = nullptr; gl* d_const_coef = nullptr; gl* d_const_lde = nullptr; gl* d_const_dig = nullptr;
+    gl* d_per_trace = nullptr;  // [n_per][P] one period of every periodic column
+    gl* d_per_lde = nullptr;    // [n_per][2P] values on the LDE coset
+    // per proof
+    gl* d_aux = nullptr;                      // second-round trace [A][n]
+    gl* d_lde_m = nullptr; gl* d_coef_m = nullptr; gl* d_dig_m = nullptr;
+    gl* d_lde_a = nullptr; gl* d_coef_a = nullptr; gl* d_dig_a = nullptr;
+    gl2 total = {0, 0};
 };
 
-// host verifier of one table proof; returns 0 or a diagnostic code
-int verify_table(int table, size_t n, AirShape shape, const gl* proof, size_t proof_len, size_t* pos, Challenger& ch);
+struct Prover {
+    std::shared_ptr<const CircuitDef> def;
+    AirShape shape = {0, 0};
+    TableDevice tab[STARK_N_TABLES];
+    // shared by the per-table tails (sized for the largest table)
+    gl* d_dig_q = nullptr; gl* d_dig_fri = nullptr; gl* d_qv = nullptr; gl* d_qcoef = nullptr; gl* d_qlde = nullptr;
+    gl2* d_ypa = nullptr; gl2* d_ypb = nullptr; gl2* d_open = nullptr; gl2* d_apow = nullptr;
+    uint32_t* d_idx = nullptr;
+    gl2* d_fri_base = nullptr; gl2* d_fri[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    gl* d_query = nullptr; size_t sz_query = 0;
+    gl2* d_rowsum = nullptr;      // per-row bus sums of the table being processed
+    gl* d_small = nullptr;        // caps / totals staging: [STARK_N_TABLES][64 + 2]
+    unsigned int* d_hist = nullptr;  // range-lookup histogram, then one int "bad" flag
+    gl* d_range_trace = nullptr;  // first-round trace of the range table
+    gl* h_pinned = nullptr; size_t sz_pinned = 0;
+    cudaEvent_t ev_phase[2 * STARK_N_TABLES + 1] = {};
+    float lde_ms[STARK_N_TABLES] = {}, merkle_ms[STARK_N_TABLES] = {};
+    std::vector<void*> owned;
+
+    int setup(tmx_ctx* ctx, std::shared_ptr<const CircuitDef> d);  // allocations + commitment of the constant columns
+    void release();
+    // round 1: histogram of table t's range lookups (t != range), range-table trace from the histogram, commitment
+    int count_lookups(tmx_ctx* ctx, int t, const gl* d_trace, cudaStream_t st);
+    int fill_range_trace(tmx_ctx* ctx, cudaStream_t st);
+    int commit_main(tmx_ctx* ctx, int t, const gl* d_trace, cudaStream_t st);
+    int finish_round1(tmx_ctx* ctx, Challenger& ch, std::vector<gl>& proof, cudaStream_t st, bool* range_ok);
+    // round 2: helper columns + running sum of every table, commitment
+    int commit_aux(tmx_ctx* ctx, int t, const gl* d_trace, gl2 beta, gl2 gamma, cudaStream_t st);
+    int finish_round2(tmx_ctx* ctx, Challenger& ch, std::vector<gl>& proof, cudaStream_t st);
+    // quotient, openings, FRI, queries of one table
+    int prove_tail(tmx_ctx* ctx, int t, gl2 beta, gl2 gamma, Challenger& ch, std::vector<gl>& proof, cudaStream_t st);
+    int d2h(std::vector<gl>& dst, const gl* src, size_t n, cudaStream_t st);
+    int alloc(void** p, size_t bytes);
+};
+
+int stark_quotient(tmx_ctx* ctx, Prover& pr, int table, const gl* d_lde_main, const gl* d_lde_aux, gl2 total, gl2 beta, gl2 gamma,
+                   const gl alpha[2], gl* d_out, cudaStream_t st);
+
+// host verifier; returns 0 or a diagnostic code (verify.cu)
+int verify_proof(const CircuitDef& def, const gl* proof, size_t n_words, const uint8_t* input, size_t input_len, const uint8_t out32[32]);
+void transcript_init(const gl digest[4], const uint8_t* input, size_t input_len, const uint8_t out32[32], Challenger& ch);
 
 }  // namespace tmx

@@ -65,90 +65,59 @@ __global__ void __launch_bounds__(64) sha256_padding_kernel(WitnessArgs a, size_
     sha256_row_cells(a.t256, a.n256, (first_chunk + blockIdx.x) * 64 + threadIdx.x, threadIdx.x, &hs);
 }
 
-__global__ void __launch_bounds__(128) sha512_padding_kernel(WitnessArgs a, size_t first_row) {
-    __shared__ Sha512Hist hs;
-    if (threadIdx.x == 0) sha512_padding_prepare(&hs);
-    __syncthreads();
-    const size_t row = first_row + (size_t)blockIdx.x * S512_ROWS_PER_CHUNK + threadIdx.x;
-    if (row < a.n512) sha512_row_cells(a.t512, a.n512, row, threadIdx.x, &hs);
-}
-
-struct LadderShared {
-    Sha512Hist h5[2];
-    EdTriple triple;
-    EdSlot slot;
-    uint8_t digest[64];
-    ge51 Ps, Ph;
-    bool ok_r;
-};
-
-// Phase 1 (latency-bound, small footprint: 64 threads, so other kernels share the SMs while it runs): per validator
-// SHA-512(R || A || M) -> h mod l, decompress A and R on two warps, run the [s]B and [h]A ladders on two warps and park
-// the canonical (res, temp) of every step in global scratch (128 B per point); verdict of the signature equation.
-__global__ void __launch_bounds__(64) ed25519_ladder_kernel(WitnessArgs a, ge_packed* __restrict__ points) {
-    __shared__ LadderShared sh;
-    const uint32_t i = blockIdx.x, tid = threadIdx.x;
-    ge_packed* res = points + (size_t)i * 1024;
-    ge_packed* tmp = res + 512;
-    if (tid == 0) {
-        effective_triple(blob_validators(a.blob) + i, &sh.triple);
-        sha512_validator_prepare(sh.triple, sh.h5, sh.digest);
-        fe256 sb = fe256_from_bytes(sh.triple.sig + 32);
-        for (int k = 0; k < 4; k++) sh.slot.s[k] = sb.w[k];
-        sc_reduce512(sh.digest, sh.slot.h);
-        sh.slot.ok = sc_lt_l(sh.slot.s);
-    }
-    __syncthreads();
-    if (tid == 0 && !ge_decompress51(sh.triple.pk, &sh.slot.A)) {
-        sh.slot.ok = false;
-        sh.slot.A = ge_identity51();
-    }
-    if (tid == 32) {
-        sh.ok_r = ge_decompress51(sh.triple.sig, &sh.slot.R);
-        if (!sh.ok_r) sh.slot.R = ge_identity51();
-    }
-    __syncthreads();
-    if (tid == 0) sh.Ps = ed_ladder(sh.slot.s, ge_base51(), res, tmp);
-    if (tid == 32) sh.Ph = ed_ladder(sh.slot.h, sh.slot.A, res + 256, tmp + 256);
-    __syncthreads();
-    if (tid == 0) a.aux[AUX_SIG_OK + i] = (sh.ok_r && ed_slot_verdict(sh.slot, sh.Ps, sh.Ph)) ? 1 : 0;
-}
-
-// Phase 2 (throughput): one thread per trace row -- 2 x 128 SHA-512 rows and 512 ladder steps per validator.
-__global__ void __launch_bounds__(512) ed25519_expand_kernel(WitnessArgs a, const ge_packed* __restrict__ points) {
+// Phase 1 (latency-bound, small footprint so other kernels share the SMs while it runs): per validator slot
+// SHA-512(R || A || M) -> h mod l, decompression of A and R, the addend table {O, B, -A, B - A}, then the 256 sequential
+// rows acc' = 2 acc + T[bs + 2 bh] in 5 x 51-bit-limb field arithmetic; the canonical accumulator of every row is parked
+// in global scratch (96 B per row) for phase 2.  Slots >= n_max are padding: zero scalars, addend O.
+__global__ void __launch_bounds__(32) ed25519_ladder_kernel(WitnessArgs a, EdSlotInfo* __restrict__ info, ge_acc_packed* __restrict__ points) {
     __shared__ Sha512Hist h5[2];
-    __shared__ uint64_t sc[2][4];
-    const uint32_t i = blockIdx.x, tid = threadIdx.x;
-    if (tid == 0) {
-        EdTriple t;
-        uint8_t digest[64];
-        effective_triple(blob_validators(a.blob) + i, &t);
-        sha512_validator_prepare(t, h5, digest);
-        fe256 sb = fe256_from_bytes(t.sig + 32);
-        for (int k = 0; k < 4; k++) sc[0][k] = sb.w[k];
-        sc_reduce512(digest, sc[1]);
+    __shared__ EdTriple triple;
+    __shared__ uint8_t digest[64];
+    const uint32_t i = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    EdSlotInfo* e = info + i;
+    ge_cached51 tab[4];
+    ge51 R = ge_identity51();
+    if (i < a.n_max) {
+        effective_triple(blob_validators(a.blob) + i, &triple);
+        sha512_validator_prepare(triple, h5, digest);
+        ed_slot_prepare(triple, digest, e, tab, &R);
+    } else {
+        for (int k = 0; k < 4; k++) e->s[k] = e->h[k] = 0;
+        ed_padding_table(tab, &e->tab);
+        e->ok = 1;
     }
-    __syncthreads();
-    if (tid < S512_ROWS_PER_VALIDATOR)
-        sha512_row_cells(a.t512, a.n512, (size_t)i * S512_ROWS_PER_VALIDATOR + tid, tid % S512_ROWS_PER_CHUNK, &h5[tid / S512_ROWS_PER_CHUNK]);
-    const uint64_t* s = sc[tid >> 8];
-    const int bit = (int)((s[(tid & 255) >> 6] >> (tid & 63)) & 1);
-    const ge_packed* res = points + (size_t)i * 1024;
-    ed_row_cells(a.ted, a.ned, (size_t)i * ED_ROWS_PER_VALIDATOR + tid, bit, res[tid], res[512 + tid]);
+    const ge_acc51 q = ed_straus_ladder(e->s, e->h, tab, points + (size_t)i * ED_ROWS_PER_VALIDATOR);
+    e->QX = fe_freeze(q.X); e->QY = fe_freeze(q.Y); e->QZ = fe_freeze(q.Z);
+    if (i < a.n_max) {
+        const bool ok = e->ok && ed_result_equals(q, R);
+        e->ok = ok ? 1u : 0u;
+        a.aux[AUX_SIG_OK + i] = ok ? 1 : 0;
+    }
 }
 
-// padding blocks of the Ed25519 table: [0]B ladders (valid rows, bit = 0)
-__global__ void __launch_bounds__(256) ed25519_padding_kernel(WitnessArgs a, size_t first_row) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    ge_packed* res = reinterpret_cast<ge_packed*>(smem_raw);
-    ge_packed* tmp = res + 256;
-    if (threadIdx.x == 0) {
-        const uint64_t zero[4] = {0, 0, 0, 0};
-        ed_ladder(zero, ge_base51(), res, tmp);
+// Phase 2 (throughput): one thread per trace row -- the 2 x 128 SHA-512 rows and the 256 Ed25519 rows of a slot.
+__global__ void __launch_bounds__(256) ed25519_expand_kernel(WitnessArgs a, const EdSlotInfo* __restrict__ info,
+                                                            const ge_acc_packed* __restrict__ points) {
+    __shared__ Sha512Hist h5[2];
+    __shared__ EdAddendTable tab;
+    const uint32_t i = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) {
+        if (i < a.n_max) {
+            EdTriple t;
+            uint8_t digest[64];
+            effective_triple(blob_validators(a.blob) + i, &t);
+            sha512_validator_prepare(t, h5, digest);
+        } else {
+            sha512_padding_prepare(&h5[0]);
+            sha512_padding_prepare(&h5[1]);
+        }
     }
+    for (int k = tid; k < 4 * 48; k += 256) tab.limb[k / 48][k % 48] = info[i].tab.limb[k / 48][k % 48];
     __syncthreads();
-    const size_t row = first_row + (size_t)blockIdx.x * 256 + threadIdx.x;
-    if (row < a.ned) ed_row_cells(a.ted, a.ned, row, 0, res[threadIdx.x], tmp[threadIdx.x]);
+    const size_t row = (size_t)i * ED_ROWS_PER_VALIDATOR + tid;
+    if (a.t512 && row < a.n512) sha512_row_cells(a.t512, a.n512, row, tid % S512_ROWS_PER_CHUNK, &h5[tid / S512_ROWS_PER_CHUNK]);
+    if (a.ted && row < a.ned) ed_row_cells(a.ted, a.ned, row, (int)tid, info[i].s, info[i].h, points[row], tab);
 }
 
 int witness_tu_init() {
@@ -204,36 +173,28 @@ static int run_sha256(tmx_ctx* ctx, const WitnessArgs& a, cudaStream_t st) {
     return TMX_OK;
 }
 
-size_t witness_points_bytes(uint32_t n_max) { return (size_t)n_max * 1024 * sizeof(ge_packed); }
+size_t witness_slot_count(uint32_t n_max) { return pow2_at_least((size_t)n_max * ED_ROWS_PER_VALIDATOR) / ED_ROWS_PER_VALIDATOR; }
+size_t witness_points_bytes(uint32_t n_max) {
+    const size_t slots = witness_slot_count(n_max);
+    return slots * sizeof(EdSlotInfo) + slots * ED_ROWS_PER_VALIDATOR * sizeof(ge_acc_packed);
+}
 
 // phase 1 only (stream-ordered); points must hold witness_points_bytes(n_max)
 int run_ed25519_ladder(tmx_ctx* ctx, const WitnessArgs& a, void* points, cudaStream_t st) {
-    // Measured: while the ladders run (one CTA on 128 of the 148 SMs, ~6 ms) the NTT passes of the SHA-256 table are kept
-    // off those SMs (different L1 / shared-memory split), so that LDE takes 6.8 ms instead of 1.6 ms.  Forcing the
-    // largest shared-memory split on the ladder kernel fixes the LDE (3.1 ms) but then the ladder's two warps share
-    // issue slots with the leaf hashing and the proof gets 2.4 ms slower overall; left as is.
-    ed25519_ladder_kernel<<<a.n_max, 64, 0, st>>>(a, (ge_packed*)points);
+    const size_t slots = witness_slot_count(a.n_max);
+    EdSlotInfo* info = (EdSlotInfo*)points;
+    ed25519_ladder_kernel<<<(unsigned)slots, 32, 0, st>>>(a, info, (ge_acc_packed*)(info + slots));
     ctx->launches++;
     TMX_CUDA(cudaGetLastError());
     return TMX_OK;
 }
 
-// phase 2 + padding rows of the SHA-512 and Ed25519 tables
+// phase 2: all rows of the SHA-512 and Ed25519 tables (padding slots included)
 int run_ed25519_expand(tmx_ctx* ctx, const WitnessArgs& a, const void* points, cudaStream_t st) {
-    ed25519_expand_kernel<<<a.n_max, 512, 0, st>>>(a, (const ge_packed*)points);
+    const size_t slots = witness_slot_count(a.n_max);
+    const EdSlotInfo* info = (const EdSlotInfo*)points;
+    ed25519_expand_kernel<<<(unsigned)slots, 256, 0, st>>>(a, info, (const ge_acc_packed*)(info + slots));
     ctx->launches++;
-    const size_t used512 = (size_t)a.n_max * S512_ROWS_PER_VALIDATOR;
-    if (a.n512 > used512) {
-        sha512_padding_kernel<<<(unsigned)((a.n512 - used512 + S512_ROWS_PER_CHUNK - 1) / S512_ROWS_PER_CHUNK), S512_ROWS_PER_CHUNK, 0, st>>>(a, used512);
-        ctx->launches++;
-    }
-    const size_t used_ed = (size_t)a.n_max * ED_ROWS_PER_VALIDATOR;
-    if (a.ned > used_ed) {
-        const size_t psmem = 512 * sizeof(ge_packed);
-        TMX_CUDA(cudaFuncSetAttribute(ed25519_padding_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-        ed25519_padding_kernel<<<(unsigned)((a.ned - used_ed + 255) / 256), 256, psmem, st>>>(a, used_ed);
-        ctx->launches++;
-    }
     TMX_CUDA(cudaGetLastError());
     return TMX_OK;
 }
@@ -278,6 +239,18 @@ extern "C" int tmx_sha256_trace(tmx_ctx* ctx, const uint8_t* d_blob, uint32_t ki
     int rc = make_args(ctx, d_blob, kind, n_max, d_t256, nullptr, nullptr, d_aux, &a);
     if (rc) return rc;
     return run_sha256(ctx, a, pick_stream(ctx, stream));
+}
+
+// K7 alone: the SHA-512 table (h = SHA-512(R || A || M) of every validator slot), without the Ed25519 rows
+extern "C" int tmx_sha512_trace(tmx_ctx* ctx, const uint8_t* d_blob, uint32_t kind, uint32_t n_max, uint64_t* d_t512, void* stream) {
+    if (!ctx || !d_blob || !d_t512) return fail(TMX_E_INPUT, "tmx_sha512_trace: NULL argument");
+    WitnessArgs a;
+    int rc = make_args(ctx, d_blob, kind, n_max, nullptr, d_t512, nullptr, nullptr, &a);
+    if (rc) return rc;
+    void* points = nullptr;
+    rc = ctx_scratch(ctx, 1, witness_points_bytes(a.n_max), &points);
+    if (rc) return rc;
+    return run_ed25519_expand(ctx, a, points, pick_stream(ctx, stream));
 }
 
 extern "C" int tmx_ed25519_trace(tmx_ctx* ctx, const uint8_t* d_blob, uint32_t kind, uint32_t n_max, uint64_t* d_t512,

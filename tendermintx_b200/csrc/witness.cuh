@@ -328,75 +328,157 @@ TMX_HD void fe256_to_limbs(const fe256& x, int32_t l[16]) {
 }
 TMX_HD int32_t p_limb(int i) { return i == 0 ? 0xFFED : (i == 15 ? 0x7FFF : 0xFFFF); }
 
-// All ED_COLS cells of one ladder row from the packed canonical (res, temp) and the scalar bit.  The operand
-// builders are the limb-wise linear combinations of DESIGN.md "Ed25519 table" (same slots as the CPU oracle).
-TMX_HD void ed_row_cells(gl* trace, size_t n_rows, size_t row, int bit, const ge_packed& res, const ge_packed& tmp) {
-    gl* p = trace + row;
-    p[(size_t)ED_BIT * n_rows] = (gl)bit;
-    int32_t X1[16], Y1[16], Z1[16], T1[16], X2[16], Y2[16], Z2[16], T2[16];
-    fe256_to_limbs(res.X, X1); fe256_to_limbs(res.Y, Y1); fe256_to_limbs(res.Z, Z1); fe256_to_limbs(res.T, T1);
-    fe256_to_limbs(tmp.X, X2); fe256_to_limbs(tmp.Y, Y2); fe256_to_limbs(tmp.Z, Z2); fe256_to_limbs(tmp.T, T2);
-    for (int i = 0; i < 16; i++) {
-        p[(size_t)(ED_RES + i) * n_rows] = (gl)X1[i];
-        p[(size_t)(ED_RES + 16 + i) * n_rows] = (gl)Y1[i];
-        p[(size_t)(ED_RES + 32 + i) * n_rows] = (gl)Z1[i];
-        p[(size_t)(ED_RES + 48 + i) * n_rows] = (gl)T1[i];
-        p[(size_t)(ED_TMP + i) * n_rows] = (gl)X2[i];
-        p[(size_t)(ED_TMP + 16 + i) * n_rows] = (gl)Y2[i];
-        p[(size_t)(ED_TMP + 32 + i) * n_rows] = (gl)Z2[i];
-        p[(size_t)(ED_TMP + 48 + i) * n_rows] = (gl)T2[i];
-    }
-    const int32_t twod[16] = {0xF159, 0x26B2, 0x9B94, 0xEBD6, 0xB156, 0x8283, 0x149A, 0x00E0,
-                              0xD130, 0xEEF3, 0x80F2, 0x198E, 0xFCE7, 0x56DF, 0xD9DC, 0x2406};
-    int32_t u[16], v[16], A[16], B[16], U[16], C[16], Dh[16], E[16], F[16], G[16], H[16], dump[16];
-    auto cells = [&](int m) { return p + (size_t)(ED_MUL + m * ED_MUL_STRIDE) * n_rows; };
-    for (int i = 0; i < 16; i++) { u[i] = Y1[i] - X1[i] + p_limb(i); v[i] = Y2[i] - X2[i] + p_limb(i); }
-    mul_gadget_cells(u, v, cells(0), n_rows, A);
-    for (int i = 0; i < 16; i++) { u[i] = Y1[i] + X1[i]; v[i] = Y2[i] + X2[i]; }
-    mul_gadget_cells(u, v, cells(1), n_rows, B);
-    mul_gadget_cells(T1, T2, cells(2), n_rows, U);
-    mul_gadget_cells(U, twod, cells(3), n_rows, C);
-    mul_gadget_cells(Z1, Z2, cells(4), n_rows, Dh);
-    for (int i = 0; i < 16; i++) {
-        E[i] = B[i] - A[i] + p_limb(i);
-        F[i] = 2 * Dh[i] - C[i] + p_limb(i);
-        G[i] = 2 * Dh[i] + C[i];
-        H[i] = B[i] + A[i];
-    }
-    mul_gadget_cells(E, F, cells(5), n_rows, dump);
-    mul_gadget_cells(G, H, cells(6), n_rows, dump);
-    mul_gadget_cells(E, H, cells(7), n_rows, dump);
-    mul_gadget_cells(F, G, cells(8), n_rows, dump);
-    int32_t* A2 = A; int32_t* B2 = B; int32_t* Cz = C; int32_t* S = U;
-    mul_gadget_cells(X2, X2, cells(9), n_rows, A2);
-    mul_gadget_cells(Y2, Y2, cells(10), n_rows, B2);
-    mul_gadget_cells(Z2, Z2, cells(11), n_rows, Cz);
-    for (int i = 0; i < 16; i++) u[i] = X2[i] + Y2[i];
-    mul_gadget_cells(u, u, cells(12), n_rows, S);
-    for (int i = 0; i < 16; i++) {
-        E[i] = S[i] - A2[i] - B2[i] + 2 * p_limb(i);
-        G[i] = B2[i] - A2[i] + p_limb(i);
-        F[i] = B2[i] - A2[i] - 2 * Cz[i] + 3 * p_limb(i);
-        H[i] = 2 * p_limb(i) - A2[i] - B2[i];
-    }
-    mul_gadget_cells(E, F, cells(13), n_rows, dump);
-    mul_gadget_cells(G, H, cells(14), n_rows, dump);
-    mul_gadget_cells(E, H, cells(15), n_rows, dump);
-    mul_gadget_cells(F, G, cells(16), n_rows, dump);
+// ---- joint (Straus) evaluation of [s]B + [h](-A): acc' = 2 acc + T[bs + 2 bh], most significant bits first ----
+// affine addend in the cached form the mixed addition consumes
+struct ge_cached51 {
+    fe51 ypx, ymx, t2d;  // y + x, y - x, 2 d x y
+};
+// canonical accumulator (X, Y, Z) of one row, 96 bytes
+struct ge_acc_packed {
+    fe256 X, Y, Z;
+};
+struct ge_acc51 {
+    fe51 X, Y, Z;
+};
+// the four addends of a slot as the ED_ADD cells hold them (48 limbs each: y + x, y - x, 2dxy); see ed_slot_table
+struct EdAddendTable {
+    int32_t limb[4][48];
+};
+
+// one row in field arithmetic: dbl-2008-hwcd (a = -1) followed by add-2008-hwcd-3 with Z2 = 1, no T output
+TMX_HD ge_acc51 ed_straus_step(const ge_acc51& p, const ge_cached51& q) {
+    const fe51 A = fe_sq(p.X), B = fe_sq(p.Y), Cz = fe_sq(p.Z);
+    const fe51 S = fe_sq(fe_add(p.X, p.Y));
+    const fe51 E = fe_sub(fe_sub(S, A), B);
+    const fe51 G = fe_sub(B, A);
+    const fe51 F = fe_sub(G, fe_add(Cz, Cz));
+    const fe51 H = fe_sub(fe_zero(), fe_add(A, B));
+    const fe51 X3 = fe_mul(E, F), Y3 = fe_mul(G, H), T3 = fe_mul(E, H), Z3 = fe_mul(F, G);
+    const fe51 a = fe_mul(fe_sub(Y3, X3), q.ymx), b = fe_mul(fe_add(Y3, X3), q.ypx), c = fe_mul(T3, q.t2d);
+    const fe51 d = fe_add(Z3, Z3);
+    const fe51 E2 = fe_sub(b, a), F2 = fe_sub(d, c), G2 = fe_add(d, c), H2 = fe_add(b, a);
+    ge_acc51 r;
+    r.X = fe_mul(E2, F2);
+    r.Y = fe_mul(G2, H2);
+    r.Z = fe_mul(F2, G2);
+    return r;
 }
 
-// One sequential ladder: stores canonical (res_i, temp_i) for the 256 rows and returns res_256.
-TMX_HD ge51 ed_ladder(const uint64_t scalar[4], const ge51& point, ge_packed* res_out, ge_packed* tmp_out) {
-    ge51 res = ge_identity51(), tmp = point;
-#pragma unroll 1
-    for (int i = 0; i < 256; i++) {
-        res_out[i] = ge_pack(res);
-        tmp_out[i] = ge_pack(tmp);
-        // continue from the canonical representatives so that the stored rows define the next ones exactly
-        if ((scalar[i >> 6] >> (i & 63)) & 1) res = ge_add51(res, tmp);
-        tmp = ge_dbl51(tmp);
+// Addend table of a slot from the decompressed (affine) public key: T = {O, B, -A, B - A}.  The field values go to
+// `tab` (for the sequential evaluation), the cell values to `cells`: canonical limbs for O and B; for -A and B - A the
+// sums / differences are taken LIMB-WISE (plus 2p where a difference could go negative), because that is the linear
+// expression of committed cells the logic table provides on the bus.  (xD, yD) = affine B - A.
+TMX_HD void ed_slot_table(const ge51& A, ge_cached51 tab[4], EdAddendTable* cells, fe256* xD_out, fe256* yD_out) {
+    const ge51 B = ge_base51();
+    tab[0].ypx = fe_one(); tab[0].ymx = fe_one(); tab[0].t2d = fe_zero();
+    tab[1].ypx = fe_add(B.Y, B.X); tab[1].ymx = fe_sub(B.Y, B.X); tab[1].t2d = fe_mul(fe_const_2d(), B.T);
+    const fe51 tA = fe_mul(fe_const_2d(), A.T);
+    tab[2].ypx = fe_sub(A.Y, A.X); tab[2].ymx = fe_add(A.Y, A.X); tab[2].t2d = fe_sub(fe_zero(), tA);
+    ge51 nA;
+    nA.X = fe_sub(fe_zero(), A.X); nA.Y = A.Y; nA.Z = fe_one(); nA.T = fe_sub(fe_zero(), A.T);
+    const ge51 D = ge_add51(B, nA);
+    const fe51 zi = fe_invert(D.Z);
+    const fe51 xD = fe_mul(D.X, zi), yD = fe_mul(D.Y, zi);
+    const fe51 tD = fe_mul(fe_const_2d(), fe_mul(xD, yD));
+    tab[3].ypx = fe_add(yD, xD); tab[3].ymx = fe_sub(yD, xD); tab[3].t2d = tD;
+    int32_t l0[16], l1[16], l2[16];
+    for (int i = 0; i < 48; i++) cells->limb[0][i] = (i == 0 || i == 16) ? 1 : 0;
+    fe256_to_limbs(fe_freeze(tab[1].ypx), l0); fe256_to_limbs(fe_freeze(tab[1].ymx), l1); fe256_to_limbs(fe_freeze(tab[1].t2d), l2);
+    for (int i = 0; i < 16; i++) { cells->limb[1][i] = l0[i]; cells->limb[1][16 + i] = l1[i]; cells->limb[1][32 + i] = l2[i]; }
+    fe256_to_limbs(fe_freeze(A.X), l0); fe256_to_limbs(fe_freeze(A.Y), l1); fe256_to_limbs(fe_freeze(tA), l2);
+    for (int i = 0; i < 16; i++) {
+        cells->limb[2][i] = l1[i] - l0[i] + 2 * p_limb(i);
+        cells->limb[2][16 + i] = l1[i] + l0[i];
+        cells->limb[2][32 + i] = 2 * p_limb(i) - l2[i];
     }
-    return res;
+    const fe256 xf = fe_freeze(xD), yf = fe_freeze(yD);
+    fe256_to_limbs(xf, l0); fe256_to_limbs(yf, l1); fe256_to_limbs(fe_freeze(tD), l2);
+    for (int i = 0; i < 16; i++) {
+        cells->limb[3][i] = l1[i] + l0[i];
+        cells->limb[3][16 + i] = l1[i] - l0[i] + 2 * p_limb(i);
+        cells->limb[3][32 + i] = l2[i];
+    }
+    if (xD_out) *xD_out = xf;
+    if (yD_out) *yD_out = yf;
+}
+TMX_HD void ed_padding_table(ge_cached51 tab[4], EdAddendTable* cells) {
+    for (int k = 0; k < 4; k++) {
+        tab[k].ypx = fe_one(); tab[k].ymx = fe_one(); tab[k].t2d = fe_zero();
+        for (int i = 0; i < 48; i++) cells->limb[k][i] = (i == 0 || i == 16) ? 1 : 0;
+    }
+}
+
+// The 256 rows of a slot, sequentially: stores the canonical accumulator BEFORE each row and returns the final one.
+// Every step continues from the canonical representative, so the stored rows define the next ones exactly.
+TMX_HD ge_acc51 ed_straus_ladder(const uint64_t s[4], const uint64_t h[4], const ge_cached51 tab[4], ge_acc_packed* acc_out) {
+    ge_acc51 acc;
+    acc.X = fe_zero(); acc.Y = fe_one(); acc.Z = fe_one();
+#pragma unroll 1
+    for (int r = 0; r < ED_ROWS_PER_VALIDATOR; r++) {
+        acc_out[r].X = fe_freeze(acc.X);
+        acc_out[r].Y = fe_freeze(acc.Y);
+        acc_out[r].Z = fe_freeze(acc.Z);
+        const int j = 255 - r;
+        const int sel = (int)((s[j >> 6] >> (j & 63)) & 1) + 2 * (int)((h[j >> 6] >> (j & 63)) & 1);
+        acc = ed_straus_step(acc, tab[sel]);
+    }
+    return acc;
+}
+
+// All ED_COLS cells of row r of a slot from the canonical accumulator before the row, the two scalars and the slot's
+// addend cells.  The operand builders are the limb-wise linear combinations of air_ed25519 (same slots as the CPU oracle).
+TMX_HD void ed_row_cells(gl* trace, size_t n_rows, size_t row, int r, const uint64_t s[4], const uint64_t h[4], const ge_acc_packed& acc,
+                         const EdAddendTable& tab) {
+    gl* p = trace + row;
+    const int j = 255 - r, pos = r & 15;
+    const int bs = (int)((s[j >> 6] >> (j & 63)) & 1), bh = (int)((h[j >> 6] >> (j & 63)) & 1);
+    // bits of the current 16-bit limb (index 15 - r / 16) already consumed by the rows above
+    const int lsh = 16 * (15 - (r >> 4));
+    const uint32_t limb_s = (uint32_t)((s[lsh >> 6] >> (lsh & 63)) & 0xFFFF), limb_h = (uint32_t)((h[lsh >> 6] >> (lsh & 63)) & 0xFFFF);
+    p[(size_t)ED_BS * n_rows] = (gl)bs;
+    p[(size_t)ED_BH * n_rows] = (gl)bh;
+    p[(size_t)ED_SACC_S * n_rows] = (gl)(pos ? limb_s >> (16 - pos) : 0);
+    p[(size_t)ED_SACC_H * n_rows] = (gl)(pos ? limb_h >> (16 - pos) : 0);
+    int32_t X1[16], Y1[16], Z1[16];
+    fe256_to_limbs(acc.X, X1); fe256_to_limbs(acc.Y, Y1); fe256_to_limbs(acc.Z, Z1);
+    const int32_t* add = tab.limb[bs + 2 * bh];
+    for (int i = 0; i < 16; i++) {
+        p[(size_t)(ED_ACC + i) * n_rows] = (gl)X1[i];
+        p[(size_t)(ED_ACC + 16 + i) * n_rows] = (gl)Y1[i];
+        p[(size_t)(ED_ACC + 32 + i) * n_rows] = (gl)Z1[i];
+    }
+    for (int i = 0; i < 48; i++) p[(size_t)(ED_ADD + i) * n_rows] = (gl)add[i];
+    int32_t u[16], A[16], B[16], C[16], S[16], E[16], F[16], G[16], H[16], X3[16], Y3[16], T3[16], Z3[16], dump[16];
+    auto cells = [&](int m) { return p + (size_t)(ED_MUL + m * ED_MUL_STRIDE) * n_rows; };
+    mul_gadget_cells(X1, X1, cells(ED_G_A), n_rows, A);
+    mul_gadget_cells(Y1, Y1, cells(ED_G_B), n_rows, B);
+    mul_gadget_cells(Z1, Z1, cells(ED_G_CZ), n_rows, C);
+    for (int i = 0; i < 16; i++) u[i] = X1[i] + Y1[i];
+    mul_gadget_cells(u, u, cells(ED_G_S), n_rows, S);
+    for (int i = 0; i < 16; i++) {
+        E[i] = S[i] - A[i] - B[i] + 2 * p_limb(i);
+        G[i] = B[i] - A[i] + p_limb(i);
+        F[i] = B[i] - A[i] - 2 * C[i] + 3 * p_limb(i);
+        H[i] = 2 * p_limb(i) - A[i] - B[i];
+    }
+    mul_gadget_cells(E, F, cells(ED_G_X3), n_rows, X3);
+    mul_gadget_cells(G, H, cells(ED_G_Y3), n_rows, Y3);
+    mul_gadget_cells(E, H, cells(ED_G_T3), n_rows, T3);
+    mul_gadget_cells(F, G, cells(ED_G_Z3), n_rows, Z3);
+    for (int i = 0; i < 16; i++) u[i] = Y3[i] - X3[i] + p_limb(i);
+    mul_gadget_cells(u, add + 16, cells(ED_G_AA), n_rows, A);
+    for (int i = 0; i < 16; i++) u[i] = Y3[i] + X3[i];
+    mul_gadget_cells(u, add, cells(ED_G_BB), n_rows, B);
+    mul_gadget_cells(T3, add + 32, cells(ED_G_CC), n_rows, C);
+    for (int i = 0; i < 16; i++) {
+        E[i] = B[i] - A[i] + p_limb(i);
+        F[i] = 2 * Z3[i] - C[i] + p_limb(i);
+        G[i] = 2 * Z3[i] + C[i];
+        H[i] = B[i] + A[i];
+    }
+    mul_gadget_cells(E, F, cells(ED_G_X4), n_rows, dump);
+    mul_gadget_cells(G, H, cells(ED_G_Y4), n_rows, dump);
+    mul_gadget_cells(F, G, cells(ED_G_Z4), n_rows, dump);
 }
 
 }  // namespace tmx

@@ -278,29 +278,43 @@ TMX_HD void sha512_validator_prepare(const EdTriple& t, Sha512Hist hs[2], uint8_
         for (int j = 0; j < 8; j++) digest[8 * k + j] = (uint8_t)(st[k] >> (56 - 8 * j));
 }
 
-// scalars and points of the two ladders of slot i; ok = false if a key / R does not decode or s >= l
-struct EdSlot {
+// What the sequential phase leaves behind for one validator slot: scalars, addend cells, the points the logic table needs
+// and the verdict of the signature equation [s]B + [h](-A) == R (cofactorless, canonical encodings required).
+struct EdSlotInfo {
     uint64_t s[4], h[4];
-    ge51 A, R;
-    bool ok;
+    EdAddendTable tab;
+    fe256 xA, yA, xR, yR, xD, yD;
+    fe256 QX, QY, QZ;
+    uint8_t digest[64];
+    uint32_t ok;
+    uint32_t pad;
 };
-TMX_HD void ed_slot_prepare(const EdTriple& t, const uint8_t digest[64], EdSlot* e) {
+// everything but the 256 sequential rows: effective triple -> h, s, decompressed A and R, addend table
+TMX_HD void ed_slot_prepare(const EdTriple& t, const uint8_t digest[64], EdSlotInfo* e, ge_cached51 tab[4], ge51* R_out) {
     fe256 sb = fe256_from_bytes(t.sig + 32);
     for (int i = 0; i < 4; i++) e->s[i] = sb.w[i];
     sc_reduce512(digest, e->h);
-    e->ok = sc_lt_l(e->s);
-    if (!ge_decompress51(t.pk, &e->A)) {
-        e->ok = false;
-        e->A = ge_identity51();
+    for (int i = 0; i < 64; i++) e->digest[i] = digest[i];
+    bool ok = sc_lt_l(e->s);
+    ge51 A, R;
+    if (!ge_decompress51(t.pk, &A)) {
+        ok = false;
+        A = ge_identity51();
     }
-    if (!ge_decompress51(t.sig, &e->R)) {
-        e->ok = false;
-        e->R = ge_identity51();
+    if (!ge_decompress51(t.sig, &R)) {
+        ok = false;
+        R = ge_identity51();
     }
+    e->xA = fe_freeze(A.X); e->yA = fe_freeze(A.Y);
+    e->xR = fe_freeze(R.X); e->yR = fe_freeze(R.Y);
+    ed_slot_table(A, tab, &e->tab, &e->xD, &e->yD);
+    e->ok = ok ? 1u : 0u;
+    *R_out = R;
 }
-// cofactorless check [s]B == R + [h]A on the two ladder results
-TMX_HD bool ed_slot_verdict(const EdSlot& e, const ge51& Ps, const ge51& Ph) { return e.ok && ge_equal51(Ps, ge_add51(Ph, e.R)); }
-
+// Q = (X : Y : Z) equals the affine R?
+TMX_HD bool ed_result_equals(const ge_acc51& q, const ge51& R) {
+    return fe256_eq(fe_freeze(fe_mul(R.X, q.Z)), fe_freeze(q.X)) && fe256_eq(fe_freeze(fe_mul(R.Y, q.Z)), fe_freeze(q.Y));
+}
 
 }  // namespace tmx
 
@@ -315,5 +329,7 @@ int witness_make_args(tmx_ctx* ctx, const uint8_t* d_blob, uint32_t kind, uint32
 int witness_run_sha256(tmx_ctx* ctx, const WitnessArgs& a, cudaStream_t st);
 int run_ed25519_ladder(tmx_ctx* ctx, const WitnessArgs& a, void* points, cudaStream_t st);
 int run_ed25519_expand(tmx_ctx* ctx, const WitnessArgs& a, const void* points, cudaStream_t st);
+// layout of the `points` scratch: EdSlotInfo[n_slots], then ge_acc_packed[n_slots][256]
+size_t witness_slot_count(uint32_t n_max);
 #endif
 }  // namespace tmx

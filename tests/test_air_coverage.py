@@ -1,8 +1,9 @@
-"""Constraint coverage of the three AIRs (oracle/air.inc = tendermintx_b200/csrc/air.cuh, same emission order; their
-equality is what the proof-byte parity tests pin).  On the trace domain: (1) an honest trace satisfies every
-constraint on every row, cyclically; (2) corrupting ANY single cell of ANY column is caught by at least one constraint
-of the two rows that read it -- no column of any table is unconstrained.  (What is NOT enforced yet is the linkage BETWEEN
-tables and to the public inputs; that is a different property.)"""
+"""Constraint coverage of the tables on the trace domain, evaluated by the oracle's interpreter over the constraint DAG of the
+build artefact (the SAME data the product's kernels and verifier compile): (1) an honest pair of first- and second-round
+traces satisfies every constraint on every row, cyclically, bus helper columns and running sum included; (2) corrupting ANY
+single cell of ANY first-round column is caught by at least one constraint of the two rows that read it -- no column of any
+table is unconstrained inside its table.  Whether the constraints are SUFFICIENT for the statement is a different property:
+tests/test_cheating_provers.py attacks that."""
 import json
 import os
 
@@ -11,7 +12,8 @@ import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 P = 2**64 - 2**32 + 1
-NAMES = ["sha256", "sha512", "ed25519"]
+NAMES = ["sha256", "sha512", "ed25519", "logic", "range"]
+BETA, GAMMA = (0x1122334455667788, 0x0102030405060708), (0x0F0E0D0C0B0A0908, 0x7766554433221100)
 
 
 @pytest.fixture(scope="module", params=["skip_3000_3100_n4", "step_10500_n4_with_dummy"])
@@ -19,22 +21,35 @@ def traces(oracle, request):
     with open(os.path.join(HERE, "golden", "fixture_vectors.json")) as f:
         c = {c["name"]: c for c in json.load(f)["cases"]}[request.param]
     blob = bytes.fromhex(c["blob"])
-    return oracle.build_traces(blob), 1 if c["kind"] == "skip" else 0, c["n_max"]
+    kind = 1 if c["kind"] == "skip" else 0
+    circ = oracle.circuit(kind, c["n_max"], "mocha-4")
+    tabs = oracle.all_traces(blob, "mocha-4")
+    aux = [oracle.aux_trace(circ, t, tabs[t], BETA, GAMMA) if tabs[t] is not None else None for t in range(oracle.N_TABLES)]
+    return circ, tabs, aux
 
 
-@pytest.mark.parametrize("table", [0, 1, 2])
+@pytest.mark.parametrize("table", [0, 1, 2, 4])
 def test_honest_trace_satisfies_every_row(oracle, traces, table):
-    tabs, kind, n_max = traces
-    t = tabs[table]
-    out = oracle.constraints_at_rows(table, t, np.arange(t.shape[1]), kind, n_max)
+    circ, tabs, aux = traces
+    t, (a, total) = tabs[table], aux[table]
+    out = oracle.constraints_at_rows(circ, table, t, a, total, BETA, GAMMA, np.arange(t.shape[1]))
     bad = np.nonzero(out.any(axis=1))[0]
     assert bad.size == 0, (NAMES[table], bad[:10])
 
 
+def test_bus_totals_balance(oracle, traces):
+    """sum over the tables of the running-sum totals is zero: every lookup is answered by the range table"""
+    circ, tabs, aux = traces
+    s0 = sum(int(a[1][0]) for a in aux if a is not None) % P
+    s1 = sum(int(a[1][1]) for a in aux if a is not None) % P
+    assert (s0, s1) == (0, 0)
+
+
 @pytest.mark.parametrize("table", [0, 1, 2])
 def test_single_cell_corruption_is_caught_in_every_column(oracle, traces, table):
-    tabs, kind, n_max = traces
+    circ, tabs, aux = traces
     t = tabs[table].copy()
+    a, total = aux[table]
     C, n = t.shape
     rng = np.random.default_rng(100 + table)
     missed = []
@@ -44,7 +59,7 @@ def test_single_cell_corruption_is_caught_in_every_column(oracle, traces, table)
             r = int(r)
             old = t[c, r]
             t[c, r] = (int(old) + 1) % P
-            out = oracle.constraints_at_rows(table, t, [(r - 1) % n, r], kind, n_max)
+            out = oracle.constraints_at_rows(circ, table, t, a, total, BETA, GAMMA, [(r - 1) % n, r])
             t[c, r] = old
             if out.any():
                 caught = True

@@ -67,27 +67,59 @@ def test_synthetic_chain_with_absent_signers(hostsim, oracle):
         assert np.array_equal(g_, w)
 
 
+CHAIN = "mocha-4"
+BETA, GAMMA = (0x1122334455667788, 0x0102030405060708), (0x0F0E0D0C0B0A0908, 0x7766554433221100)
+ALPHA = (0x0123456789ABCDEF, 0x0FEDCBA987654321)
+
+
+def _u64(x):
+    return np.array(x, dtype=np.uint64)
+
+
 @pytest.mark.parametrize("name", ["skip_3000_3100_n4", "step_10500_n4_with_dummy"])
-def test_product_air_on_the_lde_coset_equals_oracle(hostsim, oracle, name):
-    """The product's constraint code (csrc/air.cuh: the three AIRs, the periodic / public columns and their host NTT,
-    the quotient kernel's per-point logic) compiled for the host, against the oracle's quotient values at every point
-    of the LDE coset.  Coset points are generic, so every term of every constraint contributes a non-zero value."""
+def test_product_bus_and_air_on_the_lde_coset_equal_oracle(hostsim, oracle, name):
+    """The product's per-thread kernel bodies compiled for the host (csrc/stark_rows.cuh: range-lookup histogram, helper
+    columns + running sum of the bus, constraint quotient through the compiled AIR templates) against the oracle, which
+    INTERPRETS the constraint DAG of the build artefact with its own bus / quotient code: the range table's multiplicities,
+    every second-round column and the quotient values at every point of the LDE coset must agree.  Coset points are generic,
+    so every term of every constraint contributes a non-zero value."""
     c = _cases()[name]
     blob = bytes.fromhex(c["blob"])
     kind = 1 if c["kind"] == "skip" else 0
-    tabs = oracle.build_traces(blob)
-    O = oracle.lib()
+    circ = oracle.circuit(kind, c["n_max"], CHAIN)
+    shapes = circ.table_shapes()
+    tabs = oracle.all_traces(blob, CHAIN)
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
-    alpha = np.array([0x0123456789ABCDEF, 0x0FEDCBA987654321], dtype=np.uint64)
-    O.tm_debug_set_shape(ctypes.c_uint32(kind), ctypes.c_uint32(c["n_max"]))
+    beta, gamma, alpha = _u64(BETA), _u64(GAMMA), _u64(ALPHA)
+    hist = np.zeros((1 << 16) + (1 << 11) + (1 << 8) + 1, dtype=np.uint32)
     for table, t in enumerate(tabs):
-        C, n = t.shape
+        if t is None:
+            continue
+        _, log_n, C, Kc, n_per, P, H, _ = shapes[table]
+        n = 1 << log_n
+        per, cst = circ.table_data(table)
         t = np.ascontiguousarray(t)
-        lde = np.zeros((C, 2 * n), dtype=np.uint64)
-        want = np.zeros((2, 2 * n), dtype=np.uint64)
-        O.tm_debug_quotient(ctypes.c_int(table), p(t), ctypes.c_size_t(n), ctypes.c_size_t(C), p(alpha), p(lde), p(want))
+        args = (ctypes.c_uint32(kind), ctypes.c_uint32(c["n_max"]), ctypes.c_int(table))
+        if table != oracle.T_RANGE:
+            hostsim.hostsim_bus_count(*args, p(t), p(cst), p(per), ctypes.c_size_t(n), ctypes.c_size_t(P), p(hist))
+        # second-round trace
+        want_aux, want_total = oracle.aux_trace(circ, table, t, BETA, GAMMA)
+        got_aux, got_total = np.zeros_like(want_aux), np.zeros(2, dtype=np.uint64)
+        hostsim.hostsim_bus_aux(*args, ctypes.c_int(H), p(t), p(cst), p(per), ctypes.c_size_t(n), ctypes.c_size_t(P), p(beta), p(gamma),
+                                p(got_aux), p(got_total))
+        assert np.array_equal(got_total, want_total), (name, table)
+        assert np.array_equal(got_aux, want_aux), (name, table, np.argwhere(got_aux != want_aux)[:3])
+        # quotient
+        lde_m, lde_a, want = oracle.quotient(circ, table, t, want_aux, want_total, BETA, GAMMA, ALPHA)
+        lde_k = oracle.lde_batch(cst, 1) if Kc else np.zeros((1, 2 * n), dtype=np.uint64)
         got = np.zeros((2, 2 * n), dtype=np.uint64)
-        hostsim.hostsim_quotient(ctypes.c_uint32(kind), ctypes.c_uint32(c["n_max"]), ctypes.c_int(table), p(lde), ctypes.c_size_t(n),
-                                 p(alpha), p(got))
+        hostsim.hostsim_quotient(*args, p(lde_m), p(lde_k), p(lde_a), p(per), ctypes.c_int(n_per), ctypes.c_size_t(P), ctypes.c_size_t(n),
+                                 p(want_total), p(beta), p(gamma), p(alpha), p(got))
         assert want.any(axis=1).all(), table
         assert np.array_equal(got, want), (name, table, int((got != want).sum()))
+    # the range table's multiplicity columns are the histogram
+    rg = tabs[oracle.T_RANGE]
+    assert hist[-1] == 0
+    assert np.array_equal(rg[0], hist[:1 << 16].astype(np.uint64))
+    assert np.array_equal(rg[1][:1 << 11], hist[1 << 16:(1 << 16) + (1 << 11)].astype(np.uint64)) and not rg[1][1 << 11:].any()
+    assert np.array_equal(rg[2][:1 << 8], hist[(1 << 16) + (1 << 11):-1].astype(np.uint64)) and not rg[2][1 << 8:].any()

@@ -64,7 +64,7 @@ def test_unsatisfied_statement_is_not_provable(oracle, proved):
     assert status == "SIGNATURE" and p is None
 
 
-@pytest.mark.parametrize("table", [0, 1, 2])
+@pytest.mark.parametrize("table", [0, 1, 2, 4])
 def test_cheating_prover_with_one_bad_cell_is_rejected(oracle, proved, table):
     """Soundness end to end: a prover that commits to a witness with ONE wrong cell (after witness generation, so no
     assertion stops it) still emits a well-formed proof; the constraint identity at the out-of-domain point no longer

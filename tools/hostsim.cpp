@@ -5,7 +5,7 @@
 #include <cstring>
 #include <vector>
 #include "../tendermintx_b200/csrc/witness_jobs.cuh"
-#include "../tendermintx_b200/csrc/air.cuh"
+#include "../tendermintx_b200/csrc/stark_rows.cuh"
 
 using namespace tmx;
 
@@ -60,62 +60,131 @@ extern "C" int hostsim_build_traces(const uint8_t* blob, uint64_t* t256, size_t 
     sha256_padding_prepare(&hs[0]);
     for (size_t c = sha256_used_chunks(a.kind, a.n_max, a.np); (c + 1) * 64 <= n256; c++)
         for (int t = 0; t < 64; t++) sha256_row_cells(a.t256, a.n256, c * 64 + t, t, &hs[0]);
-    // validators: SHA-512 + Ed25519
-    std::vector<ge_packed> res(512), tmp(512);
+    if (!t512 || !ted) return 0;
+    // validator slots: SHA-512 + Ed25519 (padding slots included)
+    const size_t slots = ned / ED_ROWS_PER_VALIDATOR;
+    std::vector<ge_acc_packed> acc(ED_ROWS_PER_VALIDATOR);
     Sha512Hist h5[2];
-    for (uint32_t i = 0; i < a.n_max; i++) {
-        EdTriple t;
-        effective_triple(blob_validators(blob) + i, &t);
-        uint8_t digest[64];
-        sha512_validator_prepare(t, h5, digest);
-        for (int r = 0; r < S512_ROWS_PER_VALIDATOR; r++)
-            sha512_row_cells(a.t512, a.n512, (size_t)i * S512_ROWS_PER_VALIDATOR + r, r % S512_ROWS_PER_CHUNK, &h5[r / S512_ROWS_PER_CHUNK]);
-        EdSlot e;
-        ed_slot_prepare(t, digest, &e);
-        ge51 Ps = ed_ladder(e.s, ge_base51(), res.data(), tmp.data());
-        ge51 Ph = ed_ladder(e.h, e.A, res.data() + 256, tmp.data() + 256);
-        aux[AUX_SIG_OK + i] = ed_slot_verdict(e, Ps, Ph) ? 1 : 0;
-        for (int r = 0; r < 512; r++) {
-            const uint64_t* sc = r < 256 ? e.s : e.h;
-            int bit = (sc[(r & 255) >> 6] >> (r & 63)) & 1;
-            ed_row_cells(a.ted, a.ned, (size_t)i * 512 + r, bit, res[r], tmp[r]);
+    for (size_t i = 0; i < slots; i++) {
+        EdSlotInfo e;
+        memset(&e, 0, sizeof e);
+        ge_cached51 tab[4];
+        ge51 R = ge_identity51();
+        if (i < a.n_max) {
+            EdTriple t;
+            effective_triple(blob_validators(blob) + i, &t);
+            uint8_t digest[64];
+            sha512_validator_prepare(t, h5, digest);
+            ed_slot_prepare(t, digest, &e, tab, &R);
+        } else {
+            sha512_padding_prepare(&h5[0]);
+            sha512_padding_prepare(&h5[1]);
+            ed_padding_table(tab, &e.tab);
+            e.ok = 1;
         }
-    }
-    sha512_padding_prepare(&h5[0]);
-    for (size_t row = (size_t)a.n_max * S512_ROWS_PER_VALIDATOR; row < n512; row++)
-        sha512_row_cells(a.t512, a.n512, row, (int)((row - (size_t)a.n_max * S512_ROWS_PER_VALIDATOR) % S512_ROWS_PER_CHUNK), &h5[0]);
-    if ((size_t)a.n_max * 512 < ned) {
-        uint64_t zero[4] = {0, 0, 0, 0};
-        ed_ladder(zero, ge_base51(), res.data(), tmp.data());
-        for (size_t row = (size_t)a.n_max * 512; row < ned; row++) ed_row_cells(a.ted, a.ned, row, 0, res[row & 255], tmp[row & 255]);
+        const ge_acc51 q = ed_straus_ladder(e.s, e.h, tab, acc.data());
+        if (i < a.n_max) aux[AUX_SIG_OK + i] = (e.ok && ed_result_equals(q, R)) ? 1 : 0;
+        for (int r = 0; r < ED_ROWS_PER_VALIDATOR; r++) {
+            const size_t row = i * ED_ROWS_PER_VALIDATOR + r;
+            if (row < n512) sha512_row_cells(a.t512, a.n512, row, r % S512_ROWS_PER_CHUNK, &h5[r / S512_ROWS_PER_CHUNK]);
+            ed_row_cells(a.ted, a.ned, row, r, e.s, e.h, acc[r], e.tab);
+        }
     }
     return 0;
 }
 
-// quotient kernel logic (stark.cu quotient_kernel) on the host: lde [C][m] bit-reversed -> out [2][m] natural
-struct HostRow {
-    const gl* base;
-    size_t stride;
-    FB operator[](int c) const { return FB::mk(base[(size_t)c * stride]); }
-};
-extern "C" void hostsim_quotient(uint32_t kind, uint32_t n_max, int table, const uint64_t* lde, size_t n, const uint64_t alpha[2],
-                                 uint64_t* out) {
-    const unsigned log_n = log2u((uint32_t)n), log_m = log_n + 1;
-    const size_t m = n << 1;
-    std::vector<gl> tab = air_periodic_lde_table(table, log_n, h_K256, h_K512, AirShape{kind, n_max});
-    const size_t P = air_period(table, n);
-    const gl gn = gl_pow(GL_GEN, n);
-    const gl zh_inv[2] = {gl_inv(gl_sub(gn, 1)), gl_inv(gl_sub(gl_neg(gn), 1))};
-    for (size_t p = 0; p < m; p++) {
-        const uint32_t j = bitrev32((uint32_t)p, log_m);
-        const uint32_t jn = (j + 2) & (uint32_t)(m - 1);
-        const size_t pn = bitrev32(jn, log_m);
-        HostRow l{lde + p, m}, nx{lde + pn, m}, per{tab.data() + (j & (2 * P - 1)), (size_t)2 * P};
-        ConstraintAcc<FB> acc;
-        acc.acc0 = FB::c(0); acc.acc1 = FB::c(0);
-        acc.alpha0 = FB::mk(alpha[0]); acc.alpha1 = FB::mk(alpha[1]);
-        air_eval<FB>(table, l, nx, per, acc);
-        out[j] = gl_mul(acc.acc0.v, zh_inv[j & 1]);
-        out[m + j] = gl_mul(acc.acc1.v, zh_inv[j & 1]);
+// ---- the kernels' per-thread bodies (stark_rows.cuh) in a loop ----
+static std::vector<gl> periodic_lde(const uint64_t* periodic, int n_per, size_t P, size_t n) {
+    std::vector<gl> lde((size_t)n_per * 2 * P);
+    const gl sh = gl_pow(GL_GEN, n / P);
+    for (int pc = 0; pc < n_per; pc++) {
+        std::vector<gl> coef(periodic + (size_t)pc * P, periodic + (size_t)(pc + 1) * P);
+        air_host_ntt(coef, true);
+        coef.resize(2 * P, 0);
+        gl s = 1;
+        for (size_t k = 0; k < P; k++) {
+            coef[k] = gl_mul(coef[k], s);
+            s = gl_mul(s, sh);
+        }
+        air_host_ntt(coef, false);
+        std::copy(coef.begin(), coef.end(), lde.begin() + (size_t)pc * 2 * P);
     }
+    return lde;
+}
+
+template <template <int> class Fn, class... A>
+static void dispatch(int table, A&&... a) {
+    switch (table) {
+        case AIR_SHA256: Fn<AIR_SHA256>::run(a...); break;
+        case AIR_SHA512: Fn<AIR_SHA512>::run(a...); break;
+        case AIR_ED25519: Fn<AIR_ED25519>::run(a...); break;
+        case AIR_LOGIC: Fn<AIR_LOGIC>::run(a...); break;
+        default: Fn<AIR_RANGE>::run(a...); break;
+    }
+}
+template <int T> struct GenFn { static void run(const BusPassArgs& a, size_t r) { bus_gen_row<T>(a, r); } };
+template <int T> struct CountFn { static void run(const BusPassArgs& a, size_t r) { bus_count_row<T>(a, r); } };
+template <int T> struct QuotFn { static void run(const QuotientArgs& a, size_t p) { quotient_point<T>(a, p); } };
+
+static BusPassArgs pass_args(uint32_t kind, uint32_t n_max, const uint64_t* trace, const uint64_t* consts, const uint64_t* periodic,
+                             size_t n, size_t P) {
+    BusPassArgs a;
+    memset(&a, 0, sizeof a);
+    a.trace = trace; a.kconst = consts; a.per = periodic; a.n = n; a.P = (int)P;
+    a.shape = AirShape{kind, n_max};
+    return a;
+}
+
+// bus_count_kernel: hist [BUS_HIST_SIZE + 1] (last entry: out-of-range flag)
+extern "C" void hostsim_bus_count(uint32_t kind, uint32_t n_max, int table, const uint64_t* trace, const uint64_t* consts,
+                                  const uint64_t* periodic, size_t n, size_t P, uint32_t* hist) {
+    BusPassArgs a = pass_args(kind, n_max, trace, consts, periodic, n, P);
+    a.hist = hist;
+    for (size_t r = 0; r < n; r++) dispatch<CountFn>(table, a, r);
+}
+
+// bus_gen_kernel + bus_scan_kernel: aux [2 (H + 1)][n], total[2]
+extern "C" void hostsim_bus_aux(uint32_t kind, uint32_t n_max, int table, int n_helpers, const uint64_t* trace, const uint64_t* consts,
+                                const uint64_t* periodic, size_t n, size_t P, const uint64_t beta[2], const uint64_t gamma[2],
+                                uint64_t* aux, uint64_t total[2]) {
+    BusPassArgs a = pass_args(kind, n_max, trace, consts, periodic, n, P);
+    a.beta = gl2_make(beta[0], beta[1]);
+    a.gamma = gl2_make(gamma[0], gamma[1]);
+    a.aux = aux;
+    std::vector<gl2> rowsum(n);
+    a.rowsum = rowsum.data();
+    for (size_t r = 0; r < n; r++) dispatch<GenFn>(table, a, r);
+    gl2 tot = gl2_from(0);
+    for (size_t r = 0; r < n; r++) tot = gl2_add(tot, rowsum[r]);
+    const gl2 step = gl2_scale(tot, gl_inv((gl)n));
+    gl2 z = gl2_from(0);
+    for (size_t r = 0; r < n; r++) {
+        aux[(size_t)(2 * n_helpers) * n + r] = z.a0;
+        aux[(size_t)(2 * n_helpers + 1) * n + r] = z.a1;
+        z = gl2_sub(gl2_add(z, rowsum[r]), step);
+    }
+    total[0] = tot.a0;
+    total[1] = tot.a1;
+}
+
+// quotient_kernel: LDEs [cols][m] bit-reversed -> out [2][m] natural
+extern "C" void hostsim_quotient(uint32_t kind, uint32_t n_max, int table, const uint64_t* lde_m, const uint64_t* lde_k,
+                                 const uint64_t* lde_a, const uint64_t* periodic, int n_per, size_t P, size_t n, const uint64_t total[2],
+                                 const uint64_t beta[2], const uint64_t gamma[2], const uint64_t alpha[2], uint64_t* out) {
+    const unsigned log_n = log2u((uint32_t)n);
+    const std::vector<gl> tab = periodic_lde(periodic, n_per, P, n);
+    QuotientArgs qa;
+    memset(&qa, 0, sizeof qa);
+    qa.lde_m = lde_m; qa.lde_k = lde_k; qa.lde_a = lde_a;
+    qa.m = n << 1; qa.log_m = log_n + 1; qa.rate_bits = 1;
+    qa.pertab = tab.data(); qa.P = (int)P;
+    qa.shape = AirShape{kind, n_max};
+    qa.alpha[0] = alpha[0]; qa.alpha[1] = alpha[1];
+    qa.beta = gl2_make(beta[0], beta[1]); qa.gamma = gl2_make(gamma[0], gamma[1]);
+    qa.s_over_n = gl2_scale(gl2_make(total[0], total[1]), gl_inv((gl)n));
+    const gl gn = gl_pow(GL_GEN, n);
+    qa.zh_inv[0] = gl_inv(gl_sub(gn, 1));
+    qa.zh_inv[1] = gl_inv(gl_sub(gl_neg(gn), 1));
+    qa.out = out;
+    for (size_t p = 0; p < qa.m; p++) dispatch<QuotFn>(table, qa, p);
 }
