@@ -88,8 +88,8 @@ def test_fri_fold_equals_coefficient_folding(ctx, oracle):
     log_cosets, shift = 6, 7
     n = 16 << log_cosets
     lg = log_cosets + 4
-    coef = rng.integers(0, P, size=(2, n), dtype=np.uint64)  # two component polynomials of an extension-valued polynomial
-    beta = (int(rng.integers(0, P)), int(rng.integers(0, P)))
+    coef = rng.integers(0, P, size=(2, n), dtype=np.uint64, endpoint=False)  # two component polynomials of an extension-valued polynomial
+    beta = (int(rng.integers(0, P, dtype=np.uint64)), int(rng.integers(0, P, dtype=np.uint64)))
 
     def ext_mul(a, b):
         return ((a[0] * b[0] + 7 * a[1] * b[1]) % P, (a[0] * b[1] + a[1] * b[0]) % P)
