@@ -41,6 +41,7 @@ static void mark_bus_nodes(table_def_t *t) {
             continue;
         }
         for (uint64_t part = 0; part < kind; part++) {
+            t->bus_mask[t->prog[p]] = 1;
             t->bus_mask[t->prog[p + 1]] = 1;
             uint64_t len = t->prog[p + 2];
             for (uint64_t i = 0; i < len; i++) t->bus_mask[t->prog[p + 3 + i]] = 1;
@@ -138,7 +139,7 @@ int circuit_parse(const uint64_t *w, size_t nw, circuit_def_t *c) {
                 for (uint64_t part = 0; part < kind && !bad; part++) {
                     if (p + 3 > t->prog_len) { bad = 1; break; }
                     uint64_t len = t->prog[p + 2];
-                    if (t->prog[p + 1] >= t->n_nodes || len > 256 || p + 3 + len > t->prog_len) { bad = 1; break; }
+                    if (t->prog[p] >= t->n_nodes || t->prog[p + 1] >= t->n_nodes || len > 256 || p + 3 + len > t->prog_len) { bad = 1; break; }
                     for (uint64_t i = 0; i < len; i++)
                         if (t->prog[p + 3 + i] >= t->n_nodes) bad = 1;
                     p += 3 + len;

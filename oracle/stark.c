@@ -185,7 +185,7 @@ static gl2_t bus_fingerprint_b(const uint64_t *part, const gl_t *v, gl2_t beta, 
         acc.a0 = gl_add(acc.a0, v[part[3 + i]]);
         acc = gl2_mul(acc, beta);
     }
-    acc.a0 = gl_add(acc.a0, (gl_t)part[0]);
+    acc.a0 = gl_add(acc.a0, v[part[0]]);
     return gl2_add(acc, gamma);
 }
 
@@ -207,7 +207,7 @@ static e2e_t bus_fingerprint_e(const uint64_t *part, const gl2_t *v, gl2_t beta,
         acc.a0 = gl2_add(acc.a0, v[part[3 + i]]);
         acc = e2e_mul(acc, b);
     }
-    acc.a0 = gl2_add(acc.a0, gl2_from((gl_t)part[0]));
+    acc.a0 = gl2_add(acc.a0, v[part[0]]);
     return e2e_add(acc, (e2e_t){gl2_from(gamma.a0), gl2_from(gamma.a1)});
 }
 
@@ -247,9 +247,10 @@ static int count_lookups(const circuit_def_t *c, trace_t tr[TMX_N_TABLES], uint6
                         p += 3 + it[2];
                         if (v[it[1]] != GL_P - 1) continue;
                         size_t base, lim;
-                        if (it[0] == BUS_R16) { base = 0; lim = 1u << 16; }
-                        else if (it[0] == BUS_R11) { base = 1u << 16; lim = 1u << 11; }
-                        else if (it[0] == BUS_R8) { base = (1u << 16) + (1u << 11); lim = 1u << 8; }
+                        const gl_t tag = v[it[0]];
+                        if (tag == BUS_R16) { base = 0; lim = 1u << 16; }
+                        else if (tag == BUS_R11) { base = 1u << 16; lim = 1u << 11; }
+                        else if (tag == BUS_R8) { base = (1u << 16) + (1u << 11); lim = 1u << 8; }
                         else continue;
                         const gl_t val = v[it[3]];
                         if (val >= lim) {

@@ -90,13 +90,13 @@ TMX_HD Ext2<F> e2_scale(Ext2<F> a, F s) { return e2_mk<F>(a.a0 * s, a.a1 * s); }
 
 // fingerprint of (tag, tup(0) .. tup(len - 1)): gamma + tag + beta (v_0 + beta (v_1 + ...))
 template <class F, class Tup>
-TMX_HD Ext2<F> bus_fingerprint(Ext2<F> beta, Ext2<F> gamma, int tag, int len, const Tup& tup) {
+TMX_HD Ext2<F> bus_fingerprint(Ext2<F> beta, Ext2<F> gamma, F tag, int len, const Tup& tup) {
     Ext2<F> acc = e2_mk<F>(F::c(0), F::c(0));
     for (int i = len - 1; i >= 0; i--) {
         acc.a0 = acc.a0 + tup(i);
         acc = e2_mul<F>(acc, beta);
     }
-    acc.a0 = acc.a0 + F::c((uint64_t)tag);
+    acc.a0 = acc.a0 + tag;
     return e2_add<F>(acc, gamma);
 }
 
@@ -105,28 +105,32 @@ template <class F, class Bus>
 struct LookupPairs {
     Bus& bus;
     bool have;
-    int tag0;
-    F v0;
-    TMX_HD LookupPairs(Bus& b) : bus(b), have(false), tag0(0) { v0 = F::c(0); }
-    TMX_HD void push(int tag, F v) {
-        const F minus1 = F::c(0xFFFFFFFF00000000ULL);  // p - 1
+    F tag0, m0, v0;
+    TMX_HD LookupPairs(Bus& b) : bus(b), have(false) { tag0 = m0 = v0 = F::c(0); }
+    // multiplicity m (p - 1 = one lookup)
+    TMX_HD void push(F tag, F m, F v) {
         if (!have) {
             have = true;
             tag0 = tag;
+            m0 = m;
             v0 = v;
             return;
         }
         have = false;
         const F a = v0, b = v;
-        bus.two(tag0, minus1, 1, [&](int) { return a; }, tag, minus1, 1, [&](int) { return b; });
+        bus.two(tag0, m0, 1, [&](int) { return a; }, tag, m, 1, [&](int) { return b; });
     }
+    TMX_HD void push(int tag, F v) { push(F::c((uint64_t)tag), F::c(0xFFFFFFFF00000000ULL), v); }
     TMX_HD void flush() {
         if (!have) return;
         have = false;
         const F a = v0;
-        bus.one(tag0, F::c(0xFFFFFFFF00000000ULL), 1, [&](int) { return a; });
+        bus.one(tag0, m0, 1, [&](int) { return a; });
     }
 };
+// tag constants as field values
+template <class F>
+TMX_HD F bus_tag(int t) { return F::c((uint64_t)t); }
 
 constexpr int AIR_SHA256 = TMX_T_SHA256, AIR_SHA512 = TMX_T_SHA512, AIR_ED25519 = TMX_T_ED, AIR_LOGIC = TMX_T_LOGIC,
               AIR_RANGE = TMX_T_RANGE;
@@ -236,8 +240,8 @@ TMX_HD void air_sha256(const Row& l, const Row& n, const KRow& k, const Per& per
     // bus: the chunk's 16 message words (all in the schedule window on row 15) are received, its digest is sent
     const F minus_msg = F::c(0) - k[S256K_MSG];
     bus.two(
-        BUS_MSG256, minus_msg, 17, [&](int i) { return i == 0 ? k[S256K_CID] : l[S256_W + i - 1]; },
-        BUS_DIG256, k[S256K_DIG], 9, [&](int i) { return i == 0 ? k[S256K_CID] : l[S256_DG + i - 1]; });
+        bus_tag<F>(BUS_MSG256), minus_msg, 17, [&](int i) { return i == 0 ? k[S256K_CID] : l[S256_W + i - 1]; },
+        bus_tag<F>(BUS_DIG256), k[S256K_DIG], 9, [&](int i) { return i == 0 ? k[S256K_CID] : l[S256_DG + i - 1]; });
 }
 
 // ------------------------------------------------------------------------------------------ SHA-512
@@ -364,9 +368,9 @@ TMX_HD void air_sha512(const Row& l, const Row& n, const KRow& kc, const Per& pe
     const F minus_msg = F::c(0) - kc[S512K_MSG];
     const F dig_mult = kc[S512K_DIG0] * (F::c(1) - two) + kc[S512K_DIG1] * two;
     bus.two(
-        BUS_MSG512, minus_msg, 35,
+        bus_tag<F>(BUS_MSG512), minus_msg, 35,
         [&](int i) { return i == 0 ? kc[S512K_VID] : (i == 1 ? kc[S512K_CHUNK] : (i == 2 ? two : l[S512_W + i - 3])); },
-        BUS_DIG512, dig_mult, 17, [&](int i) { return i == 0 ? kc[S512K_VID] : l[S512_DG + i - 1]; });
+        bus_tag<F>(BUS_DIG512), dig_mult, 17, [&](int i) { return i == 0 ? kc[S512K_VID] : l[S512_DG + i - 1]; });
 }
 
 // ------------------------------------------------------------------------------------------ Ed25519
@@ -490,11 +494,11 @@ TMX_HD void air_ed25519(const Row& l, const Row& n, const KRow& k, const Per& pe
     rc.flush();
     const F sel = bs + (bh + bh);
     bus.two(
-        BUS_ADDEND, F::c(0) - k[EDK_ACTIVE], 50, [&](int i) { return i == 0 ? k[EDK_VID] : (i == 1 ? sel : l[ED_ADD + i - 2]); },
-        BUS_SCALAR, k[EDK_SEND16], 4, [&](int i) { return i == 0 ? k[EDK_VID] : (i == 1 ? F::c(0) : (i == 2 ? k[EDK_LIMB] : limb_s)); });
+        bus_tag<F>(BUS_ADDEND), F::c(0) - k[EDK_ACTIVE], 50, [&](int i) { return i == 0 ? k[EDK_VID] : (i == 1 ? sel : l[ED_ADD + i - 2]); },
+        bus_tag<F>(BUS_SCALAR), k[EDK_SEND16], 4, [&](int i) { return i == 0 ? k[EDK_VID] : (i == 1 ? F::c(0) : (i == 2 ? k[EDK_LIMB] : limb_s)); });
     bus.two(
-        BUS_SCALAR, k[EDK_SEND16], 4, [&](int i) { return i == 0 ? k[EDK_VID] : (i == 1 ? F::c(1) : (i == 2 ? k[EDK_LIMB] : limb_h)); },
-        BUS_EDRES, k[EDK_LAST], 49, [&](int i) { return i == 0 ? k[EDK_VID] : l[G(out_slot[(i - 1) >> 4]) + ((i - 1) & 15)]; });
+        bus_tag<F>(BUS_SCALAR), k[EDK_SEND16], 4, [&](int i) { return i == 0 ? k[EDK_VID] : (i == 1 ? F::c(1) : (i == 2 ? k[EDK_LIMB] : limb_h)); },
+        bus_tag<F>(BUS_EDRES), k[EDK_LAST], 49, [&](int i) { return i == 0 ? k[EDK_VID] : l[G(out_slot[(i - 1) >> 4]) + ((i - 1) & 15)]; });
 }
 
 // ------------------------------------------------------------------------------------------ range table
@@ -505,8 +509,8 @@ TMX_HD void air_range(const Row& l, const Row&, const KRow& k, const Per&, Emit&
     emit((F::c(1) - k[RGK_S11]) * l[RG_M11]);
     emit((F::c(1) - k[RGK_S8]) * l[RG_M8]);
     const F t = k[RGK_T];
-    bus.two(BUS_R16, l[RG_M16], 1, [&](int) { return t; }, BUS_R11, l[RG_M11], 1, [&](int) { return t; });
-    bus.one(BUS_R8, l[RG_M8], 1, [&](int) { return t; });
+    bus.two(bus_tag<F>(BUS_R16), l[RG_M16], 1, [&](int) { return t; }, bus_tag<F>(BUS_R11), l[RG_M11], 1, [&](int) { return t; });
+    bus.one(bus_tag<F>(BUS_R8), l[RG_M8], 1, [&](int) { return t; });
 }
 
 // ------------------------------------------------------------------------------------------ dispatch and table shapes

@@ -38,7 +38,7 @@ struct BusCheck {
         return H;
     }
     template <class Tup>
-    TMX_HD void one(int tag, F m, int len, const Tup& tup) {
+    TMX_HD void one(F tag, F m, int len, const Tup& tup) {
         const Ext2<F> f = bus_fingerprint<F>(beta, gamma, tag, len, tup);
         Ext2<F> c = e2_mul<F>(helper(), f);
         c.a0 = c.a0 - m;
@@ -46,7 +46,7 @@ struct BusCheck {
         emit(c.a1);
     }
     template <class TA, class TB>
-    TMX_HD void two(int tag_a, F ma, int len_a, const TA& ta, int tag_b, F mb, int len_b, const TB& tb) {
+    TMX_HD void two(F tag_a, F ma, int len_a, const TA& ta, F tag_b, F mb, int len_b, const TB& tb) {
         const Ext2<F> fa = bus_fingerprint<F>(beta, gamma, tag_a, len_a, ta);
         const Ext2<F> fb = bus_fingerprint<F>(beta, gamma, tag_b, len_b, tb);
         const Ext2<F> c = e2_sub<F>(e2_mul<F>(helper(), e2_mul<F>(fa, fb)), e2_add<F>(e2_scale<F>(fb, ma), e2_scale<F>(fa, mb)));
@@ -77,22 +77,22 @@ struct BusGen {
         sum = gl2_add(sum, H);
     }
     template <class Tup>
-    TMX_HD gl2 fp(int tag, int len, const Tup& tup) const {
+    TMX_HD gl2 fp(FB tag, int len, const Tup& tup) const {
         gl2 acc = gl2_from(0);
         for (int i = len - 1; i >= 0; i--) {
             acc.a0 = gl_add(acc.a0, tup(i).v);
             acc = gl2_mul(acc, beta);
         }
-        acc.a0 = gl_add(acc.a0, (gl)tag);
+        acc.a0 = gl_add(acc.a0, tag.v);
         return gl2_add(acc, gamma);
     }
     template <class Tup>
-    TMX_HD void one(int tag, FB m, int len, const Tup& tup) {
+    TMX_HD void one(FB tag, FB m, int len, const Tup& tup) {
         if (m.v == 0) { put(gl2_from(0)); return; }
         put(gl2_scale(gl2_inv(fp(tag, len, tup)), m.v));
     }
     template <class TA, class TB>
-    TMX_HD void two(int tag_a, FB ma, int len_a, const TA& ta, int tag_b, FB mb, int len_b, const TB& tb) {
+    TMX_HD void two(FB tag_a, FB ma, int len_a, const TA& ta, FB tag_b, FB mb, int len_b, const TB& tb) {
         if (ma.v == 0 && mb.v == 0) { put(gl2_from(0)); return; }
         const gl2 fa = fp(tag_a, len_a, ta), fb = fp(tag_b, len_b, tb);
         const gl2 num = gl2_add(gl2_scale(fb, ma.v), gl2_scale(fa, mb.v));
@@ -104,8 +104,9 @@ struct BusGen {
 struct BusCount {
     unsigned int* hist;
     int* bad;  // set when a looked-up value is outside its table (the witness cannot be proved)
-    TMX_HD void add(int tag, FB m, gl v) {
+    TMX_HD void add(FB tagf, FB m, gl v) {
         if (m.v != GL_P - 1) return;
+        const gl tag = tagf.v;
         size_t base, lim;
         if (tag == BUS_R16) { base = 0; lim = 1u << 16; }
         else if (tag == BUS_R11) { base = 1u << 16; lim = 1u << 11; }
@@ -119,9 +120,9 @@ struct BusCount {
 #endif
     }
     template <class Tup>
-    TMX_HD void one(int tag, FB m, int, const Tup& tup) { add(tag, m, tup(0).v); }
+    TMX_HD void one(FB tag, FB m, int, const Tup& tup) { add(tag, m, tup(0).v); }
     template <class TA, class TB>
-    TMX_HD void two(int tag_a, FB ma, int, const TA& ta, int tag_b, FB mb, int, const TB& tb) {
+    TMX_HD void two(FB tag_a, FB ma, int, const TA& ta, FB tag_b, FB mb, int, const TB& tb) {
         add(tag_a, ma, ta(0).v);
         add(tag_b, mb, tb(0).v);
     }

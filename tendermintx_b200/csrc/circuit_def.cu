@@ -96,8 +96,9 @@ struct SymEmit {
 };
 struct SymBus {
     template <class Tup>
-    static uint32_t push_tuple(int tag, Sym m, int len, const Tup& tup) {
-        g_sym->prog.push_back((uint64_t)tag);
+    static uint32_t push_tuple(Sym tag, Sym m, int len, const Tup& tup) {
+        if (g_sym->nodes[tag.id].deg > 1) g_sym->fail("bus tag of degree > 1");
+        g_sym->prog.push_back(tag.id);
         g_sym->prog.push_back(m.id);
         g_sym->prog.push_back((uint64_t)len);
         uint32_t deg = 0;
@@ -109,16 +110,17 @@ struct SymBus {
         return deg;
     }
     template <class Tup>
-    void one(int tag, Sym m, int len, const Tup& tup) {
+    void one(Sym tag, Sym m, int len, const Tup& tup) {
         g_sym->prog.push_back(1);
-        const uint32_t df = push_tuple(tag, m, len, tup);
+        const uint32_t df = std::max(push_tuple(tag, m, len, tup), g_sym->nodes[tag.id].deg);
         if (1 + df > 3 || g_sym->nodes[m.id].deg > 3) g_sym->fail("bus.one: degree > 3 (helper " + std::to_string(g_sym->n_helpers) + ")");
         g_sym->n_helpers++;
     }
     template <class TA, class TB>
-    void two(int tag_a, Sym ma, int len_a, const TA& ta, int tag_b, Sym mb, int len_b, const TB& tb) {
+    void two(Sym tag_a, Sym ma, int len_a, const TA& ta, Sym tag_b, Sym mb, int len_b, const TB& tb) {
         g_sym->prog.push_back(2);
-        const uint32_t da = push_tuple(tag_a, ma, len_a, ta), db = push_tuple(tag_b, mb, len_b, tb);
+        const uint32_t da = std::max(push_tuple(tag_a, ma, len_a, ta), g_sym->nodes[tag_a.id].deg);
+        const uint32_t db = std::max(push_tuple(tag_b, mb, len_b, tb), g_sym->nodes[tag_b.id].deg);
         const uint32_t dma = g_sym->nodes[ma.id].deg, dmb = g_sym->nodes[mb.id].deg;
         if (1 + da + db > 3 || dma + db > 3 || dmb + da > 3)
             g_sym->fail("bus.two: degree > 3 (helper " + std::to_string(g_sym->n_helpers) + ")");
