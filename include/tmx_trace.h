@@ -134,24 +134,38 @@
 #define RG_M16 0  /* multiplicity of t among the 16-bit lookups */
 #define RG_M11 1  /* ... among the 11-bit lookups (zero on rows >= 2^11) */
 #define RG_M8 2   /* ... among the 8-bit lookups (zero on rows >= 2^8) */
-#define RG_COLS 3
+#define RG_M1 3   /* ... among the 1-bit lookups (zero on rows >= 2) */
+#define RG_COLS 4
 #define RGK_T 0
 #define RGK_S11 1
 #define RGK_S8 2
-#define RGK_COLS 3
+#define RGK_S1 3
+#define RGK_COLS 4
 #define RG_LOG_ROWS 16
 
 /* ---------------- bus tags (first element of every message fingerprint) ---------------- */
 #define BUS_R16 1      /* (v) */
 #define BUS_R11 2      /* (v) */
 #define BUS_R8 3       /* (v) */
-#define BUS_MSG256 4   /* (chunk, w0..w15) */
-#define BUS_DIG256 5   /* (chunk, d0..d7) */
-#define BUS_MSG512 6   /* (slot, chunk, two, 32 halves) */
-#define BUS_DIG512 7   /* (slot, chunk, 16 halves) */
-#define BUS_ADDEND 8   /* (slot, selector, 48 limbs) */
-#define BUS_SCALAR 9   /* (slot, which, limb index, limb) */
-#define BUS_EDRES 10   /* (slot, X[16], Y[16], Z[16]) */
+#define BUS_R1 4       /* (v) */
+#define BUS_MSG256 5   /* (chunk, w0..w15) */
+#define BUS_DIG256 6   /* (chunk, d0..d7) */
+#define BUS_MSG512 7   /* (slot, chunk, two, 32 halves) */
+#define BUS_DIG512 8   /* (slot, 16 halves) */
+#define BUS_ADDEND 9   /* (slot, selector, 48 limbs) */
+#define BUS_SCALAR 10  /* (slot, which, limb index, limb) */
+#define BUS_EDRES 11   /* (slot, X[16], Y[16], Z[16]) */
+#define BUS_NODE 12    /* (node id, 8 big-endian words, enabled): value of a Merkle node */
+#define BUS_KEY 13     /* (8 words): public key of a target validator that signed */
+#define BUS_PKSIG 14   /* (slot, signed * 8 key words, signed): target validator -> its signature row */
+#define BUS_GLOB 15    /* (2 height words LE, 8 header words, 2 round words LE, round == 0) */
+#define BUS_FE 16      /* (wire id, 16 limbs): a curve25519 field element between logic rows */
+#define BUS_BIT 17     /* (wire id, bit) */
+#define BUS_DIGB 18    /* (slot, 16 little-endian words of the SHA-512 digest) */
+#define BUS_PUB 19     /* (kind, ...): provided by the VERIFIER from the public input / output */
+#define PUB_GLOB 1     /* (height LE words [2], target / next header words [8]) */
+#define PUB_HEIGHT 2   /* (height as 9 septets) */
+#define PUB_PREV 3     /* (previous header words [8]), step only */
 
 #define TMX_N_TABLES 5
 #define TMX_T_SHA256 0

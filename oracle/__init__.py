@@ -232,6 +232,9 @@ def _product_lib():
         _PRODUCT_LIB.tmx_circuit_artefact.restype = ctypes.c_size_t
         _PRODUCT_LIB.tmx_circuit_artefact.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_uint64,
                                                       ctypes.c_void_p, ctypes.c_size_t]
+        _PRODUCT_LIB.tmx_logic_trace.restype = ctypes.c_size_t
+        _PRODUCT_LIB.tmx_logic_trace.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p,
+                                                 ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int)]
     return _PRODUCT_LIB
 
 
@@ -304,6 +307,24 @@ def circuit(kind, n_max, chain_id, skip_max=100800):
     return _CIRCUITS[key]
 
 
+def logic_trace(public_input, blob, chain_id, force=True):
+    """First-round trace of the logic table, [cols, rows]: the witness of the plain-gate gadgets.  It is produced by the
+    product's HOST code (the table is small and has no kernel); the oracle proves with it and checks it against the
+    constraint DAG like any other table.  Returns (trace or None when the circuit has no logic table, status)."""
+    kind, n_max = _blob_shape(blob)
+    cid = chain_id.encode() if isinstance(chain_id, str) else chain_id
+    st = ctypes.c_int(0)
+    cells = _product_lib().tmx_logic_trace(kind, n_max, cid, len(cid), bytes(public_input), bytes(blob), int(force), None, 0, ctypes.byref(st))
+    if cells == 0:
+        return None, 0
+    sh = circuit(kind, n_max, chain_id).table_shapes()[T_LOGIC]
+    out = np.zeros((sh[2], 1 << sh[1]), dtype=np.uint64)
+    assert out.size == cells
+    _product_lib().tmx_logic_trace(kind, n_max, cid, len(cid), bytes(public_input), bytes(blob), int(force),
+                                   out.ctypes.data_as(ctypes.c_void_p), cells, ctypes.byref(st))
+    return out, st.value
+
+
 def _blob_shape(blob):
     kind, n_max = np.frombuffer(bytes(blob[4:12]), dtype=np.uint32)
     return int(kind), int(n_max)
@@ -317,6 +338,8 @@ def prove(public_input, blob, chain_id, skip_max=100800, logic_trace=None):
     n = ctypes.c_size_t(0)
     out = (ctypes.c_uint8 * 32)()
     lt = None
+    if logic_trace is None:
+        logic_trace, _ = globals()["logic_trace"](public_input, blob, chain_id)
     if logic_trace is not None:
         lt = np.ascontiguousarray(logic_trace, dtype=np.uint64)
     rc = lib().tm_prove(ctypes.c_void_p(c.handle), _buf(public_input), ctypes.c_size_t(len(public_input)), _buf(blob),
@@ -337,9 +360,11 @@ def verify_proof(proof, public_input, chain_id, kind, n_max, output32, skip_max=
                                  _buf(public_input), ctypes.c_size_t(len(public_input)), _buf(output32))
 
 
-def all_traces(blob, chain_id, skip_max=100800, logic_trace=None):
+def all_traces(blob, chain_id, skip_max=100800, logic_trace=None, public_input=None):
     """First-round traces of all tables (None where a table is absent), [n_cols, n_rows] each."""
     kind, n_max = _blob_shape(blob)
+    if logic_trace is None and public_input is not None:
+        logic_trace, _ = globals()["logic_trace"](public_input, blob, chain_id)
     c = circuit(kind, n_max, chain_id, skip_max)
     shapes = c.table_shapes()
     arrs, ptrs = [], (ctypes.c_void_p * N_TABLES)()

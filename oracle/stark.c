@@ -217,7 +217,7 @@ static void periodic_at_row(const table_def_t *d, size_t row, gl_t *per) {
 }
 
 /* first-round trace of the range table: how often each value is looked up by the other tables */
-#define HIST_SIZE ((1u << 16) + (1u << 11) + (1u << 8))
+#define HIST_SIZE ((1u << 16) + (1u << 11) + (1u << 8) + 2)
 static int count_lookups(const circuit_def_t *c, trace_t tr[TMX_N_TABLES], uint64_t *hist) {
     int bad = 0;
     for (int ti = 0; ti < TMX_N_TABLES; ti++) {
@@ -251,6 +251,7 @@ static int count_lookups(const circuit_def_t *c, trace_t tr[TMX_N_TABLES], uint6
                         if (tag == BUS_R16) { base = 0; lim = 1u << 16; }
                         else if (tag == BUS_R11) { base = 1u << 16; lim = 1u << 11; }
                         else if (tag == BUS_R8) { base = (1u << 16) + (1u << 11); lim = 1u << 8; }
+                        else if (tag == BUS_R1) { base = (1u << 16) + (1u << 11) + (1u << 8); lim = 2; }
                         else continue;
                         const gl_t val = v[it[3]];
                         if (val >= lim) {
@@ -668,10 +669,57 @@ static void transcript_init(challenger_t *ch, const circuit_def_t *c, const uint
     challenger_observe_many(ch, ph, 4);
 }
 
-/* the verifier's own bus terms (public input / output bindings); none until the logic table carries the links */
+/* The verifier's own bus terms: what ties the tables to the public input and output [REF circuits/skip.rs:119-133,
+ * circuits/step.rs:106-117].  The verifier CONSUMES the root of every header proof (NODE message: id, 8 big-endian words, 1) --
+ * the trusted header for the trusted validators-hash proof of a skip, the previous header for the next-validators-hash proof of
+ * a step, the proven header (out32) for all others -- and PROVIDES the height as nine varint septets (height leaf), the
+ * previous header (last-block-id leaf of a step) and (height, proven header) for the sign-bytes checks. */
+static gl2_t fingerprint_words(gl2_t beta, gl2_t gamma, uint64_t tag, const uint64_t *v, size_t n) {
+    gl2_t acc = gl2_from(0);
+    for (size_t i = n; i-- > 0;) {
+        acc.a0 = gl_add(acc.a0, v[i] % GL_P);
+        acc = gl2_mul(acc, beta);
+    }
+    acc.a0 = gl_add(acc.a0, tag);
+    return gl2_add(acc, gamma);
+}
+static uint64_t load_be64(const uint8_t *p) {
+    uint64_t v = 0;
+    for (int i = 0; i < 8; i++) v = (v << 8) | p[i];
+    return v;
+}
+static void header_words(const uint8_t *h, uint64_t *w) {
+    for (int i = 0; i < 8; i++) w[i] = ((uint64_t)h[4 * i] << 24) | ((uint64_t)h[4 * i + 1] << 16) | ((uint64_t)h[4 * i + 2] << 8) | h[4 * i + 3];
+}
 static gl2_t public_terms(const circuit_def_t *c, const uint8_t *input, const uint8_t out32[32], gl2_t beta, gl2_t gamma) {
-    (void)c; (void)input; (void)out32; (void)beta; (void)gamma;
-    return gl2_from(0);
+    gl2_t sum = gl2_from(0);
+    if (!c->t[TMX_T_LOGIC].present) return sum;
+    const int skip = c->kind == TMX_KIND_SKIP;
+    const uint64_t height = skip ? load_be64(input + 40) : load_be64(input) + 1;
+    const uint8_t *other = input + 8;
+    const uint32_t n_proofs = skip ? 4 : 5;
+    uint64_t v[16];
+    for (uint32_t kp = 0; kp < n_proofs; kp++) {
+        const uint8_t *hdr = (skip && kp == 0) || (!skip && kp == 4) ? other : out32;
+        v[0] = ((uint64_t)0x7F << 24) | ((uint64_t)kp << 8) | 4;
+        header_words(hdr, v + 1);
+        v[9] = 1;
+        sum = gl2_sub(sum, gl2_inv(fingerprint_words(beta, gamma, BUS_NODE, v, 10)));
+    }
+    if (!skip) {
+        v[0] = PUB_PREV;
+        header_words(other, v + 1);
+        sum = gl2_add(sum, gl2_inv(fingerprint_words(beta, gamma, BUS_PUB, v, 9)));
+    }
+    v[0] = PUB_HEIGHT;
+    for (int k = 0; k < 9; k++) v[1 + k] = (height >> (7 * k)) & 0x7F;
+    sum = gl2_add(sum, gl2_inv(fingerprint_words(beta, gamma, BUS_PUB, v, 10)));
+    v[0] = PUB_GLOB;
+    v[1] = height & 0xFFFFFFFFULL;
+    v[2] = height >> 32;
+    header_words(out32, v + 3);
+    sum = gl2_add(sum, gl2_inv(fingerprint_words(beta, gamma, BUS_PUB, v, 11)));
+    return sum;
 }
 
 /* debug / test hook: the NEXT tm_prove() on this thread adds one to cell (col, row) of `table` after witness generation,
@@ -736,6 +784,7 @@ static int build_range_trace(const circuit_def_t *c, trace_t tr[TMX_N_TABLES]) {
     for (size_t i = 0; i < (1u << 16) && i < n; i++) tr[TMX_T_RANGE].data[RG_M16 * n + i] = hist[i];
     for (size_t i = 0; i < (1u << 11); i++) tr[TMX_T_RANGE].data[RG_M11 * n + i] = hist[(1u << 16) + i];
     for (size_t i = 0; i < (1u << 8); i++) tr[TMX_T_RANGE].data[RG_M8 * n + i] = hist[(1u << 16) + (1u << 11) + i];
+    for (size_t i = 0; i < 2; i++) tr[TMX_T_RANGE].data[RG_M1 * n + i] = hist[(1u << 16) + (1u << 11) + (1u << 8) + i];
     free(hist);
     return bad;
 }

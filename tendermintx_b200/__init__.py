@@ -317,11 +317,11 @@ class Circuit:
         return tuple(out)
 
     def bus_count(self, table, trace):
-        """Histogram (int32 CUDA tensor, 2^16 + 2^11 + 2^8 entries) of the range lookups of a first-round trace, and the
+        """Histogram (int32 CUDA tensor, 2^16 + 2^11 + 2^8 + 2 entries: the 16-, 11-, 8- and 1-bit tables) of the range lookups of a first-round trace, and the
         out-of-range flag."""
         import torch
 
-        hist = torch.zeros((1 << 16) + (1 << 11) + (1 << 8), dtype=torch.int32, device=trace.device)
+        hist = torch.zeros((1 << 16) + (1 << 11) + (1 << 8) + 2, dtype=torch.int32, device=trace.device)
         bad = ctypes.c_int(0)
         _check(lib().tmx_bus_count(self._h, table, _ptr(trace), _ptr(hist), ctypes.byref(bad), self.ctx._stream()))
         return hist, bool(bad.value)

@@ -134,10 +134,20 @@ TMX_HD F bus_tag(int t) { return F::c((uint64_t)t); }
 
 constexpr int AIR_SHA256 = TMX_T_SHA256, AIR_SHA512 = TMX_T_SHA512, AIR_ED25519 = TMX_T_ED, AIR_LOGIC = TMX_T_LOGIC,
               AIR_RANGE = TMX_T_RANGE;
-// Circuit shape the constant columns depend on.
+// Circuit shape the constant columns and the shape-dependent constraints depend on.
 struct AirShape {
     uint32_t kind, n_max;
+    uint32_t chain_len;
+    char chain[52];
 };
+inline AirShape air_shape(uint32_t kind, uint32_t n_max, const char* chain, size_t chain_len) {
+    AirShape sh;
+    sh.kind = kind;
+    sh.n_max = n_max;
+    sh.chain_len = (uint32_t)(chain_len > 50 ? 50 : chain_len);
+    for (int i = 0; i < 52; i++) sh.chain[i] = i < (int)sh.chain_len ? chain[i] : 0;
+    return sh;
+}
 constexpr int AIR_MAX_PERIODIC = 16;
 
 // Does 64-row chunk c of the SHA-256 table continue the message of chunk c - 1?  Layout (witness_jobs.cuh): per
@@ -503,14 +513,15 @@ TMX_HD void air_ed25519(const Row& l, const Row& n, const KRow& k, const Per& pe
 
 // ------------------------------------------------------------------------------------------ range table
 // row t provides the value t (constant column RGK_T) to the 16-bit lookups with multiplicity M16, and on its first 2^11 /
-// 2^8 rows to the 11-bit / 8-bit lookups
+// 2^8 / 2 rows to the 11-bit / 8-bit / 1-bit lookups
 template <class F, class Row, class KRow, class Per, class Emit, class Bus>
 TMX_HD void air_range(const Row& l, const Row&, const KRow& k, const Per&, Emit& emit, Bus& bus) {
     emit((F::c(1) - k[RGK_S11]) * l[RG_M11]);
     emit((F::c(1) - k[RGK_S8]) * l[RG_M8]);
+    emit((F::c(1) - k[RGK_S1]) * l[RG_M1]);
     const F t = k[RGK_T];
     bus.two(bus_tag<F>(BUS_R16), l[RG_M16], 1, [&](int) { return t; }, bus_tag<F>(BUS_R11), l[RG_M11], 1, [&](int) { return t; });
-    bus.one(bus_tag<F>(BUS_R8), l[RG_M8], 1, [&](int) { return t; });
+    bus.two(bus_tag<F>(BUS_R8), l[RG_M8], 1, [&](int) { return t; }, bus_tag<F>(BUS_R1), l[RG_M1], 1, [&](int) { return t; });
 }
 
 // ------------------------------------------------------------------------------------------ dispatch and table shapes
@@ -556,7 +567,7 @@ TMX_HD size_t air_rows(int t, AirShape sh) {
 // The cross-table messages (hash inputs / digests, scalar limbs, addends, results) have their counterparty in the logic
 // table; until that table carries them their multiplicity columns are zero and only the range-check bus is live.
 #ifndef TMX_BUS_LINKS
-#define TMX_BUS_LINKS 0
+#define TMX_BUS_LINKS 1
 #endif
 
 // periodic pattern of column pc at row r of its period
@@ -628,7 +639,8 @@ TMX_HD uint64_t air_const_value(int table, int kc, size_t row, AirShape sh) {
     if (table == AIR_RANGE) {
         if (kc == RGK_T) return row;
         if (kc == RGK_S11) return row < 2048;
-        return row < 256;
+        if (kc == RGK_S8) return row < 256;
+        return row < 2;
     }
     return 0;
 }

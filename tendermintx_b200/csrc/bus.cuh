@@ -100,7 +100,7 @@ struct BusGen {
     }
 };
 
-// histogram of the range lookups (multiplicity p - 1 = -1) of one trace row: hist[0 .. 2^16) 16-bit, then 2^11, then 2^8
+// histogram of the range lookups (multiplicity p - 1 = -1) of one trace row: hist[0 .. 2^16) 16-bit, then 2^11, 2^8, 2
 struct BusCount {
     unsigned int* hist;
     int* bad;  // set when a looked-up value is outside its table (the witness cannot be proved)
@@ -111,6 +111,7 @@ struct BusCount {
         if (tag == BUS_R16) { base = 0; lim = 1u << 16; }
         else if (tag == BUS_R11) { base = 1u << 16; lim = 1u << 11; }
         else if (tag == BUS_R8) { base = (1u << 16) + (1u << 11); lim = 1u << 8; }
+        else if (tag == BUS_R1) { base = (1u << 16) + (1u << 11) + (1u << 8); lim = 2; }
         else return;
         if (v >= lim) { *bad = 1; return; }
 #if defined(__CUDA_ARCH__)
@@ -127,6 +128,6 @@ struct BusCount {
         add(tag_b, mb, tb(0).v);
     }
 };
-constexpr size_t BUS_HIST_SIZE = (1u << 16) + (1u << 11) + (1u << 8);
+constexpr size_t BUS_HIST_SIZE = (1u << 16) + (1u << 11) + (1u << 8) + 2;
 
 }  // namespace tmx

@@ -10,6 +10,7 @@
 #include "stark.cuh"
 #include "bus.cuh"
 #include "witness_jobs.cuh"
+#include "logic_plan.cuh"
 #include <cstring>
 #include <cstdio>
 #include <cstdlib>
@@ -29,6 +30,11 @@ struct tmx_circuit {
     uint8_t* d_blob = nullptr;
     uint8_t* d_aux = nullptr;
     void* d_points = nullptr;           // Ed25519 slot info + accumulators (phase 1 -> phase 2)
+    // logic table: filled on the host from the inputs and the slot infos of the sequential Ed25519 phase
+    std::shared_ptr<const LogicPlan> plan;
+    EdSlotInfo* h_slots = nullptr;      // pinned
+    gl* h_logic = nullptr;              // pinned, [LG_COLS][rows]
+    gl* d_logic = nullptr;
     cudaStream_t side = nullptr;        // second stream: the latency-bound sequential Ed25519 rows
     cudaEvent_t ev_inputs = nullptr, ev_ladder = nullptr;
     std::vector<uint8_t> h_blob;  // host copy of the resident inputs (tmx_circuit_set_inputs)
@@ -203,6 +209,15 @@ extern "C" int tmx_circuit_build(tmx_ctx* ctx, uint32_t kind, uint32_t n_max, co
         cudaEventCreateWithFlags(&c->ev_inputs, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_ladder, cudaEventDisableTiming) != cudaSuccess)
         return fail(TMX_E_CUDA, "tmx_circuit_build: cudaMalloc failed");
+    const AirShape sh = air_shape(kind, n_max, chain_id, chain_id_len);
+    if (logic_rows(sh)) {
+        c->plan = logic_plan_get(sh);
+        const size_t cells = (size_t)LG_COLS * c->plan->n_rows;
+        if (cudaMallocHost((void**)&c->h_slots, (size_t)n_max * sizeof(EdSlotInfo)) != cudaSuccess ||
+            cudaMallocHost((void**)&c->h_logic, cells * sizeof(gl)) != cudaSuccess ||
+            cudaMalloc((void**)&c->d_logic, cells * sizeof(gl)) != cudaSuccess)
+            return fail(TMX_E_CUDA, "tmx_circuit_build: logic table buffers");
+    }
     const int rc = c->prover.setup(ctx, c->def);
     if (rc) return rc;
     *out = c.release();
@@ -217,6 +232,9 @@ extern "C" void tmx_circuit_free(tmx_circuit* c) {
     if (c->d_blob) cudaFree(c->d_blob);
     if (c->d_aux) cudaFree(c->d_aux);
     if (c->d_points) cudaFree(c->d_points);
+    if (c->h_slots) cudaFreeHost(c->h_slots);
+    if (c->h_logic) cudaFreeHost(c->h_logic);
+    if (c->d_logic) cudaFree(c->d_logic);
     if (c->side) cudaStreamDestroy(c->side);
     if (c->ev_inputs) cudaEventDestroy(c->ev_inputs);
     if (c->ev_ladder) cudaEventDestroy(c->ev_ladder);
@@ -335,6 +353,7 @@ extern "C" int tmx_prove(tmx_circuit* c, const uint8_t* input, size_t input_len,
     TMX_CUDA(cudaStreamWaitEvent(c->side, c->ev_inputs, 0));
     rc = run_ed25519_ladder(ctx, wa, c->d_points, c->side);
     if (rc) return rc;
+    if (c->plan) TMX_CUDA(cudaMemcpyAsync(c->h_slots, c->d_points, (size_t)c->n_max * sizeof(EdSlotInfo), cudaMemcpyDeviceToHost, c->side));
     TMX_CUDA(cudaEventRecord(c->ev_ladder, c->side));
     rc = witness_run_sha256(ctx, wa, st);
     if (rc) return rc;
@@ -356,12 +375,25 @@ extern "C" int tmx_prove(tmx_circuit* c, const uint8_t* input, size_t input_len,
     // round 1
     if ((rc = pr.count_lookups(ctx, AIR_SHA256, c->d_trace[0], st))) return rc;
     if ((rc = pr.commit_main(ctx, AIR_SHA256, c->d_trace[0], st))) return rc;
+    // logic table: the host fills it while the GPU commits the SHA-256 table (it needs the slot infos of the sequential phase)
+    int logic_status = 0;
+    if (c->plan) {
+        TMX_CUDA(cudaEventSynchronize(c->ev_ladder));
+        const size_t cells = (size_t)LG_COLS * c->plan->n_rows;
+        memset(c->h_logic, 0, cells * sizeof(gl));
+        logic_status = logic_fill_trace(*c->plan, input, blob, c->h_slots, c->h_logic, true);
+        TMX_CUDA(cudaMemcpyAsync(c->d_logic, c->h_logic, cells * sizeof(gl), cudaMemcpyHostToDevice, st));
+    }
     TMX_CUDA(cudaStreamWaitEvent(st, c->ev_ladder, 0));
     if ((rc = run_ed25519_expand(ctx, wa, c->d_points, st))) return rc;
     if ((rc = pr.count_lookups(ctx, AIR_SHA512, c->d_trace[1], st))) return rc;
     if ((rc = pr.count_lookups(ctx, AIR_ED25519, c->d_trace[2], st))) return rc;
     if ((rc = pr.commit_main(ctx, AIR_SHA512, c->d_trace[1], st))) return rc;
     if ((rc = pr.commit_main(ctx, AIR_ED25519, c->d_trace[2], st))) return rc;
+    if (c->plan) {
+        if ((rc = pr.count_lookups(ctx, AIR_LOGIC, c->d_logic, st))) return rc;
+        if ((rc = pr.commit_main(ctx, AIR_LOGIC, c->d_logic, st))) return rc;
+    }
     if ((rc = pr.fill_range_trace(ctx, st))) return rc;
     if ((rc = pr.commit_main(ctx, AIR_RANGE, pr.d_range_trace, st))) return rc;
     std::vector<uint8_t> aux(aux_bytes(c->n_max));
@@ -378,10 +410,14 @@ extern "C" int tmx_prove(tmx_circuit* c, const uint8_t* input, size_t input_len,
         g_last_check = chk;
         return fail(TMX_E_UNSAT, "tmx_prove: witness does not satisfy the circuit (check id " + std::to_string(chk) + ")");
     }
+    if (logic_status) {
+        g_last_check = logic_status;
+        return fail(TMX_E_UNSAT, "tmx_prove: witness does not satisfy the circuit (logic table, check id " + std::to_string(logic_status) + ")");
+    }
     if (!range_ok) return fail(TMX_E_UNSAT, "tmx_prove: a witness cell is outside its range table");
     const gl2 beta = ch.get_ext(), gamma = ch.get_ext();
     // round 2
-    const gl* traces[STARK_N_TABLES] = {c->d_trace[0], c->d_trace[1], c->d_trace[2], nullptr, pr.d_range_trace};
+    const gl* traces[STARK_N_TABLES] = {c->d_trace[0], c->d_trace[1], c->d_trace[2], c->d_logic, pr.d_range_trace};
     for (int t = 0; t < STARK_N_TABLES; t++)
         if ((rc = pr.commit_aux(ctx, t, traces[t], beta, gamma, st))) return rc;
     if ((rc = pr.finish_round2(ctx, ch, w, st))) return rc;

@@ -299,7 +299,7 @@ std::shared_ptr<const CircuitDef> circuit_def_get(uint32_t kind, uint32_t n_max,
     c->n_max = n_max;
     c->skip_max = skip_max;
     c->chain_id = chain_id;
-    const AirShape sh{kind, n_max};
+    const AirShape sh = air_shape(kind, n_max, chain_id.data(), chain_id.size());
     for (int t = 0; t < TMX_N_TABLES; t++) {
         std::string err;
         if (!build_table(t, sh, c->tables[t], err)) {

@@ -290,7 +290,7 @@ TMX_HD void sc_reduce512(const uint8_t in[64], uint64_t out[4]) {
 // U, V: signed limb vectors (|limb| < 2^19); writes the 63 cells of one gadget (c[16], q[17], and the 15 carries out of the
 // odd limbs, offset by ED_W_OFFSET and split into a 16-bit and an 11-bit part) with stride `stride` starting at `cells`;
 // returns c limbs in c_out.
-TMX_HD void mul_gadget_cells(const int32_t U[16], const int32_t V[16], gl* cells, size_t stride, int32_t c_out[16]) {
+TMX_HD void mul_gadget_cells(const int32_t U[16], const int32_t V[16], gl* cells, size_t stride, int32_t c_out[16], const int32_t* W = nullptr) {
     int64_t t[31];
 #pragma unroll
     for (int k = 0; k < 31; k++) t[k] = 0;
@@ -298,6 +298,8 @@ TMX_HD void mul_gadget_cells(const int32_t U[16], const int32_t V[16], gl* cells
     for (int i = 0; i < 16; i++)
 #pragma unroll
         for (int j = 0; j < 16; j++) t[i + j] += (int64_t)U[i] * V[j];
+    if (W)  // additive operand of the logic table's gadgets: U * V + W = c + q * p
+        for (int k = 0; k < 16; k++) t[k] += W[k];
     // canonical residue: digits of N, fold 2^256 = 38, conditional subtraction of p
     int64_t d[36];
     int64_t carry = 0;

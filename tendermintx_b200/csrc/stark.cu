@@ -79,6 +79,7 @@ __global__ void range_fill_kernel(const unsigned int* __restrict__ hist, gl* __r
     trace[(size_t)RG_M16 * n + i] = hist[i];
     trace[(size_t)RG_M11 * n + i] = i < (1u << 11) ? hist[(1u << 16) + i] : 0;
     trace[(size_t)RG_M8 * n + i] = i < (1u << 8) ? hist[(1u << 16) + (1u << 11) + i] : 0;
+    trace[(size_t)RG_M1 * n + i] = i < 2 ? hist[(1u << 16) + (1u << 11) + (1u << 8) + i] : 0;
 }
 
 // after the inverse NTT of size m = 2n the buffer holds q_i * 7^i; chunk k of challenge c is coefficients
@@ -344,7 +345,7 @@ static unsigned cap_height_of(unsigned km) { return std::min<unsigned>(km, STARK
 
 int Prover::setup(tmx_ctx* ctx, std::shared_ptr<const CircuitDef> d) {
     def = d;
-    shape = AirShape{d->kind, d->n_max};
+    shape = air_shape(d->kind, d->n_max, d->chain_id.data(), d->chain_id.size());
     cudaStream_t st = ctx->stream;
     int rc;
     size_t max_m = 0, max_ct = 0;

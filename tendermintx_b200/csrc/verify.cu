@@ -95,7 +95,7 @@ gl2 fold_coset(gl x, unsigned within, const gl2 evals[16], gl2 beta) {
 static int verify_table(const CircuitDef& def, int table, const gl* cap_m, const gl* cap_a, gl2 beta, gl2 gamma, gl2 total,
                         Reader& r, Challenger& ch) {
     const TableDef& td = def.tables[table];
-    const AirShape shape{def.kind, def.n_max};
+    const AirShape shape = air_shape(def.kind, def.n_max, def.chain_id.data(), def.chain_id.size());
     const size_t n = td.rows(), m = n << STARK_RATE_BITS;
     const size_t Kc = td.n_const, C = td.n_main, A = (size_t)td.n_aux(), CT = Kc + C + A;
     const unsigned k = td.log_n, km = k + STARK_RATE_BITS;
@@ -271,7 +271,7 @@ int verify_proof(const CircuitDef& def, const gl* w, size_t n_words, const uint8
         ch.observe(cap_m[t], cap_words(t));
     }
     const gl2 beta = ch.get_ext(), gamma = ch.get_ext();
-    gl2 balance = logic_public_terms(AirShape{def.kind, def.n_max}, def.skip_max, input, out32, beta, gamma);
+    gl2 balance = logic_public_terms(air_shape(def.kind, def.n_max, def.chain_id.data(), def.chain_id.size()), def.skip_max, input, out32, beta, gamma);
     for (int t = 0; t < TMX_N_TABLES; t++) {
         if (!def.tables[t].n_main) continue;
         cap_a[t] = r.take(cap_words(t));

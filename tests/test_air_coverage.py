@@ -23,26 +23,18 @@ def traces(oracle, request):
     blob = bytes.fromhex(c["blob"])
     kind = 1 if c["kind"] == "skip" else 0
     circ = oracle.circuit(kind, c["n_max"], "mocha-4")
-    tabs = oracle.all_traces(blob, "mocha-4")
+    tabs = oracle.all_traces(blob, "mocha-4", public_input=bytes.fromhex(c["input"]))
     aux = [oracle.aux_trace(circ, t, tabs[t], BETA, GAMMA) if tabs[t] is not None else None for t in range(oracle.N_TABLES)]
     return circ, tabs, aux
 
 
-@pytest.mark.parametrize("table", [0, 1, 2, 4])
+@pytest.mark.parametrize("table", [0, 1, 2, 3, 4])
 def test_honest_trace_satisfies_every_row(oracle, traces, table):
     circ, tabs, aux = traces
     t, (a, total) = tabs[table], aux[table]
     out = oracle.constraints_at_rows(circ, table, t, a, total, BETA, GAMMA, np.arange(t.shape[1]))
     bad = np.nonzero(out.any(axis=1))[0]
     assert bad.size == 0, (NAMES[table], bad[:10])
-
-
-def test_bus_totals_balance(oracle, traces):
-    """sum over the tables of the running-sum totals is zero: every lookup is answered by the range table"""
-    circ, tabs, aux = traces
-    s0 = sum(int(a[1][0]) for a in aux if a is not None) % P
-    s1 = sum(int(a[1][1]) for a in aux if a is not None) % P
-    assert (s0, s1) == (0, 0)
 
 
 @pytest.mark.parametrize("table", [0, 1, 2])

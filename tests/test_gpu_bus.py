@@ -40,10 +40,11 @@ def test_bus_rounds_and_quotient_equal_oracle(ctx, oracle, name):
     kind, n_max = struct.unpack_from("<II", blob, 4)
     circ = oracle.circuit(kind, n_max, "mocha-4")
     shapes = circ.table_shapes()
-    tabs = oracle.all_traces(blob, "mocha-4")
+    tabs = oracle.all_traces(blob, "mocha-4", public_input=bytes.fromhex(c["input"]))
     circuit = tmx.Circuit.build(ctx, kind, n_max, tmx.Mocha4Config)
     assert list(circuit.digest()) == [int(x) for x in circ.digest()]
-    hist_total = np.zeros((1 << 16) + (1 << 11) + (1 << 8), dtype=np.uint64)
+    H16, H11, H8 = 1 << 16, (1 << 16) + (1 << 11), (1 << 16) + (1 << 11) + (1 << 8)
+    hist_total = np.zeros(H8 + 2, dtype=np.uint64)
     for table, t in enumerate(tabs):
         if t is None:
             assert circuit.table_shape(table)[0] == 0
@@ -65,9 +66,10 @@ def test_bus_rounds_and_quotient_equal_oracle(ctx, oracle, name):
         assert want_q.any(axis=1).all()
         assert np.array_equal(_host(q), want_q), (name, table)
     rg = tabs[oracle.T_RANGE]
-    assert np.array_equal(rg[0], hist_total[:1 << 16])
-    assert np.array_equal(rg[1][:1 << 11], hist_total[1 << 16:(1 << 16) + (1 << 11)])
-    assert np.array_equal(rg[2][:1 << 8], hist_total[(1 << 16) + (1 << 11):])
+    assert np.array_equal(rg[0], hist_total[:H16])
+    assert np.array_equal(rg[1][:1 << 11], hist_total[H16:H11])
+    assert np.array_equal(rg[2][:1 << 8], hist_total[H11:H8])
+    assert np.array_equal(rg[3][:2], hist_total[H8:])
     circuit.close()
 
 

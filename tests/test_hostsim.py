@@ -88,10 +88,12 @@ def test_product_bus_and_air_on_the_lde_coset_equal_oracle(hostsim, oracle, name
     kind = 1 if c["kind"] == "skip" else 0
     circ = oracle.circuit(kind, c["n_max"], CHAIN)
     shapes = circ.table_shapes()
-    tabs = oracle.all_traces(blob, CHAIN)
+    tabs = oracle.all_traces(blob, CHAIN, public_input=bytes.fromhex(c["input"]))
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     beta, gamma, alpha = _u64(BETA), _u64(GAMMA), _u64(ALPHA)
-    hist = np.zeros((1 << 16) + (1 << 11) + (1 << 8) + 1, dtype=np.uint32)
+    hostsim.hostsim_set_plan(p(np.ascontiguousarray(circ.table_data(oracle.T_LOGIC)[1])), ctypes.c_size_t(1 << shapes[oracle.T_LOGIC][1]))
+    H16, H11, H8 = 1 << 16, (1 << 16) + (1 << 11), (1 << 16) + (1 << 11) + (1 << 8)
+    hist = np.zeros(H8 + 2 + 1, dtype=np.uint32)
     for table, t in enumerate(tabs):
         if t is None:
             continue
@@ -120,6 +122,7 @@ def test_product_bus_and_air_on_the_lde_coset_equal_oracle(hostsim, oracle, name
     # the range table's multiplicity columns are the histogram
     rg = tabs[oracle.T_RANGE]
     assert hist[-1] == 0
-    assert np.array_equal(rg[0], hist[:1 << 16].astype(np.uint64))
-    assert np.array_equal(rg[1][:1 << 11], hist[1 << 16:(1 << 16) + (1 << 11)].astype(np.uint64)) and not rg[1][1 << 11:].any()
-    assert np.array_equal(rg[2][:1 << 8], hist[(1 << 16) + (1 << 11):-1].astype(np.uint64)) and not rg[2][1 << 8:].any()
+    assert np.array_equal(rg[0], hist[:H16].astype(np.uint64))
+    assert np.array_equal(rg[1][:1 << 11], hist[H16:H11].astype(np.uint64)) and not rg[1][1 << 11:].any()
+    assert np.array_equal(rg[2][:1 << 8], hist[H11:H8].astype(np.uint64)) and not rg[2][1 << 8:].any()
+    assert np.array_equal(rg[3][:2], hist[H8:H8 + 2].astype(np.uint64)) and not rg[3][2:].any()

@@ -9,6 +9,16 @@
 
 using namespace tmx;
 
+static char g_chain[64] = "mocha-4";  // chain id of the circuits the tests simulate
+extern "C" void hostsim_set_chain(const char* c) { strncpy(g_chain, c, 50); g_chain[50] = 0; }
+static const uint64_t* g_plan = nullptr;
+static size_t g_plan_rows = 0;
+extern "C" void hostsim_set_plan(const uint64_t* k, size_t rows) { g_plan = k; g_plan_rows = rows; }
+namespace tmx {
+uint64_t logic_const_value(int kc, size_t row, AirShape) { return g_plan ? g_plan[(size_t)kc * g_plan_rows + row] : 0; }
+gl2 logic_public_terms(AirShape, uint64_t, const uint8_t*, const uint8_t*, gl2, gl2) { return gl2_from(0); }
+}
+
 static unsigned log2u(uint32_t x) {
     unsigned k = 0;
     while ((1u << k) < x) k++;
@@ -131,7 +141,7 @@ static BusPassArgs pass_args(uint32_t kind, uint32_t n_max, const uint64_t* trac
     BusPassArgs a;
     memset(&a, 0, sizeof a);
     a.trace = trace; a.kconst = consts; a.per = periodic; a.n = n; a.P = (int)P;
-    a.shape = AirShape{kind, n_max};
+    a.shape = air_shape(kind, n_max, g_chain, strlen(g_chain));
     return a;
 }
 
@@ -178,7 +188,7 @@ extern "C" void hostsim_quotient(uint32_t kind, uint32_t n_max, int table, const
     qa.lde_m = lde_m; qa.lde_k = lde_k; qa.lde_a = lde_a;
     qa.m = n << 1; qa.log_m = log_n + 1; qa.rate_bits = 1;
     qa.pertab = tab.data(); qa.P = (int)P;
-    qa.shape = AirShape{kind, n_max};
+    qa.shape = air_shape(kind, n_max, g_chain, strlen(g_chain));
     qa.alpha[0] = alpha[0]; qa.alpha[1] = alpha[1];
     qa.beta = gl2_make(beta[0], beta[1]); qa.gamma = gl2_make(gamma[0], gamma[1]);
     qa.s_over_n = gl2_scale(gl2_make(total[0], total[1]), gl_inv((gl)n));
