@@ -330,6 +330,21 @@ def _blob_shape(blob):
     return int(kind), int(n_max)
 
 
+def cheat_next_proof(skip_precheck=False, patches=()):
+    """Test hooks for the NEXT prove() on this thread: skip the statement pre-check, and / or add deltas to trace cells after all
+    witness generation.  patches: iterable of (table, col, row, delta)."""
+    if skip_precheck:
+        lib().tm_debug_skip_precheck_next_proof()
+    patches = list(patches)
+    if patches:
+        n = len(patches)
+        tabs = (ctypes.c_int * n)(*[p[0] for p in patches])
+        cols = (ctypes.c_size_t * n)(*[p[1] for p in patches])
+        rows = (ctypes.c_size_t * n)(*[p[2] for p in patches])
+        deltas = (ctypes.c_uint64 * n)(*[p[3] % P for p in patches])
+        lib().tm_debug_patch_next_proof(ctypes.c_int(n), tabs, cols, rows, deltas)
+
+
 def prove(public_input, blob, chain_id, skip_max=100800, logic_trace=None):
     """CPU oracle prover.  Returns (status, proof as uint64 array or None, output32 or None)."""
     kind, n_max = _blob_shape(blob)

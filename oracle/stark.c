@@ -731,6 +731,18 @@ void tm_debug_corrupt_next_proof(int table, size_t col, size_t row) {
     g_corrupt.col = col;
     g_corrupt.row = row;
 }
+/* debug / test hook: the NEXT tm_prove() on this thread adds deltas[i] to cell (cols[i], rows[i]) of tables[i] after ALL witness
+ * generation (range-table multiplicities included), up to 16 cells: a prover that commits to a chosen invalid witness */
+static _Thread_local struct { int n, table[16]; size_t col[16], row[16]; uint64_t delta[16]; } g_patch;
+void tm_debug_patch_next_proof(int n, const int *tables, const size_t *cols, const size_t *rows, const uint64_t *deltas) {
+    g_patch.n = n > 16 ? 16 : n;
+    for (int i = 0; i < g_patch.n; i++) {
+        g_patch.table[i] = tables[i];
+        g_patch.col[i] = cols[i];
+        g_patch.row[i] = rows[i];
+        g_patch.delta[i] = deltas[i] % GL_P;
+    }
+}
 /* debug / test hook: the NEXT tm_prove() on this thread skips the statement pre-check (verify_skip / verify_step on the
  * inputs), i.e. it plays a prover that tries to prove a false statement with otherwise honest tables */
 static _Thread_local int g_skip_precheck;
@@ -826,6 +838,14 @@ int tm_prove(const void *circuit, const uint8_t *input, size_t input_len, const 
         }
         g_corrupt.active = 0;
     }
+    for (int i = 0; i < g_patch.n; i++) {
+        trace_t *t = &tr[g_patch.table[i]];
+        if (t->data) {
+            uint64_t *cell = &t->data[(g_patch.col[i] % t->n_cols) * t->n_rows + g_patch.row[i] % t->n_rows];
+            *cell = gl_add(*cell, g_patch.delta[i]);
+        }
+    }
+    g_patch.n = 0;
     challenger_t ch;
     transcript_init(&ch, c, input, input_len, out32);
     wbuf_t w = {0};

@@ -71,6 +71,32 @@ def test_unsat_reports_the_failing_check(ctx):
     circuit.close()
 
 
+def test_gpu_prover_without_the_precheck_cannot_prove_false_statements(ctx, oracle, monkeypatch):
+    """check_statement is a pre-check only: with it switched off (TMX_DEBUG_NO_PRECHECK) the GPU prover happily emits proofs for
+    doctored inputs -- a claimed output header of its choosing, a dropped validator, a bad signature -- and both verifiers
+    reject every one of them; the honest proof from the same prover object still verifies."""
+    import tendermintx_b200 as tmx
+
+    c = _cases()["skip_10000_10500_n4"]
+    pub, blob = bytes.fromhex(c["input"]), bytes.fromhex(c["blob"])
+    circuit = tmx.Circuit.build(ctx, tmx.KIND_SKIP, 4, tmx.Mocha4Config)
+    monkeypatch.setenv("TMX_DEBUG_NO_PRECHECK", "1")
+    cheats = []
+    b = bytearray(blob); b[32 + 5] ^= 1; cheats.append((pub, bytes(b)))                      # another output header
+    b = bytearray(blob); b[920 + 32 + 3] ^= 0x40; cheats.append((pub, bytes(b)))             # bad signature
+    b = bytearray(blob); b[12:16] = (int.from_bytes(b[12:16], "little") - 1).to_bytes(4, "little"); cheats.append((pub, bytes(b)))
+    bp = bytearray(pub); bp[10] ^= 1; cheats.append((bytes(bp), blob))                       # another trusted header
+    for p, bl in cheats:
+        proof, out = circuit.prove(p, bl)
+        with pytest.raises(tmx.TmxError):
+            circuit.verify(proof, p, out)
+        assert oracle.verify_proof(np.frombuffer(proof, dtype=np.uint64), p, "mocha-4", 1, 4, out) != 0
+    proof, out = circuit.prove(pub, blob)
+    circuit.verify(proof, pub, out)
+    monkeypatch.delenv("TMX_DEBUG_NO_PRECHECK")
+    circuit.close()
+
+
 def test_synthetic_celestia_skip_n16(ctx, oracle):
     import tendermintx_b200 as tmx
     from oracle import tm_inputs as ti
