@@ -76,7 +76,7 @@ def test_device_poseidon_fast_path_matches_plain_and_oracle_on_host():
         assert np.array_equal(b[i], oracle.poseidon_permute(s))
 
 
-def test_compiled_constraints_equal_the_artefact_dag_on_random_rows(oracle):
+def test_build_artefact_is_reproduced_by_the_oracle(oracle):
     """One definition, two evaluators: the product's verifier evaluates the AIR templates compiled for the extension field, the
     build artefact carries the same constraints as a DAG (obtained by running the templates on symbolic values) which the oracle
     interprets.  A proof made by the oracle from the DAG must satisfy the compiled constraints (tests/test_prove_cpu.py); here
@@ -90,6 +90,6 @@ def test_compiled_constraints_equal_the_artefact_dag_on_random_rows(oracle):
         dims = tmx.Context.trace_dims(kind, n_max)
         for t in range(3):
             assert shapes[t][0] == 1 and (1 << shapes[t][1], shapes[t][2]) == tuple(dims[t])
-        assert shapes[oracle.T_RANGE][:3] == (1, 16, 3)
+        assert shapes[oracle.T_RANGE][:3] == (1, 16, 4) and shapes[oracle.T_LOGIC][0] == 1
         # every table declares at least one bus interaction and the Ed25519 table range-checks all 14 x 63 gadget cells
         assert shapes[oracle.T_ED][6] == 14 * 63 // 2 + 2
