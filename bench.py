@@ -4,10 +4,12 @@ LDE roofline and the CPU oracle timed beside it.
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one complete skip proof (witness tables -> commitments -> quotients -> FRI -> proof bytes) of the
-synthetic 128-validator celestia chain committed under tests/golden/celestia (seed = rank, so ranks prove
-independent statements: weak scaling, no data-path collective; the only collective is the NCCL broadcast of the
-circuit artefact at start-up).  Prints ONE JSON line (rank 0).
+One "step" = one complete skip proof of the synthetic 128-validator celestia chain committed under tests/golden/celestia:
+witness tables (SHA-256, SHA-512, Ed25519 on the GPU; the small logic table on the host), first commitment round, bus
+challenges, second commitment round (helper columns + running sums of the logUp bus), then per table quotient -> openings ->
+FRI -> queries -> proof bytes.  The proof binds the whole verify_skip statement.  seed = rank, so ranks
+prove independent statements: weak scaling, no data-path collective; the only collective is the NCCL broadcast of the circuit
+artefact (constraint DAG + constant columns and their commitments) at start-up.  Prints ONE JSON line (rank 0).
 """
 import argparse
 import ctypes
@@ -24,15 +26,20 @@ sys.path.insert(0, ROOT)
 
 N_MAX = 128
 # dram__bytes_read.sum + dram__bytes_write.sum of the six ntt_pass_kernel launches that make up the LDE of the Ed25519
-# table, from profiles/r1e_ncu_ntt.raw.csv (one ncu --set full capture, per LDE).  The capture was taken when the table
-# had 1217 columns (7,383,291,392 bytes); the carry packing of the last commit of the round narrowed it to 945 and
-# left the kernel untouched.  Every pass moves every column exactly once, so the figure is scaled by 945 / 1217 until
-# the capture is retaken (first item of the next round).
-NCU_K1_TRAFFIC_BYTES = 7383291392 * 945 // 1217
+# table's first-round trace (982 columns x 2^15 rows), one ncu --set full capture of the shipped configuration:
+# profiles/r2c_ncu_ntt.raw.csv (tools/gpu_ncu.sh).
+NCU_K1_TRAFFIC_BYTES = 2985000000
 NCU_K2_WARP_INSTR_PER_PERM = 14.21e9 / 20.05e6  # = 709 (22.7 k thread instructions per permutation)
 METRIC = "skip proofs/hour (CelestiaConfig, 128 val)"
 UNIT = "proofs/hour"
 WORKLOAD = "skip circuit CelestiaConfig VALIDATOR_SET_SIZE_MAX=128 (synthetic celestia chain, 128 signers, seed=rank)"
+
+
+def common_config(in_flight=None):
+    """`config` is the same object in both arms (the driver compares them); arm-specific details go under `arm`."""
+    return {"workload": WORKLOAD, "circuit": "skip", "n_max": N_MAX, "chain_id": "celestia",
+            "statement": "verify_skip, fully bound by the proof (five tables on a logUp bus, public-input terms)",
+            "l2": "working set per proof (traces + LDEs, about 3 GB) is far larger than the 126 MB L2; no flush needed"}
 
 
 def load_case(seed):
@@ -133,6 +140,13 @@ def _run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # the CPU arm is built for THIS host (-march=native) when a compiler is there; the shipped library targets x86-64-v3
+    try:
+        subprocess.check_call(["make", "-B", "-C", os.path.join(ROOT, "oracle"), "-s", "native"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        os.environ["TMX_ORACLE_LIB"] = os.path.join(ROOT, "oracle", "_build", "liboracle_native.so")
+        native = True
+    except Exception:
+        native = False
     import oracle
     from oracle import tm_inputs as ti
 
@@ -155,7 +169,9 @@ def _run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times), "warmup": 0,
         "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (Goldilocks)",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "prover": "CPU oracle (restatement of the plonky2-style pipeline), OpenMP"},
+        "data": "synthetic", "config": common_config(),
+        "arm": {"prover": "CPU oracle (restatement of the plonky2-style pipeline; constraints interpreted from the build artefact), OpenMP",
+                "march_native": native},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{len(times)} full proof(s) of the workload (bounded to ~{int(budget_s)} s)"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -240,8 +256,10 @@ def run_ours(args):
     launches0 = ctx.launch_count()
     phase = [[0.0, 0.0] for _ in range(3)]  # per table: LDE (K1) and trace Merkle (K2) device ms summed over the proofs
 
+    lat_steps = min(args.steps, 20)
+
     def one_at_a_time():
-        for _ in range(args.steps):
+        for _ in range(lat_steps):
             circuit.prove(pub, None)
             for t, (a, b) in enumerate(circuit.last_phase_ms()):  # CUDA events recorded by the prover on its stream
                 phase[t][0] += a
@@ -277,10 +295,10 @@ def run_ours(args):
     # the Ed25519 table is 62 % of the committed cells and its LDE runs alone on the GPU (the SHA-256 table's LDE shares
     # the SMs with the Ed25519 ladders of the side stream): roofline.achieved is quoted on it, the all-tables figure beside it
     alg_bytes = 8 * dims[2][0] * dims[2][1] * 3
-    lde_ms = phase[2][0] / args.steps
+    lde_ms = phase[2][0] / lat_steps
     alg_bytes_all = sum(8 * rows * cols * 3 for rows, cols in dims)
-    lde_ms_all = sum(p[0] for p in phase) / args.steps
-    merkle_ms = sum(p[1] for p in phase) / args.steps
+    lde_ms_all = sum(p[0] for p in phase) / lat_steps
+    merkle_ms = sum(p[1] for p in phase) / lat_steps
     achieved = alg_bytes / (lde_ms / 1e3) / 1e9
     perms = sum((rows * 2) * ((cols + 7) // 8) + rows * 2 for rows, cols in dims)  # leaf sponges + inner nodes
     # the kernel-level entry points on the largest table alone (isolated launches, for comparison with the ncu captures)
@@ -318,14 +336,15 @@ def run_ours(args):
         cpu_s = time.perf_counter() - t0
         same = status == "OK" and np.array_equal(np.frombuffer(proof, dtype=np.uint64), want)
         cpu = {"value": 3600.0 / cpu_s, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-               "sample": "1 full proof of the workload by the CPU oracle prover (OpenMP, all cores)",
+               "sample": "1 full proof of the workload by the CPU oracle prover (OpenMP, all cores; x86-64-v3 build, the reference arm "
+                         "rebuilds with -march=native)",
                "proof_bytes_equal_gpu": bool(same)}
     # second roofline line SURVEY 8(d) asks for: K2 is bound by integer issue, not HBM.  Warp instructions per
     # permutation are from the ncu capture of leaf_hash_kernel (profiles/r1e_ncu_leaf_hash.raw.csv: 14.21 G warp
     # instructions for 20.05 M permutations); the time is the Ed25519 table's Merkle phase measured inside the timed proofs.
     clk = clocks.summary()
     ed_perms = (dims[2][0] * 2) * ((dims[2][1] + 7) // 8) + dims[2][0] * 2
-    k2_ed_ms = phase[2][1] / args.steps
+    k2_ed_ms = phase[2][1] / lat_steps
     k2_winstr = ed_perms * NCU_K2_WARP_INSTR_PER_PERM
     issue_peak = 148 * 4 * (clk.get("sm_mhz") or clk.get("sm_max_mhz") or 1965.0) * 1e6 / 1e9
     k2_issue = {"kernel": "leaf_hash_kernel + merkle_level_kernel of the Ed25519 table", "unit": "G warp-instructions/s",
@@ -337,34 +356,34 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64 (Goldilocks field, bytes/bits in the witness kernels)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "tables": {"sha256": dims[0], "sha512": dims[1], "ed25519": dims[2]},
-                   "in_flight": args.in_flight,
-                   "in_flight_note": "independent proofs; each prover has its own stream and buffers, the Fiat-Shamir host round "
-                                     "trips of one proof are filled by the kernels of the others (ProverPool)",
-                   "l2": "working set per proof (traces + LDEs, about 4 GB) is far larger than the 126 MB L2; no flush needed",
-                   "parallelism": f"{world} GPU(s), one rank per GPU, {args.in_flight} independent proofs in flight per GPU",
-                   "host_input_assembly_ms": assemble_ms},
+        "config": common_config(),
+        "arm": {"tables": {n: list(circuit.table_shape(t)) for t, n in enumerate(["sha256", "sha512", "ed25519", "logic", "range"])},
+                "tables_note": "[rows, first-round columns, constant columns, second-round columns] per table",
+                "in_flight": args.in_flight,
+                "in_flight_note": "independent proofs; each prover has its own stream and buffers, the Fiat-Shamir host round "
+                                  "trips of one proof are filled by the kernels of the others (ProverPool)",
+                "parallelism": f"{world} GPU(s), one rank per GPU, {args.in_flight} independent proofs in flight per GPU",
+                "host_input_assembly_ms": assemble_ms},
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": len(blob), "d2h_bytes_per_step": len(proof) + 224 + N_MAX,
                 "ms_per_step": e2e_ms / args.steps},
-        "one_proof_at_a_time": {"ms_per_proof": lat_ms / args.steps, "proofs_per_hour": world * args.steps / (lat_ms / 1e3) * 3600.0,
-                                "gpu_launches_per_proof": launches / args.steps},
+        "one_proof_at_a_time": {"ms_per_proof": lat_ms / lat_steps, "proofs_per_hour": world * lat_steps / (lat_ms / 1e3) * 3600.0,
+                                "gpu_launches_per_proof": launches / lat_steps, "proofs": lat_steps},
         "gpu_launches": launches_value,
-        "roofline": {"bound": "hbm", "kernel": "ntt_pass_kernel family (K1: iNTT + coset LDE, rate 1/2, of the Ed25519 trace table, 945 x 2^16, "
+        "roofline": {"bound": "hbm", "kernel": "ntt_pass_kernel family (K1: iNTT + coset LDE, rate 1/2, of the Ed25519 table's first-round trace, 982 x 2^15, "
                      "six launches per proof, CUDA events recorded by the prover inside the timed proofs)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_K1_TRAFFIC_BYTES, "traffic_note": "dram read+write of the six K1 launches of the Ed25519 table, "
-                     "ncu --set full (profiles/r1e_ncu_ntt.raw.csv), per proof like achieved; captured at 1217 columns and scaled "
-                     "by 945/1217 (same kernel, every pass moves every column once); re-capture pending",
+                     "ncu --set full on the shipped configuration (profiles/r2c_ncu_ntt.raw.csv), per proof like achieved",
                      "peak_source": peak_src, "algorithmic_bytes": alg_bytes, "ms": lde_ms,
-                     "ms_per_table": [p[0] / args.steps for p in phase],
+                     "ms_per_table": [p[0] / lat_steps for p in phase],
                      "all_tables": {"algorithmic_bytes": alg_bytes_all, "ms": lde_ms_all,
                                     "achieved": alg_bytes_all / (lde_ms_all / 1e3) / 1e9},
-                     "share_of_step": lde_ms_all / (lat_ms / args.steps),
+                     "share_of_step": lde_ms_all / (lat_ms / lat_steps),
                      "note": "K1 is bound by 64-bit modular-arithmetic issue and tile-load latency (ncu: ALU pipe ~70 % busy, DRAM ~20 %), so the HBM "
                              "fraction is low by construction; see DESIGN.md section 4"},
         "kernels": {"k2_poseidon_merkle_ms_per_proof": merkle_ms, "k2_Mperm_per_s": perms / merkle_ms / 1e3,
-                    "k2_ms_per_table": [p[1] / args.steps for p in phase],
-                    "k2_share_of_step": merkle_ms / (lat_ms / args.steps),
+                    "k2_ms_per_table": [p[1] / lat_steps for p in phase],
+                    "k2_share_of_step": merkle_ms / (lat_ms / lat_steps),
                     "k2_note": "dominant kernel by time; bound by integer issue (ncu: < 1 % DRAM, busiest pipe 84 %), 22.7 k instructions per permutation",
                     "k2_int_issue_roofline": k2_issue,
                     "isolated_ed25519_table": {"lde_ms": iso[0], "lde_GBps": 8 * rows * cols * 3 / iso[0] / 1e6,
@@ -381,7 +400,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=200, help="proofs in each timed region (200 = a little over ten seconds)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -27,7 +27,8 @@ struct tmx_circuit {
     std::shared_ptr<const CircuitDef> def;  // table shapes, constant columns, constraint DAG, digest
     // device state reused across proofs
     gl* d_trace[3] = {nullptr, nullptr, nullptr};
-    uint8_t* d_blob = nullptr;
+    uint8_t* d_blob = nullptr;          // resident inputs (tmx_circuit_set_inputs)
+    uint8_t* d_blob_job = nullptr;      // inputs of a proof that brings its own blob: the resident copy stays valid
     uint8_t* d_aux = nullptr;
     void* d_points = nullptr;           // Ed25519 slot info + accumulators (phase 1 -> phase 2)
     // logic table: filled on the host from the inputs and the slot infos of the sequential Ed25519 phase
@@ -203,6 +204,7 @@ extern "C" int tmx_circuit_build(tmx_ctx* ctx, uint32_t kind, uint32_t n_max, co
         if (e != cudaSuccess) return fail(TMX_E_CUDA, std::string("tmx_circuit_build: cudaMalloc: ") + cudaGetErrorString(e));
     }
     if (cudaMalloc((void**)&c->d_blob, TMX_BLOB_SIZE(kind, n_max)) != cudaSuccess ||
+        cudaMalloc((void**)&c->d_blob_job, TMX_BLOB_SIZE(kind, n_max)) != cudaSuccess ||
         cudaMalloc((void**)&c->d_aux, aux_bytes(n_max)) != cudaSuccess ||
         cudaMalloc(&c->d_points, witness_points_bytes(n_max)) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess ||
@@ -230,6 +232,7 @@ extern "C" void tmx_circuit_free(tmx_circuit* c) {
     for (int t = 0; t < 3; t++)
         if (c->d_trace[t]) cudaFree(c->d_trace[t]);
     if (c->d_blob) cudaFree(c->d_blob);
+    if (c->d_blob_job) cudaFree(c->d_blob_job);
     if (c->d_aux) cudaFree(c->d_aux);
     if (c->d_points) cudaFree(c->d_points);
     if (c->h_slots) cudaFreeHost(c->h_slots);
@@ -338,14 +341,15 @@ extern "C" int tmx_prove(tmx_circuit* c, const uint8_t* input, size_t input_len,
     cudaStream_t st = ctx->stream;
     Prover& pr = c->prover;
     // ---- witness generation on the GPU ----
+    const uint8_t* d_blob = c->d_blob;
     if (!use_resident) {
-        TMX_CUDA(cudaMemcpyAsync(c->d_blob, blob, blob_len, cudaMemcpyHostToDevice, st));
-        c->resident = false;
+        TMX_CUDA(cudaMemcpyAsync(c->d_blob_job, blob, blob_len, cudaMemcpyHostToDevice, st));
+        d_blob = c->d_blob_job;
     }
     TMX_CUDA(cudaMemsetAsync(c->d_aux, 0, aux_bytes(c->n_max), st));
     TMX_CUDA(cudaMemsetAsync(pr.d_hist, 0, (BUS_HIST_SIZE + 4) * sizeof(unsigned int), st));
     WitnessArgs wa;
-    int rc = witness_make_args(ctx, c->d_blob, c->kind, c->n_max, c->d_trace[0], c->d_trace[1], c->d_trace[2], c->d_aux, &wa);
+    int rc = witness_make_args(ctx, d_blob, c->kind, c->n_max, c->d_trace[0], c->d_trace[1], c->d_trace[2], c->d_aux, &wa);
     if (rc) return rc;
     // side stream: the sequential Ed25519 rows (one thread per validator slot, milliseconds of latency) run next to the
     // SHA-256 table's witness generation and commitment

@@ -1,6 +1,7 @@
 // tmx_ctx lifetime, error reporting, twiddle / power tables, Poseidon round-constant generation.
 #include "ctx.cuh"
 #include "poseidon.cuh"
+#include <mutex>
 #include <cstring>
 
 namespace tmx {
@@ -39,8 +40,7 @@ static void chacha8(const uint32_t key[8], uint64_t counter, uint32_t out[16]) {
     for (int i = 0; i < 16; i++) out[i] = x[i] + in[i];
 }
 
-void poseidon_generate_constants() {
-    if (g_rc_ready) return;
+static void poseidon_generate_constants_once() {
     uint64_t st = 0;
     uint32_t key[8];
     for (int i = 0; i < 8; i++) {
@@ -66,6 +66,11 @@ void poseidon_generate_constants() {
         if ((uint64_t)m <= GL_P - 1) h_poseidon_rc[n++] = (gl)(m >> 64);
     }
     g_rc_ready = true;
+}
+// tmx_verify_params may be the first caller on several threads at once: the table is written exactly once
+void poseidon_generate_constants() {
+    static std::once_flag once;
+    std::call_once(once, poseidon_generate_constants_once);
 }
 
 // ---- device tables ----

@@ -36,6 +36,7 @@ struct tmx_pool {
     std::deque<std::shared_ptr<Job>> queue;
     std::map<uint64_t, std::shared_ptr<Job>> jobs;
     uint64_t next_ticket = 1;
+    unsigned in_progress = 0;  // jobs a worker has taken off the queue and is still proving
     bool stop = false;
 
     void run(size_t k) {
@@ -47,6 +48,7 @@ struct tmx_pool {
                 if (queue.empty()) return;  // stop requested and nothing left
                 j = queue.front();
                 queue.pop_front();
+                in_progress++;
             }
             j->rc = tmx_prove(circuits[k], j->input.data(), j->input.size(), j->resident ? nullptr : j->blob.data(),
                               j->resident ? 0 : j->blob.size(), &j->proof, j->out);
@@ -57,6 +59,7 @@ struct tmx_pool {
             {
                 std::lock_guard<std::mutex> lk(m);
                 j->done = true;
+                in_progress--;
             }
             cv_done.notify_all();
         }
@@ -120,13 +123,16 @@ extern "C" int tmx_pool_create_from_artefact(int device, const char* path, unsig
 
 extern "C" int tmx_pool_set_inputs(tmx_pool* p, const uint8_t* blob, size_t blob_len) {
     if (!p || !blob) return fail(TMX_E_INPUT, "tmx_pool_set_inputs: NULL argument");
-    std::lock_guard<std::mutex> lk(p->m);
-    if (!p->queue.empty()) return fail(TMX_E_INPUT, "tmx_pool_set_inputs: proofs are still queued");
+    // the resident inputs are read by every proof that runs from them: replace them only while the pool is idle (nothing
+    // queued AND nothing being proved), and keep the lock so that no worker can start in the middle
+    std::unique_lock<std::mutex> lk(p->m);
+    p->cv_done.wait(lk, [&] { return p->queue.empty() && p->in_progress == 0; });
+    int first_rc = TMX_OK;
     for (tmx_circuit* c : p->circuits) {
-        int rc = tmx_circuit_set_inputs(c, blob, blob_len);
-        if (rc) return rc;
+        const int rc = tmx_circuit_set_inputs(c, blob, blob_len);
+        if (rc && !first_rc) first_rc = rc;  // sizes are checked before anything is copied: all circuits fail alike
     }
-    return TMX_OK;
+    return first_rc;
 }
 
 extern "C" int tmx_pool_submit(tmx_pool* p, const uint8_t* input, size_t input_len, const uint8_t* blob, size_t blob_len,

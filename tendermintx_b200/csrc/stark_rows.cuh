@@ -85,6 +85,7 @@ TMX_HD void bus_gen_row(const BusPassArgs& a, size_t r) {
     NullEmit emit;
     BusGen bus(a.beta, a.gamma, a.aux + r, a.n);
     air_eval_any<FB>(TABLE, a.shape, l, n, k, per, emit, bus);
+    bus.flush();
     a.rowsum[r] = bus.sum;
 }
 // histogram of the table's range lookups
