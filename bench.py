@@ -28,7 +28,8 @@ N_MAX = 128
 # dram__bytes_read.sum + dram__bytes_write.sum of the six ntt_pass_kernel launches that make up the LDE of the Ed25519
 # table's first-round trace (982 columns x 2^15 rows), one ncu --set full capture of the shipped configuration:
 # profiles/r2c_ncu_ntt.raw.csv (tools/gpu_ncu.sh).
-NCU_K1_TRAFFIC_BYTES = 2985000000
+NCU_K1_TRAFFIC_BYTES = 2813383936
+NCU_K1_WARP_INSTR = 1218528448  # smsp__inst_executed.sum over the same six launches (1212 thread instructions per trace cell)
 NCU_K2_WARP_INSTR_PER_PERM = 14.21e9 / 20.05e6  # = 709 (22.7 k thread instructions per permutation)
 METRIC = "skip proofs/hour (CelestiaConfig, 128 val)"
 UNIT = "proofs/hour"
@@ -379,7 +380,12 @@ def run_ours(args):
                      "all_tables": {"algorithmic_bytes": alg_bytes_all, "ms": lde_ms_all,
                                     "achieved": alg_bytes_all / (lde_ms_all / 1e3) / 1e9},
                      "share_of_step": lde_ms_all / (lat_ms / lat_steps),
-                     "note": "K1 is bound by 64-bit modular-arithmetic issue and tile-load latency (ncu: ALU pipe ~70 % busy, DRAM ~20 %), so the HBM "
+                     "issue_roofline": {"unit": "G warp-instructions/s", "achieved": NCU_K1_WARP_INSTR / (lde_ms / 1e3) / 1e9, "peak": issue_peak,
+                                        "frac": NCU_K1_WARP_INSTR / (lde_ms / 1e3) / 1e9 / issue_peak,
+                                        "note": "a rate-1/2 LDE is 45 butterfly sweeps per trace cell (iNTT + two coset NTTs of 15 stages); at 27 "
+                                                "instructions per cell and sweep the instruction-issue floor of this chip is 1.05 ms for this table, "
+                                                "i.e. 11 % of the HBM roofline is the ceiling of ANY radix-2 formulation with canonical 64-bit arithmetic"},
+                     "note": "K1 is bound by 64-bit modular-arithmetic issue (ncu: ALU pipe 70-79 % busy, issue slots 59-68 %, DRAM 25 %), so the HBM "
                              "fraction is low by construction; see DESIGN.md section 4"},
         "kernels": {"k2_poseidon_merkle_ms_per_proof": merkle_ms, "k2_Mperm_per_s": perms / merkle_ms / 1e3,
                     "k2_ms_per_table": [p[1] / lat_steps for p in phase],
