@@ -169,14 +169,33 @@ def _full_size_roundtrip(ctx, kind_name, name, n_max):
     return proof
 
 
-def test_full_size_step_n128_celestia(ctx):
-    """BASELINE config 3: step circuit, VALIDATOR_SET_SIZE_MAX = 128, consecutive headers."""
-    _full_size_roundtrip(ctx, "step", "step_n128_seed0", 128)
+def _oracle_bytes_equal(oracle, kind_name, name, n_max, proof):
+    """the same statement proved by the CPU oracle: identical bytes"""
+    from oracle import tm_inputs as ti
+
+    path, idx = _celestia_case(name)
+    th = bytes.fromhex(idx["trusted_hash"])
+    src = ti.FixtureSource(path)
+    if kind_name == "skip":
+        blob, pub = ti.skip_inputs(src, n_max, idx["trusted"], th, idx["target"]), ti.skip_public_input(idx["trusted"], th, idx["target"])
+    else:
+        blob, pub = ti.step_inputs(src, n_max, idx["trusted"], th), idx["trusted"].to_bytes(8, "big") + th
+    status, want, want_out = oracle.prove(pub, blob, "celestia")
+    assert status == "OK" and want_out.hex() == idx["target_hash"]
+    got = np.frombuffer(proof, dtype=np.uint64)
+    assert got.size == want.size and np.array_equal(got, want), f"first differing word {_first_diff(got, want)} of {want.size}"
 
 
-def test_full_size_skip_n256(ctx):
-    """BASELINE config 4: skip circuit, VALIDATOR_SET_SIZE_MAX = 256 (dYdX-class validator set)."""
-    _full_size_roundtrip(ctx, "skip", "skip_n256_seed0", 256)
+def test_full_size_step_n128_celestia(ctx, oracle):
+    """BASELINE config 3: step circuit, VALIDATOR_SET_SIZE_MAX = 128, consecutive headers; bytes equal to the CPU oracle's."""
+    proof = _full_size_roundtrip(ctx, "step", "step_n128_seed0", 128)
+    _oracle_bytes_equal(oracle, "step", "step_n128_seed0", 128, proof)
+
+
+def test_full_size_skip_n256(ctx, oracle):
+    """BASELINE config 4: skip circuit, VALIDATOR_SET_SIZE_MAX = 256 (dYdX-class validator set); bytes equal to the CPU oracle's."""
+    proof = _full_size_roundtrip(ctx, "skip", "skip_n256_seed0", 256)
+    _oracle_bytes_equal(oracle, "skip", "skip_n256_seed0", 256, proof)
 
 
 def test_skip_n128_proof_bytes_equal_oracle(ctx, oracle):

@@ -57,6 +57,18 @@ def test_witness_tables_synthetic_non_pow2_and_round(ctx, oracle):
     assert aux[224:224 + 12].all()
 
 
+@pytest.mark.parametrize("name", ["skip_3000_3100_n4", "skip_10000_10500_n32"])
+def test_gpu_tables_encode_the_specified_computations(ctx, name):
+    """The tables the KERNELS write, read against FIPS 180-4 / RFC 8032 by the independent checker (tests/spec_checker.py)."""
+    from test_trace_semantics import check_tables
+
+    c = _cases()[name]
+    blob = bytes.fromhex(c["blob"])
+    kind, n_max = struct.unpack_from("<II", blob, 4)
+    tabs, _ = ctx.witness_generate(blob, kind, n_max)
+    check_tables([t.cpu().numpy().view(np.uint64) for t in tabs], blob)
+
+
 def test_bad_signature_is_flagged(ctx, oracle):
     c = _cases()["skip_10000_10500_n4"]
     blob = bytearray.fromhex(c["blob"])
