@@ -137,6 +137,13 @@ int tmx_circuit_load(tmx_ctx *ctx, const char *path, tmx_circuit **out);
  * their commitment, digest): returns the word count and copies at most `cap` words to `out` (may be NULL). */
 size_t tmx_circuit_artefact(uint32_t kind, uint32_t n_max, const char *chain_id, size_t chain_id_len, uint64_t skip_max,
                             uint64_t *out, size_t cap);
+/* The logic table (TMX_T_LOGIC: every plain-gate gadget of verify_skip / verify_step, one gadget instance per row) of one
+ * proof, computed on the host: this is the code tmx_prove runs while the GPU commits the hash tables.  Returns the number of
+ * u64 cells ([columns][rows], column-major) and copies at most `cap` of them; *status = 0 or the id of the first failing
+ * check (tmx_last_check numbering); with `force` the table is completed past a failing check (adversarial tests commit to
+ * such tables; tmx_verify must reject the proofs). */
+size_t tmx_logic_trace(uint32_t kind, uint32_t n_max, const char *chain_id, size_t chain_id_len, const uint8_t *input,
+                       const uint8_t *blob, int force, uint64_t *out, size_t cap, int *status);
 /* shape of table t (TMX_T_* in tmx_trace.h): {rows, first-round columns, constant columns, second-round columns}; rows = 0
  * when the table is absent from the circuit */
 int tmx_circuit_table_shape(const tmx_circuit *circuit, int table, size_t out[4]);

@@ -177,6 +177,21 @@ def verify_proof(kind, n_max, config, proof, public_input, output):
                                    public_input, len(public_input), output))
 
 
+def logic_trace(kind, n_max, config, public_input, blob, force=False):
+    """The logic table (every plain-gate gadget of verify_skip / verify_step, one instance per row) of one proof, filled on
+    the host exactly as tmx_prove does.  Returns (cells as a flat u64 list in [column][row] order, status): status is 0 or
+    the id of the first failing check; with `force` the table is completed past it."""
+    public_input, blob = bytes(public_input), bytes(blob)
+    st = ctypes.c_int(0)
+    args = (kind, n_max, config.chain_id, len(config.chain_id), public_input, blob, int(force))
+    cells = lib().tmx_logic_trace(*args, None, 0, ctypes.byref(st))
+    if cells == 0:
+        raise TmxError(lib().tmx_last_error().decode() or "this circuit has no logic table")
+    out = (ctypes.c_uint64 * cells)()
+    lib().tmx_logic_trace(*args, out, cells, ctypes.byref(st))
+    return out, st.value
+
+
 def blob_size(kind, n_max):
     return 920 + 240 * n_max + (48 * n_max if kind == KIND_SKIP else 0)
 

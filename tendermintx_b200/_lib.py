@@ -61,6 +61,7 @@ def load():
         "tmx_fri_fold": (i32, [vp, u64p, u32, c.c_uint64, vp, u64p, vp]),
         "tmx_circuit_table_shape": (i32, [vp, i32, c.POINTER(sz)]),
         "tmx_circuit_artefact": (sz, [u32, u32, c.c_char_p, sz, c.c_uint64, vp, sz]),
+        "tmx_logic_trace": (sz, [u32, u32, c.c_char_p, sz, c.c_char_p, c.c_char_p, i32, vp, sz, c.POINTER(c.c_int)]),
         "tmx_pow_grind": (i32, [vp, vp, i32, u32, c.POINTER(c.c_uint64), vp]),
         "tmx_circuit_build": (i32, [vp, u32, u32, c.c_char_p, sz, c.c_uint64, c.POINTER(vp)]),
         "tmx_circuit_free": (None, [vp]),
@@ -103,7 +104,7 @@ EXPORTED_SYMBOLS = [
     "tmx_last_error", "tmx_version", "tmx_ctx_create", "tmx_ctx_destroy", "tmx_ctx_sync",
     "tmx_ctx_stream", "tmx_ctx_launch_count", "tmx_ntt", "tmx_lde", "tmx_merkle_digest_count", "tmx_poseidon_merkle",
     "tmx_poseidon_permute", "tmx_host_poseidon_permute", "tmx_trace_dims", "tmx_witness_aux_bytes", "tmx_sha256_trace", "tmx_ed25519_trace",
-    "tmx_witness_generate", "tmx_sha512_trace", "tmx_quotient", "tmx_bus_aux", "tmx_bus_count", "tmx_fri_fold", "tmx_circuit_table_shape", "tmx_circuit_artefact", "tmx_pow_grind", "tmx_circuit_build", "tmx_circuit_free", "tmx_circuit_digest",
+    "tmx_witness_generate", "tmx_sha512_trace", "tmx_quotient", "tmx_bus_aux", "tmx_bus_count", "tmx_fri_fold", "tmx_circuit_table_shape", "tmx_circuit_artefact", "tmx_logic_trace", "tmx_pow_grind", "tmx_circuit_build", "tmx_circuit_free", "tmx_circuit_digest",
     "tmx_circuit_save", "tmx_circuit_load", "tmx_prove", "tmx_last_check", "tmx_circuit_last_phase_ms", "tmx_circuit_set_inputs", "tmx_header_hash_from_fixture", "tmx_skip_inputs_from_fixture",
     "tmx_step_inputs_from_fixture", "tmx_is_valid_skip_from_fixture", "tmx_find_block_to_request", "tmx_prove_fixture",
     "tmx_pool_create", "tmx_pool_create_from_artefact", "tmx_pool_destroy", "tmx_pool_set_inputs", "tmx_pool_submit", "tmx_pool_wait", "tmx_pool_in_flight",
