@@ -262,14 +262,26 @@ def run_ours(args):
     def one_at_a_time():
         for _ in range(lat_steps):
             circuit.prove(pub, None)
-            for t, (a, b) in enumerate(circuit.last_phase_ms()):  # CUDA events recorded by the prover on its stream
-                phase[t][0] += a
-                phase[t][1] += b
+
+    def one_at_a_time_serial():
+        # TMX_SERIAL_TABLES: the prover commits its tables one after the other on ONE stream (the shipped mode runs them side
+        # by side on five), so the CUDA events it records around the K1 / K2 launches of a table time those kernels alone
+        os.environ["TMX_SERIAL_TABLES"] = "1"
+        try:
+            for _ in range(lat_steps):
+                circuit.prove(pub, None)
+                for t, (a, b) in enumerate(circuit.last_phase_ms()):
+                    phase[t][0] += a
+                    phase[t][1] += b
+        finally:
+            del os.environ["TMX_SERIAL_TABLES"]
 
     with ClockSampler(local_rank) as clocks:
-        # (1) one proof at a time, HBM-resident inputs: per-proof latency and clean per-kernel timings for the roofline
+        # (1) one proof at a time, HBM-resident inputs: per-proof latency
         lat_ms, _ = timed(one_at_a_time)
         launches = ctx.launch_count() - launches0
+        # (1b) the same proofs with the tables serialised: clean per-kernel timings for the roofline
+        serial_ms, _ = timed(one_at_a_time_serial)
         # (2) value: K proofs, `in_flight` provers on this GPU, HBM-resident inputs
         launches1 = pool.launch_count()
         dev_ms, _ = timed(lambda: pool.prove_many([(pub, None)] * args.steps))
@@ -372,14 +384,16 @@ def run_ours(args):
                                 "gpu_launches_per_proof": launches / lat_steps, "proofs": lat_steps},
         "gpu_launches": launches_value,
         "roofline": {"bound": "hbm", "kernel": "ntt_pass_kernel family (K1: iNTT + coset LDE, rate 1/2, of the Ed25519 table's first-round trace, 982 x 2^15, "
-                     "six launches per proof, CUDA events recorded by the prover inside the timed proofs)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "six launches per proof, CUDA events recorded by the prover inside timed proofs)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_K1_TRAFFIC_BYTES, "traffic_note": "dram read+write of the six K1 launches of the Ed25519 table, "
                      "ncu --set full on the shipped configuration (profiles/r2c_ncu_ntt.raw.csv), per proof like achieved",
                      "peak_source": peak_src, "algorithmic_bytes": alg_bytes, "ms": lde_ms,
                      "ms_per_table": [p[0] / lat_steps for p in phase],
                      "all_tables": {"algorithmic_bytes": alg_bytes_all, "ms": lde_ms_all,
                                     "achieved": alg_bytes_all / (lde_ms_all / 1e3) / 1e9},
-                     "share_of_step": lde_ms_all / (lat_ms / lat_steps),
+                     "share_of_step": lde_ms_all / (serial_ms / lat_steps),
+                     "timed_in": f"{lat_steps} proofs proved one at a time with the tables serialised on one stream (TMX_SERIAL_TABLES=1, "
+                                 f"{serial_ms / lat_steps:.1f} ms per proof, same proof bytes); the shipped mode overlaps the tables on five streams",
                      "issue_roofline": {"unit": "G warp-instructions/s", "achieved": NCU_K1_WARP_INSTR / (lde_ms / 1e3) / 1e9, "peak": issue_peak,
                                         "frac": NCU_K1_WARP_INSTR / (lde_ms / 1e3) / 1e9 / issue_peak,
                                         "note": "a rate-1/2 LDE is 45 butterfly sweeps per trace cell (iNTT + two coset NTTs of 15 stages); at 27 "
@@ -389,7 +403,7 @@ def run_ours(args):
                              "fraction is low by construction; see DESIGN.md section 4"},
         "kernels": {"k2_poseidon_merkle_ms_per_proof": merkle_ms, "k2_Mperm_per_s": perms / merkle_ms / 1e3,
                     "k2_ms_per_table": [p[1] / lat_steps for p in phase],
-                    "k2_share_of_step": merkle_ms / (lat_ms / lat_steps),
+                    "k2_share_of_step": merkle_ms / (serial_ms / lat_steps),
                     "k2_note": "dominant kernel by time; bound by integer issue (ncu: < 1 % DRAM, busiest pipe 84 %), 22.7 k instructions per permutation",
                     "k2_int_issue_roofline": k2_issue,
                     "isolated_ed25519_table": {"lde_ms": iso[0], "lde_GBps": 8 * rows * cols * 3 / iso[0] / 1e6,

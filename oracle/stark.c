@@ -899,7 +899,9 @@ int tm_prove(const void *circuit, const uint8_t *input, size_t input_len, const 
     for (int t = 0; t < TMX_N_TABLES; t++) {
         if (!c->t[t].present) continue;
         ptable_t *p = &pt[t];
-        prove_table_tail(p, beta, gamma, &ch, &w);
+        challenger_t fork = ch; /* each table continues on a fork of the transcript: common state + table index */
+        challenger_observe(&fork, (gl_t)t);
+        prove_table_tail(p, beta, gamma, &fork, &w);
         free(p->lde_k); free(p->coef_k); free(p->lde_m); free(p->coef_m); free(p->lde_a); free(p->coef_a);
         merkle_free(&p->tree_k); merkle_free(&p->tree_m); merkle_free(&p->tree_a);
     }
@@ -1093,7 +1095,9 @@ int tm_verify_proof(const void *circuit, const uint64_t *proof, size_t proof_len
     if (balance.a0 || balance.a1) return 200;
     for (int t = 0; t < TMX_N_TABLES; t++) {
         if (!c->t[t].present) continue;
-        int rc = verify_table_tail(c, t, cap_m[t], cap_a[t], beta, gamma, total[t], &r, &ch);
+        challenger_t fork = ch;
+        challenger_observe(&fork, (gl_t)t);
+        int rc = verify_table_tail(c, t, cap_m[t], cap_a[t], beta, gamma, total[t], &r, &fork);
         if (rc) return 10 * (t + 1) + rc;
     }
     if (r.err || r.pos != r.n) return 103;

@@ -15,6 +15,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <ctime>
+#include <memory>
+#include <string>
+#include <thread>
 
 using namespace tmx;
 
@@ -38,6 +41,11 @@ struct tmx_circuit {
     gl* d_logic = nullptr;
     cudaStream_t side = nullptr;        // second stream: the latency-bound sequential Ed25519 rows
     cudaEvent_t ev_inputs = nullptr, ev_ladder = nullptr;
+    // The tables of one commitment round are independent until their caps meet in the transcript: each is committed on its
+    // own stream (tstream[0] is the context's stream) so that the latency-bound pieces of one table (upper Merkle levels, the
+    // 4096-row logic table, one-CTA scans) run under the throughput-bound kernels of another.
+    cudaStream_t tstream[STARK_N_TABLES] = {};
+    cudaEvent_t ev_counted[STARK_N_TABLES] = {}, ev_done[STARK_N_TABLES] = {}, ev_expand = nullptr, ev_fork = nullptr;
     std::vector<uint8_t> h_blob;  // host copy of the resident inputs (tmx_circuit_set_inputs)
     bool resident = false;
     Prover prover;
@@ -209,8 +217,17 @@ extern "C" int tmx_circuit_build(tmx_ctx* ctx, uint32_t kind, uint32_t n_max, co
         cudaMalloc(&c->d_points, witness_points_bytes(n_max)) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_inputs, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->ev_ladder, cudaEventDisableTiming) != cudaSuccess)
+        cudaEventCreateWithFlags(&c->ev_ladder, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_expand, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess)
         return fail(TMX_E_CUDA, "tmx_circuit_build: cudaMalloc failed");
+    c->tstream[0] = ctx->stream;
+    for (int t = 0; t < STARK_N_TABLES; t++) {
+        if ((t && cudaStreamCreateWithFlags(&c->tstream[t], cudaStreamNonBlocking) != cudaSuccess) ||
+            cudaEventCreateWithFlags(&c->ev_counted[t], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->ev_done[t], cudaEventDisableTiming) != cudaSuccess)
+            return fail(TMX_E_CUDA, "tmx_circuit_build: stream / event creation failed");
+    }
     const AirShape sh = air_shape(kind, n_max, chain_id, chain_id_len);
     if (logic_rows(sh)) {
         c->plan = logic_plan_get(sh);
@@ -241,6 +258,13 @@ extern "C" void tmx_circuit_free(tmx_circuit* c) {
     if (c->side) cudaStreamDestroy(c->side);
     if (c->ev_inputs) cudaEventDestroy(c->ev_inputs);
     if (c->ev_ladder) cudaEventDestroy(c->ev_ladder);
+    if (c->ev_expand) cudaEventDestroy(c->ev_expand);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    for (int t = 0; t < STARK_N_TABLES; t++) {
+        if (t && c->tstream[t]) cudaStreamDestroy(c->tstream[t]);
+        if (c->ev_counted[t]) cudaEventDestroy(c->ev_counted[t]);
+        if (c->ev_done[t]) cudaEventDestroy(c->ev_done[t]);
+    }
     c->prover.release();
     delete c;
 }
@@ -376,30 +400,47 @@ extern "C" int tmx_prove(tmx_circuit* c, const uint8_t* input, size_t input_len,
     }
     Challenger ch;
     transcript_init(c->def->digest, input, input_len, out32, ch);
-    // round 1
+    // round 1: one stream per table; the range table waits for every histogram, the transcript for every cap
+    // TMX_SERIAL_TABLES=1 puts everything back on one stream and one thread (same proof bytes): per-kernel timings with
+    // CUDA events (bench.py's roofline leg, profilers) are only meaningful when nothing else shares the GPU
+    const bool serial = getenv("TMX_SERIAL_TABLES") != nullptr;
+    cudaStream_t ts[STARK_N_TABLES];
+    for (int t = 0; t < STARK_N_TABLES; t++) ts[t] = serial ? st : c->tstream[t];
     if ((rc = pr.count_lookups(ctx, AIR_SHA256, c->d_trace[0], st))) return rc;
+    TMX_CUDA(cudaEventRecord(c->ev_counted[AIR_SHA256], st));
     if ((rc = pr.commit_main(ctx, AIR_SHA256, c->d_trace[0], st))) return rc;
-    // logic table: the host fills it while the GPU commits the SHA-256 table (it needs the slot infos of the sequential phase)
+    // second phase of the Ed25519 / SHA-512 witness, then both tables side by side
+    TMX_CUDA(cudaStreamWaitEvent(ts[AIR_ED25519], c->ev_ladder, 0));
+    if ((rc = run_ed25519_expand(ctx, wa, c->d_points, ts[AIR_ED25519]))) return rc;
+    TMX_CUDA(cudaEventRecord(c->ev_expand, ts[AIR_ED25519]));
+    if ((rc = pr.count_lookups(ctx, AIR_ED25519, c->d_trace[2], ts[AIR_ED25519]))) return rc;
+    TMX_CUDA(cudaEventRecord(c->ev_counted[AIR_ED25519], ts[AIR_ED25519]));
+    if ((rc = pr.commit_main(ctx, AIR_ED25519, c->d_trace[2], ts[AIR_ED25519]))) return rc;
+    TMX_CUDA(cudaStreamWaitEvent(ts[AIR_SHA512], c->ev_expand, 0));
+    if ((rc = pr.count_lookups(ctx, AIR_SHA512, c->d_trace[1], ts[AIR_SHA512]))) return rc;
+    TMX_CUDA(cudaEventRecord(c->ev_counted[AIR_SHA512], ts[AIR_SHA512]));
+    if ((rc = pr.commit_main(ctx, AIR_SHA512, c->d_trace[1], ts[AIR_SHA512]))) return rc;
+    // logic table: the host fills it while the GPU works on the tables above (it needs the slot infos of the sequential phase)
     int logic_status = 0;
     if (c->plan) {
         TMX_CUDA(cudaEventSynchronize(c->ev_ladder));
         const size_t cells = (size_t)LG_COLS * c->plan->n_rows;
         memset(c->h_logic, 0, cells * sizeof(gl));
         logic_status = logic_fill_trace(*c->plan, input, blob, c->h_slots, c->h_logic, true);
-        TMX_CUDA(cudaMemcpyAsync(c->d_logic, c->h_logic, cells * sizeof(gl), cudaMemcpyHostToDevice, st));
+        TMX_CUDA(cudaStreamWaitEvent(ts[AIR_LOGIC], c->ev_inputs, 0));  // the histogram is cleared on the main stream
+        TMX_CUDA(cudaMemcpyAsync(c->d_logic, c->h_logic, cells * sizeof(gl), cudaMemcpyHostToDevice, ts[AIR_LOGIC]));
+        if ((rc = pr.count_lookups(ctx, AIR_LOGIC, c->d_logic, ts[AIR_LOGIC]))) return rc;
+        TMX_CUDA(cudaEventRecord(c->ev_counted[AIR_LOGIC], ts[AIR_LOGIC]));
+        if ((rc = pr.commit_main(ctx, AIR_LOGIC, c->d_logic, ts[AIR_LOGIC]))) return rc;
     }
-    TMX_CUDA(cudaStreamWaitEvent(st, c->ev_ladder, 0));
-    if ((rc = run_ed25519_expand(ctx, wa, c->d_points, st))) return rc;
-    if ((rc = pr.count_lookups(ctx, AIR_SHA512, c->d_trace[1], st))) return rc;
-    if ((rc = pr.count_lookups(ctx, AIR_ED25519, c->d_trace[2], st))) return rc;
-    if ((rc = pr.commit_main(ctx, AIR_SHA512, c->d_trace[1], st))) return rc;
-    if ((rc = pr.commit_main(ctx, AIR_ED25519, c->d_trace[2], st))) return rc;
-    if (c->plan) {
-        if ((rc = pr.count_lookups(ctx, AIR_LOGIC, c->d_logic, st))) return rc;
-        if ((rc = pr.commit_main(ctx, AIR_LOGIC, c->d_logic, st))) return rc;
+    for (int t = 0; t < AIR_RANGE; t++)
+        if (t != AIR_LOGIC || c->plan) TMX_CUDA(cudaStreamWaitEvent(ts[AIR_RANGE], c->ev_counted[t], 0));
+    if ((rc = pr.fill_range_trace(ctx, ts[AIR_RANGE]))) return rc;
+    if ((rc = pr.commit_main(ctx, AIR_RANGE, pr.d_range_trace, ts[AIR_RANGE]))) return rc;
+    for (int t = 1; t < STARK_N_TABLES; t++) {
+        TMX_CUDA(cudaEventRecord(c->ev_done[t], ts[t]));
+        TMX_CUDA(cudaStreamWaitEvent(st, c->ev_done[t], 0));
     }
-    if ((rc = pr.fill_range_trace(ctx, st))) return rc;
-    if ((rc = pr.commit_main(ctx, AIR_RANGE, pr.d_range_trace, st))) return rc;
     std::vector<uint8_t> aux(aux_bytes(c->n_max));
     TMX_CUDA(cudaMemcpyAsync(aux.data(), c->d_aux, aux.size(), cudaMemcpyDeviceToHost, st));
     bool range_ok = true;
@@ -430,11 +471,43 @@ extern "C" int tmx_prove(tmx_circuit* c, const uint8_t* input, size_t input_len,
     const gl2 beta = ch.get_ext(), gamma = ch.get_ext();
     // round 2
     const gl* traces[STARK_N_TABLES] = {c->d_trace[0], c->d_trace[1], c->d_trace[2], c->d_logic, pr.d_range_trace};
-    for (int t = 0; t < STARK_N_TABLES; t++)
-        if ((rc = pr.commit_aux(ctx, t, traces[t], beta, gamma, st))) return rc;
+    // (every stream is idle here: finish_round1 synchronised the main stream, which had joined the others; biggest table first)
+    static const int order[STARK_N_TABLES] = {AIR_ED25519, AIR_SHA512, AIR_SHA256, AIR_LOGIC, AIR_RANGE};
+    for (int i = 0; i < STARK_N_TABLES; i++)
+        if ((rc = pr.commit_aux(ctx, order[i], traces[order[i]], beta, gamma, ts[order[i]]))) return rc;
+    for (int t = 1; t < STARK_N_TABLES; t++) {
+        TMX_CUDA(cudaEventRecord(c->ev_done[t], ts[t]));
+        TMX_CUDA(cudaStreamWaitEvent(st, c->ev_done[t], 0));
+    }
     if ((rc = pr.finish_round2(ctx, ch, w, st))) return rc;
-    for (int t = 0; t < STARK_N_TABLES; t++)
-        if ((rc = pr.prove_tail(ctx, t, beta, gamma, ch, w, st))) return rc;
+    // tails: every table continues on a FORK of the transcript (the common state after round 2 plus the table index), so the
+    // five tails are independent of each other and run side by side, one host thread and one stream per table; their words
+    // enter the proof in table order
+    std::vector<gl> tail_words[STARK_N_TABLES];
+    int tail_rc[STARK_N_TABLES] = {};
+    std::string tail_err[STARK_N_TABLES];
+    auto run_tail = [&](int t) {
+        if (!c->def->tables[t].n_main) return;
+        cudaSetDevice(ctx->device);
+        Challenger fork = ch;
+        fork.observe((gl)t);
+        tail_rc[t] = pr.prove_tail(ctx, t, beta, gamma, fork, tail_words[t], ts[t]);
+        if (tail_rc[t]) tail_err[t] = tmx_last_error();
+    };
+    if (serial) {
+        for (int t = 0; t < STARK_N_TABLES; t++) run_tail(t);
+    } else {
+        std::thread workers[STARK_N_TABLES];
+        for (int t = 0; t < STARK_N_TABLES; t++)
+            if (t != AIR_ED25519) workers[t] = std::thread(run_tail, t);
+        run_tail(AIR_ED25519);
+        for (auto& th : workers)
+            if (th.joinable()) th.join();
+    }
+    for (int t = 0; t < STARK_N_TABLES; t++) {
+        if (tail_rc[t]) return fail(tail_rc[t], tail_err[t]);
+        w.insert(w.end(), tail_words[t].begin(), tail_words[t].end());
+    }
     *proof_out = p.release();
     return TMX_OK;
 }

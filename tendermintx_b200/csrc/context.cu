@@ -99,6 +99,7 @@ static int build_pow_table(tmx_ctx* ctx, gl base, unsigned log_size, gl scale, g
 }
 
 int ctx_ntt_tables(tmx_ctx* ctx, unsigned log_n, bool inverse, const NttTables** out) {
+    std::lock_guard<std::mutex> lock(ctx->tables_mu);
     auto& cache = inverse ? ctx->inv : ctx->fwd;
     auto it = cache.find(log_n);
     if (it != cache.end()) {
@@ -117,6 +118,7 @@ int ctx_ntt_tables(tmx_ctx* ctx, unsigned log_n, bool inverse, const NttTables**
 }
 
 int ctx_coset_scale(tmx_ctx* ctx, unsigned log_n, const gl** out) {
+    std::lock_guard<std::mutex> lock(ctx->tables_mu);
     auto it = ctx->coset_scale.find(log_n);
     if (it != ctx->coset_scale.end()) {
         *out = it->second;
@@ -203,4 +205,4 @@ extern "C" int tmx_ctx_sync(tmx_ctx* ctx) {
 
 extern "C" void* tmx_ctx_stream(const tmx_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
-extern "C" uint64_t tmx_ctx_launch_count(const tmx_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" uint64_t tmx_ctx_launch_count(const tmx_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }

@@ -4,6 +4,8 @@
 #include <string>
 #include <vector>
 #include <map>
+#include <atomic>
+#include <mutex>
 #include "gl.cuh"
 #include "../../include/tmx.h"
 
@@ -32,7 +34,8 @@ struct NttTables {
 struct tmx_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    uint64_t launches = 0;
+    std::atomic<uint64_t> launches{0};  // the tails of one proof launch from several host threads
+    std::mutex tables_mu;               // guards the lazily built twiddle / coset tables below
     int sm_count = 148;
     std::map<unsigned, tmx::NttTables> fwd, inv;      // keyed by log size
     std::map<unsigned, tmx::gl*> coset_scale;         // keyed by log n: 7^i / n, i < n
@@ -57,7 +60,9 @@ int lde_forward_cosets(tmx_ctx* ctx, const gl* coeffs, gl* d_out, size_t n_cols,
 int merkle_generic(tmx_ctx* ctx, const gl* base, size_t leaf_len, size_t row_stride, size_t elem_stride, unsigned log_rows,
                    unsigned cap_height, gl* d_digests, cudaStream_t st);
 // smallest w < 2^40 such that Poseidon(state with state[pos] = w)[7] has `bits` leading zero bits
-int pow_grind(tmx_ctx* ctx, const gl state[12], int pos, unsigned bits, uint64_t* witness, cudaStream_t st);
+int pow_grind(tmx_ctx* ctx, const gl state[12], int pos, unsigned bits, uint64_t* witness, gl* d_scratch, cudaStream_t st);
+// in-place transform of n_cols columns with a caller-owned temporary of the same size (tmx_ntt uses the context's scratch)
+int ntt_with_scratch(tmx_ctx* ctx, gl* d_data, size_t n_cols, unsigned log_n, bool inverse, gl* d_tmp, cudaStream_t st);
 
 // per translation unit Poseidon constant upload hooks
 int merkle_tu_init();

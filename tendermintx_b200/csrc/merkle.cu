@@ -105,15 +105,18 @@ __global__ void __launch_bounds__(128) pow_grind_kernel(const gl* __restrict__ s
     if ((s[7] >> (64 - bits)) == 0) atomicMin(best, (unsigned long long)cand);
 }
 
-int pow_grind(tmx_ctx* ctx, const gl state[12], int pos, unsigned bits, uint64_t* witness, cudaStream_t st) {
+int pow_grind(tmx_ctx* ctx, const gl state[12], int pos, unsigned bits, uint64_t* witness, gl* d_scratch, cudaStream_t st) {
     if (bits == 0) {
         *witness = 0;
         return TMX_OK;
     }
-    void* p = nullptr;
-    int rc = ctx_scratch(ctx, 3, 13 * sizeof(gl), &p);
-    if (rc) return rc;
-    gl* d_state = (gl*)p;
+    if (!d_scratch) {  // 13 words; callers that run side by side bring their own
+        void* p = nullptr;
+        int rc = ctx_scratch(ctx, 3, 13 * sizeof(gl), &p);
+        if (rc) return rc;
+        d_scratch = (gl*)p;
+    }
+    gl* d_state = d_scratch;
     unsigned long long* d_best = (unsigned long long*)(d_state + 12);
     unsigned long long best = ~0ULL;
     TMX_CUDA(cudaMemcpyAsync(d_state, state, 12 * sizeof(gl), cudaMemcpyHostToDevice, st));
@@ -144,7 +147,7 @@ extern "C" int tmx_poseidon_merkle(tmx_ctx* ctx, const uint64_t* d_cols, size_t 
 
 extern "C" int tmx_pow_grind(tmx_ctx* ctx, const uint64_t state[12], int pos, unsigned bits, uint64_t* witness, void* stream) {
     if (!ctx || !state || !witness || pos < 0 || pos >= 8 || bits > 40) return fail(TMX_E_INPUT, "tmx_pow_grind: bad arguments");
-    return pow_grind(ctx, state, pos, bits, witness, pick_stream(ctx, stream));
+    return pow_grind(ctx, state, pos, bits, witness, nullptr, pick_stream(ctx, stream));
 }
 
 // The arithmetic of the device fast path (multiplier-free linear layer, unreduced lanes) compiled for the HOST, so

@@ -335,46 +335,40 @@ static int launch_scale(tmx_ctx* ctx, gl* p, size_t n, gl s, cudaStream_t st) {
 
 using namespace tmx;
 
-extern "C" int tmx_ntt(tmx_ctx* ctx, uint64_t* d_data, size_t n_cols, unsigned log_n, int inverse, void* stream) {
-    if (!ctx || !d_data || log_n < 1 || log_n > 30) return fail(TMX_E_INPUT, "tmx_ntt: bad arguments");
-    if (n_cols == 0) return TMX_OK;
-    cudaStream_t st = pick_stream(ctx, stream);
+int tmx::ntt_with_scratch(tmx_ctx* ctx, gl* d_data, size_t n_cols, unsigned log_n, bool inverse, gl* d_tmp, cudaStream_t st) {
     const size_t n = (size_t)1 << log_n;
-    void* tmpa = nullptr;
-    void* tmpb = nullptr;
-    int rc = ctx_scratch(ctx, 0, n * n_cols * sizeof(gl), &tmpa);
-    if (rc) return rc;
     const bool multi = plan_passes(log_n).size() > 1;
     XformDesc d;
     memset(&d, 0, sizeof d);
     d.n_cols = n_cols;
     d.log_n = log_n;
-    d.inverse = inverse != 0;
+    d.inverse = inverse;
     d.natural_out = true;
+    d.in_col_stride = n;
+    d.out = d_data;
+    d.out_col_stride = n;
     if (multi) {
-        // data -> tmpa (strided passes) -> data (scatter)
+        // data -> tmp (strided passes) -> data (scatter): the scatter pass reads tmp and writes data, never aliased
         d.in = d_data;
-        d.in_col_stride = n;
-        d.tmp = (gl*)tmpa;
+        d.tmp = d_tmp;
         d.tmp_col_stride = n;
-        d.out = d_data;
-        d.out_col_stride = n;
-        // the scatter pass reads tmp and writes data: never aliased
     } else {
-        rc = ctx_scratch(ctx, 1, n * n_cols * sizeof(gl), &tmpb);
-        if (rc) return rc;
-        TMX_CUDA(cudaMemcpyAsync(tmpb, d_data, n * n_cols * sizeof(gl), cudaMemcpyDeviceToDevice, st));
-        d.in = (const gl*)tmpb;
-        d.in_col_stride = n;
-        d.out = d_data;
-        d.out_col_stride = n;
+        TMX_CUDA(cudaMemcpyAsync(d_tmp, d_data, n * n_cols * sizeof(gl), cudaMemcpyDeviceToDevice, st));
+        d.in = d_tmp;
     }
-    rc = run_xform(ctx, d, st);
+    int rc = run_xform(ctx, d, st);
     if (rc) return rc;
-    if (inverse) {
-        rc = launch_scale(ctx, d_data, n * n_cols, gl_inv((gl)n), st);
-    }
+    if (inverse) rc = launch_scale(ctx, d_data, n * n_cols, gl_inv((gl)n), st);
     return rc;
+}
+
+extern "C" int tmx_ntt(tmx_ctx* ctx, uint64_t* d_data, size_t n_cols, unsigned log_n, int inverse, void* stream) {
+    if (!ctx || !d_data || log_n < 1 || log_n > 30) return fail(TMX_E_INPUT, "tmx_ntt: bad arguments");
+    if (n_cols == 0) return TMX_OK;
+    void* tmp = nullptr;
+    int rc = ctx_scratch(ctx, 0, ((size_t)n_cols << log_n) * sizeof(gl), &tmp);
+    if (rc) return rc;
+    return ntt_with_scratch(ctx, d_data, n_cols, log_n, inverse != 0, (gl*)tmp, pick_stream(ctx, stream));
 }
 
 namespace tmx {

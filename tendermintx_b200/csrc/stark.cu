@@ -318,18 +318,19 @@ struct PhaseTimer {
 
 // device -> host through a pinned staging buffer owned by the prover (pageable destinations make every one of the
 // transcript round trips a staged, driver-synchronised copy)
-int Prover::d2h(std::vector<gl>& dst, const gl* src, size_t n, cudaStream_t st) {
-    if (sz_pinned < n) {
-        if (h_pinned) cudaFreeHost(h_pinned);
-        h_pinned = nullptr;
-        sz_pinned = 0;
+int Prover::d2h(std::vector<gl>& dst, const gl* src, size_t n, cudaStream_t st, int slot) {
+    Tail& tl = tail[slot];
+    if (tl.sz_pinned < n) {
+        if (tl.h_pinned) cudaFreeHost(tl.h_pinned);
+        tl.h_pinned = nullptr;
+        tl.sz_pinned = 0;
         const size_t want = std::max<size_t>(n + n / 4, 1 << 16);
-        TMX_CUDA(cudaMallocHost((void**)&h_pinned, want * sizeof(gl)));
-        sz_pinned = want;
+        TMX_CUDA(cudaMallocHost((void**)&tl.h_pinned, want * sizeof(gl)));
+        tl.sz_pinned = want;
     }
-    TMX_CUDA(cudaMemcpyAsync(h_pinned, src, n * sizeof(gl), cudaMemcpyDeviceToHost, st));
+    TMX_CUDA(cudaMemcpyAsync(tl.h_pinned, src, n * sizeof(gl), cudaMemcpyDeviceToHost, st));
     TMX_CUDA(cudaStreamSynchronize(st));
-    dst.assign(h_pinned, h_pinned + n);
+    dst.assign(tl.h_pinned, tl.h_pinned + n);
     return TMX_OK;
 }
 
@@ -404,29 +405,45 @@ int Prover::setup(tmx_ctx* ctx, std::shared_ptr<const CircuitDef> d) {
         }
     }
     const size_t max_n = max_m >> STARK_RATE_BITS;
-    const size_t dig_max = tmx_merkle_digest_count(ilog2(max_m), cap_height_of(ilog2(max_m)));
-    if ((rc = alloc((void**)&d_dig_q, 4 * dig_max * sizeof(gl)))) return rc;
-    if ((rc = alloc((void**)&d_dig_fri, 4 * (max_m / 4) * sizeof(gl)))) return rc;
-    if ((rc = alloc((void**)&d_qv, 2 * max_m * sizeof(gl)))) return rc;
-    if ((rc = alloc((void**)&d_qcoef, 4 * max_n * sizeof(gl)))) return rc;
-    if ((rc = alloc((void**)&d_qlde, 4 * max_m * sizeof(gl)))) return rc;
-    if ((rc = alloc((void**)&d_ypa, 2 * max_n * sizeof(gl2)))) return rc;
-    d_ypb = d_ypa + max_n;
-    if ((rc = alloc((void**)&d_open, (2 * max_ct + 4) * sizeof(gl2)))) return rc;
-    if ((rc = alloc((void**)&d_apow, (max_ct + 4) * sizeof(gl2)))) return rc;
-    if ((rc = alloc((void**)&d_idx, STARK_NUM_QUERIES * sizeof(uint32_t)))) return rc;
-    if ((rc = alloc((void**)&d_rowsum, max_n * sizeof(gl2)))) return rc;
+    for (int t = 0; t < STARK_N_TABLES; t++) {
+        const TableDef& td = def->tables[t];
+        if (!td.n_main) continue;
+        Tail& tl = tail[t];
+        const size_t n = td.rows(), m = n << STARK_RATE_BITS, ct = td.n_const + td.n_main + (size_t)td.n_aux();
+        const unsigned km = td.log_n + STARK_RATE_BITS;
+        if ((rc = alloc((void**)&tl.d_dig_q, 4 * tmx_merkle_digest_count(km, cap_height_of(km)) * sizeof(gl)))) return rc;
+        if ((rc = alloc((void**)&tl.d_dig_fri, 4 * (m / 4) * sizeof(gl)))) return rc;
+        if ((rc = alloc((void**)&tl.d_qv, 2 * m * sizeof(gl)))) return rc;
+        if ((rc = alloc((void**)&tl.d_ntt_tmp, 2 * m * sizeof(gl)))) return rc;
+        if ((rc = alloc((void**)&tl.d_pow, 16 * sizeof(gl)))) return rc;
+        if ((rc = alloc((void**)&tl.d_qcoef, 4 * n * sizeof(gl)))) return rc;
+        if ((rc = alloc((void**)&tl.d_qlde, 4 * m * sizeof(gl)))) return rc;
+        if ((rc = alloc((void**)&tl.d_ypa, 2 * n * sizeof(gl2)))) return rc;
+        tl.d_ypb = tl.d_ypa + n;
+        if ((rc = alloc((void**)&tl.d_open, (2 * ct + 4) * sizeof(gl2)))) return rc;
+        if ((rc = alloc((void**)&tl.d_apow, (ct + 4) * sizeof(gl2)))) return rc;
+        if ((rc = alloc((void**)&tl.d_idx, STARK_NUM_QUERIES * sizeof(uint32_t)))) return rc;
+        // FRI layer arrays: m, m/16, m/256, ... ext values, carved from one allocation
+        size_t tot = 0, cur = m;
+        for (int l = 0; l < 9; l++) {
+            tot += cur;
+            cur = cur >> 4 ? cur >> 4 : 1;
+        }
+        gl2* base = nullptr;
+        if ((rc = alloc((void**)&base, tot * sizeof(gl2)))) return rc;
+        cur = m;
+        for (int l = 0; l < 9; l++) {
+            tl.d_fri[l] = base;
+            base += cur;
+            cur = cur >> 4 ? cur >> 4 : 1;
+        }
+    }
+    rowsum_stride = max_n;
+    if ((rc = alloc((void**)&d_rowsum, (size_t)STARK_N_TABLES * max_n * sizeof(gl2)))) return rc;
     if ((rc = alloc((void**)&d_small, (size_t)STARK_N_TABLES * 66 * sizeof(gl)))) return rc;
     if ((rc = alloc((void**)&d_hist, (BUS_HIST_SIZE + 4) * sizeof(unsigned int)))) return rc;
     if (def->tables[AIR_RANGE].n_main)
         if ((rc = alloc((void**)&d_range_trace, def->tables[AIR_RANGE].rows() * RG_COLS * sizeof(gl)))) return rc;
-    // FRI layer arrays: m, m/16, m/256, ... ext values, carved from one allocation
-    size_t tot = 0, cur = max_m;
-    for (int l = 0; l < 9; l++) {
-        tot += cur;
-        cur = cur >> 4 ? cur >> 4 : 1;
-    }
-    if ((rc = alloc((void**)&d_fri_base, tot * sizeof(gl2)))) return rc;
     for (auto& e : ev_phase) TMX_CUDA(cudaEventCreate(&e));
     TMX_CUDA(cudaStreamSynchronize(st));
     return TMX_OK;
@@ -435,8 +452,10 @@ int Prover::setup(tmx_ctx* ctx, std::shared_ptr<const CircuitDef> d) {
 void Prover::release() {
     for (auto& e : ev_phase)
         if (e) cudaEventDestroy(e);
-    if (h_pinned) cudaFreeHost(h_pinned);
-    if (d_query) cudaFree(d_query);
+    for (auto& tl : tail) {
+        if (tl.h_pinned) cudaFreeHost(tl.h_pinned);
+        if (tl.d_query) cudaFree(tl.d_query);
+    }
     for (void* p : owned) cudaFree(p);
     *this = Prover();
 }
@@ -477,12 +496,11 @@ int Prover::commit_main(tmx_ctx* ctx, int t, const gl* d_trace, cudaStream_t st)
     const unsigned km = td.log_n + STARK_RATE_BITS;
     const size_t dig = tmx_merkle_digest_count(km, cap_height_of(km)), cap_w = 4 * ((size_t)1 << cap_height_of(km));
     int rc;
-    TMX_CUDA(cudaEventRecord(ev_phase[2 * t], st));
+    TMX_CUDA(cudaEventRecord(ev_phase[3 * t], st));
     if ((rc = tmx_lde(ctx, d_trace, tb.d_lde_m, tb.d_coef_m, td.n_main, td.log_n, STARK_RATE_BITS, st))) return rc;
-    TMX_CUDA(cudaEventRecord(ev_phase[2 * t + 1], st));
+    TMX_CUDA(cudaEventRecord(ev_phase[3 * t + 1], st));
     if ((rc = merkle_generic(ctx, tb.d_lde_m, td.n_main, 1, m, km, cap_height_of(km), tb.d_dig_m, st))) return rc;
-    if (t + 1 < STARK_N_TABLES) TMX_CUDA(cudaEventRecord(ev_phase[2 * t + 2], st));
-    else TMX_CUDA(cudaEventRecord(ev_phase[2 * STARK_N_TABLES], st));
+    TMX_CUDA(cudaEventRecord(ev_phase[3 * t + 2], st));
     TMX_CUDA(cudaMemcpyAsync(d_small + 66 * t, tb.d_dig_m + 4 * dig - cap_w, cap_w * sizeof(gl), cudaMemcpyDeviceToDevice, st));
     return TMX_OK;
 }
@@ -505,9 +523,8 @@ int Prover::finish_round1(tmx_ctx* ctx, Challenger& ch, std::vector<gl>& proof, 
     // the commitment stamps are complete: LDE / Merkle device time per table
     for (int t = 0; t < STARK_N_TABLES; t++) {
         if (!def->tables[t].n_main) continue;
-        cudaEvent_t end = t + 1 < STARK_N_TABLES ? ev_phase[2 * t + 2] : ev_phase[2 * STARK_N_TABLES];
-        cudaEventElapsedTime(&lde_ms[t], ev_phase[2 * t], ev_phase[2 * t + 1]);
-        cudaEventElapsedTime(&merkle_ms[t], ev_phase[2 * t + 1], end);
+        cudaEventElapsedTime(&lde_ms[t], ev_phase[3 * t], ev_phase[3 * t + 1]);
+        cudaEventElapsedTime(&merkle_ms[t], ev_phase[3 * t + 1], ev_phase[3 * t + 2]);
     }
     return TMX_OK;
 }
@@ -523,10 +540,10 @@ int Prover::commit_aux(tmx_ctx* ctx, int t, const gl* d_trace, gl2 beta, gl2 gam
     a.beta = beta;
     a.gamma = gamma;
     a.aux = tb.d_aux;
-    a.rowsum = d_rowsum;
+    a.rowsum = d_rowsum + (size_t)t * rowsum_stride;
     int rc = launch_bus_gen(ctx, t, a, st);
     if (rc) return rc;
-    bus_scan_kernel<<<1, 1024, 0, st>>>(d_rowsum, n, tb.d_aux + (2 * H) * n, tb.d_aux + (2 * H + 1) * n, d_small + 66 * t + 64);
+    bus_scan_kernel<<<1, 1024, 0, st>>>(a.rowsum, n, tb.d_aux + (2 * H) * n, tb.d_aux + (2 * H + 1) * n, d_small + 66 * t + 64);
     ctx->launches++;
     TMX_CUDA(cudaGetLastError());
     if ((rc = tmx_lde(ctx, tb.d_aux, tb.d_lde_a, tb.d_coef_a, A, td.log_n, STARK_RATE_BITS, st))) return rc;
@@ -554,7 +571,7 @@ int Prover::finish_round2(tmx_ctx* ctx, Challenger& ch, std::vector<gl>& proof, 
     return TMX_OK;
 }
 
-int Prover::prove_tail(tmx_ctx* ctx, int table, gl2 beta, gl2 gamma, Challenger& ch, std::vector<gl>& proof, cudaStream_t st) {
+int Prover::prove_tail(tmx_ctx* ctx, int table, gl2 beta, gl2 gamma, Challenger ch, std::vector<gl>& proof, cudaStream_t st) {
     const TableDef& td = def->tables[table];
     if (!td.n_main) return TMX_OK;
     TableDevice& tb = tab[table];
@@ -566,14 +583,10 @@ int Prover::prove_tail(tmx_ctx* ctx, int table, gl2 beta, gl2 gamma, Challenger&
     const size_t dig_t = tmx_merkle_digest_count(km, cap_h);
     int rc;
     PhaseTimer pt(st);
-    {   // FRI layer arrays of this table
-        size_t cur = m, o = 0;
-        for (int l = 0; l < 9; l++) {
-            d_fri[l] = d_fri_base + o;
-            o += cur;
-            cur = cur >> 4 ? cur >> 4 : 1;
-        }
-    }
+    Tail& tl = tail[table];
+    gl* const d_dig_q = tl.d_dig_q; gl* const d_dig_fri = tl.d_dig_fri; gl* const d_qv = tl.d_qv; gl* const d_qcoef = tl.d_qcoef;
+    gl* const d_qlde = tl.d_qlde; gl2* const d_ypa = tl.d_ypa; gl2* const d_ypb = tl.d_ypb; gl2* const d_open = tl.d_open;
+    gl2* const d_apow = tl.d_apow; uint32_t* const d_idx = tl.d_idx; gl2* const* d_fri = tl.d_fri;
     // ---- constraint challenges, quotient ----
     QuotientArgs qa;
     memset(&qa, 0, sizeof qa);
@@ -592,7 +605,7 @@ int Prover::prove_tail(tmx_ctx* ctx, int table, gl2 beta, gl2 gamma, Challenger&
     if (rc) return rc;
     pt.tick("quotient kernel");
     // values on the coset (natural order) -> coefficients of Q(7 X); the 1/m factor comes with the inverse NTT
-    rc = tmx_ntt(ctx, d_qv, 2, km, 1, st);
+    rc = ntt_with_scratch(ctx, d_qv, 2, km, true, tl.d_ntt_tmp, st);
     if (rc) return rc;
     quotient_chunks_kernel<<<(unsigned)((4 * n + 255) / 256), 256, 0, st>>>(d_qv, n, gl_inv(gl_pow(GL_GEN, n)), d_qcoef);
     ctx->launches++;
@@ -601,7 +614,7 @@ int Prover::prove_tail(tmx_ctx* ctx, int table, gl2 beta, gl2 gamma, Challenger&
     rc = merkle_generic(ctx, d_qlde, 4, 1, m, km, cap_h, d_dig_q, st);
     if (rc) return rc;
     std::vector<gl> cap;
-    rc = d2h(cap, d_dig_q + 4 * (dig_t - cap_n), 4 * cap_n, st);
+    rc = d2h(cap, d_dig_q + 4 * (dig_t - cap_n), 4 * cap_n, st, table);
     if (rc) return rc;
     proof.insert(proof.end(), cap.begin(), cap.end());
     ch.observe(cap.data(), cap.size());
@@ -630,7 +643,7 @@ int Prover::prove_tail(tmx_ctx* ctx, int table, gl2 beta, gl2 gamma, Challenger&
     TMX_CUDA(cudaGetLastError());
     pt.tick("openings kernels");
     std::vector<gl> op;
-    rc = d2h(op, reinterpret_cast<const gl*>(d_open), 2 * (2 * CT + 4), st);
+    rc = d2h(op, reinterpret_cast<const gl*>(d_open), 2 * (2 * CT + 4), st, table);
     if (rc) return rc;
     proof.insert(proof.end(), op.begin(), op.end());  // local[CT], next[CT], quotient[4] as (a0, a1) pairs
     auto ext_at = [&](size_t i) { return gl2_make(op[2 * i], op[2 * i + 1]); };
@@ -679,7 +692,7 @@ int Prover::prove_tail(tmx_ctx* ctx, int table, gl2 beta, gl2 gamma, Challenger&
         rc = merkle_generic(ctx, reinterpret_cast<const gl*>(d_fri[l]), 32, 32, 1, lg_rows, lcap_h, dg, st);
         if (rc) return rc;
         dig_used += ldig;
-        rc = d2h(cap, dg + 4 * (ldig - ((size_t)1 << lcap_h)), 4 * ((size_t)1 << lcap_h), st);
+        rc = d2h(cap, dg + 4 * (ldig - ((size_t)1 << lcap_h)), 4 * ((size_t)1 << lcap_h), st, table);
         if (rc) return rc;
         proof.insert(proof.end(), cap.begin(), cap.end());
         ch.observe(cap.data(), cap.size());
@@ -695,7 +708,7 @@ int Prover::prove_tail(tmx_ctx* ctx, int table, gl2 beta, gl2 gamma, Challenger&
     pt.tick("fri layers");
     // final polynomial: the remaining `cur` evaluations (bit-reversed) on shift * <w_cur> -> coefficients
     std::vector<gl> fin;
-    rc = d2h(fin, reinterpret_cast<const gl*>(d_fri[n_layers]), 2 * cur, st);
+    rc = d2h(fin, reinterpret_cast<const gl*>(d_fri[n_layers]), 2 * cur, st, table);
     if (rc) return rc;
     {
         const unsigned lg = ilog2(cur);
@@ -726,7 +739,7 @@ int Prover::prove_tail(tmx_ctx* ctx, int table, gl2 beta, gl2 gamma, Challenger&
         for (int i = 0; i < 12; i++) state[i] = ch.state[i];
         for (int i = 0; i < ch.n_in; i++) state[i] = ch.in[i];
         uint64_t wit = 0;
-        rc = pow_grind(ctx, state, ch.n_in, STARK_POW_BITS, &wit, st);
+        rc = pow_grind(ctx, state, ch.n_in, STARK_POW_BITS, &wit, tl.d_pow, st);
         if (rc) return rc;
         ch.observe((gl)wit);
         (void)ch.get();
@@ -741,13 +754,14 @@ int Prover::prove_tail(tmx_ctx* ctx, int table, gl2 beta, gl2 gamma, Challenger&
     size_t qlen = (Kc ? Kc + 4 * n_sib : 0) + C + 4 * n_sib + A + 4 * n_sib + 4 + 4 * n_sib;
     for (unsigned l = 0; l < n_layers; l++)
         qlen += 32 + 4 * (layer_rows_log[l] - std::min<unsigned>((unsigned)layer_rows_log[l], STARK_CAP_HEIGHT));
-    if (sz_query < qlen * STARK_NUM_QUERIES) {
-        if (d_query) TMX_CUDA(cudaFree(d_query));
-        d_query = nullptr;
-        sz_query = 0;
-        TMX_CUDA(cudaMalloc((void**)&d_query, qlen * STARK_NUM_QUERIES * sizeof(gl)));
-        sz_query = qlen * STARK_NUM_QUERIES;
+    if (tl.sz_query < qlen * STARK_NUM_QUERIES) {
+        if (tl.d_query) TMX_CUDA(cudaFree(tl.d_query));
+        tl.d_query = nullptr;
+        tl.sz_query = 0;
+        TMX_CUDA(cudaMalloc((void**)&tl.d_query, qlen * STARK_NUM_QUERIES * sizeof(gl)));
+        tl.sz_query = qlen * STARK_NUM_QUERIES;
     }
+    gl* const d_query = tl.d_query;
     size_t off = 0;
     const unsigned NQ = STARK_NUM_QUERIES;
     auto open_tree = [&](const gl* lde, size_t cols, const gl* dig) {
@@ -773,7 +787,7 @@ int Prover::prove_tail(tmx_ctx* ctx, int table, gl2 beta, gl2 gamma, Challenger&
     }
     TMX_CUDA(cudaGetLastError());
     std::vector<gl> qd;
-    rc = d2h(qd, d_query, qlen * NQ, st);
+    rc = d2h(qd, d_query, qlen * NQ, st, table);
     if (rc) return rc;
     proof.insert(proof.end(), qd.begin(), qd.end());
     pt.tick("queries");

@@ -36,18 +36,24 @@ struct Prover {
     std::shared_ptr<const CircuitDef> def;
     AirShape shape = {0, 0};
     TableDevice tab[STARK_N_TABLES];
-    // shared by the per-table tails (sized for the largest table)
-    gl* d_dig_q = nullptr; gl* d_dig_fri = nullptr; gl* d_qv = nullptr; gl* d_qcoef = nullptr; gl* d_qlde = nullptr;
-    gl2* d_ypa = nullptr; gl2* d_ypb = nullptr; gl2* d_open = nullptr; gl2* d_apow = nullptr;
-    uint32_t* d_idx = nullptr;
-    gl2* d_fri_base = nullptr; gl2* d_fri[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    gl* d_query = nullptr; size_t sz_query = 0;
-    gl2* d_rowsum = nullptr;      // per-row bus sums of the table being processed
+    // Scratch of one table's tail (quotient, openings, FRI, queries).  The tails run side by side, each on its own stream
+    // and host thread, so every table owns a full set sized for itself, including a pinned staging buffer.
+    struct Tail {
+        gl* d_dig_q = nullptr; gl* d_dig_fri = nullptr; gl* d_qv = nullptr; gl* d_qcoef = nullptr; gl* d_qlde = nullptr;
+        gl* d_ntt_tmp = nullptr; gl* d_pow = nullptr;
+        gl2* d_ypa = nullptr; gl2* d_ypb = nullptr; gl2* d_open = nullptr; gl2* d_apow = nullptr;
+        uint32_t* d_idx = nullptr;
+        gl2* d_fri[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        gl* d_query = nullptr; size_t sz_query = 0;
+        gl* h_pinned = nullptr; size_t sz_pinned = 0;
+    };
+    Tail tail[STARK_N_TABLES + 1];  // the last one: staging buffer of the commitment rounds
+    gl2* d_rowsum = nullptr;      // per-row bus sums, one region of rowsum_stride elements per table (tables run on their own streams)
+    size_t rowsum_stride = 0;
     gl* d_small = nullptr;        // caps / totals staging: [STARK_N_TABLES][64 + 2]
     unsigned int* d_hist = nullptr;  // range-lookup histogram, then one int "bad" flag
     gl* d_range_trace = nullptr;  // first-round trace of the range table
-    gl* h_pinned = nullptr; size_t sz_pinned = 0;
-    cudaEvent_t ev_phase[2 * STARK_N_TABLES + 1] = {};
+    cudaEvent_t ev_phase[3 * STARK_N_TABLES] = {};  // per table: LDE start, LDE end = Merkle start, Merkle end
     float lde_ms[STARK_N_TABLES] = {}, merkle_ms[STARK_N_TABLES] = {};
     std::vector<void*> owned;
 
@@ -62,8 +68,9 @@ struct Prover {
     int commit_aux(tmx_ctx* ctx, int t, const gl* d_trace, gl2 beta, gl2 gamma, cudaStream_t st);
     int finish_round2(tmx_ctx* ctx, Challenger& ch, std::vector<gl>& proof, cudaStream_t st);
     // quotient, openings, FRI, queries of one table
-    int prove_tail(tmx_ctx* ctx, int t, gl2 beta, gl2 gamma, Challenger& ch, std::vector<gl>& proof, cudaStream_t st);
-    int d2h(std::vector<gl>& dst, const gl* src, size_t n, cudaStream_t st);
+    // (the table's transcript is a fork of the common one: the caller passes a copy that has absorbed the table index)
+    int prove_tail(tmx_ctx* ctx, int t, gl2 beta, gl2 gamma, Challenger ch, std::vector<gl>& proof, cudaStream_t st);
+    int d2h(std::vector<gl>& dst, const gl* src, size_t n, cudaStream_t st, int slot = STARK_N_TABLES);
     int alloc(void** p, size_t bytes);
 };
 

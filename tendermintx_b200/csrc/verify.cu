@@ -284,7 +284,9 @@ int verify_proof(const CircuitDef& def, const gl* w, size_t n_words, const uint8
     if (balance.a0 != 0 || balance.a1 != 0) return 200;
     for (int t = 0; t < TMX_N_TABLES; t++) {
         if (!def.tables[t].n_main) continue;
-        const int rc = verify_table(def, t, cap_m[t], cap_a[t], beta, gamma, total[t], r, ch);
+        Challenger fork = ch;  // every table continues on its own fork of the transcript: common state + table index
+        fork.observe((gl)t);
+        const int rc = verify_table(def, t, cap_m[t], cap_a[t], beta, gamma, total[t], r, fork);
         if (rc) return 10 * (t + 1) + rc;
     }
     if (r.err || r.pos != n_words) return 103;
