@@ -16,6 +16,7 @@ int fail(int code, const std::string& msg) {
 // ---- Poseidon round constants: ChaCha8 keystream keyed by rand-0.8's seed_from_u64(0) (PCG32 expansion),
 // u64 = lo | hi << 32, mapped into [0, p) with rand's widening-multiply rejection sampler (zone = p - 1).
 gl h_poseidon_rc[POSEIDON_ROUNDS * POSEIDON_WIDTH];
+gl h_poseidon_rc_fast[(POSEIDON_ROUNDS + 1) * POSEIDON_WIDTH];
 static bool g_rc_ready = false;
 
 static inline uint32_t rol(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
@@ -64,6 +65,21 @@ static void poseidon_generate_constants_once() {
         uint64_t hi = next32();
         unsigned __int128 m = (unsigned __int128)(lo | (hi << 32)) * GL_P;
         if ((uint64_t)m <= GL_P - 1) h_poseidon_rc[n++] = (gl)(m >> 64);
+    }
+    // fast-path table (poseidon.cuh): the constants of lanes 1..11 of the partial rounds travel through the linear layers
+    for (int i = 0; i < (POSEIDON_ROUNDS + 1) * POSEIDON_WIDTH; i++)
+        h_poseidon_rc_fast[i] = i < POSEIDON_ROUNDS * POSEIDON_WIDTH ? h_poseidon_rc[i] : 0;
+    const int first = POSEIDON_HALF_FULL, last = POSEIDON_HALF_FULL + POSEIDON_PARTIAL - 1;  // partial rounds first..last
+    gl h[12];
+    for (int i = 0; i < 12; i++) h[i] = h_poseidon_rc[12 * first + i];
+    for (int r = first; r <= last; r++) {
+        gl d[12];
+        for (int i = 0; i < 12; i++) d[i] = i == 0 ? 0 : h[i];  // deferred part of this round's constants
+        poseidon_mds(d);
+        for (int i = 0; i < 12; i++) h[i] = gl_add(h_poseidon_rc[12 * (r + 1) + i], d[i]);
+        if (r > first)
+            for (int i = 1; i < 12; i++) h_poseidon_rc_fast[12 * r + i] = 0;
+        for (int i = 0; i < 12; i++) h_poseidon_rc_fast[12 * (r + 1) + i] = h[i];
     }
     g_rc_ready = true;
 }

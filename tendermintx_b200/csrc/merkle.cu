@@ -11,10 +11,14 @@
 // multiply issue (about 1.1 k Goldilocks multiplications per permutation), not by HBM.
 #include "ctx.cuh"
 #include "poseidon.cuh"
+#include <cstdlib>
 
 namespace tmx {
 
-__global__ void __launch_bounds__(128, 7) leaf_hash_kernel(const gl* __restrict__ base, size_t leaf_len, size_t row_stride,
+// Five CTAs per SM (92 registers): measured inside the pool bench against 9 / 8 / 7 / 6 / 4 / 3 CTAs per SM (56 ... 138 registers):
+// 47.8 / 46.7 / 46.6 / 46.3 / 46.4 / 46.5 ms per proof, 46.0 ms here -- instruction-level parallelism inside a permutation pays more
+// than extra warps.
+__global__ void __launch_bounds__(128, 5) leaf_hash_kernel(const gl* __restrict__ base, size_t leaf_len, size_t row_stride,
                                                          size_t elem_stride, size_t n_rows, gl* __restrict__ digests) {
     const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_rows) return;

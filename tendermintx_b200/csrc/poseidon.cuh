@@ -15,25 +15,23 @@ constexpr int POSEIDON_ROUNDS = 30;
 constexpr int POSEIDON_HALF_FULL = 4;
 constexpr int POSEIDON_PARTIAL = 22;
 
-// host copy (filled by poseidon_generate_constants, context.cu)
+// host copies (filled by poseidon_generate_constants, context.cu)
 extern gl h_poseidon_rc[POSEIDON_ROUNDS * POSEIDON_WIDTH];
+// Constants of the fast path, 30 rounds plus one all-zero round (it always adds "the next round's" constants).  Lanes
+// 1..11 pass through the 22 partial rounds linearly, so their constants are pushed forward through the linear layers:
+// a partial round adds ONE constant (lane 0), and what was deferred arrives with the constants of the first full round
+// after them:  h_{r+1} = c_{r+1} + M (h_r with lane 0 cleared),  rows 5..25 keep only lane 0 of h_r, row 26 is all of h_26.
+extern gl h_poseidon_rc_fast[(POSEIDON_ROUNDS + 1) * POSEIDON_WIDTH];
 void poseidon_generate_constants();
 
 #if defined(__CUDACC__)
-// 30 rounds of constants plus one all-zero round (the fast path always adds "the next round's" constants)
-static __constant__ gl d_poseidon_rc[(POSEIDON_ROUNDS + 1) * POSEIDON_WIDTH];
-// the same constants cut into 22/22/20-bit pieces (x, y, z; w unused) for lanes that stay in piece form
-static __constant__ uint4 d_poseidon_rcp[(POSEIDON_ROUNDS + 1) * POSEIDON_WIDTH];
+static __constant__ gl d_poseidon_rc[POSEIDON_ROUNDS * POSEIDON_WIDTH];
+static __constant__ gl d_poseidon_rc_fast[(POSEIDON_ROUNDS + 1) * POSEIDON_WIDTH];
 static inline cudaError_t poseidon_upload_constants_tu() {
     poseidon_generate_constants();
-    gl padded[(POSEIDON_ROUNDS + 1) * POSEIDON_WIDTH] = {0};
-    uint4 pieces[(POSEIDON_ROUNDS + 1) * POSEIDON_WIDTH];
-    for (int i = 0; i < POSEIDON_ROUNDS * POSEIDON_WIDTH; i++) padded[i] = h_poseidon_rc[i];
-    for (int i = 0; i < (POSEIDON_ROUNDS + 1) * POSEIDON_WIDTH; i++)
-        pieces[i] = make_uint4((uint32_t)padded[i] & 0x3FFFFFu, (uint32_t)(padded[i] >> 22) & 0x3FFFFFu, (uint32_t)(padded[i] >> 44), 0u);
-    cudaError_t e = cudaMemcpyToSymbol(d_poseidon_rcp, pieces, sizeof(pieces));
+    cudaError_t e = cudaMemcpyToSymbol(d_poseidon_rc_fast, h_poseidon_rc_fast, sizeof(h_poseidon_rc_fast));
     if (e != cudaSuccess) return e;
-    e = cudaMemcpyToSymbol(d_poseidon_rc, padded, sizeof(padded));
+    e = cudaMemcpyToSymbol(d_poseidon_rc, h_poseidon_rc, sizeof(h_poseidon_rc));
     if (e != cudaSuccess) return e;
     return cudaStreamSynchronize(cudaStreamLegacy);  // staged copies: wait for the DMA (the provers' streams are non-blocking)
 }
@@ -110,11 +108,11 @@ TMX_HD gl poseidon_sbox_nc(gl x) {
     const gl x2 = gl_sqr_nc(x), x3 = gl_mul_nc(x2, x), x4 = gl_sqr_nc(x2);
     return gl_mul_nc(x3, x4);
 }
-TMX_HD gl poseidon_rc_padded(int i) {  // 30 rounds of constants followed by one all-zero round
+TMX_HD gl poseidon_rc_fast(int i) {
 #if defined(__CUDA_ARCH__)
-    return d_poseidon_rc[i];
+    return d_poseidon_rc_fast[i];
 #else
-    return i < POSEIDON_ROUNDS * POSEIDON_WIDTH ? h_poseidon_rc[i] : 0;
+    return h_poseidon_rc_fast[i];
 #endif
 }
 // ---- multiplier-free MDS ----------------------------------------------------------------------------------------
@@ -184,17 +182,10 @@ TMX_HD gl poseidon_recombine(uint32_t o0, uint32_t o1, uint32_t o2, gl rc) {
     return v + ((0 - c) & GL_EPS);
 }
 // the same value back in piece form (carry propagation; the part above bit 64 re-enters as ov 2^32 - ov)
-TMX_HD void poseidon_normalize(uint32_t o0, uint32_t o1, uint32_t o2, int rc_index, uint32_t* p0, uint32_t* p1, uint32_t* p2) {
-#if defined(__CUDA_ARCH__)
-    const uint4 k = d_poseidon_rcp[rc_index];
-    const uint32_t k0 = k.x, k1 = k.y, k2 = k.z;
-#else
-    const gl kk = rc_index < POSEIDON_ROUNDS * POSEIDON_WIDTH ? h_poseidon_rc[rc_index] : 0;
-    const uint32_t k0 = (uint32_t)kk & 0x3FFFFFu, k1 = (uint32_t)(kk >> 22) & 0x3FFFFFu, k2 = (uint32_t)(kk >> 44);
-#endif
-    const int32_t a0 = (int32_t)(o0 + k0);
-    const int32_t a1 = (int32_t)(o1 + k1) + (a0 >> 22);
-    const int32_t a2 = (int32_t)(o2 + k2) + (a1 >> 22);
+TMX_HD void poseidon_normalize(uint32_t o0, uint32_t o1, uint32_t o2, uint32_t* p0, uint32_t* p1, uint32_t* p2) {
+    const int32_t a0 = (int32_t)o0;
+    const int32_t a1 = (int32_t)o1 + (a0 >> 22);
+    const int32_t a2 = (int32_t)o2 + (a1 >> 22);
     const int32_t ov = a2 >> 20;
     *p0 = (uint32_t)((a0 & 0x3FFFFF) - ov);
     *p1 = (uint32_t)((a1 & 0x3FFFFF) + ov * 1024);
@@ -211,7 +202,7 @@ TMX_HD void poseidon_permute_fast(gl s[12]) {
     uint32_t w0[12], w1[12], w2[12], o0[12], o1[12], o2[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) {
-        const gl x = gl_add(s[i], poseidon_rc_padded(i));  // round 0 constants (inputs are canonical)
+        const gl x = gl_add(s[i], poseidon_rc_fast(i));  // round 0 constants (inputs are canonical)
         w0[i] = (uint32_t)x;
         w1[i] = (uint32_t)(x >> 32);
         w2[i] = 0;
@@ -233,19 +224,19 @@ TMX_HD void poseidon_permute_fast(gl s[12]) {
         o1[0] += w1[0] << 3;
         o2[0] += w2[0] << 3;
         const int rc_base = 12 * (r + 1);
-        const gl x0 = poseidon_recombine(o0[0], o1[0], o2[0], poseidon_rc_padded(rc_base));
+        const gl x0 = poseidon_recombine(o0[0], o1[0], o2[0], poseidon_rc_fast(rc_base));
         w0[0] = (uint32_t)x0;
         w1[0] = (uint32_t)(x0 >> 32);
         if (words_out) {
 #pragma unroll
             for (int i = 1; i < 12; i++) {
-                const gl x = poseidon_recombine(o0[i], o1[i], o2[i], poseidon_rc_padded(rc_base + i));
+                const gl x = poseidon_recombine(o0[i], o1[i], o2[i], poseidon_rc_fast(rc_base + i));
                 w0[i] = (uint32_t)x;
                 w1[i] = (uint32_t)(x >> 32);
             }
         } else {
 #pragma unroll
-            for (int i = 1; i < 12; i++) poseidon_normalize(o0[i], o1[i], o2[i], rc_base + i, &w0[i], &w1[i], &w2[i]);
+            for (int i = 1; i < 12; i++) poseidon_normalize(o0[i], o1[i], o2[i], &w0[i], &w1[i], &w2[i]);  // (their constants are deferred)
         }
     }
 #pragma unroll
