@@ -30,7 +30,7 @@ N_MAX = 128
 # profiles/r2c_ncu_ntt.raw.csv (tools/gpu_ncu.sh).
 NCU_K1_TRAFFIC_BYTES = 2813383936
 NCU_K1_WARP_INSTR = 1218528448  # smsp__inst_executed.sum over the same six launches (1212 thread instructions per trace cell)
-NCU_K2_WARP_INSTR_PER_PERM = 14.21e9 / 20.05e6  # = 709 (22.7 k thread instructions per permutation)
+NCU_K2_WARP_INSTR_PER_PERM = 5361258496 / (65536 * 123)  # = 665 (21.3 k thread instructions per permutation), profiles/r2f_ncu_leaf_hash.raw.csv
 METRIC = "skip proofs/hour (CelestiaConfig, 128 val)"
 UNIT = "proofs/hour"
 WORKLOAD = "skip circuit CelestiaConfig VALIDATOR_SET_SIZE_MAX=128 (synthetic celestia chain, 128 signers, seed=rank)"
@@ -353,8 +353,8 @@ def run_ours(args):
                          "rebuilds with -march=native)",
                "proof_bytes_equal_gpu": bool(same)}
     # second roofline line SURVEY 8(d) asks for: K2 is bound by integer issue, not HBM.  Warp instructions per
-    # permutation are from the ncu capture of leaf_hash_kernel (profiles/r1e_ncu_leaf_hash.raw.csv: 14.21 G warp
-    # instructions for 20.05 M permutations); the time is the Ed25519 table's Merkle phase measured inside the timed proofs.
+    # permutation are from the ncu capture of leaf_hash_kernel (profiles/r2f_ncu_leaf_hash.raw.csv: 5.36 G warp
+    # instructions for the 8.06 M permutations of the Ed25519 table's first-round leaves); the time is the Ed25519 table's Merkle phase measured inside the timed proofs.
     clk = clocks.summary()
     ed_perms = (dims[2][0] * 2) * ((dims[2][1] + 7) // 8) + dims[2][0] * 2
     k2_ed_ms = phase[2][1] / lat_steps
@@ -364,7 +364,7 @@ def run_ours(args):
                 "achieved": k2_winstr / (k2_ed_ms / 1e3) / 1e9, "peak": issue_peak,
                 "frac": k2_winstr / (k2_ed_ms / 1e3) / 1e9 / issue_peak, "ms": k2_ed_ms,
                 "peak_note": "148 SMs x 4 schedulers x 1 warp instruction/clk at the sampled SM clock; the multiply (fmaheavy) pipe, "
-                             "which carries the S-box products and half of the additions, is the busiest unit at 84 % in the ncu capture"}
+                             "which carries the S-box products and half of the additions, is the busiest unit (sm__throughput 72 % in the ncu capture)"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -404,7 +404,7 @@ def run_ours(args):
         "kernels": {"k2_poseidon_merkle_ms_per_proof": merkle_ms, "k2_Mperm_per_s": perms / merkle_ms / 1e3,
                     "k2_ms_per_table": [p[1] / lat_steps for p in phase],
                     "k2_share_of_step": merkle_ms / (serial_ms / lat_steps),
-                    "k2_note": "dominant kernel by time; bound by integer issue (ncu: < 1 % DRAM, busiest pipe 84 %), 22.7 k instructions per permutation",
+                    "k2_note": "dominant kernel by time; bound by integer issue (ncu: < 1 % DRAM, busiest pipe 72 %), 21.3 k instructions per permutation",
                     "k2_int_issue_roofline": k2_issue,
                     "isolated_ed25519_table": {"lde_ms": iso[0], "lde_GBps": 8 * rows * cols * 3 / iso[0] / 1e6,
                                                "poseidon_merkle_ms": iso[1]}},

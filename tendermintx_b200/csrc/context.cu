@@ -3,6 +3,8 @@
 #include "poseidon.cuh"
 #include <mutex>
 #include <cstring>
+#include <cstdio>
+#include <cstdlib>
 
 namespace tmx {
 
@@ -81,6 +83,14 @@ static void poseidon_generate_constants_once() {
             for (int i = 1; i < 12; i++) h_poseidon_rc_fast[12 * r + i] = 0;
         for (int i = 0; i < 12; i++) h_poseidon_rc_fast[12 * (r + 1) + i] = h[i];
     }
+    // poseidon_recombine() wants a non-negative integer: the lowest piece of a lane in piece form can be as low as -2^21, and
+    // the constant added on top must cover that wherever such lanes are recombined (a fixed table: this never fires)
+    for (int r = first + 1; r <= last + 1; r++)
+        for (int i = 0; i < (r == last + 1 ? 12 : 1); i++)
+            if (h_poseidon_rc_fast[12 * r + i] < ((gl)1 << 22)) {
+                fprintf(stderr, "tmx: Poseidon fast-path constant %d/%d is too small for the piece arithmetic\n", r, i);
+                abort();
+            }
     g_rc_ready = true;
 }
 // tmx_verify_params may be the first caller on several threads at once: the table is written exactly once

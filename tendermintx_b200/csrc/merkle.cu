@@ -15,10 +15,13 @@
 
 namespace tmx {
 
+#ifndef TMX_LEAF_T
+#define TMX_LEAF_T 128
+#endif
 // Five CTAs per SM (92 registers): measured inside the pool bench against 9 / 8 / 7 / 6 / 4 / 3 CTAs per SM (56 ... 138 registers):
 // 47.8 / 46.7 / 46.6 / 46.3 / 46.4 / 46.5 ms per proof, 46.0 ms here -- instruction-level parallelism inside a permutation pays more
 // than extra warps.
-__global__ void __launch_bounds__(128, 5) leaf_hash_kernel(const gl* __restrict__ base, size_t leaf_len, size_t row_stride,
+__global__ void __launch_bounds__(TMX_LEAF_T, 640 / TMX_LEAF_T) leaf_hash_kernel(const gl* __restrict__ base, size_t leaf_len, size_t row_stride,
                                                          size_t elem_stride, size_t n_rows, gl* __restrict__ digests) {
     const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_rows) return;
@@ -72,7 +75,7 @@ int merkle_generic(tmx_ctx* ctx, const gl* base, size_t leaf_len, size_t row_str
                    unsigned cap_height, gl* d_digests, cudaStream_t st) {
     if (cap_height > log_rows) cap_height = log_rows;
     const size_t n = (size_t)1 << log_rows;
-    leaf_hash_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(base, leaf_len, row_stride, elem_stride, n, d_digests);
+    leaf_hash_kernel<<<(unsigned)((n + TMX_LEAF_T - 1) / TMX_LEAF_T), TMX_LEAF_T, 0, st>>>(base, leaf_len, row_stride, elem_stride, n, d_digests);
     ctx->launches++;
     TMX_CUDA(cudaGetLastError());
     gl* lvl = d_digests;

@@ -113,6 +113,26 @@ def test_synthetic_celestia_skip_n16(ctx, oracle):
     circuit.close()
 
 
+def test_tables_side_by_side_and_serialised_give_the_same_proof(ctx, monkeypatch):
+    """The shipped prover runs the five tables on five streams (and their tails on five host threads); TMX_SERIAL_TABLES=1
+    puts everything on one stream and one thread.  Scheduling must not leak into the proof: same bytes, repeatedly."""
+    import tendermintx_b200 as tmx
+    from oracle import tm_inputs as ti
+
+    src, t, g = ti.synthetic_source(seed=5, n_validators=16)
+    th = ti.header_hash(src.signed_header(t)["header"])
+    blob, pub = ti.skip_inputs(src, 16, t, th, g), ti.skip_public_input(t, th, g)
+    circuit = tmx.Circuit.build(ctx, tmx.KIND_SKIP, 16, tmx.CelestiaConfig)
+    proofs = [circuit.prove(pub, blob)[0] for _ in range(4)]
+    monkeypatch.setenv("TMX_SERIAL_TABLES", "1")
+    proofs += [circuit.prove(pub, blob)[0] for _ in range(2)]
+    monkeypatch.delenv("TMX_SERIAL_TABLES")
+    proofs.append(circuit.prove(pub, blob)[0])
+    assert all(p == proofs[0] for p in proofs)
+    circuit.verify(proofs[0], pub, ti.header_hash(src.signed_header(g)["header"]))
+    circuit.close()
+
+
 def test_full_size_skip_n128_celestia(ctx):
     """BASELINE config 2 at full size: prove from the fixture directory (C++ input assembly -> kernels -> proof),
     output = the fixture's block hash, CPU verifier accepts, proof is reproducible, a tampered proof is rejected."""
