@@ -228,6 +228,7 @@ extern "C" int tmx_circuit_build(tmx_ctx* ctx, uint32_t kind, uint32_t n_max, co
             cudaEventCreateWithFlags(&c->ev_done[t], cudaEventDisableTiming) != cudaSuccess)
             return fail(TMX_E_CUDA, "tmx_circuit_build: stream / event creation failed");
     }
+    cudaMemset(c->d_points, 0, witness_points_bytes(n_max));  // struct padding travels to the host with the slot infos
     const AirShape sh = air_shape(kind, n_max, chain_id, chain_id_len);
     if (logic_rows(sh)) {
         c->plan = logic_plan_get(sh);

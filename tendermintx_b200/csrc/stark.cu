@@ -445,6 +445,7 @@ int Prover::setup(tmx_ctx* ctx, std::shared_ptr<const CircuitDef> d) {
     rowsum_stride = max_n;
     if ((rc = alloc((void**)&d_rowsum, (size_t)STARK_N_TABLES * max_n * sizeof(gl2)))) return rc;
     if ((rc = alloc((void**)&d_small, (size_t)STARK_N_TABLES * 66 * sizeof(gl)))) return rc;
+    TMX_CUDA(cudaMemsetAsync(d_small, 0, (size_t)STARK_N_TABLES * 66 * sizeof(gl), st));  // the totals' slots are copied (unused) in round 1
     if ((rc = alloc((void**)&d_hist, (BUS_HIST_SIZE + 4) * sizeof(unsigned int)))) return rc;
     if (def->tables[AIR_RANGE].n_main)
         if ((rc = alloc((void**)&d_range_trace, def->tables[AIR_RANGE].rows() * RG_COLS * sizeof(gl)))) return rc;
