@@ -365,6 +365,17 @@ extern "C" int tmx_prove(tmx_circuit* c, const uint8_t* input, size_t input_len,
     TMX_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     Prover& pr = c->prover;
+    // whatever way this call ends, no stream of the circuit may still be working on its buffers when the next one starts
+    struct Quiesce {
+        tmx_circuit* c;
+        bool armed = true;
+        ~Quiesce() {
+            if (!armed) return;
+            cudaStreamSynchronize(c->side);
+            for (int t = 0; t < STARK_N_TABLES; t++)
+                if (c->tstream[t]) cudaStreamSynchronize(c->tstream[t]);
+        }
+    } quiesce{c};
     // ---- witness generation on the GPU ----
     const uint8_t* d_blob = c->d_blob;
     if (!use_resident) {
@@ -499,9 +510,18 @@ extern "C" int tmx_prove(tmx_circuit* c, const uint8_t* input, size_t input_len,
         for (int t = 0; t < STARK_N_TABLES; t++) run_tail(t);
     } else {
         std::thread workers[STARK_N_TABLES];
-        for (int t = 0; t < STARK_N_TABLES; t++)
-            if (t != AIR_ED25519) workers[t] = std::thread(run_tail, t);
+        bool started[STARK_N_TABLES] = {};
+        for (int t = 0; t < STARK_N_TABLES; t++) {
+            if (t == AIR_ED25519) continue;
+            try {  // nothing may unwind across the C ABI: a table whose thread cannot be created runs on this one
+                workers[t] = std::thread(run_tail, t);
+                started[t] = true;
+            } catch (...) {
+            }
+        }
         run_tail(AIR_ED25519);
+        for (int t = 0; t < STARK_N_TABLES; t++)
+            if (t != AIR_ED25519 && !started[t]) run_tail(t);
         for (auto& th : workers)
             if (th.joinable()) th.join();
     }
@@ -509,6 +529,7 @@ extern "C" int tmx_prove(tmx_circuit* c, const uint8_t* input, size_t input_len,
         if (tail_rc[t]) return fail(tail_rc[t], tail_err[t]);
         w.insert(w.end(), tail_words[t].begin(), tail_words[t].end());
     }
+    quiesce.armed = false;  // every tail ended with a synchronised copy on its stream; the side stream was joined in round 1
     *proof_out = p.release();
     return TMX_OK;
 }

@@ -6,7 +6,7 @@ ia, isrc, iex, ismp = hdr.index("Address"), hdr.index("Source"), hdr.index("Inst
 stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
 ops = collections.Counter(); smp = collections.Counter(); stalls = collections.Counter(); tot = 0
 for r in rows[2:]:
-    if len(r) <= iex or not r[iex]:
+    if len(r) <= iex or not r[iex] or not r[iex].isdigit():  # (a multi-kernel export repeats its header rows)
         continue
     src = re.sub(r"^@!?U?P\d+\s+", "", r[isrc].strip())
     op = src.split()[0].rstrip(";") if src else "?"
