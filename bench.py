@@ -420,7 +420,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200, help="proofs in each timed region (200 = a little over ten seconds)")
+    ap.add_argument("--steps", type=int, default=250, help="proofs in each timed region (250 = a little over eleven seconds)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
