@@ -46,6 +46,7 @@ struct Prover {
         gl2* d_fri[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
         gl* d_query = nullptr; size_t sz_query = 0;
         gl* h_pinned = nullptr; size_t sz_pinned = 0;
+        cudaEvent_t ev_wait = nullptr;  // blocking-sync event: the host thread sleeps instead of spinning while it waits
     };
     Tail tail[STARK_N_TABLES + 1];  // the last one: staging buffer of the commitment rounds
     gl2* d_rowsum = nullptr;      // per-row bus sums, one region of rowsum_stride elements per table (tables run on their own streams)
