@@ -302,7 +302,7 @@ def run_ours(args):
         return
     # ---- roofline of the dominant HBM-shaped kernel family, K1 (iNTT + coset LDE), timed INSIDE the timed proofs ----
     # algorithmic bytes of a rate-1/2 coset LDE of C columns of n rows: 8 n C (1 + 2);
-    # per proof = the sum over the three tables; achieved = bytes / (K1 device time per proof).
+    # all_tables = the three kernel-filled witness tables; achieved = bytes / (K1 device time per proof).
     peak, peak_src = measured_peaks()
     dims = tmx.Context.trace_dims(tmx.KIND_SKIP, N_MAX)
     # the Ed25519 table is 62 % of the committed cells and its LDE runs alone on the GPU (the SHA-256 table's LDE shares

@@ -102,7 +102,7 @@ int tmx_sha512_trace(tmx_ctx *ctx, const uint8_t *d_blob, uint32_t kind, uint32_
  * [s]B + [h](-A), one row per scalar-bit pair) */
 int tmx_ed25519_trace(tmx_ctx *ctx, const uint8_t *d_blob, uint32_t kind, uint32_t n_max, uint64_t *d_t512,
                       uint64_t *d_ted, uint8_t *d_aux, void *stream);
-/* all three tables */
+/* the three witness tables filled by kernels (SHA-256, SHA-512, Ed25519); the logic table is tmx_logic_trace, the range table follows from the lookups */
 int tmx_witness_generate(tmx_ctx *ctx, const uint8_t *d_blob, uint32_t kind, uint32_t n_max, uint64_t *d_t256,
                          uint64_t *d_t512, uint64_t *d_ted, uint8_t *d_aux, void *stream);
 

@@ -398,7 +398,7 @@ extern "C" int tmx_prove(tmx_circuit* c, const uint8_t* input, size_t input_len,
     rc = witness_run_sha256(ctx, wa, st);
     if (rc) return rc;
     memcpy(out32, h->header, 32);
-    // ---- proof: header, round 1, round 2, one tail per table on a shared transcript ----
+    // ---- proof: header, round 1, round 2 on the common transcript, then one tail per table on its own fork ----
     std::unique_ptr<tmx_proof> p(new tmx_proof());
     std::vector<gl>& w = p->words;
     w.push_back(STARK_PROOF_MAGIC);
