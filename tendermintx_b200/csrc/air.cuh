@@ -43,12 +43,18 @@ TMX_HD FE operator-(FE a, FE b) { return FE::mk(gl2_sub(a.v, b.v)); }
 TMX_HD FE operator*(FE a, FE b) { return FE::mk(gl2_mul(a.v, b.v)); }
 
 // Horner accumulator over the two constraint challenges: acc <- acc * alpha + c
+// acc * alpha + c
+template <class F>
+TMX_HD F horner_step(F acc, F alpha, F c) { return acc * alpha + c; }
+// base field (quotient kernels): one lazily reduced multiply-add; the accumulator stays in [0, 2^64) and whoever reads it
+// multiplies it once more (by 1 / Z_H), which canonicalises
+TMX_HD FB horner_step(FB acc, FB alpha, FB c) { return FB::mk(gl_mac_nc(acc.v, alpha.v, c.v)); }
 template <class F>
 struct ConstraintAcc {
     F acc0, acc1, alpha0, alpha1;
     TMX_HD void operator()(F c) {
-        acc0 = acc0 * alpha0 + c;
-        acc1 = acc1 * alpha1 + c;
+        acc0 = horner_step(acc0, alpha0, c);
+        acc1 = horner_step(acc1, alpha1, c);
     }
 };
 
@@ -81,18 +87,23 @@ template <class F>
 TMX_HD Ext2<F> e2_add(Ext2<F> a, Ext2<F> b) { return e2_mk<F>(a.a0 + b.a0, a.a1 + b.a1); }
 template <class F>
 TMX_HD Ext2<F> e2_sub(Ext2<F> a, Ext2<F> b) { return e2_mk<F>(a.a0 - b.a0, a.a1 - b.a1); }
+// 7 x (the non-residue of the extension)
+template <class F>
+TMX_HD F f_mul7(F x) { return F::c(7) * x; }
+TMX_HD FB f_mul7(FB x) { return FB::mk(gl_mul7(x.v)); }
 template <class F>
 TMX_HD Ext2<F> e2_mul(Ext2<F> a, Ext2<F> b) {
-    return e2_mk<F>(a.a0 * b.a0 + F::c(7) * (a.a1 * b.a1), a.a0 * b.a1 + a.a1 * b.a0);
+    return e2_mk<F>(a.a0 * b.a0 + f_mul7(a.a1 * b.a1), a.a0 * b.a1 + a.a1 * b.a0);
 }
 template <class F>
 TMX_HD Ext2<F> e2_scale(Ext2<F> a, F s) { return e2_mk<F>(a.a0 * s, a.a1 * s); }
 
 // fingerprint of (tag, tup(0) .. tup(len - 1)): gamma + tag + beta (v_0 + beta (v_1 + ...))
+// (Horner from the last element; its first step multiplies beta by a base-field value: two products, not an extension product)
 template <class F, class Tup>
 TMX_HD Ext2<F> bus_fingerprint(Ext2<F> beta, Ext2<F> gamma, F tag, int len, const Tup& tup) {
-    Ext2<F> acc = e2_mk<F>(F::c(0), F::c(0));
-    for (int i = len - 1; i >= 0; i--) {
+    Ext2<F> acc = e2_scale<F>(beta, tup(len - 1));
+    for (int i = len - 2; i >= 0; i--) {
         acc.a0 = acc.a0 + tup(i);
         acc = e2_mul<F>(acc, beta);
     }
@@ -104,13 +115,15 @@ TMX_HD Ext2<F> bus_fingerprint(Ext2<F> beta, Ext2<F> gamma, F tag, int len, cons
 template <class F, class Bus>
 struct LookupPairs {
     Bus& bus;
-    bool have;
+    bool have, unit0;
     F tag0, m0, v0;
-    TMX_HD LookupPairs(Bus& b) : bus(b), have(false) { tag0 = m0 = v0 = F::c(0); }
-    // multiplicity m (p - 1 = one lookup)
-    TMX_HD void push(F tag, F m, F v) {
+    TMX_HD LookupPairs(Bus& b) : bus(b), have(false), unit0(false) { tag0 = m0 = v0 = F::c(0); }
+    // multiplicity m (p - 1 = one lookup); `unit`: m is the constant p - 1 (two such lookups share the cheaper
+    // bus.two_lookups: same helper constraint, no products with the multiplicities)
+    TMX_HD void push(F tag, F m, F v, bool unit = false) {
         if (!have) {
             have = true;
+            unit0 = unit;
             tag0 = tag;
             m0 = m;
             v0 = v;
@@ -118,9 +131,10 @@ struct LookupPairs {
         }
         have = false;
         const F a = v0, b = v;
-        bus.two(tag0, m0, 1, [&](int) { return a; }, tag, m, 1, [&](int) { return b; });
+        if (unit0 && unit) bus.two_lookups(tag0, a, tag, b);
+        else bus.two(tag0, m0, 1, [&](int) { return a; }, tag, m, 1, [&](int) { return b; });
     }
-    TMX_HD void push(int tag, F v) { push(F::c((uint64_t)tag), F::c(0xFFFFFFFF00000000ULL), v); }
+    TMX_HD void push(int tag, F v) { push(F::c((uint64_t)tag), F::c(0xFFFFFFFF00000000ULL), v, true); }
     TMX_HD void flush() {
         if (!have) return;
         have = false;

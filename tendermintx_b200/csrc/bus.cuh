@@ -53,6 +53,15 @@ struct BusCheck {
         emit(c.a0);
         emit(c.a1);
     }
+    // two lookups (multiplicity -1 each) of single values:  H fa fb = -(fa + fb)
+    TMX_HD void two_lookups(F tag_a, F va, F tag_b, F vb) {
+        Ext2<F> fa = e2_add<F>(e2_scale<F>(beta, va), gamma), fb = e2_add<F>(e2_scale<F>(beta, vb), gamma);
+        fa.a0 = fa.a0 + tag_a;
+        fb.a0 = fb.a0 + tag_b;
+        const Ext2<F> c = e2_add<F>(e2_mul<F>(helper(), e2_mul<F>(fa, fb)), e2_add<F>(fa, fb));
+        emit(c.a0);
+        emit(c.a1);
+    }
     // an: the next row of the second-round trace; s_over_n: the table's claimed total divided by its length
     TMX_HD void finish(const AuxRow& an, Ext2<F> s_over_n) {
         const Ext2<F> z = e2_mk<F>(al[2 * h], al[2 * h + 1]), zn = e2_mk<F>(an[2 * h], an[2 * h + 1]);
@@ -106,13 +115,19 @@ struct BusGen {
     TMX_HD void put_zero() { store(h++, gl2_from(0)); }
     template <class Tup>
     TMX_HD gl2 fp(FB tag, int len, const Tup& tup) const {
-        gl2 acc = gl2_from(0);
-        for (int i = len - 1; i >= 0; i--) {
+        gl2 acc = gl2_scale(beta, tup(len - 1).v);
+        for (int i = len - 2; i >= 0; i--) {
             acc.a0 = gl_add(acc.a0, tup(i).v);
             acc = gl2_mul(acc, beta);
         }
         acc.a0 = gl_add(acc.a0, tag.v);
         return gl2_add(acc, gamma);
+    }
+    TMX_HD void two_lookups(FB tag_a, FB va, FB tag_b, FB vb) {
+        gl2 fa = gl2_add(gl2_scale(beta, va.v), gamma), fb = gl2_add(gl2_scale(beta, vb.v), gamma);
+        fa.a0 = gl_add(fa.a0, tag_a.v);
+        fb.a0 = gl_add(fb.a0, tag_b.v);
+        put(gl2_neg(gl2_add(fa, fb)), gl2_mul(fa, fb));
     }
     template <class Tup>
     TMX_HD void one(FB tag, FB m, int len, const Tup& tup) {
@@ -153,6 +168,10 @@ struct BusCount {
     TMX_HD void two(FB tag_a, FB ma, int, const TA& ta, FB tag_b, FB mb, int, const TB& tb) {
         add(tag_a, ma, ta(0).v);
         add(tag_b, mb, tb(0).v);
+    }
+    TMX_HD void two_lookups(FB tag_a, FB va, FB tag_b, FB vb) {
+        add(tag_a, FB::mk(GL_P - 1), va.v);
+        add(tag_b, FB::mk(GL_P - 1), vb.v);
     }
 };
 constexpr size_t BUS_HIST_SIZE = (1u << 16) + (1u << 11) + (1u << 8) + 2;

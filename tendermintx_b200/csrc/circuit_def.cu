@@ -126,6 +126,10 @@ struct SymBus {
             g_sym->fail("bus.two: degree > 3 (helper " + std::to_string(g_sym->n_helpers) + ")");
         g_sym->n_helpers++;
     }
+    void two_lookups(Sym tag_a, Sym va, Sym tag_b, Sym vb) {
+        const Sym m = Sym::c(GL_P - 1);
+        two(tag_a, m, 1, [&](int) { return va; }, tag_b, m, 1, [&](int) { return vb; });
+    }
 };
 
 // ------------------------------------------------------------------------------------------ host commitment of constant columns

@@ -177,6 +177,13 @@ TMX_HD gl gl_mul(gl a, gl b) {
 #endif
 }
 TMX_HD gl gl_sqr(gl a) { return gl_mul(a, a); }
+// 7 a, canonical (a < 2^64): the part above 2^64 is below 7
+TMX_HD gl gl_mul7(gl a) {
+    gl lo, hi, c;
+    gl_mul128(a, 7, &lo, &hi);
+    const gl t = gl_add_carry(lo, (hi << 32) - hi, &c);
+    return gl_canon(t + ((0 - c) & GL_EPS));
+}
 
 TMX_HD gl gl_pow(gl b, uint64_t e) {
     gl r = 1;

@@ -1,6 +1,7 @@
 # quick check of a prover change on one B200: proof equality tests, then the bench with a few in-flight depths
 set -x
 mkdir -p gpurun_out
+timeout 1200 python -m pytest tests/test_gpu_prove.py tests/test_gpu_bus.py -m gpu -x -q 2>&1 | tail -3
 
 for k in 4 2 1; do timeout 600 python bench.py --steps 100 --no-cpu-baseline --in-flight $k > gpurun_out/bench_if$k.json 2>> gpurun_out/bench.err; done
 python - <<'PY'
