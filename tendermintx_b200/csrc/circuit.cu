@@ -165,9 +165,10 @@ static int check_statement(const tmx_circuit* c, const uint8_t* input, const uin
         }
         if (memcmp(aux + AUX_SET_ROOT, h->aux_hash_proof.leaf + 2, 32)) return CHECK_TRUSTED_VALHASH;
         std::vector<uint8_t> flag(n, 0);
+        // (only enabled slots of the trusted set: what the proof enforces, see logic.cuh; the reference loops over all of them)
         for (size_t i = 0; i < n; i++)
             if (vals[i].is_signed)
-                for (size_t j = 0; j < n; j++)
+                for (size_t j = 0; j < n && j < h->nb_trusted; j++)
                     if (!memcmp(vals[i].pubkey, tf[j].pubkey, 32)) flag[j] = 1;
         bool gt = false;
         int rc = voting_threshold(power, flag, h->nb_trusted, 1, 3, &gt);

@@ -254,6 +254,10 @@ TMX_HD void air_logic(AirShape sh, const Row& l, const Row& n, const KRow& k, co
     const F e = l[H1_E], sgn = l[H1_SGN], flag = l[H1_FLAG];
     emit((s1 - fval) * (e - one));
     emit(s1 * (sgn * (one - e)));
+    // a trusted validator counts only from an enabled slot: the validators hash does not bind the fields of the padding slots
+    // (the reference sums over every flagged slot, verify.rs:392-431 -- a padding slot with a signer's key and a large
+    // power would meet the 1/3 threshold by itself)
+    emit(s1 * (flag * (one - e)));
     emit(sgn * (s1 - P(H1P_TARGET)));
     emit(flag * (s1 - P(H1P_TRUSTED)));
     emit(s1 * (l[H1_MK] * (one - sgn)));

@@ -480,7 +480,7 @@ int logic_fill_trace(const LogicPlan& p, const uint8_t* input, const uint8_t* bl
     std::vector<uint64_t> key_mult(N, 0);
     std::vector<uint8_t> flag(N, 0);
     if (skip)
-        for (uint32_t j = 0; j < N; j++)
+        for (uint32_t j = 0; j < N && j < h->nb_trusted; j++)  // enabled slots only: padding never counts (logic.cuh)
             for (uint32_t i = 0; i < N; i++)
                 if (vals[i].is_signed && !memcmp(vals[i].pubkey, tf[j].pubkey, 32)) {
                     flag[j] = 1;  // the lookup is answered by the first signed target validator with this key

@@ -148,6 +148,49 @@ def test_trusted_validator_flagged_without_a_matching_signer(oracle, honest):
     _both_reject(oracle, bad, pub, kind, c["n_max"], out)
 
 
+def test_padding_slot_of_the_trusted_set_cannot_carry_voting_power(oracle, honest):
+    """The trusted validators hash binds only the ENABLED slots.  A prover fills a padding slot of the trusted set with the key
+    of a signed target validator and a huge voting power, flags it as 'signed on target' and keeps every running sum
+    consistent: the 1/3 threshold would be met by data nobody committed to.  (The reference sums `voting_power` over all
+    flagged slots, enabled or not [REF verify.rs:392-431, voting.rs:69-86]; here a flag needs an enabled row.)"""
+    import struct
+
+    c, pub, blob, kind = _case("skip_10000_10500_n4")
+    n = c["n_max"]
+    nb_trusted = struct.unpack_from("<I", blob, 16)[0]
+    assert nb_trusted < n
+    signer = next(i for i in range(n) if blob[920 + 240 * i + 236])
+    slot, power = nb_trusted, 10**12
+    b = bytearray(blob)
+    tf = 920 + 240 * n + 48 * slot
+    b[tf:tf + 32] = blob[920 + 240 * signer:920 + 240 * signer + 32]
+    struct.pack_into("<QI", b, tf + 32, power, 37 + 6)  # 10^12 is a six-byte varint
+    blob2 = bytes(b)
+    status, proof, out = oracle.prove(pub, blob2, "mocha-4")  # padding data is free: the honest proof still goes through
+    assert status == "OK"
+    _both_accept(oracle, proof, pub, kind, n, out)
+    lt, st = oracle.logic_trace(pub, blob2, "mocha-4")
+    assert st == 0
+    circ = oracle.circuit(kind, n, "mocha-4")
+    rows = [int(r) for r in np.nonzero(circ.table_data(T_LOGIC)[1][50])[0]]  # H1 rows: trusted leaves, then target leaves
+    H1_FLAG, H1_SUM, H1_SUM4, H1_DF, H1_DF2, H1_MK = 178, 197, 201, 202, 206, 400 + 16
+    assert lt[H1_FLAG, rows[slot]] == 0
+
+    def limbs(col, row):
+        return sum(int(lt[col + k, row]) << (16 * k) for k in range(4))
+
+    patches = [(T_LOGIC, H1_FLAG, rows[slot], 1), (T_LOGIC, H1_MK, rows[n + signer], int(lt[H1_MK, rows[n + signer]]) + 1)]
+    for i in range(slot, n):
+        v = limbs(H1_SUM, rows[i]) + power
+        patches += [(T_LOGIC, H1_SUM + k, rows[i], (v >> (16 * k)) & 0xFFFF) for k in range(4)]
+        patches.append((T_LOGIC, H1_SUM4, rows[i], 4 * ((v >> 48) & 0xFFFF)))
+    d = limbs(H1_DF, rows[n - 1]) + 3 * power
+    patches += [(T_LOGIC, H1_DF + k, rows[n - 1], (d >> (16 * k)) & 0xFFFF) for k in range(4)]
+    patches.append((T_LOGIC, H1_DF2, rows[n - 1], 2 * ((d >> 48) & 0xFFFF)))
+    bad, bad_out = _cheat(oracle, pub, blob2, patches=patches)
+    _both_reject(oracle, bad, pub, kind, n, bad_out)
+
+
 def test_fewer_enabled_validators_than_the_header_commits_to(oracle, honest):
     """Dropping a non-signer from the total voting power (nb_enabled - 1) changes the validator-set root."""
     c, pub, blob, kind, proof, out = honest
