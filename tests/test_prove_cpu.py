@@ -38,12 +38,24 @@ def test_both_verifiers_reject_tampering(oracle, proved):
 
     c, pub, blob, proof, out = proved
     rng = np.random.default_rng(0)
-    for pos in [8, 100, 5000] + [int(x) for x in rng.integers(8, proof.size, 6)]:
+    # one flipped bit anywhere: header, caps of both rounds and bus totals (the first few hundred words), then openings,
+    # FRI caps, final polynomials, proof-of-work witnesses and query data of the five tables
+    for pos in list(range(0, 8)) + [8, 100, 200, 300, 5000] + [int(x) for x in rng.integers(8, proof.size, 24)]:
         bad = proof.copy()
         bad[pos] ^= 1
         assert oracle.verify_proof(bad, pub, "mocha-4", 0, 2, out) != 0, pos
         with pytest.raises(tmx.TmxError):
             tmx.verify_proof(tmx.KIND_STEP, 2, tmx.Mocha4Config, bad.tobytes(), pub, out)
+    # a word that is not a canonical field element (x + p with x < 2^32 - 1 names the same element), a trailing extra word
+    small = int(np.argmax(proof[8:] < 2**32 - 1)) + 8
+    assert proof[small] < 2**32 - 1
+    bad = proof.copy()
+    bad[small] += np.uint64(2**64 - 2**32 + 1)
+    with pytest.raises(tmx.TmxError):
+        tmx.verify_proof(tmx.KIND_STEP, 2, tmx.Mocha4Config, bad.tobytes(), pub, out)
+    with pytest.raises(tmx.TmxError):
+        tmx.verify_proof(tmx.KIND_STEP, 2, tmx.Mocha4Config, proof.tobytes() + bytes(8), pub, out)
+    assert oracle.verify_proof(np.concatenate([proof, np.zeros(1, dtype=np.uint64)]), pub, "mocha-4", 0, 2, out) != 0
     # wrong public input / output / circuit parameters
     bad_pub = bytearray(pub)
     bad_pub[3] ^= 1
