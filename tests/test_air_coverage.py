@@ -59,3 +59,49 @@ def test_single_cell_corruption_is_caught_in_every_column(oracle, traces, table)
         if not caught:
             missed.append(c)
     assert missed == [], (NAMES[table], missed)
+
+
+def test_logic_table_cells_are_bound_against_an_adaptive_prover(oracle):
+    """The logic table needs a stronger check than the one-bad-cell test above, because an adaptive prover recomputes the range
+    table's multiplicities and every helper column after changing a cell.  tools/audit_logic_free_cells.py does that for all
+    424 cells of one row per (row type, parameter vector): a cell is FREE when the AIR still holds and the bus still balances.
+    The committed result (tests/golden/logic_free_cells.json; every free cell is one the row type does not use, or a byte
+    beyond the message length) is re-checked here on a sample: bound cells must stay bound, free cells are listed."""
+    with open(os.path.join(HERE, "golden", "logic_free_cells.json")) as f:
+        audit = json.load(f)
+    with open(os.path.join(HERE, "golden", "fixture_vectors.json")) as f:
+        c = {c["name"]: c for c in json.load(f)["cases"]}[audit["case"]]
+    pub, blob, kind = bytes.fromhex(c["input"]), bytes.fromhex(c["blob"]), 1
+    circ = oracle.circuit(kind, c["n_max"], audit["chain"])
+    lt, st = oracle.logic_trace(pub, blob, audit["chain"])
+    assert st == 0
+    n = lt.shape[1]
+
+    def totals(trace):
+        tabs = oracle.all_traces(blob, audit["chain"], logic_trace=trace)
+        a3, t3 = oracle.aux_trace(circ, 3, trace, BETA, GAMMA)
+        a4, t4 = oracle.aux_trace(circ, 4, tabs[4], BETA, GAMMA)
+        return a3, t3, [(int(t3[i]) + int(t4[i])) % P for i in range(2)]
+
+    _, _, honest = totals(lt)
+    rng = np.random.default_rng(7)
+    checked = 0
+    for r, info in audit["rows"].items():
+        r, free = int(r), set(info["free"])
+        bound = [col for col in range(lt.shape[0]) if col not in free]
+        for col in rng.choice(bound, 2, replace=False):
+            verdicts = []
+            for delta in (1, P - 1):
+                t = lt.copy()
+                t[col, r] = (int(t[col, r]) + delta) % P
+                try:
+                    a3, t3, tot = totals(t)
+                except ValueError:
+                    verdicts.append("range")
+                    continue
+                ok = not oracle.constraints_at_rows(circ, 3, t, a3, t3, BETA, GAMMA, [(r - 1) % n, r]).any() and tot == honest
+                verdicts.append("free" if ok else "bound")
+                break
+            assert "free" not in verdicts, (info["type"], r, int(col))
+            checked += 1
+    assert checked >= 50
