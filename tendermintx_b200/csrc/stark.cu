@@ -23,7 +23,9 @@
 namespace tmx {
 
 // The Ed25519 row wants 218 registers (2 CTAs per SM, 11 % occupancy); capped at 128 it spills about 0.5 KB per thread to L1
-// and runs 1 ms faster (four CTAs per SM, and the co-running tables' kernels still fit beside it).
+// and runs 1 ms faster (four CTAs per SM, and the co-running tables' kernels still fit beside it).  The same cap on the two
+// SHA tables (~250 registers uncapped) makes their kernels faster when they run alone (1.2 -> 0.8 / 0.9 ms: straight-line code
+// waiting on column loads and instruction fetch) but the pool slower (46.0 against 45.6 ms per proof, A/B on one box): uncapped.
 template <int TABLE>
 __global__ void __launch_bounds__(128, TABLE == AIR_ED25519 ? 4 : 1) quotient_kernel(QuotientArgs a) {
     const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
